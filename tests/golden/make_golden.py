@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Freeze golden vectors by running the UNMODIFIED reference under injected Philox uniforms.
+
+Run in the build container only (needs ``/root/reference``):
+
+    python tests/golden/make_golden.py
+
+Writes ``tests/golden/lat_*.npz`` (one per lattice realisation: species + the four site
+energies, exactly as the reference's ``Host``/``TADF``/``Fluorescent`` constructors produced
+them) and ``tests/golden/traj_*.npz`` (initial charge/event state, the per-step trace
+``(kind, particule, initial, final, tau, draws)`` read from ``Lattice._cache[-1]``, and the final
+state and tallies).  The reference has no tests or fixtures of its own, so these
+files are the parity pin for ``oracle/frm_oracle.c`` and for the CUDA path.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_harness as rh  # noqa: E402
+
+DEFAULT_PROPS = (0.84, 0.15, 0.01)          # OLED.py:7
+LATTICE_KEYS = ("species", "homo", "lumo", "s1", "t1")
+
+# name, dims, props, charges, seed, steps, extra kwargs
+CASES = [
+    # the reference driver's own configuration (OLED.py:6-10), golden seeds 1..4
+    ("d0_s1", (10, 10, 5), DEFAULT_PROPS, 4, 1, 3000, {}),
+    ("d0_s2", (10, 10, 5), DEFAULT_PROPS, 4, 2, 3000, {}),
+    ("d0_s3", (10, 10, 5), DEFAULT_PROPS, 4, 3, 3000, {}),
+    ("d0_s4", (10, 10, 5), DEFAULT_PROPS, 4, 4, 3000, {}),
+    # BASELINE config 1: 20^3, one electron + one hole in flight; same lattice reused at C=10
+    ("c1_s1", (20, 20, 20), DEFAULT_PROPS, 1, 1, 3000, {}),
+    ("c1_s2", (20, 20, 20), DEFAULT_PROPS, 1, 2, 3000, {}),
+    ("c10_s1", (20, 20, 20), DEFAULT_PROPS, 10, 1, 2000, {}),
+    ("c10_s2", (20, 20, 20), DEFAULT_PROPS, 10, 2, 2000, {}),
+    # second trajectory on the same realisation (trajectory id != realisation id)
+    ("c1_s1_t7", (20, 20, 20), DEFAULT_PROPS, 1, 1, 1500, {"trajectory": 7}),
+    # ragged / minimal shapes: every site touches a wrap seam or a z face
+    ("tiny333_s5", (3, 3, 3), (0.5, 0.3, 0.2), 2, 5, 1500, {}),
+    ("rag456_s6", (4, 5, 6), (0.5, 0.3, 0.2), 3, 6, 2000, {}),
+    ("rag734_s7", (7, 3, 4), (0.6, 0.3, 0.1), 3, 7, 2000, {}),
+    # thin slab, many charges: blocked candidates, frozen charges (Q4), dense Coulomb sums
+    ("dense_s8", (6, 6, 3), (0.6, 0.3, 0.1), 12, 8, 2000, {}),
+    # Q1: proportions that do not sum to 1.0 are replaced by dimension/sum(dimension)
+    ("q1_s9", (6, 6, 6), (0.5, 0.3, 0.3), 2, 9, 1000, {}),
+    # field variants (sign convention Q8; zero field)
+    ("field0_s10", (8, 8, 6), DEFAULT_PROPS, 3, 10, 1500, {"electric_field": 0.0}),
+    ("field3_s11", (8, 8, 6), DEFAULT_PROPS, 3, 11, 1500, {"electric_field": 0.3}),
+    # non-zero realisation id
+    ("real3_s12", (8, 8, 8), DEFAULT_PROPS, 2, 12, 1500, {"realisation": 3, "trajectory": 5}),
+]
+
+
+def replay_case():
+    """Crafted uniforms on the TRAJ stream: exercises ``_randbelow`` rejection
+    (``random.py:264-269``: r >= limit is redrawn) and u = 0.0 (=> rng = 1.0, tau = -0.0)."""
+    from oracle import philox as px
+    n = 60000
+    u = np.array([px.uniform(99, px.STREAM_TRAJ, 0, d) for d in range(n)], dtype=np.float64)
+    top = 1.0 - 2.0 ** -53                     # largest double below 1: always >= limit unless n | 2^53
+    u[0] = top                                  # first draw of the electron injection sample -> rejected
+    u[5] = top
+    u[40] = 0.0                                 # a candidate with rng = 1.0 -> tau = -0.0 wins its min()
+    u[200:4000:97] = top                        # sprinkle rejections over re-injection choices
+    u[300:4000:131] = 0.0
+    return u
+
+
+def main():
+    os.makedirs(HERE, exist_ok=True)
+    written = {}
+    for name, dims, props, charges, seed, steps, kw in CASES:
+        out = rh.run_reference(dims, props, charges, seed, steps, **kw)
+        _write(name, out, dims, seed, kw.get("realisation", 0), written)
+    u = replay_case()
+    out = rh.run_reference((6, 5, 4), (0.6, 0.3, 0.1), 3, 99, 1500, replay_traj=u)
+    used = int(out["final_draws"][0])
+    out["replay_traj"] = u[:used + 8]
+    _write("replay_s99", out, (6, 5, 4), 99, 0, written)
+
+
+def _write(name, out, dims, seed, real, written):
+    lat_name = f"lat_{dims[0]}x{dims[1]}x{dims[2]}_s{seed}_r{real}"
+    lat = {k: out.pop(k) for k in LATTICE_KEYS}
+    if lat_name in written:
+        for k in LATTICE_KEYS:                   # same (seed, realisation) => identical lattice
+            assert np.array_equal(lat[k], written[lat_name][k]), (name, k)
+    else:
+        np.savez_compressed(os.path.join(HERE, lat_name + ".npz"), **lat)
+        written[lat_name] = lat
+    out["lattice"] = np.array(lat_name)
+    np.savez_compressed(os.path.join(HERE, f"traj_{name}.npz"), **out)
+    t = out["final_tallies"]
+    print(f"{name:12s} steps={len(out['trace_kind']):5d} emission={t[0]} recomb={t[1]} inj={t[2]} "
+          f"draws={out['final_draws'].tolist()} error={str(out['error'])!r}")
+
+
+if __name__ == "__main__":
+    main()
