@@ -1,0 +1,818 @@
+// First-Reaction-Method kernels for sm_100a: one warp owns one trajectory (one reference
+// `Lattice` instance's dynamic state); the 32 lanes are the <= 26 candidate hops of the charge
+// whose event is being regenerated (reseau.py:380-396), or cooperate on the ordered lists.
+//
+// State of a trajectory lives in shared memory for the whole launch (loaded once, stored once):
+//   pos[t]      ordered position lists  _electrons_locations / _holes_locations (reseau.py:208-209)
+//   flag[t]     the SET of sites whose Molecule.electron / .hole flag is True.  The reference's
+//               flags are toggles (molecule.py:78-86) that can disagree with the lists (two
+//               charges on one site after a stale move or a re-injection), so they are state of
+//               their own, not derived from pos[].
+//   ev_*[t]     ordered move-event lists _move_electron_events / _move_hole_events
+//   special     the single pending bound / decay / capture event (tau = 0, fires next step)
+//   cache       ring of the last 10 fired events (Lattice._cache, reseau.py:124)
+// t = 0 electrons, t = 1 holes; particule code = t + 1 (event.py:53-57).
+//
+// fp64 arithmetic that decides parity uses explicit round-to-nearest intrinsics so that no FMA
+// contraction can change a bit relative to CPython's float arithmetic; only exp() and log()
+// (CUDA libdevice vs glibc, both <= 1 ulp) can differ, which is why tau is compared at 1e-12.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "hf_philox.cuh"
+
+#define HF_FULL 0xffffffffu
+#define HF_CACHE 10
+
+// trajectory status (mirrors hf_traj_status in include/hfkmc.h)
+#define HF_ST_OK 0
+#define HF_ST_NO_EVENTS 1
+#define HF_ST_ZERO_DIVISION 2
+#define HF_ST_VALUE_ERROR 3
+#define HF_ST_REPLAY_EXHAUSTED 4
+#define HF_ST_CAPACITY 5
+
+// event / particle / exciton / species codes (event.py:43-57, molecule.py:16-21)
+#define HF_K_MOVE 1
+#define HF_K_BOUND 2
+#define HF_K_DECAY 5
+#define HF_K_CAPTURE 7
+#define HF_PART_EXCITON 3
+#define HF_XS_SINGLET 1
+#define HF_XS_TRIPLET 3
+#define HF_SPECIES_HOST 0
+
+// constants.py:3-6 and reseau.py:148-151, as CPython evaluates them
+#define HF_KT 0x1.a78f25677e0f1p-6            /* BOLTZMANN * 300.            */
+#define HF_ELECTROSTATIC 0x1.01b112ab38751p-21 /* 1/(4 pi eps0 eps_r)        */
+#define HF_RATE0 1e13                          /* 10.**13                     */
+
+struct HfScalars {                 // one per trajectory, global memory
+    int32_t n_pos[2], n_flag[2], n_ev[2];
+    int32_t special, special_site, xstate, status;
+    int32_t cache_head, cache_n;
+    uint64_t draws, spins, emission, recombination, injection, steps, fired;
+};
+
+struct HfTraceRec {                // == hf_event in include/hfkmc.h
+    int32_t initial, final_;
+    double tau;
+    uint8_t kind, particule, pad[2];
+    uint32_t spins;
+    uint64_t draws;
+};
+
+struct HfParams {
+    int32_t X, Y, Z;
+    int64_t N;
+    double field;
+    int32_t C, cap_c, cap_f;
+    int64_t B, traj_per_real;
+    uint32_t k0, k1, first_traj, first_real;
+    int64_t setsize;               // random.sample's pool/set switch for k = C (random.py:421-424)
+    // lattice [n_real][N]
+    const uint8_t *species;
+    const double *homo, *lumo;
+    // state
+    int32_t *pos[2], *flag[2], *ev_init[2], *ev_final[2];
+    double *ev_tau[2];
+    HfScalars *sc;
+    int32_t *cache_init, *cache_final, *cache_kp;   // [B][10]
+    double *cache_tau;
+    // replay / trace
+    const double *replay;
+    int64_t n_replay;
+    HfTraceRec *trace;
+    int64_t trace_first, trace_n, trace_cap;
+    unsigned long long *totals;    // channel counters, HF_N_TALLIES
+    int64_t n_steps;
+};
+
+struct HfWarp {
+    // shared-memory lists; the two particle types are adjacent: list(t) = base + t * capacity
+    double *ev_tau_b, *inv_old_b, *cache_tau;
+    int32_t *pos_b, *flag_b, *ev_init_b, *ev_final_b, *cache_init, *cache_final, *cache_kp;
+    int32_t cap_c, cap_f;
+    // warp-uniform scalars (kept as named fields so that nothing is dynamically indexed)
+    int32_t n_pos0, n_pos1, n_flag0, n_flag1, n_ev0, n_ev1;
+    int32_t special, special_site, xstate, status, cache_head, cache_n;
+    uint64_t draws, spins, emission, recombination, injection, steps, fired;
+    uint32_t ident;                // global trajectory id (Philox ident)
+    int64_t local;                 // local trajectory index
+    const uint8_t *species;        // this trajectory's realisation
+    const double *lumo, *homo;
+    unsigned c_move_e, c_move_h, c_bound, c_decay, c_capture_e, c_capture_h;
+    unsigned c_recomb_host, c_recomb_tadf, c_recomb_fluo, c_emit_tadf, c_emit_fluo;
+
+    __device__ __forceinline__ int32_t *pos(int t) const { return pos_b + t * cap_c; }
+    __device__ __forceinline__ int32_t *flag(int t) const { return flag_b + t * cap_f; }
+    __device__ __forceinline__ int32_t *ev_init(int t) const { return ev_init_b + t * cap_c; }
+    __device__ __forceinline__ int32_t *ev_final(int t) const { return ev_final_b + t * cap_c; }
+    __device__ __forceinline__ double *ev_tau(int t) const { return ev_tau_b + t * cap_c; }
+    __device__ __forceinline__ double *inv_old(int s) const { return inv_old_b + s * cap_c; }
+    __device__ __forceinline__ const double *energy(int t) const { return t ? homo : lumo; }
+    __device__ __forceinline__ int n_pos(int t) const { return t ? n_pos1 : n_pos0; }
+    __device__ __forceinline__ int n_flag(int t) const { return t ? n_flag1 : n_flag0; }
+    __device__ __forceinline__ int n_ev(int t) const { return t ? n_ev1 : n_ev0; }
+    __device__ __forceinline__ void set_n_pos(int t, int v) { if (t) n_pos1 = v; else n_pos0 = v; }
+    __device__ __forceinline__ void set_n_flag(int t, int v) { if (t) n_flag1 = v; else n_flag0 = v; }
+    __device__ __forceinline__ void set_n_ev(int t, int v) { if (t) n_ev1 = v; else n_ev0 = v; }
+};
+
+__host__ __device__ inline size_t hf_warp_smem_bytes(int cap_c, int cap_f) {
+    size_t b = 8u * (4u * cap_c + HF_CACHE) + 4u * (6u * cap_c + 2u * cap_f + 3u * HF_CACHE);
+    return (b + 15u) & ~(size_t)15u;
+}
+
+__device__ __forceinline__ void hf_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f) {
+    w.cap_c = cap_c; w.cap_f = cap_f;
+    double *d = reinterpret_cast<double *>(base);
+    w.ev_tau_b = d; d += 2 * cap_c;
+    w.inv_old_b = d; d += 2 * cap_c;
+    w.cache_tau = d; d += HF_CACHE;
+    int32_t *i = reinterpret_cast<int32_t *>(d);
+    w.pos_b = i; i += 2 * cap_c;
+    w.ev_init_b = i; i += 2 * cap_c;
+    w.ev_final_b = i; i += 2 * cap_c;
+    w.flag_b = i; i += 2 * cap_f;
+    w.cache_init = i; i += HF_CACHE;
+    w.cache_final = i; i += HF_CACHE;
+    w.cache_kp = i;
+}
+
+// ---- packed coordinates ---------------------------------------------------------------------
+__device__ __forceinline__ int hf_pack(int x, int y, int z) { return x | (y << 10) | (z << 20); }
+__device__ __forceinline__ int hf_px(int p) { return p & 1023; }
+__device__ __forceinline__ int hf_py(int p) { return (p >> 10) & 1023; }
+__device__ __forceinline__ int hf_pz(int p) { return p >> 20; }
+__device__ __forceinline__ int64_t hf_site(const HfParams &P, int p) {
+    return ((int64_t)hf_pz(p) * P.Y + hf_py(p)) * P.X + hf_px(p);
+}
+__device__ __forceinline__ int hf_pack_site(const HfParams &P, int64_t s) {
+    const int x = (int)(s % P.X), y = (int)((s / P.X) % P.Y), z = (int)(s / ((int64_t)P.X * P.Y));
+    return hf_pack(x, y, z);
+}
+// |a - b|^2 as the reference computes it: raw index differences, no minimum image (quirk Q7)
+__device__ __forceinline__ int hf_dist2(int a, int b) {
+    const int dx = hf_px(a) - hf_px(b), dy = hf_py(a) - hf_py(b), dz = hf_pz(a) - hf_pz(b);
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// ---- uniforms -------------------------------------------------------------------------------
+// d-th uniform of the trajectory's TRAJ stream; sets *exhausted when a replay buffer is short.
+__device__ __forceinline__ double hf_traj_uniform(const HfParams &P, const HfWarp &w, uint64_t d, bool *exhausted) {
+    if (P.replay) {
+        if (d >= (uint64_t)P.n_replay) { *exhausted = true; return 0.5; }
+        return P.replay[w.local * P.n_replay + (int64_t)d];
+    }
+    return hf_philox_uniform(P.k0, P.k1, HF_STREAM_TRAJ, w.ident, d);
+}
+
+// random.py:264-269 _randbelow_without_getrandbits (warp-uniform; every lane computes the same)
+__device__ __forceinline__ int64_t hf_randbelow(const HfParams &P, HfWarp &w, int64_t n, bool *exhausted) {
+    const int64_t maxsize = (int64_t)1 << 53;
+    const int64_t rem = maxsize % n;
+    const double limit = (double)(maxsize - rem) * 0x1p-53;          // exact
+    double r = hf_traj_uniform(P, w, w.draws++, exhausted);
+    while (r >= limit && !*exhausted) r = hf_traj_uniform(P, w, w.draws++, exhausted);
+    return (int64_t)floor(r * 0x1p53) % n;
+}
+
+// ---- ordered-list primitives (warp-cooperative, n is warp-uniform) ---------------------------
+__device__ __forceinline__ int hf_find_first(const int32_t *a, int n, int v, int lane) {
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const unsigned m = __ballot_sync(HF_FULL, i < n && a[i] == v);
+        if (m) return base + __ffs(m) - 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ bool hf_contains(const int32_t *a, int n, int v, int lane) {
+    return hf_find_first(a, n, v, lane) >= 0;
+}
+
+// list.remove(a[idx]) keeping the order of the rest
+__device__ __forceinline__ void hf_remove_at(int32_t *a, int n, int idx, int lane) {
+    for (int base = idx; base < n - 1; base += 32) {
+        const int i = base + lane;
+        int v = 0;
+        if (i < n - 1) v = a[i + 1];
+        __syncwarp();
+        if (i < n - 1) a[i] = v;
+        __syncwarp();
+    }
+}
+
+// Molecule.switch_electron / switch_hole (molecule.py:78-86) on the flag SET
+__device__ __forceinline__ bool hf_toggle_flag(const HfParams &P, HfWarp &w, int t, int site, int lane) {
+    const int idx = hf_find_first(w.flag(t), w.n_flag(t), site, lane);
+    if (idx >= 0) {
+        if (lane == 0) w.flag(t)[idx] = w.flag(t)[w.n_flag(t) - 1];
+        w.set_n_flag(t, w.n_flag(t) - 1);
+    } else {
+        if (w.n_flag(t) >= P.cap_f) return false;
+        if (lane == 0) w.flag(t)[w.n_flag(t)] = site;
+        w.set_n_flag(t, w.n_flag(t) + 1);
+    }
+    __syncwarp();
+    return true;
+}
+
+__device__ __forceinline__ void hf_clear_flag(HfWarp &w, int t, int site, int lane) {
+    const int idx = hf_find_first(w.flag(t), w.n_flag(t), site, lane);
+    if (idx >= 0) {
+        if (lane == 0) w.flag(t)[idx] = w.flag(t)[w.n_flag(t) - 1];
+        w.set_n_flag(t, w.n_flag(t) - 1);
+    }
+    __syncwarp();
+}
+
+// _remove_move_*_events (reseau.py:352-364) under Event.__eq__ (event.py:141-147): drop every
+// event of type t whose initial == a OR final == b (quirk Q4), keeping the order of the rest.
+__device__ __forceinline__ void hf_remove_events(HfWarp &w, int t, int a, int b, int lane) {
+    const int n = w.n_ev(t);
+    int out = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        int ini = 0, fin = 0;
+        double tau = 0.0;
+        bool keep = false;
+        if (i < n) {
+            ini = w.ev_init(t)[i]; fin = w.ev_final(t)[i]; tau = w.ev_tau(t)[i];
+            keep = !(ini == a || fin == b);
+        }
+        const unsigned m = __ballot_sync(HF_FULL, keep);
+        const int dst = out + __popc(m & ((1u << lane) - 1u));
+        __syncwarp();
+        if (keep) { w.ev_init(t)[dst] = ini; w.ev_final(t)[dst] = fin; w.ev_tau(t)[dst] = tau; }
+        __syncwarp();
+        out += __popc(m);
+    }
+    w.set_n_ev(t, out);
+}
+
+// _update_events (reseau.py:564-578): tau -= time on every pending move event
+__device__ __forceinline__ void hf_update_events(HfWarp &w, double time, int lane) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+        for (int i = lane; i < w.n_ev(t); i += 32) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
+    __syncwarp();
+}
+
+// ---- neighbour table: reseau.py:184-205 for charge_tranfer_distance == 1 (quirk Q3) ----------
+// i-th entry of _born_von_karman(p, 1, axe) for a periodic axis (always 3 entries)
+__device__ __forceinline__ int hf_bvk_xy(int p, int size, int i) {
+    if (p - 1 > -1 && p + 1 < size) return p - 1 + i;
+    if (p - 1 < 0) return i < 2 ? i : size - 1;              // [0, 1, size-1]
+    return i < 2 ? p - 1 + i : 0;                            // [size-2, size-1, 0]
+}
+// open axis z: 3 entries in the bulk, 2 on a face
+__device__ __forceinline__ int hf_bvk_z(int p, int size, int i) {
+    if (p - 1 > -1 && p + 1 < size) return p - 1 + i;
+    if (p - 1 < 0) return i;                                 // [0, 1]
+    return p - 1 + i;                                        // [size-2, size-1]
+}
+
+// One candidate hop of a charge of type t from `initial` to `cand` given its uniform u:
+// _time_move_electron / _time_move_hole (reseau.py:283-292, 315-324) with the Coulomb term of
+// reseau.py:297-313 / 329-345.  inv_old[0][j] / inv_old[1][j] hold 1/|loc_j - initial| for the
+// same-type / opposite-type lists (0 where the distance is 0).  Returns tau; *rate gets k;
+// *zero_div is set where the reference would raise ZeroDivisionError.
+__device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w, int t, int initial, int cand,
+                                              double u, double *rate, bool *zero_div) {
+    const double rng = __dsub_rn(1.0, u);                                        // 284 / 316
+    const double *E = w.energy(t);
+    double dE = __dsub_rn(__ldg(E + hf_site(P, cand)), __ldg(E + hf_site(P, initial)));   // 286 / 318
+    const double fz = t == 0 ? -P.field : P.field;                               // (-1.*E) / (1.*E)
+    dE = __dadd_rn(dE, __dmul_rn(fz, (double)(hf_pz(cand) - hf_pz(initial))));   // 287 / 319
+    double out = 0.0;
+    const int ns = w.n_pos(t), no = w.n_pos(1 - t);
+    for (int j = 0; j < ns; ++j) {                                               // 299-304 / 331-336
+        const int loc = w.pos(t)[j];
+        if (loc == initial) continue;
+        const int d2 = hf_dist2(loc, cand);
+        if (d2 == 0) { *zero_div = true; return 0.0; }
+        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+        out = __dadd_rn(out, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, w.inv_old(0)[j])));
+    }
+    for (int j = 0; j < no; ++j) {                                               // 305-312 / 337-344
+        const int loc = w.pos(1 - t)[j];
+        if (loc == cand) { out = -INFINITY; break; }
+        const double io = w.inv_old(1)[j];
+        if (io == 0.0) { *zero_div = true; return 0.0; }
+        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(loc, cand)));
+        out = __dsub_rn(out, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, io)));
+    }
+    dE = __dadd_rn(dE, out);                                                     // 288 / 320
+    double k = HF_RATE0;                                                         // 289 / 321
+    if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));                   // 290-291 / 322-323
+    *rate = k;
+    if (k == 0.0) { *zero_div = true; return 0.0; }                              // float division by zero
+    return __ddiv_rn(-log(rng), k);                                              // 292 / 324
+}
+
+// 1/|loc_j - initial| for both lists, computed once per regenerated event instead of once per
+// candidate (the reference recomputes it 26 times: SURVEY.md §8a2); same bits.
+__device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, int lane) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int32_t *list = s == 0 ? w.pos(t) : w.pos(1 - t);
+        const int n = s == 0 ? w.n_pos(t) : w.n_pos(1 - t);
+        for (int j = lane; j < n; j += 32) {
+            const int d2 = hf_dist2(list[j], initial);
+            w.inv_old(s)[j] = d2 == 0 ? 0.0 : __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+        }
+    }
+    __syncwarp();
+}
+
+// _new_move_electron_events / _new_move_hole_events (reseau.py:380-396; use_flags = true) and the
+// per-charge body of _init_move_*_events (reseau.py:240-276; use_flags = false: membership in
+// the position list).  Lanes = candidates in the reference's x-major neighbour order; one TRAJ
+// uniform per unblocked candidate in that order; first minimum wins.  Returns a status.
+__device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags, int lane) {
+    const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
+    const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
+    const int total = 9 * nz;
+    const int ix = lane / (3 * nz), iy = (lane / nz) % 3, iz = lane % nz;
+    const int cx = hf_bvk_xy(px, P.X, ix < 3 ? ix : 0), cy = hf_bvk_xy(py, P.Y, iy), cz = hf_bvk_z(pz, P.Z, iz);
+    const bool valid = lane < total && !(cx == px && cy == py && cz == pz);
+    const int cand = hf_pack(cx, cy, cz);
+    const int32_t *blk = use_flags ? w.flag(t) : w.pos(t);
+    const int nb = use_flags ? w.n_flag(t) : w.n_pos(t);
+    bool blocked = false;
+    for (int j = 0; j < nb; ++j) blocked |= (blk[j] == cand);                    // 385 / 394 ; 249 / 268
+    const bool active = valid && !blocked;
+    const unsigned mask = __ballot_sync(HF_FULL, active);
+    if (mask == 0) return HF_ST_VALUE_ERROR;                                     // min() of an empty sequence
+    hf_fill_inv_old(w, t, pos, lane);
+    double tau = INFINITY, rate = 0.0;
+    bool zero_div = false, exhausted = false;
+    if (active) {
+        const int rank = __popc(mask & ((1u << lane) - 1u));
+        const double u = hf_traj_uniform(P, w, w.draws + (uint64_t)rank, &exhausted);
+        tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
+    }
+    if (__ballot_sync(HF_FULL, exhausted)) return HF_ST_REPLAY_EXHAUSTED;
+    const unsigned zmask = __ballot_sync(HF_FULL, active && zero_div);
+    if (zmask) {                                   // draws up to and including the failing candidate
+        const int f = __ffs(zmask) - 1;
+        w.draws += (uint64_t)__popc(mask & (f == 31 ? HF_FULL : ((2u << f) - 1u)));
+        return HF_ST_ZERO_DIVISION;
+    }
+    w.draws += (uint64_t)__popc(mask);
+    // min(events): first minimum in candidate order (387 / 396)
+    int best = active ? lane : 99;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double otau = __shfl_xor_sync(HF_FULL, tau, off);
+        const int obest = __shfl_xor_sync(HF_FULL, best, off);
+        if (otau < tau || (otau == tau && obest < best)) { tau = otau; best = obest; }
+    }
+    const int fin = __shfl_sync(HF_FULL, cand, best & 31);
+    if (w.n_ev(t) >= P.cap_c) return HF_ST_CAPACITY;
+    if (lane == 0) { w.ev_init(t)[w.n_ev(t)] = pos; w.ev_final(t)[w.n_ev(t)] = fin; w.ev_tau(t)[w.n_ev(t)] = tau; }
+    w.set_n_ev(t, w.n_ev(t) + 1);
+    __syncwarp();
+    return HF_ST_OK;
+}
+
+// _electron_reinjection / _hole_reinjection (reseau.py:448-470): choice() over the free sites of
+// the injection face in x-major order, append, toggle the flag, _injection += 1.
+__device__ __forceinline__ int hf_reinject(const HfParams &P, HfWarp &w, int t, int lane) {
+    const int zf = t == 0 ? P.Z - 1 : 0;
+    const int n = w.n_pos(t);
+    const int32_t *list = w.pos(t);
+    // distinct occupied face sites
+    int n_occ = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        bool first = false;
+        if (j < n && hf_pz(list[j]) == zf) {
+            first = true;
+            for (int q = 0; q < j; ++q) first &= (list[q] != list[j]);
+        }
+        n_occ += __popc(__ballot_sync(HF_FULL, first));
+    }
+    const int64_t n_free = (int64_t)P.X * P.Y - n_occ;
+    if (n_free <= 0) return HF_ST_VALUE_ERROR;                                   // choice() of an empty sequence
+    bool exhausted = false;
+    const int64_t k = hf_randbelow(P, w, n_free, &exhausted);                    // random.py:345-350
+    if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
+    // k-th free face index f = x*Y + y: fixed point of f = k + #{distinct occupied <= f}
+    int64_t f = k;
+    for (;;) {
+        int c = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            bool hit = false;
+            if (j < n && hf_pz(list[j]) == zf && (int64_t)hf_px(list[j]) * P.Y + hf_py(list[j]) <= f) {
+                hit = true;
+                for (int q = 0; q < j; ++q) hit &= (list[q] != list[j]);
+            }
+            c += __popc(__ballot_sync(HF_FULL, hit));
+        }
+        const int64_t f2 = k + c;
+        if (f2 == f) break;
+        f = f2;
+    }
+    const int site = hf_pack((int)(f / P.Y), (int)(f % P.Y), zf);
+    if (n >= P.cap_c) return HF_ST_CAPACITY;
+    if (lane == 0) w.pos(t)[n] = site;
+    w.set_n_pos(t, n + 1);
+    __syncwarp();
+    if (!hf_toggle_flag(P, w, t, site, lane)) return HF_ST_CAPACITY;
+    w.injection += 1;
+    return HF_ST_OK;
+}
+
+// ---- state load / store ------------------------------------------------------------------------
+__device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int64_t local, int lane) {
+    const HfScalars sc = P.sc[local];
+    w.local = local;
+    w.ident = P.first_traj + (uint32_t)local;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) { w.set_n_pos(t, sc.n_pos[t]); w.set_n_flag(t, sc.n_flag[t]); w.set_n_ev(t, sc.n_ev[t]); }
+    w.special = sc.special; w.special_site = sc.special_site; w.xstate = sc.xstate; w.status = sc.status;
+    w.cache_head = sc.cache_head; w.cache_n = sc.cache_n;
+    w.draws = sc.draws; w.spins = sc.spins; w.emission = sc.emission; w.recombination = sc.recombination;
+    w.injection = sc.injection; w.steps = sc.steps; w.fired = sc.fired;
+    const int64_t r = local / P.traj_per_real;
+    w.species = P.species + r * P.N;
+    w.lumo = P.lumo + r * P.N;
+    w.homo = P.homo + r * P.N;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        for (int i = lane; i < w.n_pos(t); i += 32) w.pos(t)[i] = P.pos[t][local * P.cap_c + i];
+        for (int i = lane; i < w.n_flag(t); i += 32) w.flag(t)[i] = P.flag[t][local * P.cap_f + i];
+        for (int i = lane; i < w.n_ev(t); i += 32) {
+            w.ev_init(t)[i] = P.ev_init[t][local * P.cap_c + i];
+            w.ev_final(t)[i] = P.ev_final[t][local * P.cap_c + i];
+            w.ev_tau(t)[i] = P.ev_tau[t][local * P.cap_c + i];
+        }
+    }
+    if (lane < HF_CACHE) {
+        w.cache_init[lane] = P.cache_init[local * HF_CACHE + lane];
+        w.cache_final[lane] = P.cache_final[local * HF_CACHE + lane];
+        w.cache_kp[lane] = P.cache_kp[local * HF_CACHE + lane];
+        w.cache_tau[lane] = P.cache_tau[local * HF_CACHE + lane];
+    }
+    w.c_move_e = w.c_move_h = w.c_bound = w.c_decay = w.c_capture_e = w.c_capture_h = 0;
+    w.c_recomb_host = w.c_recomb_tadf = w.c_recomb_fluo = w.c_emit_tadf = w.c_emit_fluo = 0;
+    __syncwarp();
+}
+
+__device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int lane) {
+    const int64_t local = w.local;
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        for (int i = lane; i < w.n_pos(t); i += 32) P.pos[t][local * P.cap_c + i] = w.pos(t)[i];
+        for (int i = lane; i < w.n_flag(t); i += 32) P.flag[t][local * P.cap_f + i] = w.flag(t)[i];
+        for (int i = lane; i < w.n_ev(t); i += 32) {
+            P.ev_init[t][local * P.cap_c + i] = w.ev_init(t)[i];
+            P.ev_final[t][local * P.cap_c + i] = w.ev_final(t)[i];
+            P.ev_tau[t][local * P.cap_c + i] = w.ev_tau(t)[i];
+        }
+    }
+    if (lane < HF_CACHE) {
+        P.cache_init[local * HF_CACHE + lane] = w.cache_init[lane];
+        P.cache_final[local * HF_CACHE + lane] = w.cache_final[lane];
+        P.cache_kp[local * HF_CACHE + lane] = w.cache_kp[lane];
+        P.cache_tau[local * HF_CACHE + lane] = w.cache_tau[lane];
+    }
+    if (lane == 0) {
+        HfScalars sc;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { sc.n_pos[t] = w.n_pos(t); sc.n_flag[t] = w.n_flag(t); sc.n_ev[t] = w.n_ev(t); }
+        sc.special = w.special; sc.special_site = w.special_site; sc.xstate = w.xstate; sc.status = w.status;
+        sc.cache_head = w.cache_head; sc.cache_n = w.cache_n;
+        sc.draws = w.draws; sc.spins = w.spins; sc.emission = w.emission; sc.recombination = w.recombination;
+        sc.injection = w.injection; sc.steps = w.steps; sc.fired = w.fired;
+        P.sc[local] = sc;
+        // channel counters: one atomic per non-zero counter per trajectory per launch
+        const unsigned c[11] = {w.c_move_e, w.c_move_h, w.c_bound, w.c_decay, w.c_capture_e, w.c_capture_h,
+                                w.c_recomb_host, w.c_recomb_tadf, w.c_recomb_fluo, w.c_emit_tadf, w.c_emit_fluo};
+#pragma unroll
+        for (int i = 0; i < 11; ++i) if (c[i]) atomicAdd(P.totals + 5 + i, (unsigned long long)c[i]);
+    }
+}
+
+// ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
+// Returns HF_ST_OK when an event fired; ev_* describe it (packed coordinates).
+__device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
+                                       int *ev_init, int *ev_final, double *ev_tau) {
+    int kind, part, ini, fin;
+    double tau;
+    if (w.special) {
+        // a tau = 0 bound / decay / capture event sits later in the concatenation order than any
+        // move event and all residual taus are >= 0, so it is the pop() of reseau.py:486-487 (Q6)
+        kind = w.special & 0xff; part = w.special >> 8; ini = fin = w.special_site; tau = 0.0;
+    } else {
+        // min tau over move_e + move_h, LAST one in concatenation order on ties (Q6)
+        const int ne = w.n_ev(0), total = ne + w.n_ev(1);
+        if (total == 0) return HF_ST_NO_EVENTS;                                  // 487-488
+        double btau = INFINITY;
+        int bidx = -1;
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            if (i < total) {
+                const double ti = i < ne ? w.ev_tau(0)[i] : w.ev_tau(1)[i - ne];
+                if (bidx < 0 || ti <= btau) { btau = ti; bidx = i; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ot = __shfl_xor_sync(HF_FULL, btau, off);
+            const int oi = __shfl_xor_sync(HF_FULL, bidx, off);
+            if (oi >= 0 && (bidx < 0 || ot < btau || (ot == btau && oi > bidx))) { btau = ot; bidx = oi; }
+        }
+        const int t = bidx < ne ? 0 : 1, i = bidx - (t ? ne : 0);
+        kind = HF_K_MOVE; part = t + 1; tau = btau;
+        ini = w.ev_init(t)[i]; fin = w.ev_final(t)[i];
+    }
+    // _cache.popleft(); _cache.append(event)  (489-490)
+    if (lane == 0) {
+        w.cache_init[w.cache_head] = ini; w.cache_final[w.cache_head] = fin;
+        w.cache_kp[w.cache_head] = kind | (part << 8); w.cache_tau[w.cache_head] = tau;
+    }
+    w.cache_head = w.cache_head + 1 == HF_CACHE ? 0 : w.cache_head + 1;
+    if (w.cache_n < HF_CACHE) w.cache_n += 1;
+    *ev_kind = kind; *ev_part = part; *ev_init = ini; *ev_final = fin; *ev_tau = tau;
+
+    if (kind == HF_K_MOVE) {                                                     // 492-524
+        const int t = part - 1, o = 1 - t;
+        if (t == 0) w.c_move_e += 1; else w.c_move_h += 1;
+        hf_remove_events(w, t, ini, fin, lane);                                  // 495 / 511 (Q4)
+        if (!hf_toggle_flag(P, w, t, ini, lane)) return HF_ST_CAPACITY;          // 423-424 / 429-430
+        if (!hf_toggle_flag(P, w, t, fin, lane)) return HF_ST_CAPACITY;
+        const int idx = hf_find_first(w.pos(t), w.n_pos(t), ini, lane);          // 425-426 / 431-432
+        if (idx < 0) return HF_ST_VALUE_ERROR;
+        hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+        if (lane == 0) w.pos(t)[w.n_pos(t) - 1] = fin;
+        __syncwarp();
+        const bool opposite_here = hf_contains(w.flag(o), w.n_flag(o), fin, lane);
+        const int capture_z = t == 0 ? 0 : P.Z - 1;
+        if (!opposite_here && hf_pz(fin) != capture_z) {                         // 498-500 / 514-516
+            hf_update_events(w, tau, lane);
+            return hf_gen_move_event(P, w, t, fin, true, lane);
+        } else if (opposite_here) {                                              // 501-505 / 517-521
+            hf_remove_events(w, o, fin, fin, lane);
+            // _update_events(0.) leaves every tau unchanged (Q5)
+            w.special = HF_K_BOUND | (HF_PART_EXCITON << 8); w.special_site = fin;
+        } else {                                                                 // 506-508 / 522-524
+            hf_update_events(w, tau, lane);
+            w.special = HF_K_CAPTURE | (part << 8); w.special_site = fin;
+        }
+        return HF_ST_OK;
+    }
+    const int site = w.special_site;
+    w.special = 0;                                                               // _remove_*_event
+    if (kind == HF_K_BOUND) {                                                    // 529-533
+        w.c_bound += 1;
+        const bool both = hf_contains(w.flag(0), w.n_flag(0), site, lane) && hf_contains(w.flag(1), w.n_flag(1), site, lane);
+        if (both) {                                                              // molecule.py:88-96
+            const double r = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPIN, w.ident, w.spins);
+            w.spins += 1;
+            w.xstate = (0 <= r && r < 0.25) ? HF_XS_SINGLET : HF_XS_TRIPLET;
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                                            // 434-438
+            const int idx = hf_find_first(w.pos(t), w.n_pos(t), site, lane);
+            if (idx < 0) return HF_ST_VALUE_ERROR;
+            hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+            w.set_n_pos(t, w.n_pos(t) - 1);
+        }
+        w.special = HF_K_DECAY | (HF_PART_EXCITON << 8); w.special_site = site;
+        return HF_ST_OK;
+    }
+    if (kind == HF_K_DECAY) {                                                    // 541-547
+        w.c_decay += 1;
+        const int sp = w.species[hf_site(P, site)];
+        bool photon = false;
+        if (w.xstate) {                                                          // molecule.py:185-199, 283-297, 387-400
+            photon = sp != HF_SPECIES_HOST && w.xstate == HF_XS_SINGLET;
+            w.xstate = 0;
+            hf_clear_flag(w, 0, site, lane);
+            hf_clear_flag(w, 1, site, lane);
+        }
+        w.recombination += 1;                                                    // 472-476
+        w.c_recomb_host += sp == 0; w.c_recomb_tadf += sp == 1; w.c_recomb_fluo += sp == 2;
+        if (photon) { w.emission += 1; w.c_emit_tadf += sp == 1; w.c_emit_fluo += sp == 2; }
+        int st = hf_reinject(P, w, 0, lane);
+        if (st != HF_ST_OK) return st;
+        st = hf_gen_move_event(P, w, 0, w.pos(0)[w.n_pos(0) - 1], true, lane);
+        if (st != HF_ST_OK) return st;
+        st = hf_reinject(P, w, 1, lane);
+        if (st != HF_ST_OK) return st;
+        return hf_gen_move_event(P, w, 1, w.pos(1)[w.n_pos(1) - 1], true, lane);
+    }
+    // capture (551-561)
+    const int t = part - 1;
+    if (t == 0) w.c_capture_e += 1; else w.c_capture_h += 1;
+    if (!hf_toggle_flag(P, w, t, site, lane)) return HF_ST_CAPACITY;             // 440-446
+    const int idx = hf_find_first(w.pos(t), w.n_pos(t), site, lane);
+    if (idx < 0) return HF_ST_VALUE_ERROR;
+    hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+    w.set_n_pos(t, w.n_pos(t) - 1);
+    const int st = hf_reinject(P, w, t, lane);
+    if (st != HF_ST_OK) return st;
+    return hf_gen_move_event(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
+}
+
+// ---- kernels -------------------------------------------------------------------------------------
+// Lattice.operations(stop) (reseau.py:580-595) for every trajectory: one warp per trajectory,
+// grid-stride over trajectories.
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) hf_run_kernel(const HfParams P) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HfWarp w;
+    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f), P.cap_c, P.cap_f);
+    for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
+        hf_load_state(P, w, local, lane);
+        // a ZeroDivisionError only ends the operations() call it happened in (reseau.py:587-589)
+        if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;
+        const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
+        HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+        if (w.status == HF_ST_OK) {
+            for (int64_t i = 0; i < P.n_steps; ++i) {
+                w.steps += 1;                                                    // 582
+                int kind, part, ini, fin;
+                double tau;
+                const int st = hf_step(P, w, lane, &kind, &part, &ini, &fin, &tau);
+                if (st != HF_ST_OK) { w.status = st; break; }                    // 587-591
+                if (traced && lane == 0 && w.fired < (uint64_t)P.trace_cap) {
+                    HfTraceRec rec;
+                    rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
+                    rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
+                    rec.pad[0] = rec.pad[1] = 0;
+                    rec.spins = (uint32_t)w.spins; rec.draws = w.draws;
+                    trace[w.fired] = rec;
+                }
+                w.fired += 1;
+            }
+        }
+        hf_store_state(P, w, lane);
+    }
+}
+
+// Lattice._charges_injection + _events_creation (reseau.py:207-276): random.sample of the
+// injection sites (random.py:359-448, both the pool and the set variant), flag toggles, then one
+// initial move event per charge.
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) hf_inject_kernel(const HfParams P, int32_t *pool_scratch) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HfWarp w;
+    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f), P.cap_c, P.cap_f);
+    const int64_t molecules = (int64_t)P.X * P.Y;
+    for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
+        hf_load_state(P, w, local, lane);      // zero-initialised by the host
+        int st = HF_ST_OK;
+        bool exhausted = false;
+        int32_t *pool = pool_scratch ? pool_scratch + ((int64_t)blockIdx.x * kWarps + warp) * molecules : nullptr;
+        for (int t = 0; t < 2; ++t) {                                            // 219, 225
+            const int z = t == 0 ? P.Z - 1 : 0;
+            if (molecules <= P.setsize) {                                        // pool variant
+                for (int64_t i = lane; i < molecules; i += 32) pool[i] = (int32_t)i;
+                __syncwarp();
+                for (int i = 0; i < P.C; ++i) {
+                    const int64_t j = hf_randbelow(P, w, molecules - i, &exhausted);
+                    const int32_t pick = pool[j];
+                    __syncwarp();
+                    if (lane == 0) { pool[j] = pool[molecules - i - 1]; w.pos(t)[i] = hf_pack(pick / P.Y, pick % P.Y, z); }
+                    __syncwarp();
+                }
+            } else {                                                             // set variant
+                for (int i = 0; i < P.C; ++i) {
+                    int64_t j = hf_randbelow(P, w, molecules, &exhausted);
+                    int cand = hf_pack((int)(j / P.Y), (int)(j % P.Y), z);
+                    while (hf_contains(w.pos(t), i, cand, lane) && !exhausted) {
+                        j = hf_randbelow(P, w, molecules, &exhausted);
+                        cand = hf_pack((int)(j / P.Y), (int)(j % P.Y), z);
+                    }
+                    if (lane == 0) w.pos(t)[i] = cand;
+                    __syncwarp();
+                }
+            }
+            w.set_n_pos(t, P.C);
+        }
+        if (exhausted) st = HF_ST_REPLAY_EXHAUSTED;
+        for (int i = 0; i < P.C && st == HF_ST_OK; ++i)                          // 226-228
+            for (int t = 0; t < 2; ++t)
+                if (!hf_toggle_flag(P, w, t, w.pos(t)[i], lane)) st = HF_ST_CAPACITY;
+        for (int t = 0; t < 2 && st == HF_ST_OK; ++t)                            // 240-276
+            for (int i = 0; i < P.C && st == HF_ST_OK; ++i)
+                st = hf_gen_move_event(P, w, t, w.pos(t)[i], false, lane);
+        w.injection = 2ull * (uint64_t)P.C;                                      // 118
+        w.status = st;
+        hf_store_state(P, w, lane);
+    }
+}
+
+// Known-answer entry: tau and k of hand-built hops in the trajectory's current state.
+__global__ void hf_eval_hops_kernel(const HfParams P, int64_t local, int t, int n, const int32_t *initial,
+                                    const int32_t *final_, const double *u, double *tau, double *rate, int32_t *zero_div) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const int lane = threadIdx.x & 31;
+    HfWarp w;
+    hf_carve(w, hf_smem, P.cap_c, P.cap_f);
+    hf_load_state(P, w, local, lane);
+    for (int i = 0; i < n; ++i) {
+        const int ini = hf_pack_site(P, initial[i]), fin = hf_pack_site(P, final_[i]);
+        hf_fill_inv_old(w, t, ini, lane);
+        if (lane == 0) {
+            bool zd = false;
+            double k = 0.0;
+            tau[i] = hf_hop_time(P, w, t, ini, fin, u[i], &k, &zd);
+            rate[i] = k;
+            zero_div[i] = zd ? 1 : 0;
+        }
+        __syncwarp();
+    }
+}
+
+// Sum the per-trajectory counters into totals[0..4] and count stopped trajectories.
+__global__ void hf_reduce_kernel(const HfScalars *sc, int64_t B, unsigned long long *totals) {
+    unsigned long long v[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const HfScalars s = sc[i];
+        v[0] += s.emission; v[1] += s.recombination; v[2] += s.injection; v[3] += s.steps; v[4] += s.fired;
+        v[5] += s.status != HF_ST_OK;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(HF_FULL, v[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (v[k]) atomicAdd(totals + k, v[k]);
+        if (v[5]) atomicAdd(totals + 16, v[5]);
+    }
+}
+
+// ---- lattice generation ----------------------------------------------------------------------------
+// Species shuffle, reseau.py:164-172: random.sample([0,1,2], k=total, counts=...) is a pool-based
+// partial Fisher-Yates over range(total) (random.py:426-432) mapped through bisect over the
+// cumulative counts; quirk Q2 uses only the first X*Y selections, replicated in every interior
+// layer.  Inherently sequential: one thread per realisation; `pool` holds range(total).
+__global__ void hf_species_pool_init(int32_t *pool, int64_t total, int n_real) {
+    const int64_t n = total * n_real;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        pool[i] = (int32_t)(i % total);
+}
+
+__global__ void hf_species_shuffle(const HfParams P, int32_t *pool_all, int64_t total, int64_t n_host, int64_t n_tadf,
+                                   uint8_t *layer_all, int real_base) {
+    const int r = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    int32_t *pool = pool_all + (int64_t)r * total;
+    uint8_t *layer = layer_all + (int64_t)(real_base + r) * P.X * P.Y;
+    const uint32_t ident = P.first_real + (uint32_t)(real_base + r);
+    const int64_t maxsize = (int64_t)1 << 53;
+    uint64_t d = 0;
+    const int64_t xy = (int64_t)P.X * P.Y;
+    for (int64_t i = 0; i < xy && i < total; ++i) {
+        const int64_t n = total - i;
+        const int64_t rem = maxsize % n;
+        const double limit = (double)(maxsize - rem) * 0x1p-53;
+        double u = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPECIES, ident, d++);
+        while (u >= limit) u = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPECIES, ident, d++);
+        const int64_t j = (int64_t)floor(u * 0x1p53) % n;
+        const int32_t s = pool[j];
+        pool[j] = pool[n - 1];
+        layer[i] = (uint8_t)(s < n_host ? 0 : (s < n_host + n_tadf ? 1 : 2));   // bisect over cum_counts
+    }
+}
+
+// Site species (faces all Host, reseau.py:170,172) and the four Gaussian energies of the species
+// constructors (molecule.py:180-183 etc.; random.gauss = Box-Muller pair, random.py:543-589).
+__global__ void hf_fill_sites(const HfParams P, const uint8_t *layer_all, int n_real, uint8_t *species,
+                              double *homo, double *lumo, double *s1, double *t1) {
+    const double means[3][4] = {{6.0, -2.0, 3.50, 3.00}, {5.8, -2.6, 2.55, 2.52}, {5.25, -1.84, 2.69, 1.43}};
+    const int64_t xy = (int64_t)P.X * P.Y, n = P.N * n_real;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = g / P.N, i = g % P.N;
+        const int64_t z = i / xy, q = i % xy;
+        const int sp = (z > 0 && z < P.Z - 1) ? layer_all[r * xy + q] : 0;
+        const uint32_t ident = P.first_real + (uint32_t)r;
+        double e[4];
+#pragma unroll
+        for (int pair = 0; pair < 2; ++pair) {
+            const double ua = hf_philox_uniform(P.k0, P.k1, HF_STREAM_ENERGY, ident, (uint64_t)(4 * i + 2 * pair));
+            const double ub = hf_philox_uniform(P.k0, P.k1, HF_STREAM_ENERGY, ident, (uint64_t)(4 * i + 2 * pair + 1));
+            const double x2pi = __dmul_rn(ua, 0x1.921fb54442d18p+2);
+            const double g2rad = __dsqrt_rn(__dmul_rn(-2.0, log(__dsub_rn(1.0, ub))));
+            double sn, cs;
+            sincos(x2pi, &sn, &cs);
+            e[2 * pair] = __dadd_rn(means[sp][2 * pair], __dmul_rn(__dmul_rn(cs, g2rad), 0.1));
+            e[2 * pair + 1] = __dadd_rn(means[sp][2 * pair + 1], __dmul_rn(__dmul_rn(sn, g2rad), 0.1));
+        }
+        species[g] = (uint8_t)sp;
+        homo[g] = e[0]; lumo[g] = e[1]; s1[g] = e[2]; t1[g] = e[3];
+    }
+}

@@ -1,0 +1,43 @@
+// Philox4x32-10 and the uniform-draw contract on the device.
+//
+// The reference has no counter-based RNG (it uses unseeded MT19937: reseau.py:113,
+// molecule.py:72); parity is defined by injecting uniforms through random.Random.random()
+// (SURVEY.md §8c).  This header is the device side of that contract:
+//
+//   key     = (seed_lo, seed_hi)
+//   counter = (d_lo, d_hi, ident, stream)
+//   u       = (((w1 << 32) | w0) >> 11) * 2^-53        53-bit, like CPython's random()
+//
+//   stream 0 TRAJ    ident = trajectory   Lattice._seed after lattice creation (reseau.py:219,
+//                                          225, 284, 316, 455, 467)
+//   stream 1 SPIN    ident = trajectory   Molecule.generate_exciton (molecule.py:92)
+//   stream 2 SPECIES ident = realisation  the species shuffle (reseau.py:164-168)
+//   stream 3 ENERGY  ident = realisation  d = 4*site + j, the four gauss() calls of a site
+//                                          (molecule.py:180-183)
+#pragma once
+#include <stdint.h>
+
+#define HF_STREAM_TRAJ 0u
+#define HF_STREAM_SPIN 1u
+#define HF_STREAM_SPECIES 2u
+#define HF_STREAM_ENERGY 3u
+
+__device__ __forceinline__ uint64_t hf_philox_u64(uint32_t k0, uint32_t k1, uint32_t stream,
+                                                  uint32_t ident, uint64_t d) {
+    uint32_t c0 = (uint32_t)d, c1 = (uint32_t)(d >> 32), c2 = ident, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return ((uint64_t)c1 << 32) | c0;
+}
+
+__device__ __forceinline__ double hf_philox_uniform(uint32_t k0, uint32_t k1, uint32_t stream,
+                                                    uint32_t ident, uint64_t d) {
+    return (double)(hf_philox_u64(k0, k1, stream, ident, d) >> 11) * 0x1p-53;
+}

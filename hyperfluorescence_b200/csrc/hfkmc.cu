@@ -1,0 +1,664 @@
+// libhfkmc.so — host side of the C-ABI declared in include/hfkmc.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared ...
+// (see hyperfluorescence_b200/build.py).  No CPU path exists: without an sm_100 device
+// hf_create fails with HF_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/hfkmc.h"
+#include "hf_frm.cuh"
+
+static_assert(sizeof(HfTraceRec) == sizeof(hf_event), "trace record must match hf_event");
+static_assert(sizeof(hf_event) == 32, "hf_event is 32 bytes");
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define HF_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(HF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kMaxDim = 1023;          // packed coordinates: 10 bits per axis
+
+}  // namespace
+
+struct hf_sim {
+    hf_config cfg;
+    HfParams P;
+    int device = 0;
+    int n_real = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    bool have_lattice = false, injected = false;
+    // lattice
+    uint8_t *d_species = nullptr;
+    double *d_homo = nullptr, *d_lumo = nullptr, *d_s1 = nullptr, *d_t1 = nullptr;
+    // state
+    int32_t *d_pos = nullptr, *d_flag = nullptr, *d_ev_init = nullptr, *d_ev_final = nullptr;
+    double *d_ev_tau = nullptr;
+    HfScalars *d_sc = nullptr;
+    int32_t *d_cache_i = nullptr;      // init | final | kp, each [B][10]
+    double *d_cache_tau = nullptr;
+    unsigned long long *d_totals = nullptr, *d_sum = nullptr;
+    double *d_replay = nullptr;
+    HfTraceRec *d_trace = nullptr;
+    // launch shape of the step kernel
+    int warps = 4, grid = 1;
+    size_t smem = 0;
+    // timing of hf_run launches
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+    std::vector<cudaEvent_t> event_pool;
+    double timed_ms = 0.0;
+    int64_t timed_launches = 0;
+};
+
+namespace {
+
+template <int W>
+int configure_launch(hf_sim *s) {
+    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    const size_t smem = per_warp * W;
+    if (smem > 48 * 1024) {
+        HF_CUDA(cudaFuncSetAttribute(hf_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(cudaFuncSetAttribute(hf_inject_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int per_sm = 0;
+    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hf_run_kernel<W>, W * 32, smem));
+    if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "step kernel does not fit an SM (charges=%d)", s->P.C);
+    const int64_t need = (s->P.B + W - 1) / W;
+    const int64_t cap = (int64_t)s->sm_count * per_sm;
+    s->warps = W;
+    s->smem = smem;
+    s->grid = (int)(need < cap ? need : cap);
+    if (s->grid < 1) s->grid = 1;
+    return HF_OK;
+}
+
+int pick_launch(hf_sim *s) {
+    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    const size_t limit = 200 * 1024;
+    if (per_warp * 8 <= limit / 4) return configure_launch<8>(s);   // >= 4 CTAs of 8 warps per SM
+    if (per_warp * 4 <= limit) return configure_launch<4>(s);
+    if (per_warp <= limit) return configure_launch<1>(s);
+    return fail(HF_ERR_UNSUPPORTED, "charges=%d needs %zu B of shared memory per trajectory (limit %zu)",
+                s->P.C, per_warp, limit);
+}
+
+template <typename T>
+int dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    HF_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return HF_OK;
+}
+
+void fill_params(hf_sim *s) {
+    HfParams &P = s->P;
+    const int64_t B = P.B;
+    P.species = s->d_species; P.homo = s->d_homo; P.lumo = s->d_lumo;
+    for (int t = 0; t < 2; ++t) {
+        P.pos[t] = s->d_pos + (int64_t)t * B * P.cap_c;
+        P.flag[t] = s->d_flag + (int64_t)t * B * P.cap_f;
+        P.ev_init[t] = s->d_ev_init + (int64_t)t * B * P.cap_c;
+        P.ev_final[t] = s->d_ev_final + (int64_t)t * B * P.cap_c;
+        P.ev_tau[t] = s->d_ev_tau + (int64_t)t * B * P.cap_c;
+    }
+    P.sc = s->d_sc;
+    P.cache_init = s->d_cache_i;
+    P.cache_final = s->d_cache_i + B * HF_CACHE;
+    P.cache_kp = s->d_cache_i + 2 * B * HF_CACHE;
+    P.cache_tau = s->d_cache_tau;
+    P.totals = s->d_totals;
+}
+
+int check_traj(hf_sim *s, int64_t t) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (t < 0 || t >= s->P.B) return fail(HF_ERR_BAD_ARG, "trajectory %lld out of range [0, %lld)", (long long)t, (long long)s->P.B);
+    return HF_OK;
+}
+
+int32_t unpack_site(const hf_sim *s, int32_t p) {
+    const int x = p & 1023, y = (p >> 10) & 1023, z = p >> 20;
+    return (int32_t)(((int64_t)z * s->P.Y + y) * s->P.X + x);
+}
+
+int use_device(hf_sim *s) {
+    HF_CUDA(cudaSetDevice(s->device));
+    return HF_OK;
+}
+
+cudaEvent_t get_event(hf_sim *s) {
+    if (!s->event_pool.empty()) { cudaEvent_t e = s->event_pool.back(); s->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void fold_timing(hf_sim *s) {
+    for (auto &pr : s->timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { s->timed_ms += ms; s->timed_launches += 1; }
+        s->event_pool.push_back(pr.first);
+        s->event_pool.push_back(pr.second);
+    }
+    s->timing.clear();
+}
+
+template <int W>
+void launch_run(hf_sim *s) {
+    hf_run_kernel<W><<<s->grid, W * 32, s->smem, s->stream>>>(s->P);
+}
+template <int W>
+void launch_inject(hf_sim *s, int32_t *pool) {
+    hf_inject_kernel<W><<<s->grid, W * 32, s->smem, s->stream>>>(s->P, pool);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *hf_last_error(void) { return g_error; }
+int hf_abi_version(void) { return HF_ABI_VERSION; }
+
+int hf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int hf_create(const hf_config *c, hf_sim **out) {
+    if (!c || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    const int X = c->dims[0], Y = c->dims[1], Z = c->dims[2];
+    if (Z < 3) return fail(HF_ERR_BAD_ARG, "Expected the last component of dimension to be > 2, got %d.", Z);   // reseau.py:131
+    if (X < 2 || Y < 2) return fail(HF_ERR_BAD_ARG, "x and y dimensions must be >= 2, got (%d, %d)", X, Y);
+    if (X > kMaxDim || Y > kMaxDim || Z > kMaxDim) return fail(HF_ERR_UNSUPPORTED, "dimensions above %d are not supported", kMaxDim);
+    const int64_t N = (int64_t)X * Y * Z;
+    if (N > 0x7fffffffLL) return fail(HF_ERR_UNSUPPORTED, "more than 2^31-1 sites");
+    double pmin = c->props[0] < c->props[1] ? c->props[0] : c->props[1];
+    if (c->props[2] < pmin) pmin = c->props[2];
+    if (pmin * (double)N < 1)                                                                    // reseau.py:137-139
+        return fail(HF_ERR_BAD_ARG, "Not enough molecules for current proportions and dimension.");
+    if (c->charges < 1 || c->charges > (int64_t)X * Y)                                           // reseau.py:212-213
+        return fail(HF_ERR_BAD_ARG, "Required %d charges but only %lld molecules available.", c->charges, (long long)X * Y);
+    if (c->distance != 1)
+        return fail(HF_ERR_UNSUPPORTED, "charge_tranfer_distance=%d: only 1 is supported (the reference's neighbour table is ill-defined beyond it, quirk Q3)", c->distance);
+    if (c->n_trajectories < 1 || c->n_realisations < 1 || c->n_trajectories % c->n_realisations != 0)
+        return fail(HF_ERR_BAD_ARG, "n_realisations (%d) must divide n_trajectories (%lld)", c->n_realisations, (long long)c->n_trajectories);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(HF_ERR_NO_DEVICE, "no CUDA device visible: libhfkmc has no CPU path");
+    }
+    if (c->device < 0 || c->device >= ndev) return fail(HF_ERR_BAD_ARG, "device %d out of range (%d visible)", c->device, ndev);
+    cudaDeviceProp prop;
+    HF_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10)
+        return fail(HF_ERR_NO_DEVICE, "device %d is sm_%d%d; libhfkmc is built for sm_100a only", c->device, prop.major, prop.minor);
+
+    hf_sim *s = new (std::nothrow) hf_sim();
+    if (!s) return fail(HF_ERR_BAD_ARG, "out of host memory");
+    s->cfg = *c;
+    s->device = c->device;
+    s->n_real = c->n_realisations;
+    s->sm_count = prop.multiProcessorCount;
+    HfParams &P = s->P;
+    memset(&P, 0, sizeof(P));
+    P.X = X; P.Y = Y; P.Z = Z; P.N = N;
+    P.field = c->electric_field;
+    P.C = c->charges;
+    P.cap_c = c->charges;
+    P.cap_f = c->charges == 1 ? 2 : 2 * c->charges + 8;
+    P.B = c->n_trajectories;
+    P.traj_per_real = c->n_trajectories / c->n_realisations;
+    P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
+    P.first_traj = c->first_trajectory; P.first_real = c->first_realisation;
+    {   // random.sample's setsize for k = charges (random.py:421-424)
+        int64_t setsize = 21;
+        const int64_t k = c->charges;
+        if (k > 5) {
+            const int64_t e = (int64_t)std::ceil(std::log((double)(k * 3)) / std::log(4.0));
+            int64_t p4 = 1;
+            for (int64_t i = 0; i < e; ++i) p4 *= 4;
+            setsize += p4;
+        }
+        P.setsize = setsize;
+    }
+    int rc = HF_OK;
+    auto bail = [&](int code) { hf_destroy(s); return code; };
+    if (cudaSetDevice(s->device) != cudaSuccess) return bail(fail(HF_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(HF_ERR_CUDA, "cudaStreamCreate failed"));
+    s->own_stream = true;
+    const int64_t B = P.B, R = s->n_real;
+    if ((rc = dev_alloc(&s->d_species, (size_t)(R * N)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_homo, (size_t)(R * N)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_lumo, (size_t)(R * N)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_s1, (size_t)(R * N)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_t1, (size_t)(R * N)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_pos, (size_t)(2 * B * P.cap_c)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_flag, (size_t)(2 * B * P.cap_f)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_ev_init, (size_t)(2 * B * P.cap_c)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_ev_final, (size_t)(2 * B * P.cap_c)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_ev_tau, (size_t)(2 * B * P.cap_c)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_sc, (size_t)B))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_cache_i, (size_t)(3 * B * HF_CACHE)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_cache_tau, (size_t)(B * HF_CACHE)))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_totals, (size_t)HF_N_TALLIES))) return bail(rc);
+    if ((rc = dev_alloc(&s->d_sum, (size_t)HF_N_TALLIES))) return bail(rc);
+    fill_params(s);
+    if ((rc = pick_launch(s))) return bail(rc);
+    *out = s;
+    return HF_OK;
+}
+
+int hf_destroy(hf_sim *s) {
+    if (!s) return HF_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    fold_timing(s);
+    for (cudaEvent_t e : s->event_pool) cudaEventDestroy(e);
+    cudaFree(s->d_species); cudaFree(s->d_homo); cudaFree(s->d_lumo); cudaFree(s->d_s1); cudaFree(s->d_t1);
+    cudaFree(s->d_pos); cudaFree(s->d_flag); cudaFree(s->d_ev_init); cudaFree(s->d_ev_final); cudaFree(s->d_ev_tau);
+    cudaFree(s->d_sc); cudaFree(s->d_cache_i); cudaFree(s->d_cache_tau); cudaFree(s->d_totals); cudaFree(s->d_sum);
+    cudaFree(s->d_replay); cudaFree(s->d_trace);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return HF_OK;
+}
+
+int hf_set_stream(hf_sim *s, void *cuda_stream) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+    s->stream = (cudaStream_t)cuda_stream;
+    return HF_OK;
+}
+
+int hf_sync(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    HF_CUDA(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_generate_lattice(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const HfParams &P = s->P;
+    const int64_t xy = (int64_t)P.X * P.Y, grid_size = P.N;
+    const int64_t n_fluo = (int64_t)((double)grid_size * s->cfg.props[2]);       // reseau.py:159
+    const int64_t n_tadf = (int64_t)((double)grid_size * s->cfg.props[1]);       // reseau.py:160
+    const int64_t n_host = grid_size - 2 * xy - n_fluo - n_tadf;                 // reseau.py:161
+    const int64_t total = n_host + n_tadf + n_fluo;
+    if (total != xy * (P.Z - 2) || total <= 0)                                   // reseau.py:169
+        return fail(HF_ERR_BAD_ARG, "Size of sub_grid (%lld) and x_max*y_max*sub_z_max (%lld) must match !", (long long)total, (long long)(xy * (P.Z - 2)));
+    uint8_t *d_layer = nullptr;
+    int32_t *d_pool = nullptr;
+    if ((rc = dev_alloc(&d_layer, (size_t)(xy * s->n_real)))) return rc;
+    // realisations are shuffled in batches so that the pool scratch stays below ~1 GiB
+    int batch = (int)((int64_t)(1 << 28) / total);
+    if (batch < 1) batch = 1;
+    if (batch > s->n_real) batch = s->n_real;
+    if ((rc = dev_alloc(&d_pool, (size_t)(total * batch)))) { cudaFree(d_layer); return rc; }
+    for (int r0 = 0; r0 < s->n_real; r0 += batch) {
+        const int nb = s->n_real - r0 < batch ? s->n_real - r0 : batch;
+        hf_species_pool_init<<<s->sm_count * 8, 256, 0, s->stream>>>(d_pool, total, nb);
+        hf_species_shuffle<<<nb, 32, 0, s->stream>>>(P, d_pool, total, n_host, n_tadf, d_layer, r0);
+    }
+    hf_fill_sites<<<s->sm_count * 8, 256, 0, s->stream>>>(P, d_layer, s->n_real, s->d_species, s->d_homo, s->d_lumo, s->d_s1, s->d_t1);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_layer);
+    cudaFree(d_pool);
+    if (e != cudaSuccess) return fail(HF_ERR_CUDA, "lattice generation failed: %s", cudaGetErrorString(e));
+    HF_CUDA(cudaGetLastError());
+    s->have_lattice = true;
+    return HF_OK;
+}
+
+int hf_upload_lattice(hf_sim *s, int32_t r, const uint8_t *species, const double *homo, const double *lumo,
+                      const double *s1, const double *t1) {
+    if (!s || !species || !homo || !lumo) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (r < 0 || r >= s->n_real) return fail(HF_ERR_BAD_ARG, "realisation %d out of range", r);
+    int rc = use_device(s);
+    if (rc) return rc;
+    const size_t N = (size_t)s->P.N, off = (size_t)r * N;
+    HF_CUDA(cudaMemcpyAsync(s->d_species + off, species, N, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaMemcpyAsync(s->d_homo + off, homo, N * 8, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaMemcpyAsync(s->d_lumo + off, lumo, N * 8, cudaMemcpyHostToDevice, s->stream));
+    if (s1) HF_CUDA(cudaMemcpyAsync(s->d_s1 + off, s1, N * 8, cudaMemcpyHostToDevice, s->stream));
+    if (t1) HF_CUDA(cudaMemcpyAsync(s->d_t1 + off, t1, N * 8, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));      // the caller may free its buffers on return
+    s->have_lattice = true;
+    return HF_OK;
+}
+
+int hf_download_lattice(hf_sim *s, int32_t r, uint8_t *species, double *homo, double *lumo, double *s1, double *t1) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (r < 0 || r >= s->n_real) return fail(HF_ERR_BAD_ARG, "realisation %d out of range", r);
+    if (!s->have_lattice) return fail(HF_ERR_STATE, "no lattice yet");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const size_t N = (size_t)s->P.N, off = (size_t)r * N;
+    if (species) HF_CUDA(cudaMemcpyAsync(species, s->d_species + off, N, cudaMemcpyDeviceToHost, s->stream));
+    if (homo) HF_CUDA(cudaMemcpyAsync(homo, s->d_homo + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (lumo) HF_CUDA(cudaMemcpyAsync(lumo, s->d_lumo + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (s1) HF_CUDA(cudaMemcpyAsync(s1, s->d_s1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (t1) HF_CUDA(cudaMemcpyAsync(t1, s->d_t1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    return HF_OK;
+}
+
+int hf_set_replay(hf_sim *s, const double *u, int64_t n) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_replay);
+    s->d_replay = nullptr;
+    s->P.replay = nullptr;
+    s->P.n_replay = 0;
+    if (u) {
+        if (n < 1) return fail(HF_ERR_BAD_ARG, "replay length must be positive");
+        const size_t total = (size_t)n * (size_t)s->P.B;
+        if ((rc = dev_alloc(&s->d_replay, total))) return rc;
+        HF_CUDA(cudaMemcpyAsync(s->d_replay, u, total * 8, cudaMemcpyHostToDevice, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+        s->P.replay = s->d_replay;
+        s->P.n_replay = n;
+    }
+    return HF_OK;
+}
+
+int hf_inject(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->have_lattice) return fail(HF_ERR_STATE, "hf_inject before a lattice exists (hf_generate_lattice / hf_upload_lattice)");
+    int rc = use_device(s);
+    if (rc) return rc;
+    const HfParams &P = s->P;
+    HF_CUDA(cudaMemsetAsync(s->d_sc, 0, sizeof(HfScalars) * (size_t)P.B, s->stream));
+    HF_CUDA(cudaMemsetAsync(s->d_cache_i, 0, sizeof(int32_t) * 3 * (size_t)P.B * HF_CACHE, s->stream));
+    HF_CUDA(cudaMemsetAsync(s->d_cache_tau, 0, sizeof(double) * (size_t)P.B * HF_CACHE, s->stream));
+    HF_CUDA(cudaMemsetAsync(s->d_totals, 0, sizeof(unsigned long long) * HF_N_TALLIES, s->stream));
+    int32_t *pool = nullptr;
+    const int64_t molecules = (int64_t)P.X * P.Y;
+    if (molecules <= P.setsize)
+        if ((rc = dev_alloc(&pool, (size_t)((int64_t)s->grid * s->warps * molecules)))) return rc;
+    switch (s->warps) {
+        case 8: launch_inject<8>(s, pool); break;
+        case 4: launch_inject<4>(s, pool); break;
+        default: launch_inject<1>(s, pool); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && pool) e = cudaStreamSynchronize(s->stream);
+    cudaFree(pool);
+    if (e != cudaSuccess) return fail(HF_ERR_CUDA, "inject kernel failed: %s", cudaGetErrorString(e));
+    s->injected = true;
+    return HF_OK;
+}
+
+int hf_run(hf_sim *s, int64_t stop) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->injected) return fail(HF_ERR_STATE, "hf_run before hf_inject");
+    if (stop < 0) return fail(HF_ERR_BAD_ARG, "stop must be >= 0");
+    int rc = use_device(s);
+    if (rc) return rc;
+    s->P.n_steps = stop;
+    if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
+    cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+    HF_CUDA(cudaEventRecord(e0, s->stream));
+    switch (s->warps) {
+        case 8: launch_run<8>(s); break;
+        case 4: launch_run<4>(s); break;
+        default: launch_run<1>(s); break;
+    }
+    HF_CUDA(cudaEventRecord(e1, s->stream));
+    s->timing.emplace_back(e0, e1);
+    HF_CUDA(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_run_timing(hf_sim *s, double *total_ms, int64_t *launches) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    fold_timing(s);
+    if (total_ms) *total_ms = s->timed_ms;
+    if (launches) *launches = s->timed_launches;
+    s->timed_ms = 0.0;
+    s->timed_launches = 0;
+    return HF_OK;
+}
+
+int hf_reduce_tallies_device(hf_sim *s, void *out_device) {
+    if (!s || !out_device) return fail(HF_ERR_BAD_ARG, "null argument");
+    int rc = use_device(s);
+    if (rc) return rc;
+    unsigned long long *out = (unsigned long long *)out_device;
+    // channel counters (5..15) are accumulated by the step kernel; the rest is summed here
+    HF_CUDA(cudaMemcpyAsync(out, s->d_totals, sizeof(unsigned long long) * HF_N_TALLIES, cudaMemcpyDeviceToDevice, s->stream));
+    int blocks = (int)((s->P.B + 255) / 256);
+    if (blocks > s->sm_count * 8) blocks = s->sm_count * 8;
+    hf_reduce_kernel<<<blocks, 256, 0, s->stream>>>(s->d_sc, s->P.B, out);
+    HF_CUDA(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_read_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    int rc = hf_reduce_tallies_device(s, s->d_sum);
+    if (rc) return rc;
+    HF_CUDA(cudaMemcpyAsync(out, s->d_sum, sizeof(uint64_t) * HF_N_TALLIES, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    return HF_OK;
+}
+
+int hf_read_info(hf_sim *s, int64_t t, hf_traj_info *out) {
+    int rc = check_traj(s, t);
+    if (rc) return rc;
+    if (!out) return fail(HF_ERR_BAD_ARG, "null argument");
+    if ((rc = use_device(s))) return rc;
+    HfScalars sc;
+    HF_CUDA(cudaMemcpyAsync(&sc, s->d_sc + t, sizeof(sc), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    out->n_electrons = sc.n_pos[0]; out->n_holes = sc.n_pos[1];
+    out->n_eflags = sc.n_flag[0]; out->n_hflags = sc.n_flag[1];
+    out->n_move_e = sc.n_ev[0]; out->n_move_h = sc.n_ev[1];
+    out->special_kind = sc.special & 0xff; out->special_particule = sc.special >> 8;
+    out->special_site = sc.special ? unpack_site(s, sc.special_site) : -1;
+    out->exciton_state = sc.xstate; out->status = sc.status; out->cache_count = sc.cache_n;
+    out->draws = sc.draws; out->spins = sc.spins;
+    out->emission = sc.emission; out->recombination = sc.recombination; out->injection = sc.injection;
+    out->steps = sc.steps; out->fired = sc.fired;
+    return HF_OK;
+}
+
+static int read_list(hf_sim *s, int64_t t, const int32_t *base, int cap, int count, int32_t *sites, int32_t *n) {
+    if (!sites || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (*n < count) return fail(HF_ERR_BAD_ARG, "buffer too small: need %d, have %d", count, *n);
+    std::vector<int32_t> tmp((size_t)(count > 0 ? count : 1));
+    if (count > 0) {
+        HF_CUDA(cudaMemcpyAsync(tmp.data(), base + t * cap, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    for (int i = 0; i < count; ++i) sites[i] = unpack_site(s, tmp[(size_t)i]);
+    *n = count;
+    return HF_OK;
+}
+
+int hf_read_positions(hf_sim *s, int64_t t, int32_t which, int32_t *sites, int32_t *n) {
+    hf_traj_info info;
+    int rc = hf_read_info(s, t, &info);
+    if (rc) return rc;
+    if (which == 0) return read_list(s, t, s->P.pos[0], s->P.cap_c, info.n_electrons, sites, n);
+    if (which == 1) return read_list(s, t, s->P.pos[1], s->P.cap_c, info.n_holes, sites, n);
+    if (which == 2) {   // _excitons_locations: the exciton lives between its bound and decay steps
+        if (!sites || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+        if (info.special_kind == HF_EV_DECAY) {
+            if (*n < 1) return fail(HF_ERR_BAD_ARG, "buffer too small");
+            sites[0] = info.special_site;
+            *n = 1;
+        } else {
+            *n = 0;
+        }
+        return HF_OK;
+    }
+    return fail(HF_ERR_BAD_ARG, "which must be 0, 1 or 2");
+}
+
+int hf_read_flags(hf_sim *s, int64_t t, int32_t which, int32_t *sites, int32_t *n) {
+    hf_traj_info info;
+    int rc = hf_read_info(s, t, &info);
+    if (rc) return rc;
+    if (which != 0 && which != 1) return fail(HF_ERR_BAD_ARG, "which must be 0 or 1");
+    return read_list(s, t, s->P.flag[which], s->P.cap_f, which ? info.n_hflags : info.n_eflags, sites, n);
+}
+
+int hf_read_move_events(hf_sim *s, int64_t t, int32_t which, int32_t *initial, int32_t *final_, double *tau, int32_t *n) {
+    hf_traj_info info;
+    int rc = hf_read_info(s, t, &info);
+    if (rc) return rc;
+    if (which != 0 && which != 1) return fail(HF_ERR_BAD_ARG, "which must be 0 or 1");
+    if (!initial || !final_ || !tau || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+    const int count = which ? info.n_move_h : info.n_move_e;
+    int32_t cap = *n;
+    if ((rc = read_list(s, t, s->P.ev_init[which], s->P.cap_c, count, initial, &cap))) return rc;
+    cap = *n;
+    if ((rc = read_list(s, t, s->P.ev_final[which], s->P.cap_c, count, final_, &cap))) return rc;
+    if (count > 0) {
+        HF_CUDA(cudaMemcpyAsync(tau, s->P.ev_tau[which] + t * s->P.cap_c, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    *n = count;
+    return HF_OK;
+}
+
+int hf_read_last_events(hf_sim *s, int64_t t, hf_event *out, int32_t *n) {
+    hf_traj_info info;
+    int rc = hf_read_info(s, t, &info);
+    if (rc) return rc;
+    if (!out || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+    HfScalars sc;
+    HF_CUDA(cudaMemcpyAsync(&sc, s->d_sc + t, sizeof(sc), cudaMemcpyDeviceToHost, s->stream));
+    int32_t ci[HF_CACHE], cf[HF_CACHE], ck[HF_CACHE];
+    double ct[HF_CACHE];
+    HF_CUDA(cudaMemcpyAsync(ci, s->P.cache_init + t * HF_CACHE, sizeof(ci), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(cf, s->P.cache_final + t * HF_CACHE, sizeof(cf), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(ck, s->P.cache_kp + t * HF_CACHE, sizeof(ck), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(ct, s->P.cache_tau + t * HF_CACHE, sizeof(ct), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    const int count = sc.cache_n;
+    for (int i = 0; i < count; ++i) {          // oldest first
+        const int slot = ((sc.cache_head - count + i) % HF_CACHE + HF_CACHE) % HF_CACHE;
+        memset(&out[i], 0, sizeof(hf_event));
+        out[i].initial = unpack_site(s, ci[slot]);
+        out[i].final_ = unpack_site(s, cf[slot]);
+        out[i].tau = ct[slot];
+        out[i].kind = (uint8_t)(ck[slot] & 0xff);
+        out[i].particule = (uint8_t)(ck[slot] >> 8);
+    }
+    *n = count;
+    return HF_OK;
+}
+
+int hf_set_trace(hf_sim *s, int64_t first, int64_t n, int64_t capacity) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_trace);
+    s->d_trace = nullptr;
+    s->P.trace = nullptr;
+    s->P.trace_first = s->P.trace_n = s->P.trace_cap = 0;
+    if (n > 0) {
+        if (first < 0 || first + n > s->P.B || capacity < 1) return fail(HF_ERR_BAD_ARG, "bad trace window");
+        if ((rc = dev_alloc(&s->d_trace, (size_t)(n * capacity)))) return rc;
+        HF_CUDA(cudaMemsetAsync(s->d_trace, 0, sizeof(HfTraceRec) * (size_t)(n * capacity), s->stream));
+        s->P.trace = s->d_trace;
+        s->P.trace_first = first; s->P.trace_n = n; s->P.trace_cap = capacity;
+    }
+    return HF_OK;
+}
+
+int hf_read_trace(hf_sim *s, int64_t t, hf_event *out, int64_t *n) {
+    hf_traj_info info;
+    int rc = hf_read_info(s, t, &info);
+    if (rc) return rc;
+    if (!out || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->d_trace || t < s->P.trace_first || t >= s->P.trace_first + s->P.trace_n)
+        return fail(HF_ERR_STATE, "trajectory %lld is not traced", (long long)t);
+    int64_t count = (int64_t)info.fired < s->P.trace_cap ? (int64_t)info.fired : s->P.trace_cap;
+    if (*n < count) return fail(HF_ERR_BAD_ARG, "buffer too small: need %lld", (long long)count);
+    if (count > 0) {
+        HF_CUDA(cudaMemcpyAsync(out, s->d_trace + (t - s->P.trace_first) * s->P.trace_cap, sizeof(hf_event) * (size_t)count,
+                                cudaMemcpyDeviceToHost, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    *n = count;
+    return HF_OK;
+}
+
+int hf_eval_hops(hf_sim *s, int64_t t, int32_t particule, int32_t n, const int32_t *initial, const int32_t *final_,
+                 const double *u, double *tau, double *rate, int32_t *zero_division) {
+    int rc = check_traj(s, t);
+    if (rc) return rc;
+    if (!s->injected) return fail(HF_ERR_STATE, "hf_eval_hops before hf_inject");
+    if (particule != HF_P_ELECTRON && particule != HF_P_HOLE) return fail(HF_ERR_BAD_ARG, "particule must be 1 or 2");
+    if (n < 1 || !initial || !final_ || !u || !tau || !rate || !zero_division) return fail(HF_ERR_BAD_ARG, "bad argument");
+    for (int i = 0; i < n; ++i)
+        if (initial[i] < 0 || initial[i] >= s->P.N || final_[i] < 0 || final_[i] >= s->P.N) return fail(HF_ERR_BAD_ARG, "site out of range");
+    if ((rc = use_device(s))) return rc;
+    int32_t *d_i = nullptr, *d_zd = nullptr;
+    double *d_d = nullptr;
+    if ((rc = dev_alloc(&d_i, (size_t)(2 * n)))) return rc;
+    if ((rc = dev_alloc(&d_zd, (size_t)n))) { cudaFree(d_i); return rc; }
+    if ((rc = dev_alloc(&d_d, (size_t)(3 * n)))) { cudaFree(d_i); cudaFree(d_zd); return rc; }
+    cudaMemcpyAsync(d_i, initial, 4 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(d_i + n, final_, 4 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
+    cudaMemcpyAsync(d_d, u, 8 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
+    const size_t smem = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(hf_eval_hops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) {
+        hf_eval_hops_kernel<<<1, 32, smem, s->stream>>>(s->P, t, particule - 1, n, d_i, d_i + n, d_d, d_d + n, d_d + 2 * n, d_zd);
+        cudaMemcpyAsync(tau, d_d + n, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+        cudaMemcpyAsync(rate, d_d + 2 * n, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+        cudaMemcpyAsync(zero_division, d_zd, 4 * (size_t)n, cudaMemcpyDeviceToHost, s->stream);
+        e = cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(d_i); cudaFree(d_zd); cudaFree(d_d);
+    if (e != cudaSuccess) return fail(HF_ERR_CUDA, "hf_eval_hops failed: %s", cudaGetErrorString(e));
+    return HF_OK;
+}
+
+}  // extern "C"

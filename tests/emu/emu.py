@@ -1,0 +1,113 @@
+"""Python driver of the host-side warp emulator (tests/emu/warp_emu.h).  TEST INFRASTRUCTURE."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libemu_frm.so")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+DEPS = [os.path.join(HERE, "emu_frm.cpp"), os.path.join(HERE, "warp_emu.h"),
+        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm.cuh"),
+        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_philox.cuh")]
+
+EVENT_DTYPE = np.dtype([("initial", "<i4"), ("final", "<i4"), ("tau", "<f8"), ("kind", "u1"), ("particule", "u1"),
+                        ("pad", "u1", (2,)), ("spins", "<u4"), ("draws", "<u8")])
+assert EVENT_DTYPE.itemsize == 32
+
+
+def build():
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
+                        "-shared", "-fPIC", "-o", LIB, os.path.join(HERE, "emu_frm.cpp")], check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def unpack(packed, dims):
+    packed = np.asarray(packed, dtype=np.int64)
+    x, y, z = packed & 1023, (packed >> 10) & 1023, packed >> 20
+    return ((z * dims[1] + y) * dims[0] + x).astype(np.int32)
+
+
+def generate(dims, props, seed, realisation=0):
+    N = dims[0] * dims[1] * dims[2]
+    out = dict(species=np.zeros(N, np.uint8), homo=np.zeros(N), lumo=np.zeros(N), s1=np.zeros(N), t1=np.zeros(N))
+    d = (C.c_int32 * 3)(*dims)
+    p = (C.c_double * 3)(*props)
+    rc = lib().emu_generate(d, p, C.c_uint64(seed), C.c_uint32(realisation),
+                            *(_p(out[k]) for k in ("species", "homo", "lumo", "s1", "t1")))
+    if rc:
+        raise ValueError("emu_generate failed")
+    return out
+
+
+def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_calls=1, replay=None):
+    dims = tuple(int(v) for v in dims)
+    cap, cap_f = charges, (2 if charges == 1 else 2 * charges + 8)
+    trace_cap = stop * n_calls
+    trace = np.zeros(max(trace_cap, 1), EVENT_DTYPE)
+    ints = np.zeros(12, np.int32)
+    u64 = np.zeros(8, np.uint64)
+    lists = np.zeros(6 * cap, np.int32)
+    flags = np.zeros(2 * cap_f, np.int32)
+    taus = np.zeros(2 * cap, np.float64)
+    totals = np.zeros(20, np.uint64)
+    cache_i = np.zeros(30, np.int32)
+    cache_tau = np.zeros(10, np.float64)
+    init_lists = np.zeros(6 * cap, np.int32)
+    init_taus = np.zeros(2 * cap, np.float64)
+    init_counts = np.zeros(5, np.int32)
+    species = np.ascontiguousarray(species, np.uint8)
+    homo = np.ascontiguousarray(homo, np.float64)
+    lumo = np.ascontiguousarray(lumo, np.float64)
+    rp = None if replay is None else np.ascontiguousarray(replay, np.float64)
+    d = (C.c_int32 * 3)(*dims)
+    rc = lib().emu_run(d, C.c_double(field), C.c_int32(charges), C.c_uint64(seed), C.c_uint32(trajectory),
+                       _p(species), _p(homo), _p(lumo), None if rp is None else _p(rp),
+                       C.c_int64(0 if rp is None else rp.size), C.c_int64(stop), C.c_int32(n_calls),
+                       _p(trace), C.c_int64(trace_cap), _p(ints), _p(u64), _p(lists), _p(flags), _p(taus),
+                       _p(totals), _p(cache_i), _p(cache_tau), _p(init_lists), _p(init_taus), _p(init_counts))
+    if rc:
+        raise RuntimeError(f"emu_run failed ({rc})")
+    n_e, n_h, n_fe, n_fh, n_me, n_mh = (int(v) for v in ints[:6])
+    fired = int(u64[6])
+    out = dict(
+        trace=trace[:min(fired, trace_cap)],
+        e_pos=unpack(lists[0:n_e], dims), h_pos=unpack(lists[cap:cap + n_h], dims),
+        me_init=unpack(lists[2 * cap:2 * cap + n_me], dims), mh_init=unpack(lists[3 * cap:3 * cap + n_mh], dims),
+        me_final=unpack(lists[4 * cap:4 * cap + n_me], dims), mh_final=unpack(lists[5 * cap:5 * cap + n_mh], dims),
+        me_tau=taus[:n_me].copy(), mh_tau=taus[cap:cap + n_mh].copy(),
+        e_flags=unpack(flags[:n_fe], dims), h_flags=unpack(flags[cap_f:cap_f + n_fh], dims),
+        special=int(ints[6]), special_site=int(unpack([ints[7]], dims)[0]), xstate=int(ints[8]), status=int(ints[9]),
+        draws=int(u64[0]), spins=int(u64[1]), emission=int(u64[2]), recombination=int(u64[3]),
+        injection=int(u64[4]), steps=int(u64[5]), fired=fired, init_draws=int(u64[7]), totals=totals,
+        cache_head=int(ints[10]), cache_n=int(ints[11]),
+        cache_init=unpack(cache_i[0:10], dims), cache_final=unpack(cache_i[10:20], dims), cache_kp=cache_i[20:30].copy(),
+        cache_tau=cache_tau,
+    )
+    ne0, nh0, nme0, nmh0, st0 = (int(v) for v in init_counts)
+    out.update(
+        init_status=st0,
+        init_e_pos=unpack(init_lists[0:ne0], dims), init_h_pos=unpack(init_lists[cap:cap + nh0], dims),
+        init_me_init=unpack(init_lists[2 * cap:2 * cap + nme0], dims), init_mh_init=unpack(init_lists[3 * cap:3 * cap + nmh0], dims),
+        init_me_final=unpack(init_lists[4 * cap:4 * cap + nme0], dims), init_mh_final=unpack(init_lists[5 * cap:5 * cap + nmh0], dims),
+        init_me_tau=init_taus[:nme0].copy(), init_mh_tau=init_taus[cap:cap + nmh0].copy(),
+    )
+    return out

@@ -1,0 +1,155 @@
+// emu_frm.cpp — compiles the CUDA kernel source (hf_frm.cuh) for the host under warp_emu.h and
+// exposes a small C API for tests/test_kernel_emulated.py.  TEST INFRASTRUCTURE ONLY (see
+// warp_emu.h): one trajectory, one warp, no product code path leads here.
+#include "warp_emu.h"
+
+#include "../../hyperfluorescence_b200/csrc/hf_frm.cuh"
+
+#include <vector>
+
+namespace {
+
+struct Buffers {
+    std::vector<int32_t> pos, flag, ev_init, ev_final, cache_i;
+    std::vector<double> ev_tau, cache_tau;
+    std::vector<HfScalars> sc;
+    std::vector<unsigned long long> totals;
+    std::vector<HfTraceRec> trace;
+    std::vector<int32_t> pool;
+};
+
+void wire(HfParams &P, Buffers &b, int64_t trace_cap) {
+    const int64_t B = P.B;
+    b.pos.assign(2 * B * P.cap_c, 0); b.flag.assign(2 * B * P.cap_f, 0);
+    b.ev_init.assign(2 * B * P.cap_c, 0); b.ev_final.assign(2 * B * P.cap_c, 0); b.ev_tau.assign(2 * B * P.cap_c, 0.0);
+    b.cache_i.assign(3 * B * HF_CACHE, 0); b.cache_tau.assign(B * HF_CACHE, 0.0);
+    b.sc.assign(B, HfScalars{}); b.totals.assign(32, 0);
+    b.trace.assign(B * trace_cap + 1, HfTraceRec{});
+    for (int t = 0; t < 2; ++t) {
+        P.pos[t] = b.pos.data() + t * B * P.cap_c;
+        P.flag[t] = b.flag.data() + t * B * P.cap_f;
+        P.ev_init[t] = b.ev_init.data() + t * B * P.cap_c;
+        P.ev_final[t] = b.ev_final.data() + t * B * P.cap_c;
+        P.ev_tau[t] = b.ev_tau.data() + t * B * P.cap_c;
+    }
+    P.sc = b.sc.data();
+    P.cache_init = b.cache_i.data(); P.cache_final = b.cache_i.data() + B * HF_CACHE; P.cache_kp = b.cache_i.data() + 2 * B * HF_CACHE;
+    P.cache_tau = b.cache_tau.data();
+    P.totals = b.totals.data();
+    P.trace = b.trace.data(); P.trace_first = 0; P.trace_n = B; P.trace_cap = trace_cap;
+}
+
+struct InjectArgs { const HfParams *P; int32_t *pool; };
+void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P, x->pool); }
+void run_body(void *a) { hf_run_kernel<1>(*(const HfParams *)a); }
+
+struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
+void shuffle_body(void *a) { auto *x = (ShuffleArgs *)a; hf_species_shuffle(*x->P, x->pool, x->total, x->n_host, x->n_tadf, x->layer, 0); }
+struct FillArgs { const HfParams *P; const uint8_t *layer; uint8_t *species; double *homo, *lumo, *s1, *t1; };
+void fill_body(void *a) { auto *x = (FillArgs *)a; hf_fill_sites(*x->P, x->layer, 1, x->species, x->homo, x->lumo, x->s1, x->t1); }
+
+int64_t sample_setsize(int64_t k) {
+    int64_t setsize = 21;
+    if (k > 5) {
+        const int64_t e = (int64_t)ceil(log((double)(k * 3)) / log(4.0));
+        int64_t p4 = 1;
+        for (int64_t i = 0; i < e; ++i) p4 *= 4;
+        setsize += p4;
+    }
+    return setsize;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Lattice generation kernels for one realisation.
+int emu_generate(const int32_t dims[3], const double props[3], uint64_t seed, uint32_t realisation,
+                 uint8_t *species, double *homo, double *lumo, double *s1, double *t1) {
+    HfParams P;
+    memset(&P, 0, sizeof(P));
+    P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_real = realisation;
+    const int64_t xy = (int64_t)P.X * P.Y;
+    const int64_t n_fluo = (int64_t)((double)P.N * props[2]), n_tadf = (int64_t)((double)P.N * props[1]);
+    const int64_t n_host = P.N - 2 * xy - n_fluo - n_tadf, total = n_host + n_tadf + n_fluo;
+    if (total != xy * (P.Z - 2) || total <= 0) return 1;
+    std::vector<int32_t> pool((size_t)total);
+    for (int64_t i = 0; i < total; ++i) pool[(size_t)i] = (int32_t)i;
+    std::vector<uint8_t> layer((size_t)xy);
+    blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+    ShuffleArgs sa{&P, pool.data(), total, n_host, n_tadf, layer.data()};
+    emu_run_warp(shuffle_body, &sa);
+    FillArgs fa{&P, layer.data(), species, homo, lumo, s1, t1};
+    emu_run_warp(fill_body, &fa);
+    return 0;
+}
+
+// hf_inject + n_calls x hf_run(stop) for one trajectory on a given lattice.
+// ints_out:  n_e, n_h, n_fe, n_fh, n_me, n_mh, special, special_site(packed), xstate, status, cache_head, cache_n
+// u64_out:   draws, spins, emission, recombination, injection, steps, fired, init_draws
+// lists_out: 6 consecutive blocks of cap ints (packed coordinates): e_pos, h_pos, me_init, mh_init,
+//            me_final, mh_final; flags_out: 2 blocks of cap_f; taus_out: 2 blocks of cap doubles.
+int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed, uint32_t trajectory,
+            const uint8_t *species, const double *homo, const double *lumo,
+            const double *replay, int64_t n_replay, int64_t stop, int32_t n_calls,
+            HfTraceRec *trace_out, int64_t trace_cap,
+            int32_t *ints_out, uint64_t *u64_out, int32_t *lists_out, int32_t *flags_out, double *taus_out,
+            unsigned long long *totals_out, int32_t *cache_i_out, double *cache_tau_out,
+            int32_t *init_lists_out, double *init_taus_out, int32_t *init_counts_out) {
+    HfParams P;
+    memset(&P, 0, sizeof(P));
+    P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
+    P.field = field; P.C = charges; P.cap_c = charges; P.cap_f = charges == 1 ? 2 : 2 * charges + 8;
+    P.B = 1; P.traj_per_real = 1;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = trajectory; P.first_real = 0;
+    P.setsize = sample_setsize(charges);
+    P.species = species; P.homo = homo; P.lumo = lumo;
+    P.replay = replay; P.n_replay = n_replay;
+    Buffers b;
+    wire(P, b, trace_cap);
+    if (hf_warp_smem_bytes(P.cap_c, P.cap_f) > sizeof(hf_smem)) return 2;
+    blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+    b.pool.assign((size_t)((int64_t)P.X * P.Y), 0);
+    InjectArgs ia{&P, b.pool.data()};
+    emu_run_warp(inject_body, &ia);
+    const int cap = P.cap_c;
+    init_counts_out[0] = b.sc[0].n_pos[0]; init_counts_out[1] = b.sc[0].n_pos[1];
+    init_counts_out[2] = b.sc[0].n_ev[0]; init_counts_out[3] = b.sc[0].n_ev[1];
+    init_counts_out[4] = b.sc[0].status;
+    u64_out[7] = b.sc[0].draws;
+    for (int t = 0; t < 2; ++t)
+        for (int i = 0; i < cap; ++i) {
+            init_lists_out[(0 + t) * cap + i] = P.pos[t][i];
+            init_lists_out[(2 + t) * cap + i] = P.ev_init[t][i];
+            init_lists_out[(4 + t) * cap + i] = P.ev_final[t][i];
+            init_taus_out[t * cap + i] = P.ev_tau[t][i];
+        }
+    for (int c = 0; c < n_calls; ++c) {
+        P.n_steps = stop;
+        emu_run_warp(run_body, &P);
+    }
+    const HfScalars &sc = b.sc[0];
+    const int32_t ints[12] = {sc.n_pos[0], sc.n_pos[1], sc.n_flag[0], sc.n_flag[1], sc.n_ev[0], sc.n_ev[1],
+                              sc.special, sc.special_site, sc.xstate, sc.status, sc.cache_head, sc.cache_n};
+    memcpy(ints_out, ints, sizeof(ints));
+    const uint64_t u64s[7] = {sc.draws, sc.spins, sc.emission, sc.recombination, sc.injection, sc.steps, sc.fired};
+    memcpy(u64_out, u64s, sizeof(u64s));
+    for (int t = 0; t < 2; ++t) {
+        for (int i = 0; i < cap; ++i) {
+            lists_out[(0 + t) * cap + i] = P.pos[t][i];
+            lists_out[(2 + t) * cap + i] = P.ev_init[t][i];
+            lists_out[(4 + t) * cap + i] = P.ev_final[t][i];
+            taus_out[t * cap + i] = P.ev_tau[t][i];
+        }
+        for (int i = 0; i < P.cap_f; ++i) flags_out[t * P.cap_f + i] = P.flag[t][i];
+    }
+    memcpy(totals_out, b.totals.data(), sizeof(unsigned long long) * 20);
+    memcpy(cache_i_out, b.cache_i.data(), sizeof(int32_t) * 3 * HF_CACHE);
+    memcpy(cache_tau_out, b.cache_tau.data(), sizeof(double) * HF_CACHE);
+    const int64_t n = (int64_t)sc.fired < trace_cap ? (int64_t)sc.fired : trace_cap;
+    memcpy(trace_out, b.trace.data(), sizeof(HfTraceRec) * (size_t)n);
+    return 0;
+}
+
+}  // extern "C"

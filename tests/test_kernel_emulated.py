@@ -1,0 +1,89 @@
+"""Run the CUDA kernel SOURCE (hyperfluorescence_b200/csrc/hf_frm.cuh) lane by lane on the host
+under tests/emu/warp_emu.h and pin it to the golden vectors of the unmodified reference.
+
+This is a logic check that works without a GPU (the `-m gpu` suite repeats it on the device
+through the C-ABI).  Under emulation exp/log/sin/cos come from glibc — the same libm CPython
+uses — so here even tau is compared bit for bit."""
+import numpy as np
+import pytest
+
+from tests.conftest import load_golden
+from tests.emu import emu
+
+STATUS = {"": 0, "ZeroDivisionError": 2, "ValueError": 3}
+
+# the emulator is ~1e5x slower than the device: cap the steps per case
+DEFAULT_CAP = 3000
+
+
+def _step_cap(g):
+    if g["charges"] >= 10:
+        return 1000
+    return DEFAULT_CAP
+
+
+def _check_prefix(g, out, n):
+    assert out["init_status"] == 0
+    assert np.array_equal(out["init_e_pos"], g["init_e_pos"])
+    assert np.array_equal(out["init_h_pos"], g["init_h_pos"])
+    for k in ("me", "mh"):
+        assert np.array_equal(out[f"init_{k}_init"], g[f"init_{k}_init"])
+        assert np.array_equal(out[f"init_{k}_final"], g[f"init_{k}_final"])
+        assert np.array_equal(out[f"init_{k}_tau"], g[f"init_{k}_tau"])
+    assert out["init_draws"] == int(g["init_draws"][0])
+    tr = out["trace"]
+    assert len(tr) == n
+    assert np.array_equal(tr["kind"], g["trace_kind"][:n])
+    assert np.array_equal(tr["particule"], g["trace_particule"][:n])
+    assert np.array_equal(tr["initial"], g["trace_initial"][:n])
+    assert np.array_equal(tr["final"], g["trace_final"][:n])
+    assert np.array_equal(tr["tau"], g["trace_tau"][:n])
+    assert np.array_equal(tr["draws"].astype(np.int64), g["trace_draws"][:n])
+    assert np.array_equal(tr["spins"].astype(np.int64), g["trace_spins"][:n])
+
+
+def test_emulated_kernel_matches_reference(golden):
+    g = golden
+    total = len(g["trace_kind"])
+    complete = total <= _step_cap(g) or bool(g["error_s"])
+    stop = g["n_steps"] if complete else _step_cap(g)
+    out = emu.run(g["dims"], g["field_f"], g["charges"], g["seed_int"], g["trajectory"], g["species"], g["homo"],
+                  g["lumo"], stop=stop, replay=g.get("replay_traj"))
+    _check_prefix(g, out, total if complete else stop)
+    if complete:
+        # complete run: final lists, events, tallies and the stop reason must match too
+        assert np.array_equal(out["e_pos"], g["final_e_pos"])
+        assert np.array_equal(out["h_pos"], g["final_h_pos"])
+        for k in ("me", "mh"):
+            assert np.array_equal(out[f"{k}_init"], g[f"final_{k}_init"])
+            assert np.array_equal(out[f"{k}_final"], g[f"final_{k}_final"])
+            assert np.array_equal(out[f"{k}_tau"], g[f"final_{k}_tau"])
+        assert [out["emission"], out["recombination"], out["injection"], out["steps"]] == g["final_tallies"].tolist()
+        assert [out["draws"], out["spins"]] == g["final_draws"][:2].tolist()
+        assert out["status"] == STATUS[g["error_s"]]
+
+
+def test_emulated_split_runs_equal_one_run():
+    """operations(a); operations(b) must equal operations(a+b): state save/restore across launches."""
+    g = load_golden("d0_s4")
+    args = (g["dims"], g["field_f"], g["charges"], g["seed_int"], 0, g["species"], g["homo"], g["lumo"])
+    one = emu.run(*args, stop=600)
+    split = emu.run(*args, stop=200, n_calls=3)
+    for k in ("kind", "particule", "initial", "final", "tau", "draws"):
+        assert np.array_equal(one["trace"][k], split["trace"][k])
+    for k in ("e_pos", "h_pos", "me_tau", "mh_tau"):
+        assert np.array_equal(one[k], split[k])
+    for k in ("e_flags", "h_flags"):
+        assert np.array_equal(np.sort(one[k]), np.sort(split[k]))
+    assert np.array_equal(one["totals"], split["totals"])
+    assert one["cache_n"] == split["cache_n"] == 10
+
+
+def test_emulated_lattice_generation(golden):
+    g = golden
+    if g["dims"][0] * g["dims"][1] * g["dims"][2] > 1000:
+        pytest.skip("large lattice: covered by the oracle test and by the GPU suite")
+    a = emu.generate(g["dims"], tuple(float(p) for p in g["props"]), g["seed_int"], g["realisation"])
+    assert np.array_equal(a["species"], g["species"])
+    for k in ("homo", "lumo", "s1", "t1"):
+        np.testing.assert_allclose(a[k], g[k], rtol=0, atol=4e-16)
