@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py — KMC events/s of the hot path (BASELINE.json `metric`) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): 10^5 independent trajectories per GPU on one 64^3 lattice
+(default 0.84/0.15/0.01 host/TADF/emitter composition, charges = 1: one electron and one hole in
+flight per trajectory, field 0.1 eV/nm).  One bench "step" = one `hf_run` launch that advances
+every trajectory by EVENTS_PER_STEP KMC events (`Lattice.operations(1000)`, reseau.py:580-595).
+An "event" is one fired `_first_reaction_method` call (reseau.py:483-562).  Weak scaling: every
+rank carries its own 10^5 trajectories (global Philox ids), no data-path collective; one NCCL
+all-reduce of the tally vector after the timed region closes the run.
+
+One JSON line is printed by rank 0; see DESIGN.md §Measurement for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DIMS = (64, 64, 64)
+PROPS = (0.84, 0.15, 0.01)
+CHARGES = 1
+FIELD = 0.1
+SEED = 0x48464B4D43            # "HFKMC" 
+TRAJ_PER_GPU = 100_000
+EVENTS_PER_STEP = 1000         # KMC events per trajectory per bench step
+NEIGHBOURS = 26
+# compulsory bytes per event, no caching credit
+BYTES_PER_EVENT = NEIGHBOURS * (8 + 1) + 2 * CHARGES * 4 + 2 * CHARGES * 16 + 24 + 2
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+WORKLOAD = (f"{TRAJ_PER_GPU} trajectories/GPU x {EVENTS_PER_STEP} KMC events per step on one {DIMS[0]}^3 lattice, "
+            f"charges={CHARGES}, props={PROPS}, field={FIELD} (BASELINE configs[1])")
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("hf_run_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                parts = [p.strip() for p in out.split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_sample(cores, per_core_trajectories=1250):
+    """The CPU baseline: oracle port (oracle/frm_oracle.c, pinned bit-exactly to the unmodified
+    reference) on `cores` host threads, a bounded sample of the same workload."""
+    from oracle import frm_oracle as fo
+    lat = fo.OracleLattice.generate(DIMS, PROPS, SEED)
+    n_traj = cores * per_core_trajectories
+    t0 = time.perf_counter()
+    res = lat.run_batch(CHARGES, FIELD, SEED, 0, n_traj, EVENTS_PER_STEP, n_threads=cores)
+    dt = time.perf_counter() - t0
+    sample = (f"{n_traj} of the {TRAJ_PER_GPU} trajectories x {EVENTS_PER_STEP} events on the same {DIMS[0]}^3 lattice "
+              f"(charge injection and initial events included), {cores} threads")
+    return res["events"] / dt, sample, res
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure
+    Python and cannot travel to the GPU box, so this times its C restatement (oracle port) with all
+    host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_sample(cores, 125)
+    t0 = time.perf_counter()
+    events = 0
+    sample = ""
+    for _ in range(args.steps):
+        v, sample, res = cpu_sample(cores)
+        events += res["events"]
+    dt = time.perf_counter() - t0
+    value = events / dt
+    line = {
+        "impl": "reference", "metric": "KMC exciton events/sec (box)", "value": value, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "lattice": list(DIMS), "charges": CHARGES},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port",
+                         "sample": "each step: " + sample},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from hyperfluorescence_b200 import _native as nat
+    from hyperfluorescence_b200 import distributed as hd
+
+    rank, local_rank, world = hd.init_process_group()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hyperfluorescence_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream()
+    B, S, K, W = TRAJ_PER_GPU, EVENTS_PER_STEP, args.steps, args.warmup
+
+    # weak scaling: rank r owns global trajectories [r*B, (r+1)*B) of the one shared realisation 0
+    sim = nat.Sim(DIMS, PROPS, FIELD, CHARGES, 1, n_trajectories=B, n_realisations=1, seed=SEED,
+                  first_trajectory=rank * B, first_realisation=0, device=local_rank)
+    sim.set_stream(stream.cuda_stream)
+    sim.generate_lattice()
+    sim.inject()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(W):
+        sim.run(S)
+    torch.cuda.synchronize()
+    sim.run_timing()                                                            # reset the lib's own event timers
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                                                           # L2 flush between timed iterations
+        starts[k].record(stream)
+        sim.run(S)
+        stops[k].record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    total_ms = float(sum(step_ms))
+    lib_ms, lib_launches = sim.run_timing()                                     # same launches, timed inside the lib
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    events_total = world * B * S * K
+    value = events_total / (total_ms * 1e-3)
+    tallies = hd.all_reduce_tallies(sim)                                        # the one collective of the path
+    fired_expected = world * B * S * (K + W)
+
+    # end to end through the C-ABI with HOST buffers: lattice arrays from pinned host memory ->
+    # hf_upload_lattice (H2D), hf_inject, hf_run, hf_read_tallies (D2H), every step, wall clock.
+    host = sim.download_lattice(0)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    pinned_np = {k: v.numpy() for k, v in pinned.items()}
+    h2d = sum(v.nbytes for v in pinned_np.values())
+    d2h = nat.HF_N_TALLIES * 8
+    e2e_steps = max(2, min(K, 3))
+    def e2e_step():
+        sim.upload_lattice(0, pinned_np["species"], pinned_np["homo"], pinned_np["lumo"], pinned_np["s1"], pinned_np["t1"])
+        sim.inject()
+        sim.run(S)
+        return sim.tallies()
+    e2e_step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * S * e2e_steps / e2e_s
+
+    peak, peak_src = hbm_peak()
+    launch_s = (lib_ms / max(lib_launches, 1)) * 1e-3
+    achieved = B * S * BYTES_PER_EVENT / launch_s / 1e9
+    line = {
+        "metric": "KMC exciton events/sec (box)", "value": value, "unit": "events/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "lattice": list(DIMS), "charges": CHARGES,
+                   "trajectories_per_gpu": B, "events_per_trajectory_per_step": S,
+                   "l2": "flushed between timed steps (256 MiB memset); the 4.4 MB lattice is L2-resident by nature",
+                   "timing": "CUDA events around each hf_run on its stream, summed over steps, max over ranks",
+                   "wall_s_bracket": t_wall},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "hf_run_kernel",
+                     "bytes_per_event": BYTES_PER_EVENT, "events_per_launch": B * S,
+                     "avg_launch_ms": lib_ms / max(lib_launches, 1),
+                     "note": "path is fp64-pipe/latency bound, not HBM bound (DESIGN.md): 26 candidates x "
+                             "(exp + log + 2 sqrt + 3 div) fp64 per event against 300 algorithmic bytes"},
+        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "path": "hf_upload_lattice(pinned host) + hf_inject + hf_run + hf_read_tallies"},
+        "gpu_launches": K,
+        "clocks": clocks,
+        "tallies": dict({k: tallies[k] for k in ("emission", "recombination", "injection", "fired", "stopped")},
+                        fired_expected=fired_expected),
+    }
+    if world == 1 and rank == 0 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        v, sample, _ = cpu_sample(cores, 2500)
+        v1, _, _ = cpu_sample(1, 1250)
+        line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample,
+                                "one_core_value": v1}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not args.no_cpu:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,247 @@
+"""ctypes binding of ``libhfkmc.so`` (C-ABI in ``include/hfkmc.h``).
+
+There is no CPU implementation behind this module: if the shared library is missing, or no
+sm_100 device is visible, every entry point fails loudly.  The parity oracle under ``oracle/``
+is test infrastructure and is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhfkmc.so")
+
+HF_N_TALLIES = 20
+TALLY_NAMES = ("emission", "recombination", "injection", "steps", "fired", "move_e", "move_h", "bound", "decay",
+               "capture_e", "capture_h", "recomb_host", "recomb_tadf", "recomb_fluo", "emit_tadf", "emit_fluo", "stopped")
+
+HF_OK, HF_ERR_BAD_ARG, HF_ERR_CUDA, HF_ERR_NO_DEVICE, HF_ERR_UNSUPPORTED, HF_ERR_STATE = range(6)
+TRAJ_OK, TRAJ_NO_EVENTS, TRAJ_ZERO_DIVISION, TRAJ_VALUE_ERROR, TRAJ_REPLAY_EXHAUSTED, TRAJ_CAPACITY = range(6)
+
+
+class HfError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libhfkmc error {code}: {message}")
+        self.code = code
+
+
+class HfConfig(C.Structure):
+    _fields_ = [("dims", C.c_int32 * 3), ("props", C.c_double * 3), ("electric_field", C.c_double),
+                ("charges", C.c_int32), ("distance", C.c_int32), ("n_trajectories", C.c_int64),
+                ("n_realisations", C.c_int32), ("first_trajectory", C.c_uint32), ("first_realisation", C.c_uint32),
+                ("seed", C.c_uint64), ("flags", C.c_uint32), ("device", C.c_int32)]
+
+
+class HfEvent(C.Structure):
+    _fields_ = [("initial", C.c_int32), ("final", C.c_int32), ("tau", C.c_double), ("kind", C.c_uint8),
+                ("particule", C.c_uint8), ("pad", C.c_uint8 * 2), ("spins", C.c_uint32), ("draws", C.c_uint64)]
+
+
+EVENT_DTYPE = np.dtype([("initial", "<i4"), ("final", "<i4"), ("tau", "<f8"), ("kind", "u1"), ("particule", "u1"),
+                        ("pad", "u1", (2,)), ("spins", "<u4"), ("draws", "<u8")])
+assert EVENT_DTYPE.itemsize == C.sizeof(HfEvent) == 32
+
+
+class HfTrajInfo(C.Structure):
+    _fields_ = [("n_electrons", C.c_int32), ("n_holes", C.c_int32), ("n_eflags", C.c_int32), ("n_hflags", C.c_int32),
+                ("n_move_e", C.c_int32), ("n_move_h", C.c_int32), ("special_kind", C.c_int32),
+                ("special_particule", C.c_int32), ("special_site", C.c_int32), ("exciton_state", C.c_int32),
+                ("status", C.c_int32), ("cache_count", C.c_int32), ("draws", C.c_uint64), ("spins", C.c_uint64),
+                ("emission", C.c_uint64), ("recombination", C.c_uint64), ("injection", C.c_uint64),
+                ("steps", C.c_uint64), ("fired", C.c_uint64)]
+
+
+# name -> (restype, argtypes): every symbol include/hfkmc.h declares
+P, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+SIGNATURES = {
+    "hf_last_error": (C.c_char_p, []),
+    "hf_abi_version": (C.c_int, []),
+    "hf_device_count": (C.c_int, []),
+    "hf_create": (C.c_int, [C.POINTER(HfConfig), C.POINTER(P)]),
+    "hf_destroy": (C.c_int, [P]),
+    "hf_set_stream": (C.c_int, [P, P]),
+    "hf_sync": (C.c_int, [P]),
+    "hf_generate_lattice": (C.c_int, [P]),
+    "hf_upload_lattice": (C.c_int, [P, I32, P, P, P, P, P]),
+    "hf_download_lattice": (C.c_int, [P, I32, P, P, P, P, P]),
+    "hf_inject": (C.c_int, [P]),
+    "hf_set_replay": (C.c_int, [P, P, I64]),
+    "hf_run": (C.c_int, [P, I64]),
+    "hf_read_tallies": (C.c_int, [P, P]),
+    "hf_reduce_tallies_device": (C.c_int, [P, P]),
+    "hf_read_info": (C.c_int, [P, I64, C.POINTER(HfTrajInfo)]),
+    "hf_read_positions": (C.c_int, [P, I64, I32, P, C.POINTER(I32)]),
+    "hf_read_flags": (C.c_int, [P, I64, I32, P, C.POINTER(I32)]),
+    "hf_read_move_events": (C.c_int, [P, I64, I32, P, P, P, C.POINTER(I32)]),
+    "hf_read_last_events": (C.c_int, [P, I64, P, C.POINTER(I32)]),
+    "hf_set_trace": (C.c_int, [P, I64, I64, I64]),
+    "hf_read_trace": (C.c_int, [P, I64, P, C.POINTER(I64)]),
+    "hf_eval_hops": (C.c_int, [P, I64, I32, I32, P, P, P, P, P, P]),
+    "hf_run_timing": (C.c_int, [P, C.POINTER(F64), C.POINTER(I64)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libhfkmc.so and bind every declared symbol; raises if the library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m hyperfluorescence_b200.build` "
+                "(hyperfluorescence_b200 has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != HF_OK:
+        raise HfError(code, load().hf_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Sim:
+    """Owning wrapper of one ``hf_sim`` handle."""
+
+    def __init__(self, dims, props, electric_field, charges, distance=1, n_trajectories=1, n_realisations=1,
+                 seed=0, first_trajectory=0, first_realisation=0, device=0, flags=0):
+        lib = load()
+        cfg = HfConfig()
+        cfg.dims[:] = [int(d) for d in dims]
+        cfg.props[:] = [float(p) for p in props]
+        cfg.electric_field = float(electric_field)
+        cfg.charges, cfg.distance = int(charges), int(distance)
+        cfg.n_trajectories, cfg.n_realisations = int(n_trajectories), int(n_realisations)
+        cfg.first_trajectory, cfg.first_realisation = int(first_trajectory), int(first_realisation)
+        cfg.seed, cfg.flags, cfg.device = int(seed) & (2 ** 64 - 1), int(flags), int(device)
+        self._h = P()
+        self.dims = tuple(int(d) for d in dims)
+        self.N = self.dims[0] * self.dims[1] * self.dims[2]
+        self.charges = int(charges)
+        self.n_trajectories, self.n_realisations = int(n_trajectories), int(n_realisations)
+        check(lib.hf_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().hf_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- lattice ---------------------------------------------------------------------------
+    def generate_lattice(self):
+        check(load().hf_generate_lattice(self._h))
+
+    def upload_lattice(self, realisation, species, homo, lumo, s1=None, t1=None):
+        arrs = [np.ascontiguousarray(species, np.uint8)] + [
+            None if a is None else np.ascontiguousarray(a, np.float64) for a in (homo, lumo, s1, t1)]
+        for a in arrs:
+            if a is not None and a.size != self.N:
+                raise ValueError(f"lattice array has {a.size} entries, expected {self.N}")
+        check(load().hf_upload_lattice(self._h, int(realisation), *(ptr(a) for a in arrs)))
+
+    def download_lattice(self, realisation=0):
+        out = dict(species=np.empty(self.N, np.uint8), homo=np.empty(self.N), lumo=np.empty(self.N),
+                   s1=np.empty(self.N), t1=np.empty(self.N))
+        check(load().hf_download_lattice(self._h, int(realisation),
+                                         *(ptr(out[k]) for k in ("species", "homo", "lumo", "s1", "t1"))))
+        return out
+
+    # -- dynamics ----------------------------------------------------------------------------
+    def set_replay(self, u):
+        if u is None:
+            check(load().hf_set_replay(self._h, None, 0))
+            return
+        u = np.ascontiguousarray(u, np.float64)
+        if u.ndim == 1:
+            u = np.tile(u, (self.n_trajectories, 1)) if self.n_trajectories > 1 else u[None, :]
+        if u.shape[0] != self.n_trajectories:
+            raise ValueError("replay must have one row per trajectory")
+        u = np.ascontiguousarray(u)
+        check(load().hf_set_replay(self._h, ptr(u), u.shape[1]))
+
+    def inject(self):
+        check(load().hf_inject(self._h))
+
+    def run(self, stop):
+        check(load().hf_run(self._h, int(stop)))
+
+    def sync(self):
+        check(load().hf_sync(self._h))
+
+    def set_stream(self, cuda_stream):
+        check(load().hf_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def run_timing(self):
+        ms, n = F64(0), I64(0)
+        check(load().hf_run_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- read-back -----------------------------------------------------------------------------
+    def tallies(self):
+        out = np.zeros(HF_N_TALLIES, np.uint64)
+        check(load().hf_read_tallies(self._h, ptr(out)))
+        return {k: int(out[i]) for i, k in enumerate(TALLY_NAMES)}
+
+    def reduce_tallies_device(self, device_ptr):
+        check(load().hf_reduce_tallies_device(self._h, C.c_void_p(int(device_ptr))))
+
+    def info(self, trajectory=0):
+        info = HfTrajInfo()
+        check(load().hf_read_info(self._h, int(trajectory), C.byref(info)))
+        return info
+
+    def _list(self, fn, trajectory, which, cap):
+        out = np.zeros(max(cap, 1), np.int32)
+        n = I32(out.size)
+        check(fn(self._h, int(trajectory), int(which), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def positions(self, trajectory, which):
+        return self._list(load().hf_read_positions, trajectory, which, self.charges)
+
+    def flags(self, trajectory, which):
+        return self._list(load().hf_read_flags, trajectory, which, 2 * self.charges + 8)
+
+    def move_events(self, trajectory, which):
+        cap = max(self.charges, 1)
+        ini, fin, tau = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+        n = I32(cap)
+        check(load().hf_read_move_events(self._h, int(trajectory), int(which), ptr(ini), ptr(fin), ptr(tau), C.byref(n)))
+        return ini[:n.value].copy(), fin[:n.value].copy(), tau[:n.value].copy()
+
+    def last_events(self, trajectory=0):
+        out = np.zeros(10, EVENT_DTYPE)
+        n = I32(10)
+        check(load().hf_read_last_events(self._h, int(trajectory), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def set_trace(self, first, n, capacity):
+        check(load().hf_set_trace(self._h, int(first), int(n), int(capacity)))
+
+    def trace(self, trajectory, capacity):
+        out = np.zeros(max(int(capacity), 1), EVENT_DTYPE)
+        n = I64(out.size)
+        check(load().hf_read_trace(self._h, int(trajectory), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def eval_hops(self, trajectory, particule, initial, final, u):
+        initial = np.ascontiguousarray(initial, np.int32)
+        final = np.ascontiguousarray(final, np.int32)
+        u = np.ascontiguousarray(u, np.float64)
+        n = initial.size
+        tau, rate, zd = np.zeros(n), np.zeros(n), np.zeros(n, np.int32)
+        check(load().hf_eval_hops(self._h, int(trajectory), int(particule), n, ptr(initial), ptr(final), ptr(u),
+                                  ptr(tau), ptr(rate), ptr(zd)))
+        return tau, rate, zd

@@ -1,0 +1,15 @@
+#!/bin/bash
+# One GPU-box pass: GPU parity suite, smoke, a short bench, then the ncu launch list of the same
+# bench command.  Everything is written under gpurun_out/ (merged back by gpurun).
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.csv 2>&1
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+echo "smoke exit $?" | tee -a gpurun_out/smoke.log
+tail -3 gpurun_out/smoke.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"
+cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err

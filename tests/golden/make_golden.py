@@ -72,8 +72,36 @@ def replay_case():
     return u
 
 
+def reference_statistics(n_runs=400, dims=(3, 3, 3), props=(0.5, 0.3, 0.2), charges=2, steps=1500):
+    """Tallies of n_runs UNMODIFIED reference runs on their own Mersenne-Twister streams (the only
+    change is that each `Random()` gets a deterministic seed so the file is reproducible): the
+    statistical half of the parity contract (3 sigma on IQE and channel fractions)."""
+    import itertools
+    import random
+    reseau, molecule, _, _ = rh.import_reference()
+    counter = itertools.count(1)
+    saved = (reseau.Random, molecule.Random)
+    reseau.Random = molecule.Random = lambda: random.Random(0x5EED0000 + next(counter))
+    em, rec, inj, stp = [], [], [], []
+    try:
+        for _ in range(n_runs):
+            lat = reseau.Lattice(dims, props, charges=charges)
+            lat.operations(steps)
+            em.append(lat._emission); rec.append(lat._recombination); inj.append(lat._injection); stp.append(lat._step)
+    finally:
+        reseau.Random, molecule.Random = saved
+    np.savez_compressed(os.path.join(HERE, "stats_tiny.npz"), dims=np.array(dims), props=np.array(props),
+                        charges=np.array(charges), steps=np.array(steps), emission=np.array(em),
+                        recombination=np.array(rec), injection=np.array(inj), step=np.array(stp))
+    print(f"stats_tiny: runs={n_runs} emission/run={np.mean(em):.2f} recombination/run={np.mean(rec):.2f} "
+          f"photons/recombination={np.sum(em) / np.sum(rec):.4f}")
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
+    if "--stats-only" in sys.argv:
+        reference_statistics()
+        return
     written = {}
     for name, dims, props, charges, seed, steps, kw in CASES:
         out = rh.run_reference(dims, props, charges, seed, steps, **kw)
@@ -83,6 +111,7 @@ def main():
     used = int(out["final_draws"][0])
     out["replay_traj"] = u[:used + 8]
     _write("replay_s99", out, (6, 5, 4), 99, 0, written)
+    reference_statistics()
 
 
 def _write(name, out, dims, seed, real, written):

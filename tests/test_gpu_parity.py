@@ -1,0 +1,359 @@
+"""GPU parity suite (`-m gpu`): every test drives the CUDA path through the C-ABI
+(`hyperfluorescence_b200._native.Sim` = ctypes over libhfkmc.so, or the `Lattice` façade on top
+of it) and checks it against (a) the golden vectors frozen from the UNMODIFIED reference and
+(b) the C oracle (oracle/frm_oracle.c, itself pinned bit-exactly to those vectors).
+
+Bars (BASELINE.json north_star): event-index sequences bit-exact; rates and tau within 1e-12
+relative (CUDA exp/log vs glibc); tallies exact; statistics within 3 sigma.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TAU_RTOL = 1e-12
+STATUS = {"": 0, "ZeroDivisionError": 2, "ValueError": 3}
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from hyperfluorescence_b200 import _native
+    lib = _native.load()
+    if lib.hf_device_count() < 1:
+        pytest.fail("no sm_100 device visible: the GPU suite must run on a B200")
+    return _native
+
+
+def _sim_for(nat, g, generated=False, n_trajectories=1):
+    sim = nat.Sim(g["dims"], tuple(float(p) for p in g["props"]), g["field_f"], g["charges"], g["distance"],
+                  n_trajectories=n_trajectories, n_realisations=1, seed=g["seed_int"],
+                  first_trajectory=g["trajectory"], first_realisation=g["realisation"])
+    if generated:
+        sim.generate_lattice()
+    else:
+        sim.upload_lattice(0, g["species"], g["homo"], g["lumo"], g["s1"], g["t1"])
+    return sim
+
+
+def _assert_tau(a, b):
+    np.testing.assert_allclose(a, b, rtol=TAU_RTOL, atol=0)
+
+
+def _check_run(nat, g, sim):
+    if "replay_traj" in g:
+        sim.set_replay(g["replay_traj"])
+    sim.inject()
+    sim.sync()
+    # state right after Lattice.__init__
+    info = sim.info(0)
+    assert info.status == 0
+    assert np.array_equal(sim.positions(0, 0), g["init_e_pos"])
+    assert np.array_equal(sim.positions(0, 1), g["init_h_pos"])
+    for which, k in ((0, "me"), (1, "mh")):
+        ini, fin, tau = sim.move_events(0, which)
+        assert np.array_equal(ini, g[f"init_{k}_init"])
+        assert np.array_equal(fin, g[f"init_{k}_final"])
+        _assert_tau(tau, g[f"init_{k}_tau"])
+    assert info.draws == int(g["init_draws"][0])
+    assert info.injection == 2 * g["charges"]
+    # the step loop, in two launches to exercise state save / restore
+    n = g["n_steps"]
+    sim.set_trace(0, 1, n)
+    first = n // 3
+    sim.run(first)
+    info_mid = sim.info(0)
+    if info_mid.status == 0:
+        sim.run(n - first)
+    sim.sync()
+    tr = sim.trace(0, n)
+    total = len(g["trace_kind"])
+    assert len(tr) == total
+    assert np.array_equal(tr["kind"], g["trace_kind"])
+    assert np.array_equal(tr["particule"], g["trace_particule"])
+    assert np.array_equal(tr["initial"], g["trace_initial"])
+    assert np.array_equal(tr["final"], g["trace_final"])
+    assert np.array_equal(tr["draws"].astype(np.int64), g["trace_draws"])
+    assert np.array_equal(tr["spins"].astype(np.int64), g["trace_spins"])
+    _assert_tau(tr["tau"], g["trace_tau"])
+    # final state
+    info = sim.info(0)
+    assert info.status == STATUS[g["error_s"]]
+    assert np.array_equal(sim.positions(0, 0), g["final_e_pos"])
+    assert np.array_equal(sim.positions(0, 1), g["final_h_pos"])
+    assert np.array_equal(sim.positions(0, 2), g["final_x_pos"])
+    for which, k in ((0, "me"), (1, "mh")):
+        ini, fin, tau = sim.move_events(0, which)
+        assert np.array_equal(ini, g[f"final_{k}_init"])
+        assert np.array_equal(fin, g[f"final_{k}_final"])
+        _assert_tau(tau, g[f"final_{k}_tau"])
+    assert [info.emission, info.recombination, info.injection, info.steps] == g["final_tallies"].tolist()
+    assert [info.draws, info.spins] == g["final_draws"][:2].tolist()
+    t = sim.tallies()
+    assert [t["emission"], t["recombination"], t["injection"], t["steps"]] == g["final_tallies"].tolist()
+    assert t["fired"] == total
+    assert t["move_e"] + t["move_h"] + t["bound"] + t["decay"] + t["capture_e"] + t["capture_h"] == total
+    assert t["move_e"] == int(np.sum((g["trace_kind"] == 1) & (g["trace_particule"] == 1)))
+    assert t["decay"] == t["recombination"] == t["recomb_host"] + t["recomb_tadf"] + t["recomb_fluo"]
+    assert t["emit_tadf"] + t["emit_fluo"] == t["emission"]
+    # Lattice._cache: the last ten fired events (the reference also pushes the event of a step that raised)
+    last = sim.last_events(0)
+    if not g["error_s"]:
+        k = min(10, total)
+        assert np.array_equal(last["initial"][-k:], g["trace_initial"][-k:])
+        assert np.array_equal(last["kind"][-k:], g["trace_kind"][-k:])
+
+
+def test_golden_uploaded_lattice(nat, golden):
+    """Reference-built lattice uploaded through hf_upload_lattice: bit-identical energies, so only
+    exp/log separate the device from the reference."""
+    sim = _sim_for(nat, golden, generated=False)
+    try:
+        _check_run(nat, golden, sim)
+    finally:
+        sim.close()
+
+
+def test_golden_generated_lattice(nat, golden):
+    """Device-side lattice generation (species shuffle + Gaussian energies) from the Philox
+    streams, then the same trajectory."""
+    g = golden
+    sim = _sim_for(nat, g, generated=True)
+    try:
+        a = sim.download_lattice(0)
+        assert np.array_equal(a["species"], g["species"])
+        for k in ("homo", "lumo", "s1", "t1"):
+            np.testing.assert_allclose(a[k], g[k], rtol=0, atol=2e-15)
+        _check_run(nat, g, sim)
+    finally:
+        sim.close()
+
+
+def test_hop_rates_match_oracle(nat):
+    """Known-answer check of _time_move_electron / _time_move_hole on hand-built hops
+    (SURVEY.md §4): every neighbour hop of every charge of a 10+10-charge configuration, rates
+    and tau within 1e-12 of the oracle, ZeroDivisionError flagged alike."""
+    from oracle import frm_oracle as fo
+    from oracle import philox as px
+    g = load_golden("c10_s1")
+    sim = _sim_for(nat, g)
+    sim.inject()
+    lat = fo.OracleLattice.from_arrays(g["dims"], g["species"], g["homo"], g["lumo"])
+    base = fo.OracleTrajectory(lat, g["charges"], g["seed_int"], g["trajectory"], g["field_f"])
+    n0 = base.tallies()["draws"]
+    construction = np.array([px.uniform(g["seed_int"], px.STREAM_TRAJ, g["trajectory"], d) for d in range(n0)])
+    rng = np.random.default_rng(5)
+    try:
+        for particule, which in ((1, "electrons"), (2, "holes")):
+            ini, fin = [], []
+            for s in base.positions(which):
+                for f in lat.neighbourhood(int(s)):
+                    ini.append(int(s)); fin.append(int(f))
+            u = rng.random(len(ini))
+            u[::17] = 0.0                                           # rng = 1.0 -> tau = -0.0
+            tau, rate, zd = sim.eval_hops(0, particule, ini, fin, u)
+            for i in range(len(ini)):
+                # the oracle draws the hop's uniform from the trajectory stream: replay the
+                # construction draws, then u[i]
+                o = fo.OracleTrajectory(lat, g["charges"], g["seed_int"], g["trajectory"], g["field_f"],
+                                        replay=np.append(construction, u[i]))
+                try:
+                    expect = o.time_move(ini[i], fin[i], particule)
+                except ZeroDivisionError:
+                    assert zd[i]
+                    continue
+                assert not zd[i]
+                np.testing.assert_allclose(tau[i], expect, rtol=TAU_RTOL, atol=0)
+                assert 0.0 < rate[i] <= 1e13
+    finally:
+        sim.close()
+
+
+def test_batch_matches_oracle_per_trajectory(nat):
+    """64 trajectories sharing one realisation in one launch: every trajectory equals the oracle's
+    run of the same global trajectory id (tallies, draw counts, final positions)."""
+    from oracle import frm_oracle as fo
+    g = load_golden("d0_s2")
+    B, steps = 64, 1200
+    sim = _sim_for(nat, g, n_trajectories=B)
+    lat = fo.OracleLattice.from_arrays(g["dims"], g["species"], g["homo"], g["lumo"])
+    try:
+        sim.inject()
+        sim.set_trace(0, B, steps)
+        sim.run(steps)
+        sim.sync()
+        tot = dict(emission=0, recombination=0, injection=0, steps=0, fired=0)
+        for t in range(B):
+            o = fo.OracleTrajectory(lat, g["charges"], g["seed_int"], t, g["field_f"])
+            n, otr = o.run(steps)
+            info = sim.info(t)
+            ot = o.tallies()
+            assert info.fired == n
+            assert [info.emission, info.recombination, info.injection, info.steps, info.draws, info.spins] == \
+                [ot["emission"], ot["recombination"], ot["injection"], ot["step"], ot["draws"], ot["spins"]]
+            assert info.status == {"ok": 0, "no_events": 1, "ZeroDivisionError": 2, "ValueError": 3}[o.status]
+            tr = sim.trace(t, steps)
+            assert np.array_equal(tr["initial"], otr["initial"]) and np.array_equal(tr["final"], otr["final"])
+            assert np.array_equal(tr["kind"], otr["kind"])
+            _assert_tau(tr["tau"], otr["tau"])
+            assert np.array_equal(sim.positions(t, 0), o.positions("electrons"))
+            assert np.array_equal(sim.positions(t, 1), o.positions("holes"))
+            flags = o.flags()
+            assert np.array_equal(np.sort(sim.flags(t, 0)), np.flatnonzero(flags & 1))
+            assert np.array_equal(np.sort(sim.flags(t, 1)), np.flatnonzero(flags & 2))
+            for k in tot:
+                tot[k] += {"emission": ot["emission"], "recombination": ot["recombination"],
+                           "injection": ot["injection"], "steps": ot["step"], "fired": n}[k]
+        got = sim.tallies()
+        for k, v in tot.items():
+            assert got[k] == v, k
+    finally:
+        sim.close()
+
+
+def test_sharding_is_invisible(nat):
+    """Two handles holding trajectories [0,96) and [96,192) give the same box totals as one handle
+    holding [0,192): Philox ids are global, so results do not depend on how ranks split the work."""
+    g = load_golden("rag456_s6")
+    def totals(first, n):
+        sim = nat.Sim(g["dims"], tuple(g["props"]), g["field_f"], g["charges"], 1, n_trajectories=n,
+                      seed=g["seed_int"], first_trajectory=first)
+        try:
+            sim.upload_lattice(0, g["species"], g["homo"], g["lumo"])
+            sim.inject()
+            sim.run(700)
+            return sim.tallies()
+        finally:
+            sim.close()
+    whole, a, b = totals(0, 192), totals(0, 96), totals(96, 96)
+    for k in whole:
+        assert whole[k] == a[k] + b[k], k
+    assert whole["recombination"] > 100
+
+
+def test_facade_matches_oracle_and_oled_driver(nat, capsys):
+    """The drop-in surface: Lattice(...) / operations / get_IQE / _emission / _injection / _cache /
+    get_particules_positions, and the OLED.py driver, against the oracle for the same seed."""
+    from hyperfluorescence_b200 import OLED, Lattice
+    from hyperfluorescence_b200.event import Event, Point
+    from hyperfluorescence_b200.molecule import Fluorescent, Host, TADF
+    from oracle import frm_oracle as fo
+    dims, props, seed = (10, 10, 5), (0.84, 0.15, 0.01), 1234
+    lat = Lattice(dims, props, charges=4, seed=seed)
+    lat.operations(100)
+    olat = fo.OracleLattice.generate(dims, props, seed)
+    otr = fo.OracleTrajectory(olat, 4, seed, 0, 0.1)
+    n, tr = otr.run(100)
+    ot = otr.tallies()
+    assert lat.get_IQE() == ot["IQE"]
+    assert (lat._emission, lat._recombination, lat._injection, lat._step) == \
+        (ot["emission"], ot["recombination"], ot["injection"], ot["step"])
+    cache = lat._cache
+    assert len(cache) == 10 and all(isinstance(e, Event) for e in cache)
+    assert [lat._site(e.final) for e in cache] == tr["final"][-10:].tolist()
+    e, h, x = lat.get_particules_positions()
+    assert [lat._site(p) for p, _ in e] == otr.positions("electrons").tolist()
+    assert all(k in (Host, TADF, Fluorescent) for _, k in e + h + x)
+    mol = lat._grid[0][0][0]
+    assert isinstance(mol, Host) and mol.position == Point(0, 0, 0)
+    assert [(p.x, p.y, p.z) for p in mol.neighbourhood[:6]] == [(0, 0, 1), (0, 1, 0), (0, 1, 1), (0, 9, 0), (0, 9, 1), (1, 0, 0)]
+    a = olat.arrays()
+    np.testing.assert_allclose(mol.homo_energy, a["homo"][0], atol=2e-15)
+    # reference-style exceptions before any device work
+    with pytest.raises(TypeError):
+        Lattice([10, 10, 5], props)
+    with pytest.raises(IndexError):
+        Lattice((10, 10), props)
+    with pytest.raises(ValueError):
+        Lattice((10, 10, 2), props)
+    with pytest.raises(ValueError):
+        Lattice((3, 3, 3), props)
+    with pytest.raises(ValueError):
+        Lattice((4, 4, 8), (0.5, 0.3, 0.2), charges=17)
+    lat.close()
+    test = OLED.main(seed=7)
+    out = capsys.readouterr().out
+    assert "IQE :" in out and "emissions :" in out and "injections :" in out
+    assert test._injection >= 8
+    test.close()
+
+
+def test_zero_division_is_swallowed_like_the_reference(nat, capsys):
+    """dense_s8 hits ZeroDivisionError at step 111 (two electrons on one site): operations() prints
+    the cache and returns without refreshing IQE; a later call continues (reseau.py:585-589)."""
+    from hyperfluorescence_b200 import Lattice
+    g = load_golden("dense_s8")
+    lat = Lattice(g["dims"], tuple(float(p) for p in g["props"]), charges=g["charges"], seed=g["seed_int"],
+                  lattice=dict(species=g["species"], homo=g["homo"], lumo=g["lumo"]))
+    lat.operations(2000)
+    out = capsys.readouterr().out
+    assert out.startswith("deque([")
+    assert lat.get_IQE() == 0.0
+    assert lat._step == int(g["final_tallies"][3])
+    lat.operations(5)             # continues after the swallowed exception
+    assert lat._step > int(g["final_tallies"][3])
+    lat.close()
+
+
+def test_full_size_properties(nat):
+    """BASELINE config 2 at full size (64^3 lattice, 10^5 trajectories): size-independent properties.
+    Event accounting closes, the run is deterministic, and a sample of trajectories equals the oracle."""
+    from oracle import frm_oracle as fo
+    dims, props, seed, B, steps = (64, 64, 64), (0.84, 0.15, 0.01), 20261019, 100_000, 300
+    def run():
+        sim = nat.Sim(dims, props, 0.1, 1, 1, n_trajectories=B, seed=seed)
+        sim.generate_lattice()
+        sim.inject()
+        sim.run(steps)
+        t = sim.tallies()
+        sample = {i: (sim.info(i).draws, sim.positions(i, 0).tolist(), sim.positions(i, 1).tolist())
+                  for i in (0, 1, 77, 31337, B - 1)}
+        lat = sim.download_lattice(0)
+        sim.close()
+        return t, sample, lat
+    t1, s1, lat1 = run()
+    t2, s2, _ = run()
+    assert t1 == t2 and s1 == s2                                   # determinism
+    assert t1["steps"] == B * steps and t1["fired"] == B * steps and t1["stopped"] == 0
+    assert t1["move_e"] + t1["move_h"] + t1["bound"] + t1["decay"] + t1["capture_e"] + t1["capture_h"] == t1["fired"]
+    assert t1["injection"] == 2 * B + 2 * t1["decay"] + t1["capture_e"] + t1["capture_h"]
+    olat = fo.OracleLattice.generate(dims, props, seed)
+    a = olat.arrays()
+    assert np.array_equal(a["species"], lat1["species"])
+    np.testing.assert_allclose(lat1["lumo"], a["lumo"], rtol=0, atol=2e-15)
+    for i, (draws, e, h) in s1.items():
+        o = fo.OracleTrajectory(olat, 1, seed, i, 0.1)
+        o.run(steps, trace=False)
+        assert o.tallies()["draws"] == draws
+        assert o.positions("electrons").tolist() == e and o.positions("holes").tolist() == h
+
+
+def test_statistics_within_three_sigma_of_reference(nat):
+    """Photons per recombination, recombinations per run and IQE over 20 000 device trajectories
+    against the UNMODIFIED reference run with its own Mersenne-Twister streams
+    (tests/golden/stats_tiny.npz, make_golden.py): within 3 sigma."""
+    import os
+    from tests.conftest import GOLDEN_DIR
+    ref = np.load(os.path.join(GOLDEN_DIR, "stats_tiny.npz"))
+    dims = tuple(int(v) for v in ref["dims"])
+    props = tuple(float(v) for v in ref["props"])
+    charges, steps = int(ref["charges"]), int(ref["steps"])
+    B = R = 20_000                       # one trajectory per lattice realisation, like the reference runs
+    sim = nat.Sim(dims, props, 0.1, charges, 1, n_trajectories=B, n_realisations=R, seed=4242)
+    try:
+        sim.generate_lattice()
+        sim.inject()
+        sim.run(steps)
+        sim.sync()
+        infos = [sim.info(i) for i in range(B)]
+        em = np.array([i.emission for i in infos], float)
+        rec = np.array([i.recombination for i in infos], float)
+        inj = np.array([i.injection for i in infos], float)
+    finally:
+        sim.close()
+    for name, ours, theirs in (("recombination", rec, ref["recombination"].astype(float)),
+                               ("emission", em, ref["emission"].astype(float)),
+                               ("IQE", 200.0 * em / inj, 200.0 * ref["emission"] / ref["injection"])):
+        sigma = np.sqrt(ours.var(ddof=1) / ours.size + theirs.var(ddof=1) / theirs.size)
+        assert abs(ours.mean() - theirs.mean()) < 3 * sigma, (name, ours.mean(), theirs.mean(), sigma)
