@@ -78,7 +78,7 @@ struct HfParams {
     int32_t *pos[2], *flag[2], *ev_init[2], *ev_final[2];
     double *ev_tau[2];
     HfScalars *sc;
-    int32_t *cache_init, *cache_final, *cache_kp;   // [B][10]
+    int32_t *cache_init, *cache_final, *cache_kp;   // [10][B] (slot-major)
     double *cache_tau;
     // replay / trace
     const double *replay;
@@ -453,11 +453,11 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
             w.ev_tau(t)[i] = P.ev_tau[t][local * P.cap_c + i];
         }
     }
-    if (lane < HF_CACHE) {
-        w.cache_init[lane] = P.cache_init[local * HF_CACHE + lane];
-        w.cache_final[lane] = P.cache_final[local * HF_CACHE + lane];
-        w.cache_kp[lane] = P.cache_kp[local * HF_CACHE + lane];
-        w.cache_tau[lane] = P.cache_tau[local * HF_CACHE + lane];
+    if (lane < HF_CACHE) {                 // ring stored slot-major: [slot][trajectory]
+        w.cache_init[lane] = P.cache_init[lane * P.B + local];
+        w.cache_final[lane] = P.cache_final[lane * P.B + local];
+        w.cache_kp[lane] = P.cache_kp[lane * P.B + local];
+        w.cache_tau[lane] = P.cache_tau[lane * P.B + local];
     }
     w.c_move_e = w.c_move_h = w.c_bound = w.c_decay = w.c_capture_e = w.c_capture_h = 0;
     w.c_recomb_host = w.c_recomb_tadf = w.c_recomb_fluo = w.c_emit_tadf = w.c_emit_fluo = 0;
@@ -478,10 +478,10 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
         }
     }
     if (lane < HF_CACHE) {
-        P.cache_init[local * HF_CACHE + lane] = w.cache_init[lane];
-        P.cache_final[local * HF_CACHE + lane] = w.cache_final[lane];
-        P.cache_kp[local * HF_CACHE + lane] = w.cache_kp[lane];
-        P.cache_tau[local * HF_CACHE + lane] = w.cache_tau[lane];
+        P.cache_init[lane * P.B + local] = w.cache_init[lane];
+        P.cache_final[lane * P.B + local] = w.cache_final[lane];
+        P.cache_kp[lane * P.B + local] = w.cache_kp[lane];
+        P.cache_tau[lane * P.B + local] = w.cache_tau[lane];
     }
     if (lane == 0) {
         HfScalars sc;
@@ -544,7 +544,6 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
 
     if (kind == HF_K_MOVE) {                                                     // 492-524
         const int t = part - 1, o = 1 - t;
-        if (t == 0) w.c_move_e += 1; else w.c_move_h += 1;
         hf_remove_events(w, t, ini, fin, lane);                                  // 495 / 511 (Q4)
         if (!hf_toggle_flag(P, w, t, ini, lane)) return HF_ST_CAPACITY;          // 423-424 / 429-430
         if (!hf_toggle_flag(P, w, t, fin, lane)) return HF_ST_CAPACITY;
@@ -571,7 +570,6 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     const int site = w.special_site;
     w.special = 0;                                                               // _remove_*_event
     if (kind == HF_K_BOUND) {                                                    // 529-533
-        w.c_bound += 1;
         const bool both = hf_contains(w.flag(0), w.n_flag(0), site, lane) && hf_contains(w.flag(1), w.n_flag(1), site, lane);
         if (both) {                                                              // molecule.py:88-96
             const double r = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPIN, w.ident, w.spins);
@@ -589,7 +587,6 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         return HF_ST_OK;
     }
     if (kind == HF_K_DECAY) {                                                    // 541-547
-        w.c_decay += 1;
         const int sp = w.species[hf_site(P, site)];
         bool photon = false;
         if (w.xstate) {                                                          // molecule.py:185-199, 283-297, 387-400
@@ -611,7 +608,6 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     }
     // capture (551-561)
     const int t = part - 1;
-    if (t == 0) w.c_capture_e += 1; else w.c_capture_h += 1;
     if (!hf_toggle_flag(P, w, t, site, lane)) return HF_ST_CAPACITY;             // 440-446
     const int idx = hf_find_first(w.pos(t), w.n_pos(t), site, lane);
     if (idx < 0) return HF_ST_VALUE_ERROR;
@@ -644,6 +640,10 @@ __global__ void __launch_bounds__(kWarps * 32) hf_run_kernel(const HfParams P) {
                 double tau;
                 const int st = hf_step(P, w, lane, &kind, &part, &ini, &fin, &tau);
                 if (st != HF_ST_OK) { w.status = st; break; }                    // 587-591
+                if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
+                else if (kind == HF_K_BOUND) w.c_bound += 1;
+                else if (kind == HF_K_DECAY) w.c_decay += 1;
+                else { if (part == 1) w.c_capture_e += 1; else w.c_capture_h += 1; }
                 if (traced && lane == 0 && w.fired < (uint64_t)P.trace_cap) {
                     HfTraceRec rec;
                     rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);

@@ -1,0 +1,294 @@
+// Thread-per-trajectory First-Reaction-Method kernel for charges == 1 (one electron and one hole
+// in flight per trajectory: BASELINE configs 1, 2, 3 and 5).
+//
+// Why a second kernel: ncu on the warp-per-trajectory kernel (profiles/r01a_*) showed 1174 warp
+// instructions per event at 26/32 active lanes and an fp64 pipe only 12.7 % busy — the step is
+// bound by the warp-wide bookkeeping of the ordered lists, not by the rate arithmetic.  With a
+// single charge of each type the lists degenerate to one slot each, so the whole trajectory state
+// fits in registers and every lane can run its own trajectory: the 17-26 candidate hops become a
+// per-thread loop, no shuffles, no shared memory, 32/32 lanes busy.
+//
+// Semantics are those of hf_frm.cuh (same citations), specialised by these facts about C = 1:
+//   * the Molecule.electron / .hole flags always agree with the position lists (no second charge
+//     of the same type can ever desynchronise the toggles), except on the exciton's site between
+//     its `bound` and `decay` steps, when no candidate is evaluated;
+//   * a candidate is therefore never blocked (the only same-type charge is the one moving): every
+//     regenerated event draws exactly 26 (bulk) or 17 (z face) uniforms;
+//   * the same-type Coulomb loop only meets the moving charge itself (skipped, reseau.py:300/332);
+//     the opposite-type loop has at most one term;
+//   * re-injection always finds its own list empty: choice() is randbelow(X*Y) (reseau.py:448-470).
+// If any of these were ever violated the kernel stops the trajectory with HF_ST_CAPACITY instead
+// of continuing with a wrong state.  State is exchanged through the same global arrays as the
+// warp kernel (cap_c = 1, cap_f = 2), so the two kernels can be cross-checked on the same handle.
+#pragma once
+#include "hf_frm.cuh"
+
+struct HfC1 {
+    // named scalars + select accessors: nothing is dynamically indexed, everything stays in registers
+    int32_t e_pos, h_pos;      // packed position or -1
+    int32_t e_fin, h_fin;      // pending move event: final site or -1
+    double e_tau, h_tau;
+    int32_t special, special_site, xstate, status, cache_head, cache_n;
+    uint64_t draws, spins, emission, recombination, injection, steps, fired;
+
+    __device__ __forceinline__ int32_t pos(int t) const { return t ? h_pos : e_pos; }
+    __device__ __forceinline__ int32_t fin(int t) const { return t ? h_fin : e_fin; }
+    __device__ __forceinline__ double tau(int t) const { return t ? h_tau : e_tau; }
+    __device__ __forceinline__ void set_pos(int t, int32_t v) { if (t) h_pos = v; else e_pos = v; }
+    __device__ __forceinline__ void set_fin(int t, int32_t v) { if (t) h_fin = v; else e_fin = v; }
+    __device__ __forceinline__ void set_tau(int t, double v) { if (t) h_tau = v; else e_tau = v; }
+};
+
+struct HfC1Counters {
+    unsigned move_e, move_h, bound, decay, capture_e, capture_h, recomb_host, recomb_tadf, recomb_fluo, emit_tadf, emit_fluo;
+};
+
+__device__ __forceinline__ double hf_c1_uniform(const HfParams &P, int64_t local, uint32_t ident, uint64_t d, bool *exhausted) {
+    if (P.replay) {
+        if (d >= (uint64_t)P.n_replay) { *exhausted = true; return 0.5; }
+        return P.replay[local * P.n_replay + (int64_t)d];
+    }
+    return hf_philox_uniform(P.k0, P.k1, HF_STREAM_TRAJ, ident, d);
+}
+
+// _electron_reinjection / _hole_reinjection with an empty own list (reseau.py:448-470)
+__device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t, int64_t local, uint32_t ident) {
+    if (s.pos(t) >= 0) return HF_ST_CAPACITY;                                    // C = 1 invariant
+    const int64_t n = (int64_t)P.X * P.Y;
+    const int64_t maxsize = (int64_t)1 << 53;
+    const int64_t rem = maxsize % n;
+    const double limit = (double)(maxsize - rem) * 0x1p-53;
+    bool exhausted = false;
+    double r = hf_c1_uniform(P, local, ident, s.draws++, &exhausted);            // random.py:264-269
+    while (r >= limit && !exhausted) r = hf_c1_uniform(P, local, ident, s.draws++, &exhausted);
+    if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
+    const int64_t k = (int64_t)floor(r * 0x1p53) % n;
+    s.set_pos(t, hf_pack((int)(k / P.Y), (int)(k % P.Y), t == 0 ? P.Z - 1 : 0));
+    s.injection += 1;
+    return HF_ST_OK;
+}
+
+// _new_move_electron_events / _new_move_hole_events for the single charge of type t
+// (reseau.py:380-396): sequential loop over the neighbour list in the reference's order, first
+// minimum wins.  t is a RUNTIME value on purpose: lanes regenerating an electron event and lanes
+// regenerating a hole event run the same instructions (only the energy array and the sign of
+// the field term differ), so a warp with a mix of both does not serialise.
+__device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, const double *homo, int t, HfC1 &s,
+                                         int64_t local, uint32_t ident) {
+    const int pos = s.pos(t), other = s.pos(1 - t);
+    const double *__restrict__ E = t ? homo : lumo;
+    const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
+    const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
+    const bool other_has = other >= 0;
+    uint64_t d = s.draws;
+    double inv_old = 0.0;
+    if (other_has) {
+        const int d2 = hf_dist2(other, pos);
+        if (d2 == 0) { s.draws = d + 1; return HF_ST_ZERO_DIVISION; }            // 1/old_r.norm(), first candidate
+        inv_old = __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+    }
+    const double e_init = __ldg(E + hf_site(P, pos));
+    const double fz = t == 0 ? -P.field : P.field;                               // reseau.py:287 / 319
+    const int64_t plane = (int64_t)P.X * P.Y;
+    double best = 0.0;
+    int32_t bfin = -1;
+    bool exhausted = false;
+    for (int ix = 0; ix < 3; ++ix) {
+        const int cx = hf_bvk_xy(px, P.X, ix);
+        for (int iy = 0; iy < 3; ++iy) {
+            const int cy = hf_bvk_xy(py, P.Y, iy);
+            const int64_t row = (int64_t)cy * P.X + cx;
+            for (int iz = 0; iz < nz; ++iz) {
+                const int cz = hf_bvk_z(pz, P.Z, iz);
+                if (cx == px && cy == py && cz == pz) continue;                  // reseau.py:188
+                const int cand = hf_pack(cx, cy, cz);
+                const double u = hf_c1_uniform(P, local, ident, d++, &exhausted);
+                const double rng = __dsub_rn(1.0, u);                            // 284 / 316
+                double dE = __dsub_rn(__ldg(E + row + cz * plane), e_init);      // 286 / 318
+                dE = __dadd_rn(dE, __dmul_rn(fz, (double)(cz - pz)));
+                double out = 0.0;
+                if (other_has) {                                                 // 305-312 / 337-344
+                    if (other == cand) {
+                        out = -INFINITY;
+                    } else {
+                        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(other, cand)));
+                        out = __dsub_rn(0.0, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, inv_old)));
+                    }
+                }
+                dE = __dadd_rn(dE, out);                                         // 288 / 320
+                double k = HF_RATE0;
+                if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));       // 290-291 / 322-323
+                if (k == 0.0) { s.draws = d; return HF_ST_ZERO_DIVISION; }
+                const double tau = __ddiv_rn(-log(rng), k);                      // 292 / 324
+                if (bfin < 0 || tau < best) { best = tau; bfin = cand; }         // min(): first minimum
+            }
+        }
+    }
+    s.draws = d;
+    if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
+    s.set_fin(t, bfin);
+    s.set_tau(t, best);
+    return HF_ST_OK;
+}
+
+// _first_reaction_method (reseau.py:483-562) for one thread's trajectory.  Bookkeeping first;
+// the (at most two) event regenerations it asks for are queued in `gen` (bits 0-1: first type,
+// bit 2: re-inject it first; bits 4-5 / 6: second one, only after a decay) and executed by the
+// caller's common tail so that the whole warp runs the candidate loop together.
+#define HF_GEN_NONE 0
+__device__ __forceinline__ int hf_c1_step(const HfParams &P, const uint8_t *species, HfC1 &s, HfC1Counters &c,
+                                          int64_t local, uint32_t ident, int *gen,
+                                          int *ev_kind, int *ev_part, int *ev_init, int *ev_final, double *ev_tau) {
+    int kind, part, ini, fin;
+    double tau;
+    *gen = HF_GEN_NONE;
+    if (s.special) {
+        kind = s.special & 0xff; part = s.special >> 8; ini = fin = s.special_site; tau = 0.0;
+    } else {
+        const bool he = s.e_fin >= 0, hh = s.h_fin >= 0;
+        if (!he && !hh) return HF_ST_NO_EVENTS;                                  // 487-488
+        const int t = (hh && (!he || s.h_tau <= s.e_tau)) ? 1 : 0;               // ties: last in concat order (Q6)
+        kind = HF_K_MOVE; part = t + 1; ini = s.pos(t); fin = s.fin(t); tau = s.tau(t);
+    }
+    // _cache (489-490): slot-major ring in global memory, coalesced across the warp's trajectories
+    {
+        const int64_t at = (int64_t)s.cache_head * P.B + local;
+        P.cache_init[at] = ini; P.cache_final[at] = fin; P.cache_kp[at] = kind | (part << 8); P.cache_tau[at] = tau;
+        s.cache_head = s.cache_head + 1 == HF_CACHE ? 0 : s.cache_head + 1;
+        if (s.cache_n < HF_CACHE) s.cache_n += 1;
+    }
+    *ev_kind = kind; *ev_part = part; *ev_init = ini; *ev_final = fin; *ev_tau = tau;
+
+    if (kind == HF_K_MOVE) {                                                     // 492-524
+        const int t = part - 1, o = 1 - t;
+        if (ini < 0) return HF_ST_VALUE_ERROR;
+        s.set_fin(t, -1);                                                        // 495 / 511: its own event
+        s.set_pos(t, fin);                                                       // 422-432
+        const bool opposite_here = s.pos(o) == fin;
+        const int capture_z = t == 0 ? 0 : P.Z - 1;
+        if (!opposite_here && hf_pz(fin) != capture_z) {                         // 498-500 / 514-516
+            if (s.fin(o) >= 0) s.set_tau(o, __dsub_rn(s.tau(o), tau));           // _update_events
+            *gen = 8 | t;
+        } else if (opposite_here) {                                              // 501-505 / 517-521 (Q5)
+            s.set_fin(o, -1);
+            s.special = HF_K_BOUND | (HF_PART_EXCITON << 8); s.special_site = fin;
+        } else {                                                                 // 506-508 / 522-524
+            if (s.fin(o) >= 0) s.set_tau(o, __dsub_rn(s.tau(o), tau));
+            s.special = HF_K_CAPTURE | (part << 8); s.special_site = fin;
+        }
+        return HF_ST_OK;
+    }
+    const int site = s.special_site;
+    s.special = 0;
+    if (kind == HF_K_BOUND) {                                                    // 529-533
+        if (s.e_pos != site || s.h_pos != site) return HF_ST_VALUE_ERROR;
+        const double r = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPIN, ident, s.spins);   // molecule.py:88-96
+        s.spins += 1;
+        s.xstate = (0 <= r && r < 0.25) ? HF_XS_SINGLET : HF_XS_TRIPLET;
+        s.e_pos = s.h_pos = -1;                                                  // 434-438
+        s.special = HF_K_DECAY | (HF_PART_EXCITON << 8); s.special_site = site;
+        return HF_ST_OK;
+    }
+    if (kind == HF_K_DECAY) {                                                    // 541-547
+        const int sp = species[hf_site(P, site)];
+        bool photon = false;
+        if (s.xstate) { photon = sp != HF_SPECIES_HOST && s.xstate == HF_XS_SINGLET; s.xstate = 0; }
+        s.recombination += 1;                                                    // 472-476
+        c.recomb_host += sp == 0; c.recomb_tadf += sp == 1; c.recomb_fluo += sp == 2;
+        if (photon) { s.emission += 1; c.emit_tadf += sp == 1; c.emit_fluo += sp == 2; }
+        *gen = (8 | 4 | 0) | ((8 | 4 | 1) << 4);                                 // re-inject + regenerate e, then h
+        return HF_ST_OK;
+    }
+    const int t = part - 1;                                                      // capture 551-561
+    if (s.pos(t) != site) return HF_ST_VALUE_ERROR;
+    s.set_pos(t, -1);                                                            // 440-446
+    *gen = 8 | 4 | t;
+    return HF_ST_OK;
+}
+
+__device__ __forceinline__ void hf_c1_load(const HfParams &P, HfC1 &s, int64_t local) {
+    const HfScalars sc = P.sc[local];
+    s.e_pos = sc.n_pos[0] > 0 ? P.pos[0][local] : -1;
+    s.h_pos = sc.n_pos[1] > 0 ? P.pos[1][local] : -1;
+    s.e_fin = sc.n_ev[0] > 0 ? P.ev_final[0][local] : -1;
+    s.h_fin = sc.n_ev[1] > 0 ? P.ev_final[1][local] : -1;
+    s.e_tau = sc.n_ev[0] > 0 ? P.ev_tau[0][local] : 0.0;
+    s.h_tau = sc.n_ev[1] > 0 ? P.ev_tau[1][local] : 0.0;
+    s.special = sc.special; s.special_site = sc.special_site; s.xstate = sc.xstate; s.status = sc.status;
+    s.cache_head = sc.cache_head; s.cache_n = sc.cache_n;
+    s.draws = sc.draws; s.spins = sc.spins; s.emission = sc.emission; s.recombination = sc.recombination;
+    s.injection = sc.injection; s.steps = sc.steps; s.fired = sc.fired;
+}
+
+__device__ __forceinline__ void hf_c1_store(const HfParams &P, const HfC1 &s, const HfC1Counters &c, int64_t local) {
+    HfScalars sc;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        sc.n_pos[t] = s.pos(t) >= 0;
+        sc.n_ev[t] = s.fin(t) >= 0;
+        if (s.pos(t) >= 0) P.pos[t][local] = s.pos(t);
+        if (s.fin(t) >= 0) { P.ev_init[t][local] = s.pos(t); P.ev_final[t][local] = s.fin(t); P.ev_tau[t][local] = s.tau(t); }
+        // flag sets (cap_f = 2): the charge's own site; on the exciton's site both flags stay set
+        // until the decay step clears them (molecule.py:185-199)
+        const bool lingering = (s.special & 0xff) == HF_K_DECAY;
+        const int fsite = lingering ? s.special_site : s.pos(t);
+        sc.n_flag[t] = fsite >= 0;
+        if (fsite >= 0) P.flag[t][local * P.cap_f] = fsite;
+    }
+    sc.special = s.special; sc.special_site = s.special_site; sc.xstate = s.xstate; sc.status = s.status;
+    sc.cache_head = s.cache_head; sc.cache_n = s.cache_n;
+    sc.draws = s.draws; sc.spins = s.spins; sc.emission = s.emission; sc.recombination = s.recombination;
+    sc.injection = s.injection; sc.steps = s.steps; sc.fired = s.fired;
+    P.sc[local] = sc;
+    // channel counters: warp-aggregate, one atomic per non-zero counter per warp per launch
+    const unsigned v[11] = {c.move_e, c.move_h, c.bound, c.decay, c.capture_e, c.capture_h,
+                            c.recomb_host, c.recomb_tadf, c.recomb_fluo, c.emit_tadf, c.emit_fluo};
+#pragma unroll
+    for (int i = 0; i < 11; ++i)
+        if (v[i]) atomicAdd(P.totals + 5 + i, (unsigned long long)v[i]);
+}
+
+// Lattice.operations(stop) for charges == 1: one thread per trajectory.
+__global__ void __launch_bounds__(128, 6) hf_run_c1_kernel(const HfParams P) {
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= P.B) return;
+    HfC1 s;
+    HfC1Counters c = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    hf_c1_load(P, s, local);
+    const uint32_t ident = P.first_traj + (uint32_t)local;
+    const int64_t r = local / P.traj_per_real;
+    const uint8_t *species = P.species + r * P.N;
+    const double *lumo = P.lumo + r * P.N, *homo = P.homo + r * P.N;
+    if (s.status == HF_ST_ZERO_DIVISION || s.status == HF_ST_NO_EVENTS) s.status = HF_ST_OK;
+    const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
+    HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+    if (s.status == HF_ST_OK) {
+        for (int64_t i = 0; i < P.n_steps; ++i) {
+            s.steps += 1;                                                        // 582
+            int kind, part, ini, fin, gen;
+            double tau;
+            int st = hf_c1_step(P, species, s, c, local, ident, &gen, &kind, &part, &ini, &fin, &tau);
+            // common tail: the queued regenerations (one for a move or a capture, two for a decay)
+            for (; st == HF_ST_OK && gen; gen >>= 4) {
+                const int t = gen & 1;
+                if (gen & 4) st = hf_c1_reinject(P, s, t, local, ident);
+                if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, t, s, local, ident);
+            }
+            if (st != HF_ST_OK) { s.status = st; break; }                        // 587-591
+            if (kind == HF_K_MOVE) { if (part == 1) c.move_e += 1; else c.move_h += 1; }
+            else if (kind == HF_K_BOUND) c.bound += 1;
+            else if (kind == HF_K_DECAY) c.decay += 1;
+            else { if (part == 1) c.capture_e += 1; else c.capture_h += 1; }
+            if (traced && s.fired < (uint64_t)P.trace_cap) {
+                HfTraceRec rec;
+                rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
+                rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
+                rec.pad[0] = rec.pad[1] = 0;
+                rec.spins = (uint32_t)s.spins; rec.draws = s.draws;
+                trace[s.fired] = rec;
+            }
+            s.fired += 1;
+        }
+    }
+    hf_c1_store(P, s, c, local);
+}

@@ -13,6 +13,7 @@
 
 #include "../../include/hfkmc.h"
 #include "hf_frm.cuh"
+#include "hf_frm_c1.cuh"
 
 static_assert(sizeof(HfTraceRec) == sizeof(hf_event), "trace record must match hf_event");
 static_assert(sizeof(hf_event) == 32, "hf_event is 32 bytes");
@@ -436,10 +437,17 @@ int hf_run(hf_sim *s, int64_t stop) {
     if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
     cudaEvent_t e0 = get_event(s), e1 = get_event(s);
     HF_CUDA(cudaEventRecord(e0, s->stream));
-    switch (s->warps) {
-        case 8: launch_run<8>(s); break;
-        case 4: launch_run<4>(s); break;
-        default: launch_run<1>(s); break;
+    if (s->P.C == 1 && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
+        // one thread per trajectory (hf_frm_c1.cuh)
+        const int threads = 128;
+        const int64_t blocks = (s->P.B + threads - 1) / threads;
+        hf_run_c1_kernel<<<(unsigned)blocks, threads, 0, s->stream>>>(s->P);
+    } else {
+        switch (s->warps) {
+            case 8: launch_run<8>(s); break;
+            case 4: launch_run<4>(s); break;
+            default: launch_run<1>(s); break;
+        }
     }
     HF_CUDA(cudaEventRecord(e1, s->stream));
     s->timing.emplace_back(e0, e1);
@@ -572,10 +580,11 @@ int hf_read_last_events(hf_sim *s, int64_t t, hf_event *out, int32_t *n) {
     HF_CUDA(cudaMemcpyAsync(&sc, s->d_sc + t, sizeof(sc), cudaMemcpyDeviceToHost, s->stream));
     int32_t ci[HF_CACHE], cf[HF_CACHE], ck[HF_CACHE];
     double ct[HF_CACHE];
-    HF_CUDA(cudaMemcpyAsync(ci, s->P.cache_init + t * HF_CACHE, sizeof(ci), cudaMemcpyDeviceToHost, s->stream));
-    HF_CUDA(cudaMemcpyAsync(cf, s->P.cache_final + t * HF_CACHE, sizeof(cf), cudaMemcpyDeviceToHost, s->stream));
-    HF_CUDA(cudaMemcpyAsync(ck, s->P.cache_kp + t * HF_CACHE, sizeof(ck), cudaMemcpyDeviceToHost, s->stream));
-    HF_CUDA(cudaMemcpyAsync(ct, s->P.cache_tau + t * HF_CACHE, sizeof(ct), cudaMemcpyDeviceToHost, s->stream));
+    const size_t pitch4 = sizeof(int32_t) * (size_t)s->P.B, pitch8 = sizeof(double) * (size_t)s->P.B;   // ring is [slot][trajectory]
+    HF_CUDA(cudaMemcpy2DAsync(ci, sizeof(int32_t), s->P.cache_init + t, pitch4, sizeof(int32_t), HF_CACHE, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpy2DAsync(cf, sizeof(int32_t), s->P.cache_final + t, pitch4, sizeof(int32_t), HF_CACHE, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpy2DAsync(ck, sizeof(int32_t), s->P.cache_kp + t, pitch4, sizeof(int32_t), HF_CACHE, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpy2DAsync(ct, sizeof(double), s->P.cache_tau + t, pitch8, sizeof(double), HF_CACHE, cudaMemcpyDeviceToHost, s->stream));
     HF_CUDA(cudaStreamSynchronize(s->stream));
     const int count = sc.cache_n;
     for (int i = 0; i < count; ++i) {          // oldest first

@@ -1,0 +1,14 @@
+#!/bin/bash
+# ncu evidence for the step kernel: (1) plain run of the exact command, (2) launch list with
+# device times, (3) one full capture of hf_run_kernel.  Output under gpurun_out/.
+set -u
+mkdir -p gpurun_out
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu"
+$CMD > gpurun_out/plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo "launch list exit $?"
+$CMD > gpurun_out/plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:hf_run -s 1 -c 1 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
+echo "full capture exit $?"
+tail -3 gpurun_out/ncu_full.log
+ls -la gpurun_out

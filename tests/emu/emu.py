@@ -12,6 +12,7 @@ LIB = os.path.join(HERE, "libemu_frm.so")
 ROOT = os.path.dirname(os.path.dirname(HERE))
 DEPS = [os.path.join(HERE, "emu_frm.cpp"), os.path.join(HERE, "warp_emu.h"),
         os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm.cuh"),
+        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm_c1.cuh"),
         os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_philox.cuh")]
 
 EVENT_DTYPE = np.dtype([("initial", "<i4"), ("final", "<i4"), ("tau", "<f8"), ("kind", "u1"), ("particule", "u1"),
@@ -111,3 +112,36 @@ def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_cal
         init_me_tau=init_taus[:nme0].copy(), init_mh_tau=init_taus[cap:cap + nmh0].copy(),
     )
     return out
+
+
+SCALARS_DTYPE = np.dtype([("n_pos", "<i4", (2,)), ("n_flag", "<i4", (2,)), ("n_ev", "<i4", (2,)), ("special", "<i4"),
+                          ("special_site", "<i4"), ("xstate", "<i4"), ("status", "<i4"), ("cache_head", "<i4"),
+                          ("cache_n", "<i4"), ("draws", "<u8"), ("spins", "<u8"), ("emission", "<u8"),
+                          ("recombination", "<u8"), ("injection", "<u8"), ("steps", "<u8"), ("fired", "<u8")])
+assert SCALARS_DTYPE.itemsize == 104
+
+
+def run_batch_c1(dims, field, seed, first_traj, B, use_c1, species, homo, lumo, stop, n_calls=1):
+    """B <= 32 charges == 1 trajectories through hf_inject + hf_run with either step kernel."""
+    dims = tuple(int(v) for v in dims)
+    cap = stop * n_calls
+    trace = np.zeros((B, max(cap, 1)), EVENT_DTYPE)
+    sc = np.zeros(B, SCALARS_DTYPE)
+    pos, ev_init, ev_final = (np.zeros((2, B), np.int32) for _ in range(3))
+    ev_tau = np.zeros((2, B), np.float64)
+    flag = np.zeros((2, B, 2), np.int32)
+    cache_i = np.zeros((3, 10, B), np.int32)
+    cache_tau = np.zeros((10, B), np.float64)
+    totals = np.zeros(20, np.uint64)
+    species = np.ascontiguousarray(species, np.uint8)
+    homo = np.ascontiguousarray(homo, np.float64)
+    lumo = np.ascontiguousarray(lumo, np.float64)
+    d = (C.c_int32 * 3)(*dims)
+    rc = lib().emu_run_batch_c1(d, C.c_double(field), C.c_uint64(seed), C.c_uint32(first_traj), C.c_int32(B),
+                                C.c_int32(1 if use_c1 else 0), _p(species), _p(homo), _p(lumo), C.c_int64(stop),
+                                C.c_int32(n_calls), _p(trace), C.c_int64(max(cap, 1)), _p(sc), _p(pos), _p(ev_init),
+                                _p(ev_final), _p(ev_tau), _p(flag), _p(cache_i), _p(cache_tau), _p(totals))
+    if rc:
+        raise RuntimeError(f"emu_run_batch_c1 failed ({rc})")
+    return dict(trace=trace, sc=sc, pos=pos, ev_init=ev_init, ev_final=ev_final, ev_tau=ev_tau, flag=flag,
+                cache_i=cache_i, cache_tau=cache_tau, totals=totals)

@@ -4,6 +4,7 @@
 #include "warp_emu.h"
 
 #include "../../hyperfluorescence_b200/csrc/hf_frm.cuh"
+#include "../../hyperfluorescence_b200/csrc/hf_frm_c1.cuh"
 
 #include <vector>
 
@@ -42,6 +43,7 @@ void wire(HfParams &P, Buffers &b, int64_t trace_cap) {
 struct InjectArgs { const HfParams *P; int32_t *pool; };
 void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P, x->pool); }
 void run_body(void *a) { hf_run_kernel<1>(*(const HfParams *)a); }
+void run_c1_body(void *a) { hf_run_c1_kernel(*(const HfParams *)a); }
 
 struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
 void shuffle_body(void *a) { auto *x = (ShuffleArgs *)a; hf_species_shuffle(*x->P, x->pool, x->total, x->n_host, x->n_tadf, x->layer, 0); }
@@ -149,6 +151,48 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
     memcpy(cache_tau_out, b.cache_tau.data(), sizeof(double) * HF_CACHE);
     const int64_t n = (int64_t)sc.fired < trace_cap ? (int64_t)sc.fired : trace_cap;
     memcpy(trace_out, b.trace.data(), sizeof(HfTraceRec) * (size_t)n);
+    return 0;
+}
+
+// Batch of B <= 32 trajectories (global ids first_traj ..) with charges == 1 on one lattice:
+// hf_inject, then n_calls x hf_run(stop) with either the thread-per-trajectory kernel (use_c1, each
+// emulated lane owns one trajectory) or the warp kernel (one trajectory after the other).
+// Outputs per trajectory b: trace_out[b*trace_cap ..], sc_out[b] (raw HfScalars), and the raw
+// global arrays pos/ev_init/ev_final ([2][B]), ev_tau ([2][B]), flag ([2][B][2]), cache ([3][10][B], tau [10][B]).
+int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_t first_traj, int32_t B, int32_t use_c1,
+                     const uint8_t *species, const double *homo, const double *lumo, int64_t stop, int32_t n_calls,
+                     HfTraceRec *trace_out, int64_t trace_cap, HfScalars *sc_out, int32_t *pos_out, int32_t *ev_init_out,
+                     int32_t *ev_final_out, double *ev_tau_out, int32_t *flag_out, int32_t *cache_i_out,
+                     double *cache_tau_out, unsigned long long *totals_out) {
+    if (B < 1 || B > 32) return 3;
+    HfParams P;
+    memset(&P, 0, sizeof(P));
+    P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
+    P.field = field; P.C = 1; P.cap_c = 1; P.cap_f = 2;
+    P.B = B; P.traj_per_real = B;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = first_traj; P.first_real = 0;
+    P.setsize = sample_setsize(1);
+    P.species = species; P.homo = homo; P.lumo = lumo;
+    Buffers b;
+    wire(P, b, trace_cap);
+    blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+    b.pool.assign((size_t)((int64_t)P.X * P.Y), 0);
+    InjectArgs ia{&P, b.pool.data()};
+    emu_run_warp(inject_body, &ia);
+    for (int c = 0; c < n_calls; ++c) {
+        P.n_steps = stop;
+        emu_run_warp(use_c1 ? run_c1_body : run_body, &P);
+    }
+    memcpy(trace_out, b.trace.data(), sizeof(HfTraceRec) * (size_t)(B * trace_cap));
+    memcpy(sc_out, b.sc.data(), sizeof(HfScalars) * (size_t)B);
+    memcpy(pos_out, b.pos.data(), sizeof(int32_t) * 2 * (size_t)B);
+    memcpy(ev_init_out, b.ev_init.data(), sizeof(int32_t) * 2 * (size_t)B);
+    memcpy(ev_final_out, b.ev_final.data(), sizeof(int32_t) * 2 * (size_t)B);
+    memcpy(ev_tau_out, b.ev_tau.data(), sizeof(double) * 2 * (size_t)B);
+    memcpy(flag_out, b.flag.data(), sizeof(int32_t) * 4 * (size_t)B);
+    memcpy(cache_i_out, b.cache_i.data(), sizeof(int32_t) * 3 * HF_CACHE * (size_t)B);
+    memcpy(cache_tau_out, b.cache_tau.data(), sizeof(double) * HF_CACHE * (size_t)B);
+    memcpy(totals_out, b.totals.data(), sizeof(unsigned long long) * 20);
     return 0;
 }
 

@@ -87,3 +87,58 @@ def test_emulated_lattice_generation(golden):
     assert np.array_equal(a["species"], g["species"])
     for k in ("homo", "lumo", "s1", "t1"):
         np.testing.assert_allclose(a[k], g[k], rtol=0, atol=4e-16)
+
+
+def _c1_compare(a, b, B):
+    """Everything the two step kernels leave behind must be identical."""
+    for k in ("kind", "particule", "initial", "final", "tau", "draws", "spins"):
+        assert np.array_equal(a["trace"][k], b["trace"][k]), k
+    assert np.array_equal(a["totals"], b["totals"])
+    assert np.array_equal(a["cache_i"], b["cache_i"]) and np.array_equal(a["cache_tau"], b["cache_tau"])
+    for name in a["sc"].dtype.names:
+        assert np.array_equal(a["sc"][name], b["sc"][name]), name
+    for t in range(2):
+        for i in range(B):
+            if a["sc"]["n_pos"][i, t]:
+                assert a["pos"][t, i] == b["pos"][t, i]
+            if a["sc"]["n_ev"][i, t]:
+                assert (a["ev_init"][t, i], a["ev_final"][t, i], a["ev_tau"][t, i]) == \
+                    (b["ev_init"][t, i], b["ev_final"][t, i], b["ev_tau"][t, i])
+            if a["sc"]["n_flag"][i, t]:
+                assert a["flag"][t, i, 0] == b["flag"][t, i, 0]
+
+
+@pytest.mark.parametrize("name,first", [("c1_s1", 0), ("c1_s2", 0)])
+def test_emulated_c1_thread_kernel_matches_reference_and_warp_kernel(name, first):
+    """The thread-per-trajectory kernel (charges == 1): trajectory 0 (and 7 for seed 1) against the
+    golden vectors, and all 32 lanes against the warp kernel, bit for bit."""
+    g = load_golden(name)
+    B, stop = 32, 600
+    args = (g["dims"], g["field_f"], g["seed_int"], first, B)
+    lat = (g["species"], g["homo"], g["lumo"])
+    c1 = emu.run_batch_c1(*args, True, *lat, stop=stop // 3, n_calls=3)
+    wk = emu.run_batch_c1(*args, False, *lat, stop=stop)
+    _c1_compare(c1, wk, B)
+    for traj, gold in ((0, g),) + (((7, load_golden("c1_s1_t7")),) if name == "c1_s1" else ()):
+        tr = c1["trace"][traj]
+        n = min(stop, len(gold["trace_kind"]))
+        assert np.array_equal(tr["kind"][:n], gold["trace_kind"][:n])
+        assert np.array_equal(tr["initial"][:n], gold["trace_initial"][:n])
+        assert np.array_equal(tr["final"][:n], gold["trace_final"][:n])
+        assert np.array_equal(tr["tau"][:n], gold["trace_tau"][:n])
+        assert np.array_equal(tr["draws"][:n].astype(np.int64), gold["trace_draws"][:n])
+
+
+def test_emulated_c1_thread_kernel_recombination_paths():
+    """A tiny lattice where bound / decay / capture / re-injection fire constantly: the thread kernel
+    must follow the warp kernel (itself pinned to the reference) through every rare branch."""
+    g = load_golden("tiny333_s5")
+    B, stop = 32, 600
+    args = (g["dims"], g["field_f"], 4321, 100, B)
+    lat = (g["species"], g["homo"], g["lumo"])
+    c1 = emu.run_batch_c1(*args, True, *lat, stop=stop // 4, n_calls=4)
+    wk = emu.run_batch_c1(*args, False, *lat, stop=stop)
+    _c1_compare(c1, wk, B)
+    t = c1["totals"]
+    assert t[7] > 250 and t[8] > 250 and t[9] + t[10] > 50          # bound, decay, captures all exercised
+    assert int(c1["sc"]["recombination"].sum()) == int(t[8])
