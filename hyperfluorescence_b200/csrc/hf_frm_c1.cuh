@@ -68,64 +68,159 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
     return HF_ST_OK;
 }
 
+#define HF_C1_THREADS 128
+#define HF_C1_MAXCAND 27
+// relative half-width of the "could be the minimum" window of the screening pass, see hf_c1_gen
+#define HF_C1_WINDOW 0x1p-9f
+
+// Exact waiting time of one candidate hop (reseau.py:283-292 / 315-324 with the Coulomb term of
+// 297-313 / 329-345 reduced to the single opposite charge): the same operation sequence as
+// hf_hop_time in hf_frm.cuh, hence the same bits.
+__device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, int64_t cand_site, double e_init, double fz,
+                                                  int dz, bool other_has, int other, int cand, double inv_old,
+                                                  double u, bool *rate_is_zero) {
+    const double rng = __dsub_rn(1.0, u);                                        // 284 / 316
+    double dE = __dsub_rn(__ldg(E + cand_site), e_init);                         // 286 / 318
+    dE = __dadd_rn(dE, __dmul_rn(fz, (double)dz));                               // 287 / 319
+    double out = 0.0;
+    if (other_has) {                                                             // 305-312 / 337-344
+        if (other == cand) {
+            out = -INFINITY;
+        } else {
+            const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(other, cand)));
+            out = __dsub_rn(0.0, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, inv_old)));
+        }
+    }
+    dE = __dadd_rn(dE, out);                                                     // 288 / 320
+    double k = HF_RATE0;
+    if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));                   // 290-291 / 322-323
+    *rate_is_zero = k == 0.0;
+    return __ddiv_rn(-log(rng), k);                                              // 292 / 324
+}
+
 // _new_move_electron_events / _new_move_hole_events for the single charge of type t
-// (reseau.py:380-396): sequential loop over the neighbour list in the reference's order, first
-// minimum wins.  t is a RUNTIME value on purpose: lanes regenerating an electron event and lanes
-// regenerating a hole event run the same instructions (only the energy array and the sign of
-// the field term differ), so a warp with a mix of both does not serialise.
+// (reseau.py:380-396): min() over the 17-26 candidate hops, first minimum wins.
+//
+// t is a RUNTIME value on purpose: lanes regenerating an electron event and lanes regenerating a
+// hole event run the same instructions (only the energy array and the sign of the field term
+// differ), so a warp with a mix of both does not serialise.
+//
+// Screen-then-verify.  Evaluating exp(), log(), a square root and three divisions in fp64 for all
+// 26 candidates costs ~420 instructions per candidate (ncu, profiles/r01b_*), yet only the
+// minimum is kept.  Pass 1 computes a cheap fp32 estimate a_i of 1e13 * tau_i for every candidate
+// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by 4e-5:
+//   -log(rng): rng >= 2^-6 away from 1: __logf abs error 2^-21.41 on |log| >= 0.0157  -> 2.7e-5
+//              otherwise the series u + u^2/2 + u^3/3 (truncation u^3/4 <= 9.5e-7)      -> 1.3e-6
+//   exp(dE/kT): float rounding of x (6e-8 x) + __expf (2 + 1.173 x ulp), x <= 88        -> 1.2e-5
+//              neglected Coulomb term (<= 1e-9 eV -> 4e-8 in x)                         -> 4e-8
+// Every candidate whose estimate lies within a factor 1 + 2^-9 (50x that bound) of the smallest
+// estimate is then evaluated EXACTLY, in candidate order, by hf_c1_exact_tau; the first minimum
+// among those is the reference's min().  A candidate outside the window has
+// tau_i >= a_i (1 - 4e-5) > a_min (1 + 2^-9)(1 - 4e-5) > a_min (1 + 4e-5) >= tau of the best
+// estimate, so it can neither win nor tie.  Estimates that overflow (x > 88) are +inf and only
+// matter when all are (then every candidate is verified); candidates with x > 700 are always
+// verified because the reference raises ZeroDivisionError when any rate underflows to 0.
+// Result: bit-identical events and taus at ~1.06 exact evaluations per event instead of 26.
 __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, const double *homo, int t, HfC1 &s,
-                                         int64_t local, uint32_t ident) {
+                                         int64_t local, uint32_t ident, float *approx /* [l * HF_C1_THREADS] */) {
     const int pos = s.pos(t), other = s.pos(1 - t);
     const double *__restrict__ E = t ? homo : lumo;
     const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
     const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
-    const bool other_has = other >= 0;
-    uint64_t d = s.draws;
-    double inv_old = 0.0;
-    if (other_has) {
-        const int d2 = hf_dist2(other, pos);
-        if (d2 == 0) { s.draws = d + 1; return HF_ST_ZERO_DIVISION; }            // 1/old_r.norm(), first candidate
-        inv_old = __ddiv_rn(1.0, __dsqrt_rn((double)d2));
-    }
+    const int total = 9 * nz;
+    const uint64_t d0 = s.draws;
+    if (other >= 0 && other == pos) { s.draws = d0 + 1; return HF_ST_ZERO_DIVISION; }   // 1/old_r.norm(), first candidate
     const double e_init = __ldg(E + hf_site(P, pos));
     const double fz = t == 0 ? -P.field : P.field;                               // reseau.py:287 / 319
     const int64_t plane = (int64_t)P.X * P.Y;
-    double best = 0.0;
-    int32_t bfin = -1;
-    bool exhausted = false;
-    for (int ix = 0; ix < 3; ++ix) {
-        const int cx = hf_bvk_xy(px, P.X, ix);
-        for (int iy = 0; iy < 3; ++iy) {
-            const int cy = hf_bvk_xy(py, P.Y, iy);
-            const int64_t row = (int64_t)cy * P.X + cx;
-            for (int iz = 0; iz < nz; ++iz) {
-                const int cz = hf_bvk_z(pz, P.Z, iz);
-                if (cx == px && cy == py && cz == pz) continue;                  // reseau.py:188
-                const int cand = hf_pack(cx, cy, cz);
-                const double u = hf_c1_uniform(P, local, ident, d++, &exhausted);
-                const double rng = __dsub_rn(1.0, u);                            // 284 / 316
-                double dE = __dsub_rn(__ldg(E + row + cz * plane), e_init);      // 286 / 318
-                dE = __dadd_rn(dE, __dmul_rn(fz, (double)(cz - pz)));
-                double out = 0.0;
-                if (other_has) {                                                 // 305-312 / 337-344
-                    if (other == cand) {
-                        out = -INFINITY;
-                    } else {
-                        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(other, cand)));
-                        out = __dsub_rn(0.0, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, inv_old)));
+
+    // ---- pass 0: gather the candidates' energies (all loads in flight together), store dE as
+    //      fp32 in this thread's shared-memory column; remember where `self` sits ----
+    int self_l = -1;
+    {
+        int l = 0;
+        for (int ix = 0; ix < 3; ++ix) {
+            const int cx = hf_bvk_xy(px, P.X, ix);
+#pragma unroll
+            for (int iy = 0; iy < 3; ++iy) {
+                const int cy = hf_bvk_xy(py, P.Y, iy);
+                const double *row = E + ((int64_t)cy * P.X + cx);
+#pragma unroll
+                for (int iz = 0; iz < 3; ++iz) {
+                    if (iz < nz) {
+                        const int cz = hf_bvk_z(pz, P.Z, iz);
+                        const int cand = hf_pack(cx, cy, cz);
+                        if (cand == pos) self_l = l;
+                        const double dE = (__ldg(row + cz * plane) - e_init) + fz * (double)(cz - pz);
+                        approx[l * HF_C1_THREADS] = cand == other ? -INFINITY : (float)dE;   // onto the opposite charge: k = 1e13
+                        ++l;
                     }
                 }
-                dE = __dadd_rn(dE, out);                                         // 288 / 320
-                double k = HF_RATE0;
-                if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));       // 290-291 / 322-323
-                if (k == 0.0) { s.draws = d; return HF_ST_ZERO_DIVISION; }
-                const double tau = __ddiv_rn(-log(rng), k);                      // 292 / 324
-                if (bfin < 0 || tau < best) { best = tau; bfin = cand; }         // min(): first minimum
             }
         }
     }
-    s.draws = d;
-    if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
+    // ---- pass 1: fp32 estimates a_l of 1e13 * tau_l.  Uniform d0 + r belongs to Philox block
+    //      (d0 >> 1) + ((p + r) >> 1), half (p + r) & 1 with p = d0 & 1: looping over q = p + r in
+    //      pairs makes every lane compute its blocks at the same iterations ----
+    const int n = total - 1;                                                     // never blocked when C = 1
+    const int p = (int)(d0 & 1);
+    const float inv_kt = (float)(1.0 / HF_KT);
+    float amin = INFINITY;
+    unsigned forced = 0;
+    bool exhausted = false;
+    for (int j = 0; 2 * j < n + p; ++j) {
+        HfPhiloxBlock blk = {0, 0, 0, 0};
+        if (!P.replay) blk = hf_philox_block(P.k0, P.k1, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = 2 * j + h - p;
+            if (r < 0 || r >= n) continue;
+            const int l = r + (r >= self_l ? 1 : 0);
+            const double u = P.replay ? hf_c1_uniform(P, local, ident, d0 + (uint64_t)r, &exhausted)
+                                      : hf_block_uniform(blk, (uint64_t)h);
+            float t0;
+            if (u < 0x1p-6) {
+                const float uf = (float)u;
+                t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+            } else {
+                t0 = -__logf((float)(1.0 - u));
+            }
+            float a = t0;
+            const float x = approx[l * HF_C1_THREADS] * inv_kt;
+            if (x > 0.0f) a = t0 * __expf(x);
+            if (x > 700.0f) forced |= 1u << l;
+            if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
+            approx[l * HF_C1_THREADS] = a;
+            amin = fminf(amin, a);
+        }
+    }
+    if (exhausted) { s.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
+    // ---- candidates that could be the minimum ----
+    const float thr = amin * (1.0f + HF_C1_WINDOW);
+    unsigned mask = forced;
+    for (int i = 0; i < total; ++i)
+        if (i != self_l && !(approx[i * HF_C1_THREADS] > thr)) mask |= 1u << i;
+    // ---- pass 2: exact evaluation in candidate order, first minimum ----
+    const bool other_has = other >= 0;
+    double inv_old = 0.0;
+    if (other_has) inv_old = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(other, pos)));
+    double best = 0.0;
+    int32_t bfin = -1;
+    while (mask) {
+        const int i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int ix = i / (3 * nz), iy = (i / nz) % 3, iz = i % nz;
+        const int cx = hf_bvk_xy(px, P.X, ix), cy = hf_bvk_xy(py, P.Y, iy), cz = hf_bvk_z(pz, P.Z, iz);
+        const int cand = hf_pack(cx, cy, cz);
+        const uint64_t di = d0 + (uint64_t)(i - (i > self_l ? 1 : 0));
+        const double u = hf_c1_uniform(P, local, ident, di, &exhausted);
+        bool rate_is_zero;
+        const double tau = hf_c1_exact_tau(E, ((int64_t)cz * P.Y + cy) * P.X + cx, e_init, fz, cz - pz, other_has, other,
+                                           cand, inv_old, u, &rate_is_zero);
+        if (rate_is_zero) { s.draws = di + 1; return HF_ST_ZERO_DIVISION; }      // float division by zero
+        if (bfin < 0 || tau < best) { best = tau; bfin = cand; }                 // min(): first minimum
+    }
+    s.draws = d0 + (uint64_t)n;
     s.set_fin(t, bfin);
     s.set_tau(t, best);
     return HF_ST_OK;
@@ -249,7 +344,9 @@ __device__ __forceinline__ void hf_c1_store(const HfParams &P, const HfC1 &s, co
 }
 
 // Lattice.operations(stop) for charges == 1: one thread per trajectory.
-__global__ void __launch_bounds__(128, 6) hf_run_c1_kernel(const HfParams P) {
+__global__ void __launch_bounds__(HF_C1_THREADS, 6) hf_run_c1_kernel(const HfParams P) {
+    __shared__ float approx_all[HF_C1_MAXCAND * HF_C1_THREADS];
+    float *approx = approx_all + threadIdx.x;
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= P.B) return;
     HfC1 s;
@@ -272,7 +369,7 @@ __global__ void __launch_bounds__(128, 6) hf_run_c1_kernel(const HfParams P) {
             for (; st == HF_ST_OK && gen; gen >>= 4) {
                 const int t = gen & 1;
                 if (gen & 4) st = hf_c1_reinject(P, s, t, local, ident);
-                if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, t, s, local, ident);
+                if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, t, s, local, ident, approx);
             }
             if (st != HF_ST_OK) { s.status = st; break; }                        // 587-591
             if (kind == HF_K_MOVE) { if (part == 1) c.move_e += 1; else c.move_h += 1; }

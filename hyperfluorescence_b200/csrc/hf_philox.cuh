@@ -5,8 +5,9 @@
 // (SURVEY.md §8c).  This header is the device side of that contract:
 //
 //   key     = (seed_lo, seed_hi)
-//   counter = (d_lo, d_hi, ident, stream)
-//   u       = (((w1 << 32) | w0) >> 11) * 2^-53        53-bit, like CPython's random()
+//   counter = (b_lo, b_hi, ident, stream),  b = d >> 1   (one block yields two uniforms)
+//   (lo,hi) = d even ? (w0, w1) : (w2, w3)
+//   u       = (((hi << 32) | lo) >> 11) * 2^-53          53-bit, like CPython's random()
 //
 //   stream 0 TRAJ    ident = trajectory   Lattice._seed after lattice creation (reseau.py:219,
 //                                          225, 284, 316, 455, 467)
@@ -22,9 +23,12 @@
 #define HF_STREAM_SPECIES 2u
 #define HF_STREAM_ENERGY 3u
 
-__device__ __forceinline__ uint64_t hf_philox_u64(uint32_t k0, uint32_t k1, uint32_t stream,
-                                                  uint32_t ident, uint64_t d) {
-    uint32_t c0 = (uint32_t)d, c1 = (uint32_t)(d >> 32), c2 = ident, c3 = stream;
+struct HfPhiloxBlock { uint32_t w0, w1, w2, w3; };
+
+// Block b of stream (stream, ident): the two uniforms d = 2b and d = 2b + 1.
+__device__ __forceinline__ HfPhiloxBlock hf_philox_block(uint32_t k0, uint32_t k1, uint32_t stream,
+                                                         uint32_t ident, uint64_t b) {
+    uint32_t c0 = (uint32_t)b, c1 = (uint32_t)(b >> 32), c2 = ident, c3 = stream;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -34,10 +38,16 @@ __device__ __forceinline__ uint64_t hf_philox_u64(uint32_t k0, uint32_t k1, uint
         c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
-    return ((uint64_t)c1 << 32) | c0;
+    HfPhiloxBlock out = {c0, c1, c2, c3};
+    return out;
+}
+
+__device__ __forceinline__ double hf_block_uniform(const HfPhiloxBlock &blk, uint64_t d) {
+    const uint64_t w = (d & 1) ? (((uint64_t)blk.w3 << 32) | blk.w2) : (((uint64_t)blk.w1 << 32) | blk.w0);
+    return (double)(w >> 11) * 0x1p-53;
 }
 
 __device__ __forceinline__ double hf_philox_uniform(uint32_t k0, uint32_t k1, uint32_t stream,
                                                     uint32_t ident, uint64_t d) {
-    return (double)(hf_philox_u64(k0, k1, stream, ident, d) >> 11) * 0x1p-53;
+    return hf_block_uniform(hf_philox_block(k0, k1, stream, ident, d >> 1), d);
 }

@@ -439,7 +439,7 @@ int hf_run(hf_sim *s, int64_t stop) {
     HF_CUDA(cudaEventRecord(e0, s->stream));
     if (s->P.C == 1 && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
         // one thread per trajectory (hf_frm_c1.cuh)
-        const int threads = 128;
+        const int threads = HF_C1_THREADS;
         const int64_t blocks = (s->P.B + threads - 1) / threads;
         hf_run_c1_kernel<<<(unsigned)blocks, threads, 0, s->stream>>>(s->P);
     } else {

@@ -15,9 +15,11 @@ Draw contract
 ``uniform(seed, stream, ident, d)`` is the d-th uniform of stream ``stream`` of object ``ident``:
 
     key     = (seed & 0xffffffff, seed >> 32)
-    counter = (d & 0xffffffff, d >> 32, ident, stream)
+    b       = d >> 1                                          one Philox block yields two uniforms
+    counter = (b & 0xffffffff, b >> 32, ident, stream)
     w       = philox4x32_10(counter, key)
-    u       = (((w[1] << 32) | w[0]) >> 11) * 2**-53          in [0, 1), 53-bit like CPython's random()
+    (lo,hi) = (w[0], w[1]) if d is even else (w[2], w[3])
+    u       = (((hi << 32) | lo) >> 11) * 2**-53              in [0, 1), 53-bit like CPython's random()
 
 Streams:
 
@@ -70,9 +72,11 @@ def philox4x32_10(counter, key):
 
 def mantissa(seed: int, stream: int, ident: int, d: int) -> int:
     """The 53-bit integer m with uniform = m * 2**-53."""
-    w = philox4x32_10((d & MASK32, (d >> 32) & MASK32, ident & MASK32, stream & MASK32),
+    b = d >> 1
+    w = philox4x32_10((b & MASK32, (b >> 32) & MASK32, ident & MASK32, stream & MASK32),
                       (seed & MASK32, (seed >> 32) & MASK32))
-    return ((w[1] << 32) | w[0]) >> 11
+    lo, hi = (w[0], w[1]) if (d & 1) == 0 else (w[2], w[3])
+    return ((hi << 32) | lo) >> 11
 
 
 def uniform(seed: int, stream: int, ident: int, d: int) -> float:

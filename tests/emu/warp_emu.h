@@ -150,6 +150,9 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
+// fast-math intrinsics used by the screening pass (glibc's math.h reserves the __logf/__expf names)
+#define __logf(x) logf(x)
+#define __expf(x) expf(x)
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     unsigned long long old = *p; *p += v; return old;
 }
