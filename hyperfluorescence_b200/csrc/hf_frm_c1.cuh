@@ -165,7 +165,8 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     const int n = total - 1;                                                     // never blocked when C = 1
     const int p = (int)(d0 & 1);
     const float inv_kt = (float)(1.0 / HF_KT);
-    float amin = INFINITY;
+    float amin = INFINITY, amin2 = INFINITY;                                     // two smallest estimates
+    int lmin = 0;
     unsigned forced = 0;
     bool exhausted = false;
     for (int j = 0; 2 * j < n + p; ++j) {
@@ -191,15 +192,18 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
             if (x > 700.0f) forced |= 1u << l;
             if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
             approx[l * HF_C1_THREADS] = a;
-            amin = fminf(amin, a);
+            if (a < amin) { amin2 = amin; amin = a; lmin = l; }
+            else if (!(a >= amin2)) amin2 = a;                                   // also catches NaN
         }
     }
     if (exhausted) { s.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
-    // ---- candidates that could be the minimum ----
+    // ---- candidates that could be the minimum: usually only the best estimate ----
     const float thr = amin * (1.0f + HF_C1_WINDOW);
-    unsigned mask = forced;
-    for (int i = 0; i < total; ++i)
-        if (i != self_l && !(approx[i * HF_C1_THREADS] > thr)) mask |= 1u << i;
+    unsigned mask = forced | (1u << lmin);
+    if (!(amin2 > thr)) {                                                        // a runner-up inside the window: scan
+        for (int i = 0; i < total; ++i)
+            if (i != self_l && !(approx[i * HF_C1_THREADS] > thr)) mask |= 1u << i;
+    }
     // ---- pass 2: exact evaluation in candidate order, first minimum ----
     const bool other_has = other >= 0;
     double inv_old = 0.0;
