@@ -240,11 +240,12 @@ def run_ours(args):
                    "timing": "CUDA events around each hf_run on its stream, summed over steps, max over ranks",
                    "wall_s_bracket": t_wall},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "hf_run_kernel",
+                     "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "hf_run_c1_kernel",
                      "bytes_per_event": BYTES_PER_EVENT, "events_per_launch": B * S,
                      "avg_launch_ms": lib_ms / max(lib_launches, 1),
-                     "note": "path is fp64-pipe/latency bound, not HBM bound (DESIGN.md): 26 candidates x "
-                             "(exp + log + 2 sqrt + 3 div) fp64 per event against 300 algorithmic bytes"},
+                     "note": "not HBM-bound: the 4.4 MB lattice is L2-resident and trajectory state stays in registers "
+                             "for the whole launch (ncu: dram bytes per launch in `traffic`, issue slots 63 % busy); "
+                             "see DESIGN.md section 3 and profiles/"},
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "hf_upload_lattice(pinned host) + hf_inject + hf_run + hf_read_tallies"},
         "gpu_launches": K,
