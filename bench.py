@@ -253,6 +253,8 @@ def run_ours(args):
         "tallies": dict({k: tallies[k] for k in ("emission", "recombination", "injection", "fired", "stopped")},
                         fired_expected=fired_expected),
     }
+    if not args.no_ga:
+        line["ga"] = ga_fitness_rate(rank, local_rank, world)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_sample(cores, 2500)
@@ -266,6 +268,40 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+GA_DIMS, GA_CHARGES, GA_POPULATION, GA_TRAJECTORIES, GA_STEPS = (10, 10, 5), 4, 256, 10_000, 500
+
+
+def ga_fitness_rate(rank, local_rank, world):
+    """BASELINE configs[2]: one fitness sweep of 256 composition candidates x 10^4 trajectories on the
+    reference driver's device (OLED.py:6-10: 10x10x5, charges = 4), population sharded over the
+    ranks, fitness = IQE (reseau.py:595).  Timed end to end: lattice generation, injection, stepping,
+    per-candidate tallies, all-gather."""
+    import numpy as np
+    import torch
+    from hyperfluorescence_b200.evolution import Compositions, DeviceFitness, GAConfig
+    cfg = GAConfig(population=GA_POPULATION, trajectories_per_candidate=GA_TRAJECTORIES, steps=GA_STEPS)
+    fit = DeviceFitness(GA_DIMS, charges=GA_CHARGES, cfg=cfg, seed=SEED, device=local_rank, rank=rank, world=world)
+    pop = Compositions(GA_DIMS).random(np.random.default_rng(7), GA_POPULATION)
+    fit(pop)                                                        # warm-up (allocations, first launch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    f = fit(pop)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    fit.close()
+    return {"metric": "GA fitness evals/sec", "value": GA_POPULATION / dt, "unit": "evals/s",
+            "events_per_s": GA_POPULATION * GA_TRAJECTORIES * GA_STEPS / dt,
+            "config": {"lattice": list(GA_DIMS), "charges": GA_CHARGES, "population": GA_POPULATION,
+                       "trajectories_per_candidate": GA_TRAJECTORIES, "events_per_trajectory": GA_STEPS,
+                       "sharding": f"{GA_POPULATION // world} candidates per GPU"},
+            "best_iqe_percent": float(f.max()), "mean_iqe_percent": float(f.mean())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +309,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.no_cpu:
         args.warmup = 3

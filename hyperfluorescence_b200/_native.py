@@ -54,6 +54,12 @@ class HfTrajInfo(C.Structure):
                 ("steps", C.c_uint64), ("fired", C.c_uint64)]
 
 
+INFO_DTYPE = np.dtype([(n, "<i4") for n in ("n_electrons", "n_holes", "n_eflags", "n_hflags", "n_move_e", "n_move_h",
+                                             "special_kind", "special_particule", "special_site", "exciton_state",
+                                             "status", "cache_count")] +
+                      [(n, "<u8") for n in ("draws", "spins", "emission", "recombination", "injection", "steps", "fired")])
+assert INFO_DTYPE.itemsize == C.sizeof(HfTrajInfo)
+
 # name -> (restype, argtypes): every symbol include/hfkmc.h declares
 P, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 SIGNATURES = {
@@ -65,6 +71,9 @@ SIGNATURES = {
     "hf_set_stream": (C.c_int, [P, P]),
     "hf_sync": (C.c_int, [P]),
     "hf_generate_lattice": (C.c_int, [P]),
+    "hf_generate_lattice_mixed": (C.c_int, [P, P]),
+    "hf_read_realisation_tallies": (C.c_int, [P, P]),
+    "hf_read_infos": (C.c_int, [P, I64, I64, P]),
     "hf_upload_lattice": (C.c_int, [P, I32, P, P, P, P, P]),
     "hf_download_lattice": (C.c_int, [P, I32, P, P, P, P, P]),
     "hf_inject": (C.c_int, [P]),
@@ -142,6 +151,25 @@ class Sim:
     # -- lattice ---------------------------------------------------------------------------
     def generate_lattice(self):
         check(load().hf_generate_lattice(self._h))
+
+    def generate_lattice_mixed(self, props):
+        """One (host, tadf, fluo) composition per realisation; props has shape (n_realisations, 3)."""
+        props = np.ascontiguousarray(props, np.float64)
+        if props.shape != (self.n_realisations, 3):
+            raise ValueError(f"props must have shape ({self.n_realisations}, 3)")
+        check(load().hf_generate_lattice_mixed(self._h, ptr(props)))
+
+    def realisation_tallies(self):
+        out = np.zeros((self.n_realisations, 5), np.uint64)
+        check(load().hf_read_realisation_tallies(self._h, ptr(out)))
+        return {k: out[:, i].astype(np.int64) for i, k in enumerate(("emission", "recombination", "injection", "steps", "fired"))}
+
+    def infos(self, first=0, n=None):
+        """Structured array of the scalar state of trajectories [first, first + n)."""
+        n = self.n_trajectories - first if n is None else n
+        out = (HfTrajInfo * n)()
+        check(load().hf_read_infos(self._h, int(first), int(n), out))
+        return np.frombuffer(out, dtype=INFO_DTYPE).copy()
 
     def upload_lattice(self, realisation, species, homo, lumo, s1=None, t1=None):
         arrs = [np.ascontiguousarray(species, np.uint8)] + [

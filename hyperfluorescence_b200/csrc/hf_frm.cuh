@@ -755,6 +755,30 @@ __global__ void hf_reduce_kernel(const HfScalars *sc, int64_t B, unsigned long l
     }
 }
 
+// Per-realisation sums (one block per realisation): emission, recombination, injection, steps,
+// fired — the fitness inputs of a composition sweep (one composition per realisation).
+__global__ void hf_reduce_realisations_kernel(const HfScalars *sc, int64_t traj_per_real, unsigned long long *out) {
+    __shared__ unsigned long long part[5][32];
+    const int64_t base = (int64_t)blockIdx.x * traj_per_real;
+    unsigned long long v[5] = {0, 0, 0, 0, 0};
+    for (int64_t i = threadIdx.x; i < traj_per_real; i += blockDim.x) {
+        const HfScalars s = sc[base + i];
+        v[0] += s.emission; v[1] += s.recombination; v[2] += s.injection; v[3] += s.steps; v[4] += s.fired;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(HF_FULL, v[k], off);
+        if ((threadIdx.x & 31) == 0) part[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[threadIdx.x][w];
+        out[(int64_t)blockIdx.x * 5 + threadIdx.x] = t;
+    }
+}
+
 // ---- lattice generation ----------------------------------------------------------------------------
 // Species shuffle, reseau.py:164-172: random.sample([0,1,2], k=total, counts=...) is a pool-based
 // partial Fisher-Yates over range(total) (random.py:426-432) mapped through bisect over the
@@ -766,10 +790,11 @@ __global__ void hf_species_pool_init(int32_t *pool, int64_t total, int n_real) {
         pool[i] = (int32_t)(i % total);
 }
 
-__global__ void hf_species_shuffle(const HfParams P, int32_t *pool_all, int64_t total, int64_t n_host, int64_t n_tadf,
-                                   uint8_t *layer_all, int real_base) {
+__global__ void hf_species_shuffle(const HfParams P, int32_t *pool_all, int64_t total, const int64_t *n_host_all,
+                                   const int64_t *n_tadf_all, uint8_t *layer_all, int real_base) {
     const int r = blockIdx.x;
     if (threadIdx.x != 0) return;
+    const int64_t n_host = n_host_all[real_base + r], n_tadf = n_tadf_all[real_base + r];   // per-realisation composition
     int32_t *pool = pool_all + (int64_t)r * total;
     uint8_t *layer = layer_all + (int64_t)(real_base + r) * P.X * P.Y;
     const uint32_t ident = P.first_real + (uint32_t)(real_base + r);

@@ -311,38 +311,98 @@ int hf_sync(hf_sim *s) {
     return HF_OK;
 }
 
-int hf_generate_lattice(hf_sim *s) {
-    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+static int generate_lattice_impl(hf_sim *s, const double *props /* [n_real][3] */) {
     int rc = use_device(s);
     if (rc) return rc;
     const HfParams &P = s->P;
     const int64_t xy = (int64_t)P.X * P.Y, grid_size = P.N;
-    const int64_t n_fluo = (int64_t)((double)grid_size * s->cfg.props[2]);       // reseau.py:159
-    const int64_t n_tadf = (int64_t)((double)grid_size * s->cfg.props[1]);       // reseau.py:160
-    const int64_t n_host = grid_size - 2 * xy - n_fluo - n_tadf;                 // reseau.py:161
-    const int64_t total = n_host + n_tadf + n_fluo;
-    if (total != xy * (P.Z - 2) || total <= 0)                                   // reseau.py:169
-        return fail(HF_ERR_BAD_ARG, "Size of sub_grid (%lld) and x_max*y_max*sub_z_max (%lld) must match !", (long long)total, (long long)(xy * (P.Z - 2)));
+    std::vector<int64_t> counts((size_t)(2 * s->n_real));
+    int64_t total = 0;
+    for (int r = 0; r < s->n_real; ++r) {
+        const double *pr = props + 3 * r;
+        const int64_t n_fluo = (int64_t)((double)grid_size * pr[2]);              // reseau.py:159
+        const int64_t n_tadf = (int64_t)((double)grid_size * pr[1]);              // reseau.py:160
+        const int64_t n_host = grid_size - 2 * xy - n_fluo - n_tadf;              // reseau.py:161
+        total = n_host + n_tadf + n_fluo;
+        if (total != xy * (P.Z - 2) || total <= 0 || n_fluo < 0 || n_tadf < 0)    // reseau.py:169
+            return fail(HF_ERR_BAD_ARG, "realisation %d: Size of sub_grid (%lld) and x_max*y_max*sub_z_max (%lld) must match !",
+                        r, (long long)total, (long long)(xy * (P.Z - 2)));
+        counts[(size_t)r] = n_host;
+        counts[(size_t)(s->n_real + r)] = n_tadf;
+    }
     uint8_t *d_layer = nullptr;
     int32_t *d_pool = nullptr;
+    int64_t *d_counts = nullptr;
     if ((rc = dev_alloc(&d_layer, (size_t)(xy * s->n_real)))) return rc;
+    if ((rc = dev_alloc(&d_counts, counts.size()))) { cudaFree(d_layer); return rc; }
     // realisations are shuffled in batches so that the pool scratch stays below ~1 GiB
     int batch = (int)((int64_t)(1 << 28) / total);
     if (batch < 1) batch = 1;
     if (batch > s->n_real) batch = s->n_real;
-    if ((rc = dev_alloc(&d_pool, (size_t)(total * batch)))) { cudaFree(d_layer); return rc; }
+    if ((rc = dev_alloc(&d_pool, (size_t)(total * batch)))) { cudaFree(d_layer); cudaFree(d_counts); return rc; }
+    cudaMemcpyAsync(d_counts, counts.data(), counts.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream);
     for (int r0 = 0; r0 < s->n_real; r0 += batch) {
         const int nb = s->n_real - r0 < batch ? s->n_real - r0 : batch;
         hf_species_pool_init<<<s->sm_count * 8, 256, 0, s->stream>>>(d_pool, total, nb);
-        hf_species_shuffle<<<nb, 32, 0, s->stream>>>(P, d_pool, total, n_host, n_tadf, d_layer, r0);
+        hf_species_shuffle<<<nb, 32, 0, s->stream>>>(P, d_pool, total, d_counts, d_counts + s->n_real, d_layer, r0);
     }
     hf_fill_sites<<<s->sm_count * 8, 256, 0, s->stream>>>(P, d_layer, s->n_real, s->d_species, s->d_homo, s->d_lumo, s->d_s1, s->d_t1);
     cudaError_t e = cudaStreamSynchronize(s->stream);
     cudaFree(d_layer);
     cudaFree(d_pool);
+    cudaFree(d_counts);
     if (e != cudaSuccess) return fail(HF_ERR_CUDA, "lattice generation failed: %s", cudaGetErrorString(e));
     HF_CUDA(cudaGetLastError());
     s->have_lattice = true;
+    return HF_OK;
+}
+
+int hf_generate_lattice(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    std::vector<double> props((size_t)(3 * s->n_real));
+    for (int r = 0; r < s->n_real; ++r)
+        for (int k = 0; k < 3; ++k) props[(size_t)(3 * r + k)] = s->cfg.props[k];
+    return generate_lattice_impl(s, props.data());
+}
+
+int hf_generate_lattice_mixed(hf_sim *s, const double *props) {
+    if (!s || !props) return fail(HF_ERR_BAD_ARG, "null argument");
+    return generate_lattice_impl(s, props);
+}
+
+int hf_read_realisation_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    int rc = use_device(s);
+    if (rc) return rc;
+    unsigned long long *d_out = nullptr;
+    if ((rc = dev_alloc(&d_out, (size_t)(5 * s->n_real)))) return rc;
+    hf_reduce_realisations_kernel<<<s->n_real, 256, 0, s->stream>>>(s->d_sc, s->P.traj_per_real, d_out);
+    cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * 5 * (size_t)s->n_real, cudaMemcpyDeviceToHost, s->stream);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(HF_ERR_CUDA, "hf_read_realisation_tallies failed: %s", cudaGetErrorString(e));
+    return HF_OK;
+}
+
+int hf_read_infos(hf_sim *s, int64_t first, int64_t n, hf_traj_info *out) {
+    int rc = check_traj(s, first);
+    if (rc) return rc;
+    if (n < 1 || first + n > s->P.B || !out) return fail(HF_ERR_BAD_ARG, "bad range");
+    if ((rc = use_device(s))) return rc;
+    std::vector<HfScalars> tmp((size_t)n);
+    HF_CUDA(cudaMemcpyAsync(tmp.data(), s->d_sc + first, sizeof(HfScalars) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < n; ++i) {
+        const HfScalars &sc = tmp[(size_t)i];
+        hf_traj_info &o = out[i];
+        o.n_electrons = sc.n_pos[0]; o.n_holes = sc.n_pos[1]; o.n_eflags = sc.n_flag[0]; o.n_hflags = sc.n_flag[1];
+        o.n_move_e = sc.n_ev[0]; o.n_move_h = sc.n_ev[1];
+        o.special_kind = sc.special & 0xff; o.special_particule = sc.special >> 8;
+        o.special_site = sc.special ? unpack_site(s, sc.special_site) : -1;
+        o.exciton_state = sc.xstate; o.status = sc.status; o.cache_count = sc.cache_n;
+        o.draws = sc.draws; o.spins = sc.spins; o.emission = sc.emission; o.recombination = sc.recombination;
+        o.injection = sc.injection; o.steps = sc.steps; o.fired = sc.fired;
+    }
     return HF_OK;
 }
 

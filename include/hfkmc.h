@@ -145,6 +145,11 @@ int hf_sync(hf_sim *sim);
  * (molecule.py:156-183, 252-281, 358-385), on the device, for every realisation, from the
  * Philox SPECIES / ENERGY streams (draw contract in DESIGN.md). */
 int hf_generate_lattice(hf_sim *sim);
+/* Same, with one composition per realisation: props[n_realisations][3] = (host, tadf, fluo) after
+ * Q1.  This is the fitness kernel of the composition sweep the reference names as its goal
+ * ("optimize the device through the molecules proportions", README.md:2): candidate r is
+ * realisation r, its trajectories are the n_trajectories / n_realisations that run on it. */
+int hf_generate_lattice_mixed(hf_sim *sim, const double *props);
 /* Import a lattice built elsewhere (e.g. by the reference): replaces Lattice._grid's
  * molecules for one realisation.  s1 / t1 may be NULL. */
 int hf_upload_lattice(hf_sim *sim, int32_t realisation, const uint8_t *species, const double *homo,
@@ -172,8 +177,14 @@ int hf_read_tallies(hf_sim *sim, uint64_t *out);
  * NCCL all-reduce across ranks without a host round trip). */
 int hf_reduce_tallies_device(hf_sim *sim, void *out_device);
 
+/* Per-realisation sums, out[n_realisations][5] = _emission, _recombination, _injection, _step,
+ * events fired (reseau.py:118-122) over the trajectories of each realisation. */
+int hf_read_realisation_tallies(hf_sim *sim, uint64_t *out);
+
 /* Per-trajectory scalar state (reseau.py:118-123). */
 int hf_read_info(hf_sim *sim, int64_t trajectory, hf_traj_info *out);
+/* The same for trajectories [first, first + n) in one copy. */
+int hf_read_infos(hf_sim *sim, int64_t first, int64_t n, hf_traj_info *out);
 /* Lattice._electrons_locations / _holes_locations / _excitons_locations in list order
  * (which = 0 / 1 / 2; reseau.py:208-210, 617-621).  *n in: capacity, out: length. */
 int hf_read_positions(hf_sim *sim, int64_t trajectory, int32_t which, int32_t *sites, int32_t *n);

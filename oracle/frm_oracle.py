@@ -86,9 +86,10 @@ class OracleLattice:
         self._h = lib().hfo_lattice_alloc(*self.dims)
 
     @classmethod
-    def generate(cls, dims, props, seed, realisation=0):
+    def generate(cls, dims, props, seed, realisation=0, resolved=False):
+        """``resolved=True``: props are taken as they are (already past quirk Q1)."""
         self = cls(dims)
-        pr = np.array(resolve_proportions(dims, props), dtype=np.float64)
+        pr = np.array(props if resolved else resolve_proportions(dims, props), dtype=np.float64)
         st = lib().hfo_lattice_generate(self._h, _ptr(pr), int(seed), int(realisation))
         if st != 0:
             raise ValueError(f"lattice generation failed: {STATUS[st]}")

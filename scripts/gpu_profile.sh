@@ -3,7 +3,7 @@
 # device times, (3) one full capture of hf_run_kernel.  Output under gpurun_out/.
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 1 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 1 --no-cpu --no-ga"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"

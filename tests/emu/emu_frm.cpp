@@ -46,7 +46,7 @@ void run_body(void *a) { hf_run_kernel<1>(*(const HfParams *)a); }
 void run_c1_body(void *a) { hf_run_c1_kernel(*(const HfParams *)a); }
 
 struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
-void shuffle_body(void *a) { auto *x = (ShuffleArgs *)a; hf_species_shuffle(*x->P, x->pool, x->total, x->n_host, x->n_tadf, x->layer, 0); }
+void shuffle_body(void *a) { auto *x = (ShuffleArgs *)a; hf_species_shuffle(*x->P, x->pool, x->total, &x->n_host, &x->n_tadf, x->layer, 0); }
 struct FillArgs { const HfParams *P; const uint8_t *layer; uint8_t *species; double *homo, *lumo, *s1, *t1; };
 void fill_body(void *a) { auto *x = (FillArgs *)a; hf_fill_sites(*x->P, x->layer, 1, x->species, x->homo, x->lumo, x->s1, x->t1); }
 

@@ -120,6 +120,8 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return r;
 }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu_collective(EMU_SYNCWARP, 0, mask); }
+// one emulated warp per block: a block barrier is a warp barrier
+static inline void __syncthreads() { emu_collective(EMU_SYNCWARP, 0, 0xffffffffu); }
 
 template <typename T>
 static inline uint64_t emu_bits(T v) { uint64_t b = 0; memcpy(&b, &v, sizeof(T)); return b; }

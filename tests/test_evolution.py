@@ -1,0 +1,71 @@
+"""Composition GA: host logic on the CPU, fitness kernel against the oracle on the GPU."""
+import numpy as np
+import pytest
+
+from hyperfluorescence_b200.evolution import CompositionGA, Compositions, DeviceFitness, GAConfig, next_generation
+
+
+def test_compositions_round_trip_and_constraints():
+    comps = Compositions((10, 10, 5))
+    rng = np.random.default_rng(0)
+    pop = comps.random(rng, 500)
+    assert pop.shape == (500, 2) and pop.min() >= 1 and (pop.sum(1) <= comps.max_dopants).all()
+    props = comps.proportions(pop)
+    assert np.allclose(props.sum(1), 1.0)
+    # the reference's own reduction of proportions to counts (reseau.py:159-160)
+    assert np.array_equal(np.array([int(comps.N * p) for p in props[:, 1]]), pop[:, 0])
+    assert np.array_equal(np.array([int(comps.N * p) for p in props[:, 2]]), pop[:, 1])
+    assert (props.min(1) * comps.N >= 1).all()                     # reseau.py:137
+    wild = comps.clip(np.array([[-5.0, 1e9], [0.2, 0.2], [3.6, 7.4]]))
+    assert wild.min() >= 1 and (wild.sum(1) <= comps.max_dopants).all() and wild[2].tolist() == [4, 7]
+
+
+def test_ga_converges_on_a_synthetic_landscape():
+    dims = (10, 10, 5)
+    comps = Compositions(dims)
+    target = np.array([60.0, 12.0])
+    fitness = lambda pop: -np.sum((np.asarray(pop, float) - target) ** 2, axis=1)
+    ga = CompositionGA(dims, fitness, GAConfig(population=64, elite=4), seed=3)
+    first = ga.step().max()
+    out = ga.run(40)
+    assert out["best_fitness"] > first and out["best_fitness"] > -9.0
+    assert abs(out["best_counts"][0] - 60) <= 3 and abs(out["best_counts"][1] - 12) <= 3
+    assert all(h2["best_fitness"] >= h1["best_fitness"] for h1, h2 in zip(ga.history, ga.history[1:]))   # elitism
+    assert abs(sum(out["best_proportions"]) - 1.0) < 1e-12
+
+
+def test_next_generation_is_deterministic_and_valid():
+    comps, cfg = Compositions((8, 8, 6)), GAConfig(population=32, elite=2)
+    pop = comps.random(np.random.default_rng(1), 32)
+    fit = np.arange(32, dtype=float)
+    a = next_generation(pop, fit, comps, cfg, np.random.default_rng(9))
+    b = next_generation(pop, fit, comps, cfg, np.random.default_rng(9))
+    assert np.array_equal(a, b) and a.shape == pop.shape
+    assert np.array_equal(a[0], pop[31]) and np.array_equal(a[1], pop[30])       # elites first
+    assert a.min() >= 1 and (a.sum(1) <= comps.max_dopants).all()
+
+
+@pytest.mark.gpu
+def test_device_fitness_equals_oracle_per_candidate():
+    """Each candidate's emission / injection / recombination sums on the GPU equal the oracle's
+    run of the same composition, realisation id and trajectory ids; IQE follows reseau.py:595."""
+    from oracle import frm_oracle as fo
+    dims, charges, seed = (10, 10, 5), 4, 99
+    cfg = GAConfig(population=12, trajectories_per_candidate=40, steps=600)
+    comps = Compositions(dims)
+    pop = comps.random(np.random.default_rng(2), cfg.population)
+    fit_fn = DeviceFitness(dims, charges=charges, cfg=cfg, seed=seed)
+    fit = fit_fn(pop)
+    t = fit_fn.last_tallies
+    props = comps.proportions(pop)
+    for r in range(cfg.population):
+        lat = fo.OracleLattice.generate(dims, tuple(props[r]), seed, realisation=r, resolved=True)
+        o = lat.run_batch(charges, 0.1, seed, r * cfg.trajectories_per_candidate, cfg.trajectories_per_candidate, cfg.steps)
+        assert (int(t["emission"][r]), int(t["recombination"][r]), int(t["injection"][r]), int(t["fired"][r])) == \
+            (o["emission"], o["recombination"], o["injection"], o["events"])
+        assert fit[r] == 100.0 * 2.0 * o["emission"] / o["injection"]
+    assert t["recombination"].sum() > 50
+    ga = CompositionGA(dims, fit_fn, cfg, seed=5)
+    out = ga.run(3)
+    assert len(out["history"]) == 3 and out["best_fitness"] >= 0.0
+    fit_fn.close()
