@@ -54,6 +54,17 @@ class HfTrajInfo(C.Structure):
                 ("steps", C.c_uint64), ("fired", C.c_uint64)]
 
 
+class HfXParams(C.Structure):
+    _fields_ = [("cutoff", C.c_double), ("forster_radius", (C.c_double * 3) * 3),
+                ("dexter_prefactor", (C.c_double * 3) * 3), ("dexter_length", C.c_double),
+                ("k_isc", C.c_double * 3), ("k_risc", C.c_double * 3), ("k_rad", (C.c_double * 2) * 3),
+                ("k_nonrad", (C.c_double * 2) * 3), ("singlet_fraction", C.c_double), ("outcoupling", C.c_double)]
+
+
+HF_XT_N = 16
+XT_NAMES = ("generated", "events", "forster", "dexter", "isc", "risc", "rad_host", "rad_tadf", "rad_fluo",
+            "nonrad_s_host", "nonrad_s_tadf", "nonrad_s_fluo", "nonrad_t_host", "nonrad_t_tadf", "nonrad_t_fluo")
+
 INFO_DTYPE = np.dtype([(n, "<i4") for n in ("n_electrons", "n_holes", "n_eflags", "n_hflags", "n_move_e", "n_move_h",
                                              "special_kind", "special_particule", "special_site", "exciton_state",
                                              "status", "cache_count")] +
@@ -90,6 +101,16 @@ SIGNATURES = {
     "hf_read_trace": (C.c_int, [P, I64, P, C.POINTER(I64)]),
     "hf_eval_hops": (C.c_int, [P, I64, I32, I32, P, P, P, P, P, P]),
     "hf_run_timing": (C.c_int, [P, C.POINTER(F64), C.POINTER(I64)]),
+    "hf_x_default_params": (C.c_int, [C.POINTER(HfXParams)]),
+    "hf_x_configure": (C.c_int, [P, C.POINTER(HfXParams)]),
+    "hf_x_spawn": (C.c_int, [P]),
+    "hf_x_run": (C.c_int, [P, I64]),
+    "hf_x_read_tallies": (C.c_int, [P, P]),
+    "hf_x_read_realisation_tallies": (C.c_int, [P, P]),
+    "hf_x_read_tables": (C.c_int, [P, C.POINTER(I32), P, P, P, P, P]),
+    "hf_x_download_weights": (C.c_int, [P, I32, P, P]),
+    "hf_x_read_state": (C.c_int, [P, I64, I64, P, P, P, P, P]),
+    "hf_x_read_trace": (C.c_int, [P, I64, P, C.POINTER(I64)]),
 }
 
 _lib = None
@@ -273,3 +294,86 @@ class Sim:
         check(load().hf_eval_hops(self._h, int(trajectory), int(particule), n, ptr(initial), ptr(final), ptr(u),
                                   ptr(tau), ptr(rate), ptr(zd)))
         return tau, rate, zd
+
+    # -- exciton trajectories (Path X) -----------------------------------------------------------
+    def x_configure(self, params: "HfXParams | None" = None):
+        if params is None:
+            params = x_default_params()
+        check(load().hf_x_configure(self._h, C.byref(params)))
+
+    def x_spawn(self):
+        check(load().hf_x_spawn(self._h))
+
+    def x_run(self, n_events):
+        check(load().hf_x_run(self._h, int(n_events)))
+
+    def x_tallies(self):
+        out = np.zeros(HF_XT_N, np.uint64)
+        check(load().hf_x_read_tallies(self._h, ptr(out)))
+        return {k: int(out[i]) for i, k in enumerate(XT_NAMES)}
+
+    def x_realisation_tallies(self):
+        out = np.zeros((self.n_realisations, HF_XT_N), np.uint64)
+        check(load().hf_x_read_realisation_tallies(self._h, ptr(out)))
+        return {k: out[:, i].astype(np.int64) for i, k in enumerate(XT_NAMES)}
+
+    def x_tables(self):
+        n = I32(0)
+        check(load().hf_x_read_tables(self._h, C.byref(n), None, None, None, None, None))
+        m = n.value
+        off, g6, gd = np.zeros((m, 3), np.int8), np.zeros(m), np.zeros(m)
+        kf, kd = np.zeros((3, 3)), np.zeros((3, 3))
+        n = I32(m)
+        check(load().hf_x_read_tables(self._h, C.byref(n), ptr(off), ptr(g6), ptr(gd), ptr(kf), ptr(kd)))
+        return dict(offsets=off, g6=g6, gd=gd, kf=kf, kd=kd)
+
+    def x_weights(self, realisation=0):
+        ws1, wt1 = np.zeros(self.N), np.zeros(self.N)
+        check(load().hf_x_download_weights(self._h, int(realisation), ptr(ws1), ptr(wt1)))
+        return ws1, wt1
+
+    def x_state(self, first=0, n=None):
+        n = self.n_trajectories - first if n is None else int(n)
+        site, spin = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        time, life, draws = np.zeros(n), np.zeros(n), np.zeros(n, np.uint64)
+        check(load().hf_x_read_state(self._h, int(first), n, ptr(site), ptr(spin), ptr(time), ptr(draws), ptr(life)))
+        return dict(site=site, spin=spin, time=time, draws=draws, lifetime_sum=life)
+
+    def x_trace(self, trajectory, capacity):
+        out = np.zeros(max(int(capacity), 1), EVENT_DTYPE)
+        n = I64(out.size)
+        check(load().hf_x_read_trace(self._h, int(trajectory), ptr(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
+def x_default_params() -> HfXParams:
+    p = HfXParams()
+    check(load().hf_x_default_params(C.byref(p)))
+    return p
+
+
+def x_params_to_dict(p: HfXParams) -> dict:
+    return dict(cutoff=p.cutoff, forster_radius=np.array([[p.forster_radius[a][b] for b in range(3)] for a in range(3)]),
+                dexter_prefactor=np.array([[p.dexter_prefactor[a][b] for b in range(3)] for a in range(3)]),
+                dexter_length=p.dexter_length, k_isc=np.array(list(p.k_isc)), k_risc=np.array(list(p.k_risc)),
+                k_rad=np.array([[p.k_rad[a][s] for s in range(2)] for a in range(3)]),
+                k_nonrad=np.array([[p.k_nonrad[a][s] for s in range(2)] for a in range(3)]),
+                singlet_fraction=p.singlet_fraction, outcoupling=p.outcoupling)
+
+
+def x_params_from_dict(d: dict) -> HfXParams:
+    p = x_default_params()
+    for k, v in d.items():
+        if k in ("cutoff", "dexter_length", "singlet_fraction", "outcoupling"):
+            setattr(p, k, float(v))
+        elif k in ("k_isc", "k_risc"):
+            for a in range(3):
+                getattr(p, k)[a] = float(v[a])
+        elif k in ("forster_radius", "dexter_prefactor", "k_rad", "k_nonrad"):
+            arr = np.asarray(v, dtype=np.float64)
+            for a in range(arr.shape[0]):
+                for b in range(arr.shape[1]):
+                    getattr(p, k)[a][b] = float(arr[a, b])
+        else:
+            raise KeyError(k)
+    return p

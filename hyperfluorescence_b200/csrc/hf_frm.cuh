@@ -149,6 +149,9 @@ __device__ __forceinline__ int hf_pz(int p) { return p >> 20; }
 __device__ __forceinline__ int64_t hf_site(const HfParams &P, int p) {
     return ((int64_t)hf_pz(p) * P.Y + hf_py(p)) * P.X + hf_px(p);
 }
+__device__ __forceinline__ int64_t hf_site(int X, int Y, int p) {
+    return ((int64_t)hf_pz(p) * Y + hf_py(p)) * X + hf_px(p);
+}
 __device__ __forceinline__ int hf_pack_site(const HfParams &P, int64_t s) {
     const int x = (int)(s % P.X), y = (int)((s / P.X) % P.Y), z = (int)(s / ((int64_t)P.X * P.Y));
     return hf_pack(x, y, z);

@@ -14,6 +14,7 @@
 #include "../../include/hfkmc.h"
 #include "hf_frm.cuh"
 #include "hf_frm_c1.cuh"
+#include "hf_exciton.cuh"
 
 static_assert(sizeof(HfTraceRec) == sizeof(hf_event), "trace record must match hf_event");
 static_assert(sizeof(hf_event) == 32, "hf_event is 32 bytes");
@@ -65,6 +66,18 @@ struct hf_sim {
     // launch shape of the step kernel
     int warps = 4, grid = 1;
     size_t smem = 0;
+    // exciton path (hf_x_*)
+    bool x_configured = false, x_spawned = false;
+    HfxParams X;
+    hf_x_params x_params;
+    std::vector<int8_t> x_offsets;
+    std::vector<double> x_g6, x_gd;
+    int32_t *d_x_off = nullptr, *d_x_site = nullptr, *d_x_spin = nullptr;
+    double *d_x_g6 = nullptr, *d_x_gd = nullptr, *d_ws1 = nullptr, *d_wt1 = nullptr, *d_x_time = nullptr, *d_x_life = nullptr;
+    uint64_t *d_x_draws = nullptr, *d_x_trace_len = nullptr;
+    unsigned long long *d_x_totals = nullptr;
+    int x_warps = 8, x_grid = 1;
+    size_t x_smem = 0;
     // timing of hf_run launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -174,6 +187,21 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 }
 
 }  // namespace
+
+template <int W>
+int x_configure_launch(hf_sim *s) {
+    const size_t padded = hfx_padded_channels(s->X.M);
+    const size_t smem = 8 * (2 * (size_t)s->X.M + W * padded) + 4 * (size_t)s->X.M;
+    if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "cutoff too large: %zu B of shared memory", smem);
+    if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hfx_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfx_run_kernel<W>, W * 32, smem));
+    if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "exciton kernel does not fit an SM");
+    const int64_t need = (s->X.B + W - 1) / W, cap = (int64_t)s->sm_count * per_sm;
+    s->x_warps = W; s->x_smem = smem; s->x_grid = (int)(need < cap ? need : cap);
+    if (s->x_grid < 1) s->x_grid = 1;
+    return HF_OK;
+}
 
 extern "C" {
 
@@ -287,6 +315,9 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_pos); cudaFree(s->d_flag); cudaFree(s->d_ev_init); cudaFree(s->d_ev_final); cudaFree(s->d_ev_tau);
     cudaFree(s->d_sc); cudaFree(s->d_cache_i); cudaFree(s->d_cache_tau); cudaFree(s->d_totals); cudaFree(s->d_sum);
     cudaFree(s->d_replay); cudaFree(s->d_trace);
+    cudaFree(s->d_x_off); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
+    cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
+    cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HF_OK;
@@ -676,6 +707,12 @@ int hf_set_trace(hf_sim *s, int64_t first, int64_t n, int64_t capacity) {
         s->P.trace = s->d_trace;
         s->P.trace_first = first; s->P.trace_n = n; s->P.trace_cap = capacity;
     }
+    cudaFree(s->d_x_trace_len);
+    s->d_x_trace_len = nullptr;
+    if (n > 0) {
+        if ((rc = dev_alloc(&s->d_x_trace_len, (size_t)n))) return rc;
+        HF_CUDA(cudaMemsetAsync(s->d_x_trace_len, 0, sizeof(uint64_t) * (size_t)n, s->stream));
+    }
     return HF_OK;
 }
 
@@ -727,6 +764,230 @@ int hf_eval_hops(hf_sim *s, int64_t t, int32_t particule, int32_t n, const int32
     }
     cudaFree(d_i); cudaFree(d_zd); cudaFree(d_d);
     if (e != cudaSuccess) return fail(HF_ERR_CUDA, "hf_eval_hops failed: %s", cudaGetErrorString(e));
+    return HF_OK;
+}
+
+// ---- exciton trajectories (Path X; model specified by oracle/exciton_oracle.c) ----------------------
+
+int hf_x_default_params(hf_x_params *p) {
+    if (!p) return fail(HF_ERR_BAD_ARG, "null argument");
+    memset(p, 0, sizeof(*p));
+    // None of these values comes from the reference (it has no exciton dynamics).  They are
+    // order-of-magnitude literature values for a DPEPO / ACRSA / TBPe hyperfluorescent stack.
+    p->cutoff = 4.0;
+    const double r0[3][3] = {{1.0, 3.0, 3.5},      // host  -> host, TADF, fluorescent
+                             {0.5, 2.0, 4.0},      // TADF  -> ...   (TADF -> emitter is the hyperfluorescence channel)
+                             {0.5, 1.0, 2.5}};     // fluo  -> ...
+    const double kd0[3][3] = {{1e10, 1e10, 1e10}, {1e10, 1e10, 1e10}, {1e10, 1e10, 1e10}};
+    memcpy(p->forster_radius, r0, sizeof(r0));
+    memcpy(p->dexter_prefactor, kd0, sizeof(kd0));
+    p->dexter_length = 0.5;
+    const double isc[3] = {1e5, 1e7, 1e5}, risc[3] = {0.0, 1e7, 0.0};
+    memcpy(p->k_isc, isc, sizeof(isc));
+    memcpy(p->k_risc, risc, sizeof(risc));
+    const double rad[3][2] = {{0.0, 0.0}, {1e7, 0.0}, {2e8, 0.0}};          // hosts do not emit in the visible (molecule.py:396-400)
+    const double nonrad[3][2] = {{2e8, 1e3}, {1e6, 1e4}, {1e7, 1e5}};
+    memcpy(p->k_rad, rad, sizeof(rad));
+    memcpy(p->k_nonrad, nonrad, sizeof(nonrad));
+    p->singlet_fraction = 0.25;                                              // molecule.py:93
+    p->outcoupling = 0.2;
+    return HF_OK;
+}
+
+int hf_x_configure(hf_sim *s, const hf_x_params *p) {
+    if (!s || !p) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->have_lattice) return fail(HF_ERR_STATE, "hf_x_configure before a lattice exists");
+    if (!(p->cutoff >= 1.0) || p->cutoff > 12.0) return fail(HF_ERR_BAD_ARG, "cutoff must be in [1, 12] lattice constants");
+    const int R = (int)std::floor(p->cutoff);
+    if (s->P.X < 2 * R + 1 || s->P.Y < 2 * R + 1)
+        return fail(HF_ERR_BAD_ARG, "x and y must be >= 2*cutoff+1 = %d for unique periodic images", 2 * R + 1);
+    if (!(p->dexter_length > 0.0)) return fail(HF_ERR_BAD_ARG, "dexter_length must be positive");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    s->x_params = *p;
+    // neighbour table: dz-major, dx fastest (consecutive lanes read consecutive x)
+    s->x_offsets.clear(); s->x_g6.clear(); s->x_gd.clear();
+    std::vector<int32_t> packed;
+    const double rc2 = p->cutoff * p->cutoff;
+    for (int dz = -R; dz <= R; ++dz)
+        for (int dy = -R; dy <= R; ++dy)
+            for (int dx = -R; dx <= R; ++dx) {
+                const int d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 == 0 || (double)d2 > rc2) continue;
+                s->x_offsets.push_back((int8_t)dx); s->x_offsets.push_back((int8_t)dy); s->x_offsets.push_back((int8_t)dz);
+                const double d2d = (double)d2;
+                s->x_g6.push_back(1.0 / ((d2d * d2d) * d2d));                       // r^-6, lattice constant 1 nm
+                s->x_gd.push_back(std::exp(-2.0 * std::sqrt(d2d) / p->dexter_length));
+                packed.push_back((dx + 128) | ((dy + 128) << 8) | ((dz + 128) << 16));
+            }
+    HfxParams &X = s->X;
+    memset(&X, 0, sizeof(X));
+    X.X = s->P.X; X.Y = s->P.Y; X.Z = s->P.Z; X.N = s->P.N; X.B = s->P.B; X.traj_per_real = s->P.traj_per_real;
+    X.k0 = s->P.k0; X.k1 = s->P.k1; X.first_traj = s->P.first_traj;
+    X.M = (int32_t)packed.size();
+    for (int a = 0; a < 3; ++a) {
+        const double ks = p->k_rad[a][0] + p->k_nonrad[a][0];                       // donor singlet decay rate
+        for (int b = 0; b < 3; ++b) {
+            const double r0 = p->forster_radius[a][b], r3 = (r0 * r0) * r0;
+            X.kf[3 * a + b] = ks * (r3 * r3);
+            X.kd[3 * a + b] = p->dexter_prefactor[a][b];
+        }
+        X.k_isc[a] = p->k_isc[a]; X.k_risc[a] = p->k_risc[a];
+        for (int sp = 0; sp < 2; ++sp) { X.k_rad[2 * a + sp] = p->k_rad[a][sp]; X.k_nonrad[2 * a + sp] = p->k_nonrad[a][sp]; }
+    }
+    X.singlet_fraction = p->singlet_fraction;
+    cudaFree(s->d_x_off); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
+    s->d_x_off = nullptr; s->d_x_g6 = nullptr; s->d_x_gd = nullptr;
+    const size_t M = packed.size(), RN = (size_t)s->n_real * (size_t)s->P.N, B = (size_t)s->P.B;
+    if ((rc = dev_alloc(&s->d_x_off, M))) return rc;
+    if ((rc = dev_alloc(&s->d_x_g6, M))) return rc;
+    if ((rc = dev_alloc(&s->d_x_gd, M))) return rc;
+    HF_CUDA(cudaMemcpyAsync(s->d_x_off, packed.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaMemcpyAsync(s->d_x_g6, s->x_g6.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaMemcpyAsync(s->d_x_gd, s->x_gd.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
+    if (!s->d_ws1) {
+        if ((rc = dev_alloc(&s->d_ws1, RN))) return rc;
+        if ((rc = dev_alloc(&s->d_wt1, RN))) return rc;
+        if ((rc = dev_alloc(&s->d_x_site, B))) return rc;
+        if ((rc = dev_alloc(&s->d_x_spin, B))) return rc;
+        if ((rc = dev_alloc(&s->d_x_time, B))) return rc;
+        if ((rc = dev_alloc(&s->d_x_life, B))) return rc;
+        if ((rc = dev_alloc(&s->d_x_draws, B))) return rc;
+        if ((rc = dev_alloc(&s->d_x_totals, (size_t)s->n_real * HFX_T_N))) return rc;
+    }
+    hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_s1, s->d_t1, s->d_ws1, s->d_wt1, (int64_t)RN);
+    X.offsets = s->d_x_off; X.g6 = s->d_x_g6; X.gd = s->d_x_gd;
+    X.species = s->d_species; X.ws1 = s->d_ws1; X.wt1 = s->d_wt1;
+    X.site = s->d_x_site; X.spin = s->d_x_spin; X.time = s->d_x_time; X.lifetime = s->d_x_life; X.draws = s->d_x_draws;
+    X.totals = s->d_x_totals;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    HF_CUDA(cudaGetLastError());
+    if ((rc = x_configure_launch<8>(s))) return rc;
+    s->x_configured = true;
+    s->x_spawned = false;
+    return HF_OK;
+}
+
+int hf_x_spawn(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "hf_x_spawn before hf_x_configure");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaMemsetAsync(s->d_x_totals, 0, sizeof(unsigned long long) * (size_t)s->n_real * HFX_T_N, s->stream));
+    if (s->d_x_trace_len) HF_CUDA(cudaMemsetAsync(s->d_x_trace_len, 0, sizeof(uint64_t) * (size_t)s->P.trace_n, s->stream));
+    const int threads = 256;
+    hfx_spawn_kernel<<<(unsigned)((s->X.B + threads - 1) / threads), threads, 0, s->stream>>>(s->X);
+    HF_CUDA(cudaGetLastError());
+    s->x_spawned = true;
+    return HF_OK;
+}
+
+int hf_x_run(hf_sim *s, int64_t n_events) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->x_spawned) return fail(HF_ERR_STATE, "hf_x_run before hf_x_spawn");
+    if (n_events < 0) return fail(HF_ERR_BAD_ARG, "n_events must be >= 0");
+    int rc = use_device(s);
+    if (rc) return rc;
+    s->X.n_events = n_events;
+    s->X.trace = s->d_trace; s->X.trace_first = s->P.trace_first; s->X.trace_n = s->P.trace_n; s->X.trace_cap = s->P.trace_cap;
+    s->X.trace_len = s->d_x_trace_len;
+    if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
+    cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+    HF_CUDA(cudaEventRecord(e0, s->stream));
+    hfx_run_kernel<8><<<s->x_grid, 8 * 32, s->x_smem, s->stream>>>(s->X);
+    HF_CUDA(cudaEventRecord(e1, s->stream));
+    s->timing.emplace_back(e0, e1);
+    HF_CUDA(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_x_read_realisation_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "exciton path not configured");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaMemcpyAsync(out, s->d_x_totals, sizeof(uint64_t) * (size_t)s->n_real * HFX_T_N, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    return HF_OK;
+}
+
+int hf_x_read_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    std::vector<uint64_t> all((size_t)(s ? s->n_real : 0) * HFX_T_N);
+    int rc = hf_x_read_realisation_tallies(s, all.data());
+    if (rc) return rc;
+    for (int k = 0; k < HFX_T_N; ++k) out[k] = 0;
+    for (int r = 0; r < s->n_real; ++r)
+        for (int k = 0; k < HFX_T_N; ++k) out[k] += all[(size_t)r * HFX_T_N + k];
+    return HF_OK;
+}
+
+int hf_x_read_tables(hf_sim *s, int32_t *n_offsets, int8_t *offsets, double *g6, double *gd, double *kf, double *kd) {
+    if (!s || !n_offsets) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "exciton path not configured");
+    const int32_t M = s->X.M;
+    if (offsets || g6 || gd) {
+        if (*n_offsets < M) return fail(HF_ERR_BAD_ARG, "buffer too small: need %d offsets", M);
+        if (offsets) memcpy(offsets, s->x_offsets.data(), (size_t)M * 3);
+        if (g6) memcpy(g6, s->x_g6.data(), sizeof(double) * (size_t)M);
+        if (gd) memcpy(gd, s->x_gd.data(), sizeof(double) * (size_t)M);
+    }
+    if (kf) memcpy(kf, s->X.kf, sizeof(double) * 9);
+    if (kd) memcpy(kd, s->X.kd, sizeof(double) * 9);
+    *n_offsets = M;
+    return HF_OK;
+}
+
+int hf_x_download_weights(hf_sim *s, int32_t r, double *ws1, double *wt1) {
+    if (!s || !ws1 || !wt1) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "exciton path not configured");
+    if (r < 0 || r >= s->n_real) return fail(HF_ERR_BAD_ARG, "realisation %d out of range", r);
+    int rc = use_device(s);
+    if (rc) return rc;
+    const size_t N = (size_t)s->P.N, off = (size_t)r * N;
+    HF_CUDA(cudaMemcpyAsync(ws1, s->d_ws1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(wt1, s->d_wt1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    return HF_OK;
+}
+
+int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t *spin, double *time, uint64_t *draws,
+                    double *lifetime_sum) {
+    int rc = check_traj(s, first);
+    if (rc) return rc;
+    if (!s->x_spawned) return fail(HF_ERR_STATE, "no excitons yet");
+    if (n < 1 || first + n > s->P.B) return fail(HF_ERR_BAD_ARG, "bad range");
+    if ((rc = use_device(s))) return rc;
+    std::vector<int32_t> packed((size_t)n);
+    HF_CUDA(cudaMemcpyAsync(packed.data(), s->d_x_site + first, 4 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (spin) HF_CUDA(cudaMemcpyAsync(spin, s->d_x_spin + first, 4 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (time) HF_CUDA(cudaMemcpyAsync(time, s->d_x_time + first, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (draws) HF_CUDA(cudaMemcpyAsync(draws, s->d_x_draws + first, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    if (lifetime_sum) HF_CUDA(cudaMemcpyAsync(lifetime_sum, s->d_x_life + first, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    if (site) for (int64_t i = 0; i < n; ++i) site[i] = unpack_site(s, packed[(size_t)i]);
+    return HF_OK;
+}
+
+int hf_x_read_trace(hf_sim *s, int64_t t, hf_event *out, int64_t *n) {
+    int rc = check_traj(s, t);
+    if (rc) return rc;
+    if (!out || !n) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->d_trace || !s->d_x_trace_len || t < s->P.trace_first || t >= s->P.trace_first + s->P.trace_n)
+        return fail(HF_ERR_STATE, "trajectory %lld is not traced", (long long)t);
+    if ((rc = use_device(s))) return rc;
+    uint64_t len = 0;
+    HF_CUDA(cudaMemcpyAsync(&len, s->d_x_trace_len + (t - s->P.trace_first), 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    int64_t count = (int64_t)len < s->P.trace_cap ? (int64_t)len : s->P.trace_cap;
+    if (*n < count) return fail(HF_ERR_BAD_ARG, "buffer too small: need %lld", (long long)count);
+    if (count > 0) {
+        HF_CUDA(cudaMemcpyAsync(out, s->d_trace + (t - s->P.trace_first) * s->P.trace_cap, sizeof(hf_event) * (size_t)count,
+                                cudaMemcpyDeviceToHost, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    *n = count;
     return HF_OK;
 }
 

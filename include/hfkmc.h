@@ -212,6 +212,66 @@ int hf_eval_hops(hf_sim *sim, int64_t trajectory, int32_t particule, int32_t n, 
  * last call, measured with CUDA events on the handle's stream, and their count. */
 int hf_run_timing(hf_sim *sim, double *total_ms, int64_t *launches);
 
+/* =====================================================================================================
+ * Exciton trajectories ("Path X").  The reference has NO implementation of these (parity unpinned):
+ * it only provides the slots — event codes ISC / Forster / decay (event.py:43-51), the empty
+ * _move_exciton_events / _isc_events lists (reseau.py:233-235), the `...` branches of the dispatcher
+ * (reseau.py:526-550), TADF.intersystem_crossing (molecule.py:299-307), the singlet fraction
+ * (molecule.py:93) and the per-site S1 / T1 energies (molecule.py:182-183).  The model is this
+ * library's own; it is specified by oracle/exciton_oracle.c and DESIGN.md section 9.
+ * One exciton per trajectory of the handle, on the handle's lattice realisations; rejection-free
+ * (BKL) event selection; a decayed exciton is replaced by a new one at a random interior site.
+ * ===================================================================================================== */
+
+/* Rate-law parameters; species index 0 host, 1 TADF, 2 fluorescent; spin index 0 singlet, 1 triplet.
+ * None of these numbers exists in the reference: hf_x_default_params documents the defaults. */
+typedef struct hf_x_params {
+    double cutoff;                    /* transfer cutoff radius in lattice constants (1 nm)              */
+    double forster_radius[3][3];      /* R0[donor][acceptor] in nm: k = k_S(donor) (R0 / r)^6            */
+    double dexter_prefactor[3][3];    /* k_D0[donor][acceptor] in 1/s: k = k_D0 exp(-2 r / L)           */
+    double dexter_length;             /* L in nm                                                          */
+    double k_isc[3];                  /* S -> T, 1/s                                                      */
+    double k_risc[3];                 /* T -> S prefactor, 1/s, times min(1, exp(-(S1 - T1)/kT))         */
+    double k_rad[3][2];               /* radiative decay [species][spin], 1/s                            */
+    double k_nonrad[3][2];            /* non-radiative decay [species][spin], 1/s                        */
+    double singlet_fraction;          /* 0.25 (molecule.py:93)                                            */
+    double outcoupling;               /* EQE = outcoupling * photons / excitons (reporting only)         */
+} hf_x_params;
+
+/* Box totals of the exciton path (u64 each). */
+enum {
+    HF_XT_GENERATED = 0, HF_XT_EVENTS = 1, HF_XT_FORSTER = 2, HF_XT_DEXTER = 3, HF_XT_ISC = 4, HF_XT_RISC = 5,
+    HF_XT_RAD_HOST = 6, HF_XT_RAD_TADF = 7, HF_XT_RAD_FLUO = 8,
+    HF_XT_NONRAD_S_HOST = 9, HF_XT_NONRAD_S_TADF = 10, HF_XT_NONRAD_S_FLUO = 11,
+    HF_XT_NONRAD_T_HOST = 12, HF_XT_NONRAD_T_TADF = 13, HF_XT_NONRAD_T_FLUO = 14,
+    HF_XT_N = 16
+};
+
+int hf_x_default_params(hf_x_params *out);
+/* Build the neighbour / rate tables, the per-site Boltzmann weights exp(-S1/kT), exp(-T1/kT) of
+ * every realisation (needs a lattice) and the exciton state of every trajectory. */
+int hf_x_configure(hf_sim *sim, const hf_x_params *params);
+/* Create the first exciton of every trajectory (fills the slot of _form_exciton, reseau.py:434-438). */
+int hf_x_spawn(hf_sim *sim);
+/* n_events rejection-free KMC events for every trajectory (fills reseau.py:526-550). */
+int hf_x_run(hf_sim *sim, int64_t n_events);
+/* out[HF_XT_N] summed over realisations; hf_x_read_realisation_tallies: out[n_realisations][HF_XT_N]. */
+int hf_x_read_tallies(hf_sim *sim, uint64_t *out);
+int hf_x_read_realisation_tallies(hf_sim *sim, uint64_t *out);
+/* Tables as the device uses them.  *n_offsets in: capacity, out: M.  offsets[M][3] = dx, dy, dz;
+ * g6[M] = r^-6; gd[M] = exp(-2r/L); kf[9], kd[9] = [donor][acceptor] prefactors. */
+int hf_x_read_tables(hf_sim *sim, int32_t *n_offsets, int8_t *offsets, double *g6, double *gd, double *kf, double *kd);
+/* Per-site Boltzmann weights of one realisation. */
+int hf_x_download_weights(hf_sim *sim, int32_t realisation, double *ws1, double *wt1);
+/* Exciton state of trajectories [first, first + n): site, spin (HF_X_*), time since creation,
+ * XTRAJ draws consumed, summed lifetimes of the decayed excitons. */
+int hf_x_read_state(hf_sim *sim, int64_t first, int64_t n, int32_t *site, int32_t *spin, double *time,
+                    uint64_t *draws, double *lifetime_sum);
+/* Trace of the exciton events of the window set with hf_set_trace: kind = HF_EV_FORSTER / HF_EV_MOVE
+ * (Dexter) / HF_EV_ISC / HF_EV_DECAY, particule = HF_P_EXCITON, tau = waiting time, spins = channel
+ * index, pad[0] = spin of the trajectory's exciton after the step (the new one after a decay). */
+int hf_x_read_trace(hf_sim *sim, int64_t trajectory, hf_event *out, int64_t *n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 DEPS = [os.path.join(HERE, "emu_frm.cpp"), os.path.join(HERE, "warp_emu.h"),
         os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm.cuh"),
         os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm_c1.cuh"),
+        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_exciton.cuh"),
         os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_philox.cuh")]
 
 EVENT_DTYPE = np.dtype([("initial", "<i4"), ("final", "<i4"), ("tau", "<f8"), ("kind", "u1"), ("particule", "u1"),
@@ -145,3 +146,22 @@ def run_batch_c1(dims, field, seed, first_traj, B, use_c1, species, homo, lumo, 
         raise RuntimeError(f"emu_run_batch_c1 failed ({rc})")
     return dict(trace=trace, sc=sc, pos=pos, ev_init=ev_init, ev_final=ev_final, ev_tau=ev_tau, flag=flag,
                 cache_i=cache_i, cache_tau=cache_tau, totals=totals)
+
+
+def x_run(oracle, seed, first_traj, B, n_events, n_calls=1):
+    """The exciton kernels under emulation, with the model / lattice held by an ExcitonOracle."""
+    o = oracle
+    cap = n_events * n_calls
+    trace = np.zeros((B, max(cap, 1)), EVENT_DTYPE)
+    site, spin = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    time, life, draws = np.zeros(B), np.zeros(B), np.zeros(B, np.uint64)
+    totals = np.zeros(16, np.uint64)
+    d = (C.c_int32 * 3)(*o.dims)
+    rc = lib().emu_x_run(d, _p(o.species), _p(o.ws1), _p(o.wt1), C.c_int32(len(o.g6)), _p(o.off), _p(o.g6), _p(o.gd),
+                         _p(o.kf), _p(o.kd), _p(o.k_isc), _p(o.k_risc), _p(o.k_rad), _p(o.k_nonrad),
+                         C.c_double(o.params["singlet_fraction"]), C.c_uint64(seed), C.c_uint32(first_traj), C.c_int32(B),
+                         C.c_int64(n_events), C.c_int32(n_calls), _p(trace), C.c_int64(max(cap, 1)), _p(site), _p(spin),
+                         _p(time), _p(life), _p(draws), _p(totals))
+    if rc:
+        raise RuntimeError(f"emu_x_run failed ({rc})")
+    return dict(trace=trace, site=site, spin=spin, time=time, lifetime_sum=life, draws=draws, totals=totals)

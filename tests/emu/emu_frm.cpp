@@ -5,6 +5,7 @@
 
 #include "../../hyperfluorescence_b200/csrc/hf_frm.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_frm_c1.cuh"
+#include "../../hyperfluorescence_b200/csrc/hf_exciton.cuh"
 
 #include <vector>
 
@@ -193,6 +194,52 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
     memcpy(cache_i_out, b.cache_i.data(), sizeof(int32_t) * 3 * HF_CACHE * (size_t)B);
     memcpy(cache_tau_out, b.cache_tau.data(), sizeof(double) * HF_CACHE * (size_t)B);
     memcpy(totals_out, b.totals.data(), sizeof(unsigned long long) * 20);
+    return 0;
+}
+
+static void x_spawn_body(void *a) { hfx_spawn_kernel(*(const HfxParams *)a); }
+static void x_run_body(void *a) { hfx_run_kernel<1>(*(const HfxParams *)a); }
+
+// Exciton path: B <= 32 trajectories on one lattice, hfx_spawn + n_calls x hfx_run(n_events).
+int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, const double *wt1, int32_t M,
+              const int8_t *offsets, const double *g6, const double *gd, const double *kf, const double *kd,
+              const double *k_isc, const double *k_risc, const double *k_rad, const double *k_nonrad,
+              double singlet_fraction, uint64_t seed, uint32_t first_traj, int32_t B, int64_t n_events, int32_t n_calls,
+              HfTraceRec *trace_out, int64_t trace_cap, int32_t *site_out, int32_t *spin_out, double *time_out,
+              double *life_out, uint64_t *draws_out, unsigned long long *totals_out) {
+    if (B < 1 || B > 32) return 3;
+    HfxParams P;
+    memset(&P, 0, sizeof(P));
+    P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z; P.B = B; P.traj_per_real = B;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = first_traj;
+    P.M = M;
+    std::vector<int32_t> packed((size_t)M);
+    for (int m = 0; m < M; ++m) packed[(size_t)m] = (offsets[3 * m] + 128) | ((offsets[3 * m + 1] + 128) << 8) | ((offsets[3 * m + 2] + 128) << 16);
+    P.offsets = packed.data(); P.g6 = g6; P.gd = gd;
+    memcpy(P.kf, kf, sizeof(P.kf)); memcpy(P.kd, kd, sizeof(P.kd));
+    memcpy(P.k_isc, k_isc, sizeof(P.k_isc)); memcpy(P.k_risc, k_risc, sizeof(P.k_risc));
+    memcpy(P.k_rad, k_rad, sizeof(P.k_rad)); memcpy(P.k_nonrad, k_nonrad, sizeof(P.k_nonrad));
+    P.singlet_fraction = singlet_fraction;
+    P.species = species; P.ws1 = ws1; P.wt1 = wt1;
+    std::vector<int32_t> site((size_t)B), spin((size_t)B);
+    std::vector<double> time((size_t)B), life((size_t)B);
+    std::vector<uint64_t> draws((size_t)B), tlen((size_t)B, 0);
+    std::vector<unsigned long long> totals(HFX_T_N, 0);
+    std::vector<HfTraceRec> trace((size_t)(B * trace_cap + 1));
+    P.site = site.data(); P.spin = spin.data(); P.time = time.data(); P.lifetime = life.data(); P.draws = draws.data();
+    P.totals = totals.data();
+    P.trace = trace.data(); P.trace_first = 0; P.trace_n = B; P.trace_cap = trace_cap; P.trace_len = tlen.data();
+    if (8 * (2 * (size_t)M + hfx_padded_channels(M)) + 4 * (size_t)M > sizeof(hf_smem)) return 2;
+    blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+    emu_run_warp(x_spawn_body, &P);
+    for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(x_run_body, &P); }
+    memcpy(trace_out, trace.data(), sizeof(HfTraceRec) * (size_t)(B * trace_cap));
+    for (int b = 0; b < B; ++b) {
+        const int p = site[(size_t)b];
+        site_out[b] = (int32_t)((((int64_t)(p >> 20)) * P.Y + ((p >> 10) & 1023)) * P.X + (p & 1023));
+        spin_out[b] = spin[(size_t)b]; time_out[b] = time[(size_t)b]; life_out[b] = life[(size_t)b]; draws_out[b] = draws[(size_t)b];
+    }
+    memcpy(totals_out, totals.data(), sizeof(unsigned long long) * HFX_T_N);
     return 0;
 }
 

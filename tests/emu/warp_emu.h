@@ -34,7 +34,7 @@ static emu_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 
 alignas(16) unsigned char hf_smem[1 << 20];
 
 // ---- scheduler ---------------------------------------------------------------------------------
-enum { EMU_BALLOT = 1, EMU_SHFL = 2, EMU_SHFL_XOR = 3, EMU_SYNCWARP = 4 };
+enum { EMU_BALLOT = 1, EMU_SHFL = 2, EMU_SHFL_XOR = 3, EMU_SYNCWARP = 4, EMU_SHFL_UP = 5 };
 
 struct emu_warp {
     ucontext_t main_ctx, lane_ctx[32];
@@ -140,9 +140,17 @@ static inline T __shfl_xor_sync(unsigned mask, T v, int lane_mask) {
     return emu_unbits<T>(s[(me ^ lane_mask) & 31]);
 }
 
+template <typename T>
+static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+    const int me = g_emu.cur;
+    uint64_t *s = emu_collective(EMU_SHFL_UP, emu_bits(v), mask);
+    return me >= (int)delta ? emu_unbits<T>(s[me - (int)delta]) : v;
+}
+
 // ---- scalar intrinsics -----------------------------------------------------------------------------
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <typename T>
 static inline T __ldg(const T *p) { return *p; }

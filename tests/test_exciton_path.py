@@ -1,0 +1,141 @@
+"""Exciton path ("Path X").  The reference has no exciton dynamics, so there is no
+golden vector from it: parity is UNPINNED and these tests check the CUDA kernel against this
+repository's own specification (oracle/exciton_oracle.c) — bit for bit on event sequences and
+tallies — plus closed-form properties of the model."""
+import numpy as np
+import pytest
+
+from oracle import exciton_oracle as xo
+from oracle import frm_oracle as fo
+from tests.emu import emu
+
+
+def _oracle(dims, seed, params=None, props=(0.84, 0.15, 0.01)):
+    lat = fo.OracleLattice.generate(dims, props, seed).arrays()
+    ws1, wt1 = xo.weights(lat["s1"], lat["t1"])
+    return xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params or xo.default_params()), lat
+
+
+def test_tables():
+    for rc, m in ((1.0, 6), (1.5, 18), (3.0, 122), (4.0, 256), (5.0, 514)):      # SURVEY.md §8d candidate counts
+        p = dict(xo.default_params(), cutoff=rc)
+        t = xo.tables(p)
+        assert len(t["g6"]) == m
+        off = t["offsets"].astype(int)
+        d2 = (off ** 2).sum(1)
+        assert np.allclose(t["g6"], d2.astype(float) ** -3) and np.allclose(t["gd"], np.exp(-2 * np.sqrt(d2) / 0.5))
+        keys = [tuple(o[::-1]) for o in off]                                      # dz-major, dx fastest
+        assert keys == sorted(keys)
+    t = xo.tables(xo.default_params())
+    assert t["kf"][1, 2] == (1e7 + 1e6) * (4.0 ** 3) ** 2
+
+
+def test_oracle_closed_forms():
+    """Sanity of the specification itself on cases with known answers."""
+    dims = (12, 12, 6)
+    p = xo.default_params()
+    # no transfer, no spin flip: every exciton decays on its birth site; photons only from singlets
+    # on TADF / fluorescent sites with probability k_rad / (k_rad + k_nonrad)
+    p0 = dict(p, forster_radius=np.zeros((3, 3)), dexter_prefactor=np.zeros((3, 3)), k_isc=np.zeros(3), k_risc=np.zeros(3))
+    o, lat = _oracle(dims, 3, p0, props=(0.5, 0.3, 0.2))
+    b = o.run_batch(11, 0, 400, 200, n_threads=4)
+    assert b["forster"] == b["dexter"] == b["isc"] == b["risc"] == 0
+    assert b["events"] == 400 * 200 and b["generated"] == 400 + b["events"]       # every event is a decay
+    n = b["events"]
+    interior = lat["species"].reshape(6, 12, 12)[1:-1].ravel()
+    f_tadf, f_fluo = (interior == 1).mean(), (interior == 2).mean()
+    expect = 0.25 * (f_tadf * 1e7 / (1e7 + 1e6) + f_fluo * 2e8 / (2e8 + 1e7))
+    got = (b["rad_tadf"] + b["rad_fluo"]) / n
+    assert abs(got - expect) < 4 * np.sqrt(expect * (1 - expect) / n)
+    assert b["rad_host"] == 0
+    triplets = b["nonrad_t_host"] + b["nonrad_t_tadf"] + b["nonrad_t_fluo"]
+    assert abs(triplets / n - 0.75) < 4 * np.sqrt(0.75 * 0.25 / n)               # molecule.py:93
+
+
+@pytest.mark.parametrize("dims,cutoff,seed", [((12, 12, 6), 4.0, 5), ((9, 10, 5), 3.0, 6), ((8, 8, 8), 1.5, 7)])
+def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed):
+    """hfx_spawn_kernel + hfx_run_kernel run lane by lane on the host (tests/emu): identical event
+    sequences, channels, spins, waiting times, final states and tallies for 32 trajectories."""
+    p = dict(xo.default_params(), cutoff=cutoff)
+    o, _ = _oracle(dims, seed, p, props=(0.6, 0.3, 0.1))
+    B, n = 32, 250
+    dev = emu.x_run(o, seed * 1000 + 1, 40, B, n // 2, n_calls=2)
+    tot = np.zeros(16, np.int64)
+    for b in range(B):
+        ref = o.run(seed * 1000 + 1, 40 + b, n)
+        tr = dev["trace"][b]
+        assert np.array_equal(tr["kind"], ref["trace"]["kind"])
+        assert np.array_equal(tr["initial"], ref["trace"]["initial"]) and np.array_equal(tr["final"], ref["trace"]["final"])
+        assert np.array_equal(tr["spins"].astype(np.int32), ref["trace"]["channel"])
+        assert np.array_equal(tr["pad"][:, 0], ref["trace"]["spin"])
+        assert np.array_equal(tr["tau"], ref["trace"]["dt"])                     # same libm under emulation
+        assert (dev["site"][b], dev["spin"][b], int(dev["draws"][b])) == (ref["site"], ref["spin"], ref["draws"])
+        assert dev["lifetime_sum"][b] == ref["lifetime_sum"]
+        tot += np.array([ref["tallies"][k] for k in xo.XT_NAMES[:15]] + [0])
+    assert np.array_equal(dev["totals"].astype(np.int64), tot)
+    assert tot[2] > 0 and tot[3] > 0 and tot[4] + tot[5] > 0 and tot[6:15].sum() > 0   # every kind of event occurred
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_path_equals_specification():
+    """Through the C-ABI on the device: 2048 trajectories on 2 realisations; traces of 16 of them,
+    all final states and the per-realisation tallies equal the oracle run on the device's own
+    Boltzmann weights and tables (identical inputs => identical selection, bit for bit)."""
+    from hyperfluorescence_b200 import _native as nat
+    dims, props, seed, B, R, n = (24, 24, 12), (0.84, 0.15, 0.01), 77, 2048, 2, 300
+    sim = nat.Sim(dims, props, 0.1, 1, 1, n_trajectories=B, n_realisations=R, seed=seed, first_trajectory=1000)
+    try:
+        sim.generate_lattice()
+        sim.x_configure()
+        tab = sim.x_tables()
+        ref_tab = xo.tables(xo.default_params())
+        assert np.array_equal(tab["offsets"], ref_tab["offsets"]) and np.array_equal(tab["g6"], ref_tab["g6"])
+        np.testing.assert_allclose(tab["gd"], ref_tab["gd"], rtol=1e-15)
+        assert np.array_equal(tab["kf"], ref_tab["kf"]) and np.array_equal(tab["kd"], ref_tab["kd"])
+        sim.set_trace(0, 16, n)
+        sim.x_spawn()
+        sim.x_run(n // 3)
+        sim.x_run(n - n // 3)
+        sim.sync()
+        st = sim.x_state()
+        per_real = sim.x_realisation_tallies()
+        params = nat.x_params_to_dict(nat.x_default_params())
+        for r in range(R):
+            lat = sim.download_lattice(r)
+            ws1, wt1 = sim.x_weights(r)
+            np.testing.assert_allclose(ws1, np.exp(-lat["s1"] / xo.KT), rtol=1e-13)
+            o = xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params, tab)
+            lo, hi = r * (B // R), (r + 1) * (B // R)
+            sample = list(range(lo, lo + 16 if r == 0 else lo + 4)) + list(range(hi - 40, hi))
+            for b in sample:
+                ref = o.run(seed, 1000 + b, n)
+                assert (st["site"][b], st["spin"][b], int(st["draws"][b])) == (ref["site"], ref["spin"], ref["draws"])
+                np.testing.assert_allclose(st["lifetime_sum"][b], ref["lifetime_sum"], rtol=1e-12)
+                if b < 16:
+                    tr = sim.x_trace(b, n)
+                    assert np.array_equal(tr["kind"], ref["trace"]["kind"]) and np.array_equal(tr["final"], ref["trace"]["final"])
+                    assert np.array_equal(tr["spins"].astype(np.int32), ref["trace"]["channel"])
+                    np.testing.assert_allclose(tr["tau"], ref["trace"]["dt"], rtol=1e-12)
+            whole = o.run_batch(seed, 1000 + lo, B // R, n, n_threads=8)
+            for k in xo.XT_NAMES[:15]:
+                assert int(per_real[k][r]) == whole[k], (r, k)
+        tot = sim.x_tallies()
+        assert tot["events"] == B * n and tot["generated"] == B + sum(tot[k] for k in tot if k.startswith(("rad_", "nonrad_")))
+    finally:
+        sim.close()
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_ensemble_api():
+    from hyperfluorescence_b200.excitons import ExcitonEnsemble
+    ens = ExcitonEnsemble((20, 20, 20), trajectories=4096, seed=5)
+    ens.run(2000)
+    s = ens.summary()
+    assert s["events"] == 4096 * 2000 and s["excitons_decayed"] > 10_000
+    assert 0.3 < s["iqe"] < 0.8 and abs(s["eqe"] - 0.2 * s["iqe"]) < 1e-15
+    assert abs(sum(s["channels"].values()) - 1.0) < 1e-12
+    assert s["channels"]["rad_host"] == 0.0                          # hosts never emit (molecule.py:396-400)
+    assert s["channels"]["rad_fluo"] > 0.02                          # hyperfluorescence: TADF -> emitter transfer
+    with pytest.raises(ValueError):
+        ExcitonEnsemble((20, 20, 2))
+    ens.close()
