@@ -255,6 +255,7 @@ def run_ours(args):
     }
     if not args.no_ga:
         line["ga"] = ga_fitness_rate(rank, local_rank, world)
+        line["exciton_path"] = exciton_rate(rank, local_rank, world)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_sample(cores, 2500)
@@ -302,6 +303,51 @@ def ga_fitness_rate(rank, local_rank, world):
             "best_iqe_percent": float(f.max()), "mean_iqe_percent": float(f.mean())}
 
 
+X_L, X_TRAJ_PER_GPU, X_EVENTS, X_CUTOFF = 128, 1_000_000, 100, 4.0
+
+
+def exciton_rate(rank, local_rank, world):
+    """The north_star's own target configuration for the exciton path (own model, parity unpinned:
+    the reference has no exciton dynamics): 128^3 lattice, 10^6 concurrent single-exciton
+    trajectories per GPU, cutoff 4 lattice constants (256 transfer channels + 3 on-site), rejection-free
+    selection; events/s over all ranks and the algorithmic-bytes roofline fraction of SURVEY.md 8(d)."""
+    import torch
+    from hyperfluorescence_b200 import _native as nat
+    sim = nat.Sim((X_L, X_L, X_L), PROPS, FIELD, 1, 1, n_trajectories=X_TRAJ_PER_GPU, seed=SEED,
+                  first_trajectory=rank * X_TRAJ_PER_GPU, device=local_rank)
+    sim.generate_lattice()
+    sim.x_configure(nat.x_params_from_dict(dict(cutoff=X_CUTOFF)))
+    sim.x_spawn()
+    for _ in range(2):
+        sim.x_run(X_EVENTS)
+    sim.sync()
+    sim.run_timing()
+    for _ in range(3):
+        sim.x_run(X_EVENTS)
+    ms, n = sim.run_timing()
+    m = int(sim.x_tables()["g6"].size)
+    t = sim.x_tallies()
+    sim.close()
+    if world > 1:
+        import torch.distributed as dist
+        v = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms = float(v.item())
+    events = world * X_TRAJ_PER_GPU * X_EVENTS * n
+    bytes_per_event = m * (1 + 8) + (m + 7) // 8 + 2 * 21 + 16                  # SURVEY.md 8(d), Path X
+    peak, _ = hbm_peak()
+    rate = events / (ms * 1e-3)
+    decayed = max(1, t["generated"] - X_TRAJ_PER_GPU)
+    return {"metric": "KMC exciton events/sec (box), exciton path", "value": rate, "unit": "events/s",
+            "config": {"lattice": [X_L] * 3, "trajectories_per_gpu": X_TRAJ_PER_GPU, "cutoff": X_CUTOFF,
+                       "channels": m + 3, "events_per_trajectory_per_launch": X_EVENTS,
+                       "model": "own (parity unpinned): DESIGN.md section 9, oracle/exciton_oracle.c"},
+            "roofline": {"bound": "hbm", "bytes_per_event": bytes_per_event,
+                         "achieved": rate * bytes_per_event / world / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel"},
+            "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -309,7 +355,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep leg")
+    ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep and exciton-path legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.no_cpu:
         args.warmup = 3

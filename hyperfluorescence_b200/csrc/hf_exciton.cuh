@@ -13,11 +13,18 @@
 //            triplet: Dexter  (kD[a][b] * exp(-2r/L)) * min(1, wt1[j]/wt1[i])
 //   M        singlet: ISC k_isc[a]        triplet: RISC k_risc[a] * min(1, ws1[i]/wt1[i])
 //   M+1      radiative decay k_rad[a][s]        M+2  non-radiative decay k_nonrad[a][s]
-// ws1 / wt1 are per-site Boltzmann weights exp(-E/kT) precomputed once per lattice, so the
-// selection path contains only IEEE multiplies, adds, compares and one division: the device and
-// the oracle produce identical prefix sums and therefore identical event sequences.  The
-// neighbour table is ordered dz-major, dx fastest, so consecutive lanes read consecutive x: a
-// warp's gather touches each (dy, dz) row of the cutoff sphere as one contiguous run.
+// ws1 / wt1 are per-site Boltzmann weights exp(-E/kT) precomputed once per lattice, with the site's
+// species code stored in the two least-significant mantissa bits (one 8-byte load delivers the
+// acceptor's weight AND its species; the tag moves a weight by <= 3 ulp).  The selection path then
+// contains only IEEE multiplies, adds, compares and one division: the device and the oracle
+// produce identical sums and therefore identical event sequences.  The neighbour table is ordered
+// dz-major, dx fastest, so consecutive lanes read consecutive x: a warp's gather touches each
+// (dy, dz) row of the cutoff sphere as one contiguous run.
+//
+// Canonical summation order (specification): channel c -> lane c % 32, slot c / 32; each lane
+// sums its slots in order (S_l), one Kogge-Stone scan over the 32 lane sums gives L_l and the total
+// R; the chosen lane is the first with L_l > u_sel * R, and inside it the prefix restarts from
+// L_{l-1} and walks the lane's slots.  One scan per event instead of one per 32 channels.
 #pragma once
 #include "hf_frm.cuh"
 
@@ -45,13 +52,14 @@ struct HfxParams {
     int64_t N, B, traj_per_real;
     uint32_t k0, k1, first_traj;
     int32_t M;                        // neighbour offsets
+    int32_t R;                        // ceil(cutoff): sites at least R away from the x / y seams need no wrap
     const int32_t *offsets;           // [M] packed (dx+128) | (dy+128) << 8 | (dz+128) << 16
+    const int32_t *lin;               // [M] dz*X*Y + dy*X + dx
     const double *g6, *gd;            // [M]
     double kf[9], kd[9];              // [donor][acceptor]
     double k_isc[3], k_risc[3], k_rad[6], k_nonrad[6];
     double singlet_fraction;
-    const uint8_t *species;           // [n_real][N]
-    const double *ws1, *wt1;          // [n_real][N]
+    const double *ws1, *wt1;          // [n_real][N] tagged weights
     // state [B]
     int32_t *site, *spin;
     double *time, *lifetime;
@@ -65,11 +73,16 @@ struct HfxParams {
 
 __host__ __device__ inline size_t hfx_padded_channels(int M) { return (size_t)((M + 3 + 31) & ~31); }
 
-// per-site Boltzmann weights exp(-E / kT)
-__global__ void hfx_weights_kernel(const double *s1, const double *t1, double *ws1, double *wt1, int64_t n) {
+// per-site tagged Boltzmann weights: exp(-E / kT) with the species code in the two low mantissa bits
+__device__ __forceinline__ double hfx_tag(double w, unsigned species) {
+    return __longlong_as_double((__double_as_longlong(w) & ~3ll) | (long long)species);
+}
+__device__ __forceinline__ int hfx_tag_of(double w) { return (int)(__double_as_longlong(w) & 3ll); }
+
+__global__ void hfx_weights_kernel(const uint8_t *species, const double *s1, const double *t1, double *ws1, double *wt1, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        ws1[i] = exp(-(s1[i] / HF_KT));
-        wt1[i] = exp(-(t1[i] / HF_KT));
+        ws1[i] = hfx_tag(exp(-(s1[i] / HF_KT)), species[i]);
+        wt1[i] = hfx_tag(exp(-(t1[i] / HF_KT)), species[i]);
     }
 }
 
@@ -99,146 +112,203 @@ __global__ void hfx_spawn_kernel(const HfxParams P) {
     atomicAdd(P.totals + (local / P.traj_per_real) * HFX_T_N + HFX_T_GENERATED, 1ull);
 }
 
+__host__ __device__ inline size_t hfx_smem_bytes(int M, int warps) {
+    // g6, gd (f64) | per-warp rates (f64) | per-warp donor prefactors (4 f64) | lin, off (i32) | per-warp counters (u32)
+    return 8 * (2 * (size_t)M + (size_t)warps * (hfx_padded_channels(M) + 4)) + 4 * (2 * (size_t)M + (size_t)warps * HFX_T_N);
+}
+
+// Pin a value in a register: nvcc otherwise re-derives kernel parameters and pointers built from
+// them inside the hot loop (LDC + IMAD chains) to save registers, which costs more issue slots than
+// it saves (ncu, profiles/r01e_*).  An empty asm with a read-write operand makes the value opaque.
+#if defined(__CUDA_ARCH__)
+#define HFX_PIN32(x) asm volatile("" : "+r"(x))
+#define HFX_PIN64(x) asm volatile("" : "+l"(x))
+#define HFX_PINF64(x) asm volatile("" : "+d"(x))
+#else
+#define HFX_PIN32(x) (void)0
+#define HFX_PIN64(x) (void)0
+#define HFX_PINF64(x) (void)0
+#endif
+
+#ifndef HFX_MIN_BLOCKS
+#define HFX_MIN_BLOCKS 4
+#endif
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32) hfx_run_kernel(const HfxParams P) {
+__global__ void __launch_bounds__(kWarps * 32, HFX_MIN_BLOCKS) hfx_run_kernel(const HfxParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int padded = (int)hfx_padded_channels(P.M);
-    // shared: neighbour tables (per CTA) then one prefix array per warp
+    int M = P.M;
+    HFX_PIN32(M);
+    const int padded = (int)hfx_padded_channels(M), K = padded >> 5, Kfull = M >> 5;
     double *s_g6 = reinterpret_cast<double *>(hf_smem);
-    double *s_gd = s_g6 + P.M;
-    double *s_prefix = s_gd + P.M + (size_t)warp * padded;
-    int32_t *s_off = reinterpret_cast<int32_t *>(s_gd + P.M + (size_t)kWarps * padded);
-    for (int m = threadIdx.x; m < P.M; m += kWarps * 32) { s_g6[m] = P.g6[m]; s_gd[m] = P.gd[m]; s_off[m] = P.offsets[m]; }
+    double *s_gd = s_g6 + M;
+    double *s_rates = s_gd + M + (size_t)warp * padded;
+    double *s_pref = s_gd + M + (size_t)kWarps * padded + 4 * warp;            // this event's kF[a][.] or kD[a][.]
+    int32_t *s_lin = reinterpret_cast<int32_t *>(s_gd + M + (size_t)kWarps * (padded + 4));
+    int32_t *s_off = s_lin + M;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_off + M) + warp * HFX_T_N;
+    for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = P.g6[m]; s_gd[m] = P.gd[m]; s_lin[m] = P.lin[m]; s_off[m] = P.offsets[m]; }
     __syncthreads();
-    const int64_t plane = (int64_t)P.X * P.Y;
-    const int C = P.M + 3;
+    int plane = P.X * P.Y, dim_x = P.X, dim_y = P.Y;
+    unsigned n_sites = (unsigned)P.N;
+    HFX_PIN32(plane); HFX_PIN32(dim_x); HFX_PIN32(dim_y); HFX_PIN32(n_sites);
 
     for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
         const uint32_t ident = P.first_traj + (uint32_t)local;
         const int64_t r = local / P.traj_per_real;
-        const uint8_t *__restrict__ species = P.species + r * P.N;
         const double *__restrict__ ws1 = P.ws1 + r * P.N, *__restrict__ wt1 = P.wt1 + r * P.N;
         int site = P.site[local], spin = P.spin[local];
         double time = P.time[local], lifetime = P.lifetime[local];
         uint64_t draws = P.draws[local];
-        unsigned cnt[HFX_T_N];
-#pragma unroll
-        for (int k = 0; k < HFX_T_N; ++k) cnt[k] = 0;
+        if (lane < HFX_T_N) s_cnt[lane] = 0;
         const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
         uint64_t trace_at = traced ? P.trace_len[local - P.trace_first] : 0;
+        __syncwarp();
 
         for (int64_t e = 0; e < P.n_events; ++e) {
             const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-            const int64_t i = (int64_t)pz * plane + (int64_t)py * P.X + px;
-            const int a = species[i];
+            const int i = pz * plane + py * dim_x + px;
             const bool singlet = spin == HFX_SINGLET;
-            const double *__restrict__ w = singlet ? ws1 : wt1;
-            const double *s_g = singlet ? s_g6 : s_gd;
-            const double wi = w[i];
-            const double inv_wi = __ddiv_rn(1.0, wi);
-            const double p0 = singlet ? P.kf[3 * a] : P.kd[3 * a], p1 = singlet ? P.kf[3 * a + 1] : P.kd[3 * a + 1],
-                         p2 = singlet ? P.kf[3 * a + 2] : P.kd[3 * a + 2];
-            double base = 0.0;
-            for (int q = 0; q < padded; q += 32) {
-                const int c = q + lane;
+            const double *w = singlet ? ws1 : wt1;
+            HFX_PIN64(w);
+            const double wi = __ldg(w + i);
+            const int a = hfx_tag_of(wi);
+            double inv_wi = __ddiv_rn(1.0, wi);
+            HFX_PINF64(inv_wi);
+            if (lane < 3) s_pref[lane] = singlet ? P.kf[3 * a + lane] : P.kd[3 * a + lane];
+            __syncwarp();
+            const bool interior = px >= P.R && px < dim_x - P.R && py >= P.R && py < dim_y - P.R;   // no periodic wrap needed
+            double S = 0.0;
+            {   // full slots: every lane owns a transfer channel
+                const double *g = (singlet ? s_g6 : s_gd) + lane;
+                const int32_t *lin = s_lin + lane, *off = s_off + lane;
+                double *out = s_rates + lane;
+                for (int k = 0; k < Kfull; ++k, g += 32, lin += 32, off += 32, out += 32) {
+                    int j;
+                    bool ok;
+                    if (interior) {
+                        j = i + *lin;
+                        ok = (unsigned)j < n_sites;                             // open z: out of range <=> outside [0, N)
+                    } else {
+                        const int o = *off;
+                        const int zz = pz + ((o >> 16) & 255) - 128;
+                        int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                        if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
+                        if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
+                        ok = zz >= 0 && zz < P.Z;
+                        j = zz * plane + yy * dim_x + xx;
+                    }
+                    double rate = 0.0;
+                    if (ok) {
+                        const double wj = __ldg(w + j);
+                        rate = __dmul_rn(__dmul_rn(s_pref[hfx_tag_of(wj)], *g), fmin(__dmul_rn(wj, inv_wi), 1.0));
+                    }
+                    *out = rate;
+                    S = __dadd_rn(S, rate);
+                }
+            }
+            for (int k = Kfull; k < K; ++k) {   // tail slot(s): the remaining transfer channels and the three on-site ones
+                const int c = (k << 5) + lane;
                 double rate = 0.0;
-                if (c < P.M) {
+                if (c < M) {
                     const int o = s_off[c];
                     const int zz = pz + ((o >> 16) & 255) - 128;
+                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                    if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
+                    if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
                     if (zz >= 0 && zz < P.Z) {
-                        int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                        if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
-                        if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
-                        const int64_t j = (int64_t)zz * plane + (int64_t)yy * P.X + xx;
-                        const int b = __ldg(species + j);
-                        const double wj = __ldg(w + j);
-                        const double pref = b == 0 ? p0 : (b == 1 ? p1 : p2);
-                        const double boltz = fmin(__dmul_rn(wj, inv_wi), 1.0);
-                        rate = __dmul_rn(__dmul_rn(pref, s_g[c]), boltz);
+                        const double wj = __ldg(w + (zz * plane + yy * P.X + xx));
+                        rate = __dmul_rn(__dmul_rn(s_pref[hfx_tag_of(wj)], (singlet ? s_g6 : s_gd)[c]), fmin(__dmul_rn(wj, inv_wi), 1.0));
                     }
-                } else if (c == P.M) {
-                    rate = singlet ? P.k_isc[a] : __dmul_rn(P.k_risc[a], fmin(__dmul_rn(ws1[i], __ddiv_rn(1.0, wt1[i])), 1.0));
-                } else if (c == P.M + 1) {
+                } else if (c == M) {
+                    rate = singlet ? P.k_isc[a] : __dmul_rn(P.k_risc[a], fmin(__dmul_rn(__ldg(ws1 + i), inv_wi), 1.0));   // inv_wi = 1/wt1[i] for a triplet
+                } else if (c == M + 1) {
                     rate = P.k_rad[2 * a + (singlet ? 0 : 1)];
-                } else if (c == P.M + 2) {
+                } else if (c == M + 2) {
                     rate = P.k_nonrad[2 * a + (singlet ? 0 : 1)];
                 }
-                // inclusive Kogge-Stone scan of the chunk (canonical order of the specification)
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double up = __shfl_up_sync(HF_FULL, rate, off);
-                    if (lane >= off) rate = __dadd_rn(rate, up);
-                }
-                s_prefix[c] = __dadd_rn(base, rate);
-                base = __dadd_rn(base, __shfl_sync(HF_FULL, rate, 31));
+                s_rates[c] = rate;
+                S = __dadd_rn(S, rate);
             }
-            __syncwarp();
-            const double R = base;
+            // one inclusive Kogge-Stone scan over the 32 lane sums
+            double L = S;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const double up = __shfl_up_sync(HF_FULL, L, off);
+                if (lane >= off) L = __dadd_rn(L, up);
+            }
+            const double R = __shfl_sync(HF_FULL, L, 31);
             const HfPhiloxBlock blk = hf_philox_block(P.k0, P.k1, HF_STREAM_XTRAJ, ident, draws >> 1);
             draws += 2;
             const double u_sel = hf_block_uniform(blk, 0), u_time = hf_block_uniform(blk, 1);
             const double target = __dmul_rn(u_sel, R);
-            int chosen = -1;
-            for (int q = 0; q < padded && chosen < 0; q += 32) {
-                const int c = q + lane;
-                const unsigned m = __ballot_sync(HF_FULL, c < C && s_prefix[c] > target);
-                if (m) chosen = q + __ffs(m) - 1;
-            }
-            if (chosen < 0) {      // rounding left u_sel * R >= P_last: the last channel with a non-zero rate
-                for (int q = padded - 32; q >= 0 && chosen < 0; q -= 32) {
-                    const int c = q + lane;
-                    const double prev = c > 0 ? s_prefix[c - 1] : 0.0;
-                    const unsigned m = __ballot_sync(HF_FULL, c < C && s_prefix[c] > prev);
-                    if (m) chosen = q + 31 - __clz(m);
+            const unsigned over = __ballot_sync(HF_FULL, L > target);
+            const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
+            const int lstar = over ? __ffs(over) - 1 : 31 - __clz(nonzero);
+            const double below = __shfl_sync(HF_FULL, L, (lstar + 31) & 31);
+            // in-lane walk: lane k accumulates the chosen lane's rates of slots 0..k in slot order, so
+            // lane k holds the running sum after slot k and one ballot finds the first that passes target
+            double acc = lstar > 0 ? below : 0.0, mine = 0.0;
+            {
+                const double *rk = s_rates + lstar;
+                for (int k = 0; k < K; ++k, rk += 32) {
+                    const double v = *rk;
+                    if (k <= lane) acc = __dadd_rn(acc, v);
+                    if (k == lane) mine = v;
                 }
             }
+            const unsigned in_k = K >= 32 ? HF_FULL : ((1u << K) - 1u);
+            const unsigned passed = __ballot_sync(HF_FULL, acc > target) & in_k;
+            const unsigned live = __ballot_sync(HF_FULL, mine > 0.0) & in_k;
+            const int slot = passed ? __ffs(passed) - 1 : 31 - __clz(live);
+            const int chosen = (slot << 5) + lstar;
             const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
             time = __dadd_rn(time, dt);
-            cnt[HFX_T_EVENTS] += 1;
-            int kind, fin = site;
-            if (chosen < P.M) {
+            int kind, fin = site, tally;
+            if (chosen < M) {
                 const int o = s_off[chosen];
                 int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
                 if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
                 if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
                 fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
-                if (singlet) { kind = HFX_K_FORSTER; cnt[HFX_T_FORSTER] += 1; }
-                else { kind = HFX_K_MOVE; cnt[HFX_T_DEXTER] += 1; }
-            } else if (chosen == P.M) {
-                kind = HFX_K_ISC;                                        // molecule.py:299-307
-                if (singlet) { spin = HFX_TRIPLET; cnt[HFX_T_ISC] += 1; }
-                else { spin = HFX_SINGLET; cnt[HFX_T_RISC] += 1; }
+                kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
+                tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+            } else if (chosen == M) {
+                kind = HFX_K_ISC;                                               // molecule.py:299-307
+                tally = singlet ? HFX_T_ISC : HFX_T_RISC;
+                spin = singlet ? HFX_TRIPLET : HFX_SINGLET;
             } else {
                 kind = HFX_K_DECAY;
-                if (chosen == P.M + 1) { cnt[HFX_T_RAD] += a == 0; cnt[HFX_T_RAD + 1] += a == 1; cnt[HFX_T_RAD + 2] += a == 2; }
-                else if (singlet) { cnt[HFX_T_NONRAD_S] += a == 0; cnt[HFX_T_NONRAD_S + 1] += a == 1; cnt[HFX_T_NONRAD_S + 2] += a == 2; }
-                else { cnt[HFX_T_NONRAD_T] += a == 0; cnt[HFX_T_NONRAD_T + 1] += a == 1; cnt[HFX_T_NONRAD_T + 2] += a == 2; }
+                tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
             }
             int site_after = fin;
             if (kind == HFX_K_DECAY) {
                 lifetime = __dadd_rn(lifetime, time);
                 hfx_spawn(P, ident, draws, site_after, spin, time);
-                cnt[HFX_T_GENERATED] += 1;
             }
-            if (traced && lane == 0 && trace_at < (uint64_t)P.trace_cap) {
-                HfTraceRec rec;
-                rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
-                rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
-                rec.pad[0] = (uint8_t)spin; rec.pad[1] = 0;     // spin of the trajectory's exciton after the step
-                rec.spins = (uint32_t)chosen; rec.draws = draws;
-                P.trace[(local - P.trace_first) * P.trace_cap + trace_at] = rec;
+            if (lane == 0) {
+                s_cnt[HFX_T_EVENTS] += 1;
+                s_cnt[tally] += 1;
+                if (kind == HFX_K_DECAY) s_cnt[HFX_T_GENERATED] += 1;
+                if (traced && trace_at < (uint64_t)P.trace_cap) {
+                    HfTraceRec rec;
+                    rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
+                    rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
+                    rec.pad[0] = (uint8_t)spin; rec.pad[1] = 0;     // spin of the trajectory's exciton after the step
+                    rec.spins = (uint32_t)chosen; rec.draws = draws;
+                    P.trace[(local - P.trace_first) * P.trace_cap + trace_at] = rec;
+                }
             }
             trace_at += 1;
             site = site_after;
-            __syncwarp();
+            __syncwarp();                                                       // s_rates / s_pref are rewritten by the next event
         }
         if (lane == 0) {
             P.site[local] = site; P.spin[local] = spin; P.time[local] = time; P.lifetime[local] = lifetime; P.draws[local] = draws;
             if (traced) P.trace_len[local - P.trace_first] = trace_at;
-#pragma unroll
-            for (int k = 0; k < HFX_T_N; ++k)
-                if (cnt[k]) atomicAdd(P.totals + r * HFX_T_N + k, (unsigned long long)cnt[k]);
         }
+        __syncwarp();
+        if (lane < HFX_T_N && s_cnt[lane]) atomicAdd(P.totals + r * HFX_T_N + lane, (unsigned long long)s_cnt[lane]);
+        __syncwarp();
     }
 }

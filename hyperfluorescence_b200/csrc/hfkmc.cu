@@ -72,7 +72,7 @@ struct hf_sim {
     hf_x_params x_params;
     std::vector<int8_t> x_offsets;
     std::vector<double> x_g6, x_gd;
-    int32_t *d_x_off = nullptr, *d_x_site = nullptr, *d_x_spin = nullptr;
+    int32_t *d_x_off = nullptr, *d_x_lin = nullptr, *d_x_site = nullptr, *d_x_spin = nullptr;
     double *d_x_g6 = nullptr, *d_x_gd = nullptr, *d_ws1 = nullptr, *d_wt1 = nullptr, *d_x_time = nullptr, *d_x_life = nullptr;
     uint64_t *d_x_draws = nullptr, *d_x_trace_len = nullptr;
     unsigned long long *d_x_totals = nullptr;
@@ -190,8 +190,7 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 
 template <int W>
 int x_configure_launch(hf_sim *s) {
-    const size_t padded = hfx_padded_channels(s->X.M);
-    const size_t smem = 8 * (2 * (size_t)s->X.M + W * padded) + 4 * (size_t)s->X.M;
+    const size_t smem = hfx_smem_bytes(s->X.M, W);
     if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "cutoff too large: %zu B of shared memory", smem);
     if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hfx_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -315,7 +314,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_pos); cudaFree(s->d_flag); cudaFree(s->d_ev_init); cudaFree(s->d_ev_final); cudaFree(s->d_ev_tau);
     cudaFree(s->d_sc); cudaFree(s->d_cache_i); cudaFree(s->d_cache_tau); cudaFree(s->d_totals); cudaFree(s->d_sum);
     cudaFree(s->d_replay); cudaFree(s->d_trace);
-    cudaFree(s->d_x_off); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
+    cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -797,7 +796,8 @@ int hf_x_default_params(hf_x_params *p) {
 int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if (!s || !p) return fail(HF_ERR_BAD_ARG, "null argument");
     if (!s->have_lattice) return fail(HF_ERR_STATE, "hf_x_configure before a lattice exists");
-    if (!(p->cutoff >= 1.0) || p->cutoff > 12.0) return fail(HF_ERR_BAD_ARG, "cutoff must be in [1, 12] lattice constants");
+    if (!(p->cutoff >= 1.0) || p->cutoff > 6.0)      // <= 32 slots per lane: (M + 3) <= 1024 channels
+        return fail(HF_ERR_BAD_ARG, "cutoff must be in [1, 6] lattice constants");
     const int R = (int)std::floor(p->cutoff);
     if (s->P.X < 2 * R + 1 || s->P.Y < 2 * R + 1)
         return fail(HF_ERR_BAD_ARG, "x and y must be >= 2*cutoff+1 = %d for unique periodic images", 2 * R + 1);
@@ -808,7 +808,7 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     s->x_params = *p;
     // neighbour table: dz-major, dx fastest (consecutive lanes read consecutive x)
     s->x_offsets.clear(); s->x_g6.clear(); s->x_gd.clear();
-    std::vector<int32_t> packed;
+    std::vector<int32_t> packed, lin;
     const double rc2 = p->cutoff * p->cutoff;
     for (int dz = -R; dz <= R; ++dz)
         for (int dy = -R; dy <= R; ++dy)
@@ -820,12 +820,14 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
                 s->x_g6.push_back(1.0 / ((d2d * d2d) * d2d));                       // r^-6, lattice constant 1 nm
                 s->x_gd.push_back(std::exp(-2.0 * std::sqrt(d2d) / p->dexter_length));
                 packed.push_back((dx + 128) | ((dy + 128) << 8) | ((dz + 128) << 16));
+                lin.push_back((int32_t)((int64_t)dz * s->P.X * s->P.Y + (int64_t)dy * s->P.X + dx));
             }
     HfxParams &X = s->X;
     memset(&X, 0, sizeof(X));
     X.X = s->P.X; X.Y = s->P.Y; X.Z = s->P.Z; X.N = s->P.N; X.B = s->P.B; X.traj_per_real = s->P.traj_per_real;
     X.k0 = s->P.k0; X.k1 = s->P.k1; X.first_traj = s->P.first_traj;
     X.M = (int32_t)packed.size();
+    X.R = (int32_t)std::ceil(p->cutoff);
     for (int a = 0; a < 3; ++a) {
         const double ks = p->k_rad[a][0] + p->k_nonrad[a][0];                       // donor singlet decay rate
         for (int b = 0; b < 3; ++b) {
@@ -837,13 +839,15 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
         for (int sp = 0; sp < 2; ++sp) { X.k_rad[2 * a + sp] = p->k_rad[a][sp]; X.k_nonrad[2 * a + sp] = p->k_nonrad[a][sp]; }
     }
     X.singlet_fraction = p->singlet_fraction;
-    cudaFree(s->d_x_off); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
-    s->d_x_off = nullptr; s->d_x_g6 = nullptr; s->d_x_gd = nullptr;
+    cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
+    s->d_x_off = nullptr; s->d_x_lin = nullptr; s->d_x_g6 = nullptr; s->d_x_gd = nullptr;
     const size_t M = packed.size(), RN = (size_t)s->n_real * (size_t)s->P.N, B = (size_t)s->P.B;
     if ((rc = dev_alloc(&s->d_x_off, M))) return rc;
+    if ((rc = dev_alloc(&s->d_x_lin, M))) return rc;
     if ((rc = dev_alloc(&s->d_x_g6, M))) return rc;
     if ((rc = dev_alloc(&s->d_x_gd, M))) return rc;
     HF_CUDA(cudaMemcpyAsync(s->d_x_off, packed.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaMemcpyAsync(s->d_x_lin, lin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_g6, s->x_g6.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_gd, s->x_gd.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
     if (!s->d_ws1) {
@@ -856,9 +860,9 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
         if ((rc = dev_alloc(&s->d_x_draws, B))) return rc;
         if ((rc = dev_alloc(&s->d_x_totals, (size_t)s->n_real * HFX_T_N))) return rc;
     }
-    hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_s1, s->d_t1, s->d_ws1, s->d_wt1, (int64_t)RN);
-    X.offsets = s->d_x_off; X.g6 = s->d_x_g6; X.gd = s->d_x_gd;
-    X.species = s->d_species; X.ws1 = s->d_ws1; X.wt1 = s->d_wt1;
+    hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_ws1, s->d_wt1, (int64_t)RN);
+    X.offsets = s->d_x_off; X.lin = s->d_x_lin; X.g6 = s->d_x_g6; X.gd = s->d_x_gd;
+    X.ws1 = s->d_ws1; X.wt1 = s->d_wt1;
     X.site = s->d_x_site; X.spin = s->d_x_spin; X.time = s->d_x_time; X.lifetime = s->d_x_life; X.draws = s->d_x_draws;
     X.totals = s->d_x_totals;
     HF_CUDA(cudaStreamSynchronize(s->stream));

@@ -12,9 +12,12 @@
  * declared in DESIGN.md §9; this file is the specification the CUDA kernel is tested against, not a
  * restatement of reference code.
  *
- * Model.  One exciton per trajectory on a lattice realisation (species u8, Boltzmann weights
- * ws1 = exp(-S1/kT), wt1 = exp(-T1/kT) per site, precomputed so that no transcendental sits on
- * the selection path).  Channels of an exciton on site i with species a and spin s:
+ * Model.  One exciton per trajectory on a lattice realisation, described by two per-site arrays
+ * of TAGGED Boltzmann weights: ws1 = exp(-S1/kT), wt1 = exp(-T1/kT) whose two least-significant
+ * mantissa bits are replaced by the site's species code (0 host, 1 TADF, 2 fluorescent).  The tag
+ * perturbs a weight by at most 3 ulp (an energy shift of ~1e-17 eV) and lets one 8-byte load
+ * deliver both the acceptor's weight and its species; precomputing the weights keeps every
+ * transcendental off the selection path.  Channels of an exciton on site i (species a, spin s):
  *   m = 0..M-1   transfer to neighbour j = i + offset[m] (periodic x, y; open z; j invalid -> 0)
  *                singlet: Forster  k = (kF[a][b] * g6[m]) * min(1, ws1[j] / ws1[i])
  *                triplet: Dexter   k = (kD[a][b] * gD[m]) * min(1, wt1[j] / wt1[i])
@@ -22,14 +25,17 @@
  *   M+1          radiative decay      k_rad[a][s]
  *   M+2          non-radiative decay  k_nonrad[a][s]
  * Rejection-free selection: inclusive prefix sums P_c in the canonical order below, total R,
- * target = u_sel * R, first channel with P_c > target (the last channel with P_c > P_{c-1} if
- * rounding leaves none); waiting time dt = -log(1 - u_time) / R.  (u_sel, u_time) are the two halves of Philox
+ * (canonical order below); waiting time dt = -log(1 - u_time) / R.  (u_sel, u_time) are the two halves of Philox
  * block `draws / 2` of stream 4 (XTRAJ) of the trajectory.  A decayed exciton is replaced at once
  * by a new one: site = interior site floor(u_a * n_interior), spin singlet iff u_b < 0.25.
  *
- * Canonical summation order (what makes the prefix sums reproducible bit for bit on a warp):
- * channels are taken in chunks of 32; inside a chunk an inclusive Kogge-Stone scan (offsets 1, 2,
- * 4, 8, 16, every stage reading the previous stage); chunk totals are accumulated sequentially.
+ * Canonical summation order (what makes the selection reproducible bit for bit on a warp):
+ * channel c belongs to lane l = c % 32, slot k = c / 32.  S_l = rate(0,l) + rate(1,l) + ... summed
+ * in slot order from 0.0; L = inclusive Kogge-Stone scan of S over the 32 lanes (offsets 1, 2, 4,
+ * 8, 16, every stage reading the previous one); R = L_31; target = u_sel * R.  The chosen lane is
+ * the first with L_l > target (if rounding leaves none: the last lane with S_l > 0); inside it the
+ * prefix restarts from L_{l-1} (0 for lane 0) and adds the lane's rates in slot order, the chosen
+ * slot being the first whose running sum exceeds target (if none: the lane's last non-zero rate).
  */
 #include <math.h>
 #include <stdint.h>
@@ -105,19 +111,21 @@ static void spawn(const hfx_model *m, hfx_state *s, uint64_t seed, uint32_t iden
 }
 
 static double min1(double v) { return v < 1.0 ? v : 1.0; }
+static int tag_of(double w) { uint64_t b; memcpy(&b, &w, 8); return (int)(b & 3); }
 
-/* One BKL event.  rates/prefix are scratch arrays of (M + 3 rounded up to 32) doubles. */
-static void step(const hfx_model *m, hfx_state *s, uint64_t seed, uint32_t ident, double *rates, double *prefix,
+/* One BKL event.  rates is a scratch array of (M + 3 rounded up to 32) doubles. */
+static void step(const hfx_model *m, hfx_state *s, uint64_t seed, uint32_t ident, double *rates, double *unused,
                  int *ev_kind, int64_t *ev_initial, int64_t *ev_final, double *ev_dt, int *ev_channel) {
+    (void)unused;
     const int64_t plane = (int64_t)m->X * m->Y;
     const int64_t i = ((int64_t)s->z * m->Y + s->y) * m->X + s->x;
-    const int a = m->species[i];
     const int sidx = s->spin == X_SINGLET ? 0 : 1;
     const double *w = sidx == 0 ? m->ws1 : m->wt1;
     const double *g = sidx == 0 ? m->g6 : m->gd;
+    const int a = tag_of(w[i]);
     const double *pref = (sidx == 0 ? m->kf : m->kd) + 3 * a;
     const double inv_wi = 1.0 / w[i];
-    const int C = m->M + 3, padded = (C + 31) & ~31;
+    const int C = m->M + 3, padded = (C + 31) & ~31, K = padded / 32;
     for (int c = 0; c < padded; ++c) rates[c] = 0.0;
     for (int c = 0; c < m->M; ++c) {
         const int zz = s->z + m->offsets[3 * c + 2];
@@ -126,32 +134,42 @@ static void step(const hfx_model *m, hfx_state *s, uint64_t seed, uint32_t ident
         if (xx < 0) xx += m->X; else if (xx >= m->X) xx -= m->X;
         if (yy < 0) yy += m->Y; else if (yy >= m->Y) yy -= m->Y;
         const int64_t j = (int64_t)zz * plane + (int64_t)yy * m->X + xx;
-        rates[c] = (pref[m->species[j]] * g[c]) * min1(w[j] * inv_wi);
+        rates[c] = (pref[tag_of(w[j])] * g[c]) * min1(w[j] * inv_wi);
     }
     rates[m->M] = sidx == 0 ? m->k_isc[a] : m->k_risc[a] * min1(m->ws1[i] * (1.0 / m->wt1[i]));
     rates[m->M + 1] = m->k_rad[2 * a + sidx];
     rates[m->M + 2] = m->k_nonrad[2 * a + sidx];
-    /* canonical prefix sums: Kogge-Stone inside chunks of 32, chunk totals accumulated in order */
-    double base = 0.0;
-    for (int q = 0; q < padded; q += 32) {
-        double cur[32], nxt[32];
-        memcpy(cur, rates + q, sizeof(cur));
-        for (int off = 1; off < 32; off <<= 1) {
-            for (int l = 0; l < 32; ++l) nxt[l] = l >= off ? cur[l] + cur[l - off] : cur[l];
-            memcpy(cur, nxt, sizeof(cur));
-        }
-        for (int l = 0; l < 32; ++l) prefix[q + l] = base + cur[l];
-        base = base + cur[31];
+    /* canonical order: per-lane sums in slot order, Kogge-Stone scan over the lanes */
+    double S[32], L[32], nxt[32];
+    for (int l = 0; l < 32; ++l) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc = acc + rates[k * 32 + l];
+        S[l] = acc;
     }
-    const double R = base;
+    memcpy(L, S, sizeof(L));
+    for (int off = 1; off < 32; off <<= 1) {
+        for (int l = 0; l < 32; ++l) nxt[l] = l >= off ? L[l] + L[l - off] : L[l];
+        memcpy(L, nxt, sizeof(L));
+    }
+    const double R = L[31];
     double u_sel, u_time;
     block_uniforms(seed, STREAM_XTRAJ, ident, s->draws >> 1, &u_sel, &u_time);
     s->draws += 2;
     const double target = u_sel * R;
-    int chosen = -1;
-    for (int c = 0; c < C; ++c) if (prefix[c] > target) { chosen = c; break; }
-    if (chosen < 0)      /* rounding left u_sel * R >= P_last: the last channel that moved the prefix sum */
-        for (int c = C - 1; c >= 0; --c) if (prefix[c] > (c > 0 ? prefix[c - 1] : 0.0)) { chosen = c; break; }
+    int lane = -1;
+    for (int l = 0; l < 32; ++l) if (L[l] > target) { lane = l; break; }
+    if (lane < 0) for (int l = 31; l >= 0; --l) if (S[l] > 0.0) { lane = l; break; }
+    int slot = -1, last_nonzero = -1;
+    double acc = lane > 0 ? L[lane - 1] : 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double r = rates[k * 32 + lane];
+        acc = acc + r;
+        if (r > 0.0) last_nonzero = k;
+        if (slot < 0 && acc > target) slot = k;
+    }
+    if (slot < 0) slot = last_nonzero;
+    const int chosen = slot * 32 + lane;
+    (void)C;
     const double dt = -log(1.0 - u_time) / R;
     s->time += dt;
     s->tallies[XT_EVENTS] += 1;

@@ -74,14 +74,22 @@ def tables(params):
                 kd=np.array(params["dexter_prefactor"], dtype=np.float64))
 
 
-def weights(s1, t1):
-    """exp(-E/kT) per site with the host libm (the device computes its own; tests pass the device's
-    arrays to the oracle so that both sides start from identical inputs)."""
-    return np.exp(-(np.asarray(s1) / KT)), np.exp(-(np.asarray(t1) / KT))
+def tag(w, species):
+    """Replace the two least-significant mantissa bits of each weight by the species code."""
+    bits = np.ascontiguousarray(w, np.float64).view(np.uint64)
+    return ((bits & ~np.uint64(3)) | np.asarray(species, np.uint64)).view(np.float64)
+
+
+def weights(s1, t1, species):
+    """Tagged Boltzmann weights exp(-E/kT) per site with the host libm (the device computes its own
+    with CUDA's exp; tests pass the device's arrays to the oracle so that both sides start from
+    identical inputs)."""
+    return tag(np.exp(-(np.asarray(s1) / KT)), species), tag(np.exp(-(np.asarray(t1) / KT)), species)
 
 
 class ExcitonOracle:
     def __init__(self, dims, species, ws1, wt1, params, tab=None):
+        """ws1 / wt1 are the TAGGED weights; species is kept only for reference."""
         self.dims = tuple(int(d) for d in dims)
         self.species = np.ascontiguousarray(species, np.uint8)
         self.ws1 = np.ascontiguousarray(ws1, np.float64)

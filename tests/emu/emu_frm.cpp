@@ -215,12 +215,20 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     P.M = M;
     std::vector<int32_t> packed((size_t)M);
     for (int m = 0; m < M; ++m) packed[(size_t)m] = (offsets[3 * m] + 128) | ((offsets[3 * m + 1] + 128) << 8) | ((offsets[3 * m + 2] + 128) << 16);
+    std::vector<int32_t> lin((size_t)M);
+    int maxr = 0;
+    for (int m = 0; m < M; ++m) {
+        lin[(size_t)m] = (int32_t)((int64_t)offsets[3 * m + 2] * P.X * P.Y + (int64_t)offsets[3 * m + 1] * P.X + offsets[3 * m]);
+        for (int k = 0; k < 3; ++k) { const int v = offsets[3 * m + k] < 0 ? -offsets[3 * m + k] : offsets[3 * m + k]; if (v > maxr) maxr = v; }
+    }
+    P.R = maxr; P.lin = lin.data();
     P.offsets = packed.data(); P.g6 = g6; P.gd = gd;
     memcpy(P.kf, kf, sizeof(P.kf)); memcpy(P.kd, kd, sizeof(P.kd));
     memcpy(P.k_isc, k_isc, sizeof(P.k_isc)); memcpy(P.k_risc, k_risc, sizeof(P.k_risc));
     memcpy(P.k_rad, k_rad, sizeof(P.k_rad)); memcpy(P.k_nonrad, k_nonrad, sizeof(P.k_nonrad));
     P.singlet_fraction = singlet_fraction;
-    P.species = species; P.ws1 = ws1; P.wt1 = wt1;
+    (void)species;
+    P.ws1 = ws1; P.wt1 = wt1;
     std::vector<int32_t> site((size_t)B), spin((size_t)B);
     std::vector<double> time((size_t)B), life((size_t)B);
     std::vector<uint64_t> draws((size_t)B), tlen((size_t)B, 0);
@@ -229,7 +237,7 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     P.site = site.data(); P.spin = spin.data(); P.time = time.data(); P.lifetime = life.data(); P.draws = draws.data();
     P.totals = totals.data();
     P.trace = trace.data(); P.trace_first = 0; P.trace_n = B; P.trace_cap = trace_cap; P.trace_len = tlen.data();
-    if (8 * (2 * (size_t)M + hfx_padded_channels(M)) + 4 * (size_t)M > sizeof(hf_smem)) return 2;
+    if (hfx_smem_bytes(M, 1) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     emu_run_warp(x_spawn_body, &P);
     for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(x_run_body, &P); }

@@ -12,7 +12,7 @@ from tests.emu import emu
 
 def _oracle(dims, seed, params=None, props=(0.84, 0.15, 0.01)):
     lat = fo.OracleLattice.generate(dims, props, seed).arrays()
-    ws1, wt1 = xo.weights(lat["s1"], lat["t1"])
+    ws1, wt1 = xo.weights(lat["s1"], lat["t1"], lat["species"])
     return xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params or xo.default_params()), lat
 
 
@@ -104,6 +104,7 @@ def test_gpu_exciton_path_equals_specification():
             lat = sim.download_lattice(r)
             ws1, wt1 = sim.x_weights(r)
             np.testing.assert_allclose(ws1, np.exp(-lat["s1"] / xo.KT), rtol=1e-13)
+            assert np.array_equal(ws1.view(np.uint64) & np.uint64(3), lat["species"].astype(np.uint64))     # the species tag
             o = xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params, tab)
             lo, hi = r * (B // R), (r + 1) * (B // R)
             sample = list(range(lo, lo + 16 if r == 0 else lo + 4)) + list(range(hi - 40, hi))
