@@ -1,5 +1,5 @@
-// Exciton trajectories ("Path X"): one warp per exciton, rejection-free (BKL)
-// selection by a warp-shuffle inclusive prefix scan over the transfer / spin-flip / decay rates.
+// Exciton trajectories ("Path X"): warp-per-exciton rate evaluation, rejection-free
+// (BKL) selection by a warp-shuffle inclusive prefix scan over the transfer / spin-flip / decay rates.
 //
 // PARITY UNPINNED: the reference has no exciton dynamics (only the event codes event.py:43-51,
 // the empty lists reseau.py:233-235, the `...` stubs reseau.py:526-550, TADF.intersystem_crossing
@@ -19,12 +19,26 @@
 // contains only IEEE multiplies, adds, compares and one division: the device and the oracle
 // produce identical sums and therefore identical event sequences.  The neighbour table is ordered
 // dz-major, dx fastest, so consecutive lanes read consecutive x: a warp's gather touches each
-// (dy, dz) row of the cutoff sphere as one contiguous run.
+// (dy, dz) row of the cutoff sphere as one contiguous run.  Each realisation's weight arrays carry
+// a halo of R zero planes below z = 0 and above z = Z - 1: a transfer through an open face reads a
+// zero weight and gets rate 0.0 without a bounds test.
 //
 // Canonical summation order (specification): channel c -> lane c % 32, slot c / 32; each lane
 // sums its slots in order (S_l), one Kogge-Stone scan over the 32 lane sums gives L_l and the total
 // R; the chosen lane is the first with L_l > u_sel * R, and inside it the prefix restarts from
 // L_{l-1} and walks the lane's slots.  One scan per event instead of one per 32 channels.
+//
+// Execution shape (v3).  A warp owns 32 trajectories at a time and alternates two phases per event:
+//   A  warp per exciton: for e = 0..31 the 32 lanes evaluate exciton e's M + 3 rates (lane = channel
+//      % 32, coalesced gathers, distance factors and linear offsets of the lane's channels held in
+//      registers, the next exciton's gathers in flight while this one's are consumed), reduce them
+//      to lane sums, scan them with shuffles and park the 32 prefix sums in shared memory;
+//   B  thread per exciton: lane e draws exciton e's Philox block, finds the lane and the slot of
+//      the chosen channel (re-evaluating only that lane's K rates, bit-identically), advances the
+//      clock and applies the event.
+// Everything that is per-event overhead (Philox, log, the divisions, bookkeeping, tallies) thereby
+// costs one warp instruction per 32 events instead of one per event: ~1030 -> ~190 warp
+// instructions per event at M = 256 (profiles/r01e_* vs r01f_*).
 #pragma once
 #include "hf_frm.cuh"
 
@@ -59,7 +73,8 @@ struct HfxParams {
     double kf[9], kd[9];              // [donor][acceptor]
     double k_isc[3], k_risc[3], k_rad[6], k_nonrad[6];
     double singlet_fraction;
-    const double *ws1, *wt1;          // [n_real][N] tagged weights
+    const double *ws1, *wt1;          // [n_real][w_stride] tagged weights; site 0 of a realisation at + w_halo
+    int64_t w_stride, w_halo;         // w_stride = N + 2 * w_halo, w_halo = R planes of zeros on either side in z
     // state [B]
     int32_t *site, *spin;
     double *time, *lifetime;
@@ -79,10 +94,14 @@ __device__ __forceinline__ double hfx_tag(double w, unsigned species) {
 }
 __device__ __forceinline__ int hfx_tag_of(double w) { return (int)(__double_as_longlong(w) & 3ll); }
 
-__global__ void hfx_weights_kernel(const uint8_t *species, const double *s1, const double *t1, double *ws1, double *wt1, int64_t n) {
+// ws1 / wt1 must be zero-filled beforehand (the halo planes stay +0.0, species tag 0)
+__global__ void hfx_weights_kernel(const uint8_t *species, const double *s1, const double *t1, double *ws1, double *wt1,
+                                   int64_t n_sites, int64_t n_real, int64_t w_stride, int64_t w_halo) {
+    const int64_t n = n_sites * n_real;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        ws1[i] = hfx_tag(exp(-(s1[i] / HF_KT)), species[i]);
-        wt1[i] = hfx_tag(exp(-(t1[i] / HF_KT)), species[i]);
+        const int64_t o = (i / n_sites) * w_stride + w_halo + i % n_sites;
+        ws1[o] = hfx_tag(exp(-(s1[i] / HF_KT)), species[i]);
+        wt1[o] = hfx_tag(exp(-(t1[i] / HF_KT)), species[i]);
     }
 }
 
@@ -112,203 +131,274 @@ __global__ void hfx_spawn_kernel(const HfxParams P) {
     atomicAdd(P.totals + (local / P.traj_per_real) * HFX_T_N + HFX_T_GENERATED, 1ull);
 }
 
+struct __align__(16) HfxRec {         // phase A's view of one exciton (written by its lane, read by the whole warp)
+    const double *wp;                 // &w[site] in the exciton's spin manifold (realisation and halo included)
+    double inv_wi;                    // 1 / w[site]
+    int32_t site;                     // packed x, y, z
+    int32_t meta;                     // bit 0: singlet; bits 1-2: donor species; bit 3: no periodic wrap within the cutoff
+    double onsite[3];                 // channels M, M+1, M+2
+    double pad;
+};
+
+#define HFX_L_STRIDE 33               // doubles per exciton row of prefix sums (odd: conflict-free column reads)
+#define HFX_N_K 36                    // kf[9] kd[9] k_isc[3] k_risc[3] k_rad[6] k_nonrad[6]
+
 __host__ __device__ inline size_t hfx_smem_bytes(int M, int warps) {
-    // g6, gd (f64) | per-warp rates (f64) | per-warp donor prefactors (4 f64) | lin, off (i32) | per-warp counters (u32)
-    return 8 * (2 * (size_t)M + (size_t)warps * (hfx_padded_channels(M) + 4)) + 4 * (2 * (size_t)M + (size_t)warps * HFX_T_N);
+    // g6, gd, rate constants (f64) | per-warp prefix sums (f64) | per-warp exciton records | lin, off (i32) |
+    // per-warp tallies [HFX_T_N][32] (u32) | per-warp non-zero masks (u32)
+    return 8 * (2 * (size_t)M + HFX_N_K + (size_t)warps * 32 * HFX_L_STRIDE) + sizeof(HfxRec) * 32 * (size_t)warps +
+           4 * (2 * (size_t)M + (size_t)warps * (HFX_T_N * 32 + 32));
 }
 
-// Pin a value in a register: nvcc otherwise re-derives kernel parameters and pointers built from
-// them inside the hot loop (LDC + IMAD chains) to save registers, which costs more issue slots than
-// it saves (ncu, profiles/r01e_*).  An empty asm with a read-write operand makes the value opaque.
-#if defined(__CUDA_ARCH__)
-#define HFX_PIN32(x) asm volatile("" : "+r"(x))
-#define HFX_PIN64(x) asm volatile("" : "+l"(x))
-#define HFX_PINF64(x) asm volatile("" : "+d"(x))
-#else
-#define HFX_PIN32(x) (void)0
-#define HFX_PIN64(x) (void)0
-#define HFX_PINF64(x) (void)0
-#endif
+__device__ __forceinline__ double hfx_min1(double v) { return v < 1.0 ? v : 1.0; }
 
-#ifndef HFX_MIN_BLOCKS
-#define HFX_MIN_BLOCKS 4
-#endif
-template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32, HFX_MIN_BLOCKS) hfx_run_kernel(const HfxParams P) {
+// Offset (in sites) from an exciton on (px, py, pz) to the neighbour of packed offset o: periodic in
+// x and y, straight through in z (the halo absorbs z outside [0, Z)).
+__device__ __forceinline__ int hfx_delta(int o, int px, int py, int dim_x, int dim_y, int plane) {
+    const int dx = (o & 255) - 128, dy = ((o >> 8) & 255) - 128, dz = ((o >> 16) & 255) - 128;
+    int xx = px + dx, yy = py + dy;
+    if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
+    if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
+    return dz * plane + (yy - py) * dim_x + (xx - px);
+}
+
+// rate of one transfer channel, the arithmetic of the specification: (pref[b] * g) * min(1, wj / wi)
+__device__ __forceinline__ double hfx_rate(const double *pref, double g, double wj, double inv_wi) {
+    return __dmul_rn(__dmul_rn(pref[hfx_tag_of(wj)], g), hfx_min1(__dmul_rn(wj, inv_wi)));
+}
+
+template <int KF>
+struct HfxLaneTables {                // this lane's channels of the KF full slots, in registers
+    int32_t lin[KF > 0 ? KF : 1];
+    double g6[KF > 0 ? KF : 1], gd[KF > 0 ? KF : 1];
+};
+
+// Phase A, loads: the weights of exciton `rec`'s neighbours on this lane's channels of the full slots.
+template <int KF>
+__device__ __forceinline__ void hfx_gather(const HfxRec *rec, const HfxLaneTables<KF> &T, const int32_t *s_off_lane,
+                                           int dim_x, int dim_y, int plane, double (&buf)[KF > 0 ? KF : 1]) {
+    const double *wp = rec->wp;
+    if (rec->meta & 8) {
+#pragma unroll
+        for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + T.lin[k]);
+    } else {
+        const int site = rec->site, px = hf_px(site), py = hf_py(site);
+#pragma unroll
+        for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + hfx_delta(s_off_lane[32 * k], px, py, dim_x, dim_y, plane));
+    }
+}
+
+template <int KF, bool kSinglet>
+__device__ __forceinline__ double hfx_lane_sum(const HfxLaneTables<KF> &T, const double *pref, double inv_wi,
+                                               const double (&buf)[KF > 0 ? KF : 1]) {
+    double S = 0.0;
+#pragma unroll
+    for (int k = 0; k < KF; ++k) S = __dadd_rn(S, hfx_rate(pref, kSinglet ? T.g6[k] : T.gd[k], buf[k], inv_wi));
+    return S;
+}
+
+// KF > 0: M / 32 == KF full slots with register-resident tables and prefetch; KF == 0: any M, tables in shared memory.
+template <int kWarps, int KF, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const HfxParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int M = P.M;
-    HFX_PIN32(M);
-    const int padded = (int)hfx_padded_channels(M), K = padded >> 5, Kfull = M >> 5;
+    const int M = P.M, K = (int)(hfx_padded_channels(M) >> 5), Kfull = M >> 5;
     double *s_g6 = reinterpret_cast<double *>(hf_smem);
     double *s_gd = s_g6 + M;
-    double *s_rates = s_gd + M + (size_t)warp * padded;
-    double *s_pref = s_gd + M + (size_t)kWarps * padded + 4 * warp;            // this event's kF[a][.] or kD[a][.]
-    int32_t *s_lin = reinterpret_cast<int32_t *>(s_gd + M + (size_t)kWarps * (padded + 4));
+    double *s_k = s_gd + M;
+    double *s_L = s_k + HFX_N_K + (size_t)warp * (32 * HFX_L_STRIDE);
+    HfxRec *s_rec = reinterpret_cast<HfxRec *>(s_k + HFX_N_K + (size_t)kWarps * (32 * HFX_L_STRIDE)) + 32 * warp;
+    int32_t *s_lin = reinterpret_cast<int32_t *>(s_rec - 32 * warp + 32 * kWarps);
     int32_t *s_off = s_lin + M;
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_off + M) + warp * HFX_T_N;
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_off + M) + warp * (HFX_T_N * 32);
+    unsigned *s_nz = reinterpret_cast<unsigned *>(s_off + M) + kWarps * (HFX_T_N * 32) + warp * 32;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = P.g6[m]; s_gd[m] = P.gd[m]; s_lin[m] = P.lin[m]; s_off[m] = P.offsets[m]; }
+    if (threadIdx.x < 9) { s_k[threadIdx.x] = P.kf[threadIdx.x]; s_k[9 + threadIdx.x] = P.kd[threadIdx.x]; }
+    if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = P.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = P.k_risc[threadIdx.x]; }
+    if (threadIdx.x < 6) { s_k[24 + threadIdx.x] = P.k_rad[threadIdx.x]; s_k[30 + threadIdx.x] = P.k_nonrad[threadIdx.x]; }
     __syncthreads();
-    int plane = P.X * P.Y, dim_x = P.X, dim_y = P.Y;
-    unsigned n_sites = (unsigned)P.N;
-    HFX_PIN32(plane); HFX_PIN32(dim_x); HFX_PIN32(dim_y); HFX_PIN32(n_sites);
-
-    for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
-        const uint32_t ident = P.first_traj + (uint32_t)local;
-        const int64_t r = local / P.traj_per_real;
-        const double *__restrict__ ws1 = P.ws1 + r * P.N, *__restrict__ wt1 = P.wt1 + r * P.N;
-        int site = P.site[local], spin = P.spin[local];
-        double time = P.time[local], lifetime = P.lifetime[local];
-        uint64_t draws = P.draws[local];
-        if (lane < HFX_T_N) s_cnt[lane] = 0;
-        const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
-        uint64_t trace_at = traced ? P.trace_len[local - P.trace_first] : 0;
-        __syncwarp();
-
-        for (int64_t e = 0; e < P.n_events; ++e) {
-            const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-            const int i = pz * plane + py * dim_x + px;
-            const bool singlet = spin == HFX_SINGLET;
-            const double *w = singlet ? ws1 : wt1;
-            HFX_PIN64(w);
-            const double wi = __ldg(w + i);
-            const int a = hfx_tag_of(wi);
-            double inv_wi = __ddiv_rn(1.0, wi);
-            HFX_PINF64(inv_wi);
-            if (lane < 3) s_pref[lane] = singlet ? P.kf[3 * a + lane] : P.kd[3 * a + lane];
-            __syncwarp();
-            const bool interior = px >= P.R && px < dim_x - P.R && py >= P.R && py < dim_y - P.R;   // no periodic wrap needed
-            double S = 0.0;
-            {   // full slots: every lane owns a transfer channel
-                const double *g = (singlet ? s_g6 : s_gd) + lane;
-                const int32_t *lin = s_lin + lane, *off = s_off + lane;
-                double *out = s_rates + lane;
-                for (int k = 0; k < Kfull; ++k, g += 32, lin += 32, off += 32, out += 32) {
-                    int j;
-                    bool ok;
-                    if (interior) {
-                        j = i + *lin;
-                        ok = (unsigned)j < n_sites;                             // open z: out of range <=> outside [0, N)
-                    } else {
-                        const int o = *off;
-                        const int zz = pz + ((o >> 16) & 255) - 128;
-                        int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                        if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
-                        if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
-                        ok = zz >= 0 && zz < P.Z;
-                        j = zz * plane + yy * dim_x + xx;
-                    }
-                    double rate = 0.0;
-                    if (ok) {
-                        const double wj = __ldg(w + j);
-                        rate = __dmul_rn(__dmul_rn(s_pref[hfx_tag_of(wj)], *g), fmin(__dmul_rn(wj, inv_wi), 1.0));
-                    }
-                    *out = rate;
-                    S = __dadd_rn(S, rate);
-                }
-            }
-            for (int k = Kfull; k < K; ++k) {   // tail slot(s): the remaining transfer channels and the three on-site ones
-                const int c = (k << 5) + lane;
-                double rate = 0.0;
-                if (c < M) {
-                    const int o = s_off[c];
-                    const int zz = pz + ((o >> 16) & 255) - 128;
-                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                    if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
-                    if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
-                    if (zz >= 0 && zz < P.Z) {
-                        const double wj = __ldg(w + (zz * plane + yy * P.X + xx));
-                        rate = __dmul_rn(__dmul_rn(s_pref[hfx_tag_of(wj)], (singlet ? s_g6 : s_gd)[c]), fmin(__dmul_rn(wj, inv_wi), 1.0));
-                    }
-                } else if (c == M) {
-                    rate = singlet ? P.k_isc[a] : __dmul_rn(P.k_risc[a], fmin(__dmul_rn(__ldg(ws1 + i), inv_wi), 1.0));   // inv_wi = 1/wt1[i] for a triplet
-                } else if (c == M + 1) {
-                    rate = P.k_rad[2 * a + (singlet ? 0 : 1)];
-                } else if (c == M + 2) {
-                    rate = P.k_nonrad[2 * a + (singlet ? 0 : 1)];
-                }
-                s_rates[c] = rate;
-                S = __dadd_rn(S, rate);
-            }
-            // one inclusive Kogge-Stone scan over the 32 lane sums
-            double L = S;
+    const int plane = P.X * P.Y, dim_x = P.X, dim_y = P.Y;
+    HfxLaneTables<KF> T;
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const double up = __shfl_up_sync(HF_FULL, L, off);
-                if (lane >= off) L = __dadd_rn(L, up);
-            }
-            const double R = __shfl_sync(HF_FULL, L, 31);
-            const HfPhiloxBlock blk = hf_philox_block(P.k0, P.k1, HF_STREAM_XTRAJ, ident, draws >> 1);
-            draws += 2;
-            const double u_sel = hf_block_uniform(blk, 0), u_time = hf_block_uniform(blk, 1);
-            const double target = __dmul_rn(u_sel, R);
-            const unsigned over = __ballot_sync(HF_FULL, L > target);
-            const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
-            const int lstar = over ? __ffs(over) - 1 : 31 - __clz(nonzero);
-            const double below = __shfl_sync(HF_FULL, L, (lstar + 31) & 31);
-            // in-lane walk: lane k accumulates the chosen lane's rates of slots 0..k in slot order, so
-            // lane k holds the running sum after slot k and one ballot finds the first that passes target
-            double acc = lstar > 0 ? below : 0.0, mine = 0.0;
-            {
-                const double *rk = s_rates + lstar;
-                for (int k = 0; k < K; ++k, rk += 32) {
-                    const double v = *rk;
-                    if (k <= lane) acc = __dadd_rn(acc, v);
-                    if (k == lane) mine = v;
-                }
-            }
-            const unsigned in_k = K >= 32 ? HF_FULL : ((1u << K) - 1u);
-            const unsigned passed = __ballot_sync(HF_FULL, acc > target) & in_k;
-            const unsigned live = __ballot_sync(HF_FULL, mine > 0.0) & in_k;
-            const int slot = passed ? __ffs(passed) - 1 : 31 - __clz(live);
-            const int chosen = (slot << 5) + lstar;
-            const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
-            time = __dadd_rn(time, dt);
-            int kind, fin = site, tally;
-            if (chosen < M) {
-                const int o = s_off[chosen];
-                int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
-                if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
-                fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
-                kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
-                tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
-            } else if (chosen == M) {
-                kind = HFX_K_ISC;                                               // molecule.py:299-307
-                tally = singlet ? HFX_T_ISC : HFX_T_RISC;
-                spin = singlet ? HFX_TRIPLET : HFX_SINGLET;
-            } else {
-                kind = HFX_K_DECAY;
-                tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
-            }
-            int site_after = fin;
-            if (kind == HFX_K_DECAY) {
-                lifetime = __dadd_rn(lifetime, time);
-                hfx_spawn(P, ident, draws, site_after, spin, time);
-            }
-            if (lane == 0) {
-                s_cnt[HFX_T_EVENTS] += 1;
-                s_cnt[tally] += 1;
-                if (kind == HFX_K_DECAY) s_cnt[HFX_T_GENERATED] += 1;
-                if (traced && trace_at < (uint64_t)P.trace_cap) {
-                    HfTraceRec rec;
-                    rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
-                    rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
-                    rec.pad[0] = (uint8_t)spin; rec.pad[1] = 0;     // spin of the trajectory's exciton after the step
-                    rec.spins = (uint32_t)chosen; rec.draws = draws;
-                    P.trace[(local - P.trace_first) * P.trace_cap + trace_at] = rec;
-                }
-            }
-            trace_at += 1;
-            site = site_after;
-            __syncwarp();                                                       // s_rates / s_pref are rewritten by the next event
+    for (int k = 0; k < KF; ++k) { T.lin[k] = s_lin[32 * k + lane]; T.g6[k] = s_g6[32 * k + lane]; T.gd[k] = s_gd[32 * k + lane]; }
+    const int32_t *s_off_lane = s_off + lane;
+
+    const int64_t n_blocks = (P.B + 31) >> 5;
+    for (int64_t blk = (int64_t)blockIdx.x * kWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarps) {
+        const int64_t local = (blk << 5) + lane;
+        const int count = (int)(P.B - (blk << 5) < 32 ? P.B - (blk << 5) : 32);
+        const bool active = lane < count;
+        const uint32_t ident = P.first_traj + (uint32_t)local;
+        const int64_t r = (active ? local : (blk << 5)) / P.traj_per_real;
+        const double *ws1 = P.ws1 + r * P.w_stride + P.w_halo, *wt1 = P.wt1 + r * P.w_stride + P.w_halo;
+        int site = 0, spin = HFX_SINGLET;
+        double time = 0.0, lifetime = 0.0;
+        uint64_t draws = 0, trace_at = 0;
+        bool traced = false;
+        if (active) {
+            site = P.site[local]; spin = P.spin[local]; time = P.time[local]; lifetime = P.lifetime[local]; draws = P.draws[local];
+            traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
+            if (traced) trace_at = P.trace_len[local - P.trace_first];
         }
-        if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < HFX_T_N; ++t) s_cnt[t * 32 + lane] = 0;
+
+        for (int64_t ev = 0; ev < P.n_events; ++ev) {
+            // ---- this lane's exciton: its record for phase A and its random numbers ----
+            const bool singlet = spin == HFX_SINGLET;
+            const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+            const int64_t i = (int64_t)pz * plane + py * dim_x + px;
+            const double *wp = (singlet ? ws1 : wt1) + i;
+            double inv_wi = 0.0, r_flip = 0.0, r_rad = 0.0, r_nonrad = 0.0, u_sel = 0.0, u_time = 0.0;
+            int a = 0;
+            const double *pref = s_k;
+            if (active) {
+                const double wi = __ldg(wp);
+                a = hfx_tag_of(wi);
+                inv_wi = __ddiv_rn(1.0, wi);
+                pref = s_k + (singlet ? 0 : 9) + 3 * a;
+                r_flip = singlet ? s_k[18 + a] : __dmul_rn(s_k[21 + a], hfx_min1(__dmul_rn(__ldg(ws1 + i), inv_wi)));   // inv_wi = 1/wt1[i] for a triplet
+                r_rad = s_k[24 + 2 * a + (singlet ? 0 : 1)];
+                r_nonrad = s_k[30 + 2 * a + (singlet ? 0 : 1)];
+                const bool nowrap = px >= P.R && px < dim_x - P.R && py >= P.R && py < dim_y - P.R;
+                HfxRec rec;
+                rec.wp = wp; rec.inv_wi = inv_wi; rec.site = site; rec.meta = (singlet ? 1 : 0) | (a << 1) | (nowrap ? 8 : 0);
+                rec.onsite[0] = r_flip; rec.onsite[1] = r_rad; rec.onsite[2] = r_nonrad; rec.pad = 0.0;
+                s_rec[lane] = rec;
+                const HfPhiloxBlock rnd = hf_philox_block(P.k0, P.k1, HF_STREAM_XTRAJ, ident, draws >> 1);
+                draws += 2;
+                u_sel = hf_block_uniform(rnd, 0); u_time = hf_block_uniform(rnd, 1);
+            }
+            __syncwarp();
+
+            // ---- phase A: the warp evaluates one exciton at a time ----
+            double buf0[KF > 0 ? KF : 1], buf1[KF > 0 ? KF : 1];
+            if (KF > 0) hfx_gather<KF>(s_rec, T, s_off_lane, dim_x, dim_y, plane, buf0);
+            for (int e = 0; e < count; ++e) {
+                const HfxRec *rec = s_rec + e;
+                const int meta = rec->meta;
+                const double e_inv = rec->inv_wi;
+                const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);
+                double S;
+                if (KF > 0) {
+                    // the next exciton's gathers go out before this one's are consumed (two register buffers, swapped by parity)
+                    if (e & 1) {
+                        if (e + 1 < count) hfx_gather<KF>(rec + 1, T, s_off_lane, dim_x, dim_y, plane, buf0);
+                        S = (meta & 1) ? hfx_lane_sum<KF, true>(T, e_pref, e_inv, buf1) : hfx_lane_sum<KF, false>(T, e_pref, e_inv, buf1);
+                    } else {
+                        if (e + 1 < count) hfx_gather<KF>(rec + 1, T, s_off_lane, dim_x, dim_y, plane, buf1);
+                        S = (meta & 1) ? hfx_lane_sum<KF, true>(T, e_pref, e_inv, buf0) : hfx_lane_sum<KF, false>(T, e_pref, e_inv, buf0);
+                    }
+                } else {
+                    S = 0.0;
+                }
+                {   // slots not covered above: the remaining transfer channels and the three on-site ones
+                    const int site_e = rec->site, ex = hf_px(site_e), ey = hf_py(site_e);
+                    const double *g = (meta & 1) ? s_g6 : s_gd;
+                    for (int k = (KF > 0 ? KF : 0); k < K; ++k) {
+                        const int c = (k << 5) + lane;
+                        double rate = 0.0;
+                        if (c < M) rate = hfx_rate(e_pref, g[c], __ldg(rec->wp + hfx_delta(s_off[c], ex, ey, dim_x, dim_y, plane)), e_inv);
+                        else if (c < M + 3) rate = rec->onsite[c - M];
+                        S = __dadd_rn(S, rate);
+                    }
+                }
+                // one inclusive Kogge-Stone scan over the 32 lane sums
+                double L = S;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double up = __shfl_up_sync(HF_FULL, L, off);
+                    if (lane >= off) L = __dadd_rn(L, up);
+                }
+                s_L[e * HFX_L_STRIDE + lane] = L;
+                const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
+                if (lane == 0) s_nz[e] = nonzero;
+            }
+            __syncwarp();
+
+            // ---- phase B: every lane selects and applies its own exciton's event ----
+            if (active) {
+                const double *row = s_L + lane * HFX_L_STRIDE;
+                const double R = row[31];
+                const double target = __dmul_rn(u_sel, R);
+                int lstar = -1;
+#pragma unroll 8
+                for (int l = 31; l >= 0; --l) if (row[l] > target) lstar = l;     // first lane whose prefix passes the target
+                if (lstar < 0) { const unsigned nz = s_nz[lane]; lstar = nz ? 31 - __clz(nz) : 0; }
+                double acc = lstar > 0 ? row[lstar - 1] : 0.0;
+                int slot = -1, last_live = -1;
+                const double *g = singlet ? s_g6 : s_gd;
+                for (int k = 0; k < K; ++k) {                                     // the chosen lane's rates again, same inputs, same arithmetic
+                    const int c = (k << 5) + lstar;
+                    double rate = 0.0;
+                    if (c < M) rate = hfx_rate(pref, g[c], __ldg(wp + hfx_delta(s_off[c], px, py, dim_x, dim_y, plane)), inv_wi);
+                    else if (c == M) rate = r_flip;
+                    else if (c == M + 1) rate = r_rad;
+                    else if (c == M + 2) rate = r_nonrad;
+                    acc = __dadd_rn(acc, rate);
+                    if (rate > 0.0) last_live = k;
+                    if (slot < 0 && acc > target) slot = k;
+                }
+                if (slot < 0) slot = last_live < 0 ? K - 1 : last_live;
+                const int chosen = (slot << 5) + lstar;
+                const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
+                time = __dadd_rn(time, dt);
+                int kind, fin = site, tally;
+                if (chosen < M) {
+                    const int o = s_off[chosen];
+                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                    if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
+                    if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
+                    fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
+                    kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
+                    tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+                } else if (chosen == M) {
+                    kind = HFX_K_ISC;                                             // molecule.py:299-307
+                    tally = singlet ? HFX_T_ISC : HFX_T_RISC;
+                    spin = singlet ? HFX_TRIPLET : HFX_SINGLET;
+                } else {
+                    kind = HFX_K_DECAY;
+                    tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
+                }
+                int site_after = fin;
+                s_cnt[HFX_T_EVENTS * 32 + lane] += 1;
+                s_cnt[tally * 32 + lane] += 1;
+                if (kind == HFX_K_DECAY) {
+                    lifetime = __dadd_rn(lifetime, time);
+                    hfx_spawn(P, ident, draws, site_after, spin, time);
+                    s_cnt[HFX_T_GENERATED * 32 + lane] += 1;
+                }
+                if (traced) {
+                    if (trace_at < (uint64_t)P.trace_cap) {
+                        HfTraceRec rec;
+                        rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
+                        rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
+                        rec.pad[0] = (uint8_t)spin; rec.pad[1] = 0;     // spin of the trajectory's exciton after the step
+                        rec.spins = (uint32_t)chosen; rec.draws = draws;
+                        P.trace[(local - P.trace_first) * P.trace_cap + trace_at] = rec;
+                    }
+                    trace_at += 1;
+                }
+                site = site_after;
+            }
+        }
+        if (active) {
             P.site[local] = site; P.spin[local] = spin; P.time[local] = time; P.lifetime[local] = lifetime; P.draws[local] = draws;
             if (traced) P.trace_len[local - P.trace_first] = trace_at;
         }
-        __syncwarp();
-        if (lane < HFX_T_N && s_cnt[lane]) atomicAdd(P.totals + r * HFX_T_N + lane, (unsigned long long)s_cnt[lane]);
+        // tallies: one atomic per counter and warp when the 32 trajectories share a realisation
+        const int64_t r_first = __shfl_sync(HF_FULL, r, 0), r_last = __shfl_sync(HF_FULL, r, 31);
+        const bool uniform = r_first == r_last;
+        for (int t = 0; t < HFX_T_N; ++t) {
+            unsigned v = s_cnt[t * 32 + lane];
+            if (uniform) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(HF_FULL, v, off);
+                if (lane == 0 && v) atomicAdd(P.totals + r * HFX_T_N + t, (unsigned long long)v);
+            } else if (v) {
+                atomicAdd(P.totals + r * HFX_T_N + t, (unsigned long long)v);
+            }
+        }
         __syncwarp();
     }
 }

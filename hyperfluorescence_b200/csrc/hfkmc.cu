@@ -188,16 +188,30 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 
 }  // namespace
 
-template <int W>
+// The exciton step kernel for a neighbour count M: register-resident tables when M / 32 is one of the
+// instantiated slot counts (cutoff 3, 4, 5 lattice constants), the generic shared-memory variant otherwise.
+typedef void (*hfx_kernel_fn)(const HfxParams);
+constexpr int kXWarps = 8;
+static hfx_kernel_fn x_pick_kernel(int M) {
+    switch (M >> 5) {
+        case 3: return hfx_run_kernel<kXWarps, 3, 2>;
+        case 8: return hfx_run_kernel<kXWarps, 8, 2>;
+        case 16: return hfx_run_kernel<kXWarps, 16, 1>;
+        default: return hfx_run_kernel<kXWarps, 0, 2>;
+    }
+}
+
 int x_configure_launch(hf_sim *s) {
-    const size_t smem = hfx_smem_bytes(s->X.M, W);
+    const size_t smem = hfx_smem_bytes(s->X.M, kXWarps);
     if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "cutoff too large: %zu B of shared memory", smem);
-    if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hfx_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hfx_kernel_fn fn = x_pick_kernel(s->X.M);
+    if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfx_run_kernel<W>, W * 32, smem));
+    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kXWarps * 32, smem));
     if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "exciton kernel does not fit an SM");
-    const int64_t need = (s->X.B + W - 1) / W, cap = (int64_t)s->sm_count * per_sm;
-    s->x_warps = W; s->x_smem = smem; s->x_grid = (int)(need < cap ? need : cap);
+    const int64_t blocks = (s->X.B + 31) / 32;                                    // a warp owns 32 trajectories at a time
+    const int64_t need = (blocks + kXWarps - 1) / kXWarps, cap = (int64_t)s->sm_count * per_sm;
+    s->x_warps = kXWarps; s->x_smem = smem; s->x_grid = (int)(need < cap ? need : cap);
     if (s->x_grid < 1) s->x_grid = 1;
     return HF_OK;
 }
@@ -841,7 +855,10 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     X.singlet_fraction = p->singlet_fraction;
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     s->d_x_off = nullptr; s->d_x_lin = nullptr; s->d_x_g6 = nullptr; s->d_x_gd = nullptr;
-    const size_t M = packed.size(), RN = (size_t)s->n_real * (size_t)s->P.N, B = (size_t)s->P.B;
+    // weights: R zero planes below and above every realisation (an open-face transfer reads weight 0)
+    X.w_halo = (int64_t)X.R * s->P.X * s->P.Y;
+    X.w_stride = s->P.N + 2 * X.w_halo;
+    const size_t M = packed.size(), RN = (size_t)s->n_real * (size_t)X.w_stride, B = (size_t)s->P.B;
     if ((rc = dev_alloc(&s->d_x_off, M))) return rc;
     if ((rc = dev_alloc(&s->d_x_lin, M))) return rc;
     if ((rc = dev_alloc(&s->d_x_g6, M))) return rc;
@@ -850,9 +867,13 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     HF_CUDA(cudaMemcpyAsync(s->d_x_lin, lin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_g6, s->x_g6.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_gd, s->x_gd.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
-    if (!s->d_ws1) {
-        if ((rc = dev_alloc(&s->d_ws1, RN))) return rc;
-        if ((rc = dev_alloc(&s->d_wt1, RN))) return rc;
+    cudaFree(s->d_ws1); cudaFree(s->d_wt1);
+    s->d_ws1 = nullptr; s->d_wt1 = nullptr;
+    if ((rc = dev_alloc(&s->d_ws1, RN))) return rc;
+    if ((rc = dev_alloc(&s->d_wt1, RN))) return rc;
+    HF_CUDA(cudaMemsetAsync(s->d_ws1, 0, 8 * RN, s->stream));
+    HF_CUDA(cudaMemsetAsync(s->d_wt1, 0, 8 * RN, s->stream));
+    if (!s->d_x_site) {
         if ((rc = dev_alloc(&s->d_x_site, B))) return rc;
         if ((rc = dev_alloc(&s->d_x_spin, B))) return rc;
         if ((rc = dev_alloc(&s->d_x_time, B))) return rc;
@@ -860,14 +881,15 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
         if ((rc = dev_alloc(&s->d_x_draws, B))) return rc;
         if ((rc = dev_alloc(&s->d_x_totals, (size_t)s->n_real * HFX_T_N))) return rc;
     }
-    hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_ws1, s->d_wt1, (int64_t)RN);
+    hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_ws1, s->d_wt1, (int64_t)s->P.N,
+                                                               (int64_t)s->n_real, X.w_stride, X.w_halo);
     X.offsets = s->d_x_off; X.lin = s->d_x_lin; X.g6 = s->d_x_g6; X.gd = s->d_x_gd;
     X.ws1 = s->d_ws1; X.wt1 = s->d_wt1;
     X.site = s->d_x_site; X.spin = s->d_x_spin; X.time = s->d_x_time; X.lifetime = s->d_x_life; X.draws = s->d_x_draws;
     X.totals = s->d_x_totals;
     HF_CUDA(cudaStreamSynchronize(s->stream));
     HF_CUDA(cudaGetLastError());
-    if ((rc = x_configure_launch<8>(s))) return rc;
+    if ((rc = x_configure_launch(s))) return rc;
     s->x_configured = true;
     s->x_spawned = false;
     return HF_OK;
@@ -899,7 +921,7 @@ int hf_x_run(hf_sim *s, int64_t n_events) {
     if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
     cudaEvent_t e0 = get_event(s), e1 = get_event(s);
     HF_CUDA(cudaEventRecord(e0, s->stream));
-    hfx_run_kernel<8><<<s->x_grid, 8 * 32, s->x_smem, s->stream>>>(s->X);
+    x_pick_kernel(s->X.M)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(s->X);
     HF_CUDA(cudaEventRecord(e1, s->stream));
     s->timing.emplace_back(e0, e1);
     HF_CUDA(cudaGetLastError());
@@ -949,7 +971,7 @@ int hf_x_download_weights(hf_sim *s, int32_t r, double *ws1, double *wt1) {
     if (r < 0 || r >= s->n_real) return fail(HF_ERR_BAD_ARG, "realisation %d out of range", r);
     int rc = use_device(s);
     if (rc) return rc;
-    const size_t N = (size_t)s->P.N, off = (size_t)r * N;
+    const size_t N = (size_t)s->P.N, off = (size_t)r * (size_t)s->X.w_stride + (size_t)s->X.w_halo;
     HF_CUDA(cudaMemcpyAsync(ws1, s->d_ws1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
     HF_CUDA(cudaMemcpyAsync(wt1, s->d_wt1 + off, N * 8, cudaMemcpyDeviceToHost, s->stream));
     HF_CUDA(cudaStreamSynchronize(s->stream));

@@ -198,14 +198,17 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
 }
 
 static void x_spawn_body(void *a) { hfx_spawn_kernel(*(const HfxParams *)a); }
-static void x_run_body(void *a) { hfx_run_kernel<1>(*(const HfxParams *)a); }
+// the same two variants the library picks (x_pick_kernel): register tables when M / 32 is instantiated, generic otherwise
+static void x_run_body_generic(void *a) { hfx_run_kernel<1, 0, 1>(*(const HfxParams *)a); }
+static void x_run_body_k3(void *a) { hfx_run_kernel<1, 3, 1>(*(const HfxParams *)a); }
+static void x_run_body_k8(void *a) { hfx_run_kernel<1, 8, 1>(*(const HfxParams *)a); }
 
 // Exciton path: B <= 32 trajectories on one lattice, hfx_spawn + n_calls x hfx_run(n_events).
 int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, const double *wt1, int32_t M,
               const int8_t *offsets, const double *g6, const double *gd, const double *kf, const double *kd,
               const double *k_isc, const double *k_risc, const double *k_rad, const double *k_nonrad,
               double singlet_fraction, uint64_t seed, uint32_t first_traj, int32_t B, int64_t n_events, int32_t n_calls,
-              HfTraceRec *trace_out, int64_t trace_cap, int32_t *site_out, int32_t *spin_out, double *time_out,
+              int32_t generic, HfTraceRec *trace_out, int64_t trace_cap, int32_t *site_out, int32_t *spin_out, double *time_out,
               double *life_out, uint64_t *draws_out, unsigned long long *totals_out) {
     if (B < 1 || B > 32) return 3;
     HfxParams P;
@@ -228,7 +231,12 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     memcpy(P.k_rad, k_rad, sizeof(P.k_rad)); memcpy(P.k_nonrad, k_nonrad, sizeof(P.k_nonrad));
     P.singlet_fraction = singlet_fraction;
     (void)species;
-    P.ws1 = ws1; P.wt1 = wt1;
+    // the device layout: R zero planes below and above the lattice
+    P.w_halo = (int64_t)maxr * P.X * P.Y; P.w_stride = P.N + 2 * P.w_halo;
+    std::vector<double> hs1((size_t)P.w_stride, 0.0), ht1((size_t)P.w_stride, 0.0);
+    memcpy(hs1.data() + P.w_halo, ws1, sizeof(double) * (size_t)P.N);
+    memcpy(ht1.data() + P.w_halo, wt1, sizeof(double) * (size_t)P.N);
+    P.ws1 = hs1.data(); P.wt1 = ht1.data();
     std::vector<int32_t> site((size_t)B), spin((size_t)B);
     std::vector<double> time((size_t)B), life((size_t)B);
     std::vector<uint64_t> draws((size_t)B), tlen((size_t)B, 0);
@@ -240,7 +248,8 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     if (hfx_smem_bytes(M, 1) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     emu_run_warp(x_spawn_body, &P);
-    for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(x_run_body, &P); }
+    void (*body)(void *) = generic ? x_run_body_generic : (M >> 5) == 3 ? x_run_body_k3 : (M >> 5) == 8 ? x_run_body_k8 : x_run_body_generic;
+    for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(body, &P); }
     memcpy(trace_out, trace.data(), sizeof(HfTraceRec) * (size_t)(B * trace_cap));
     for (int b = 0; b < B; ++b) {
         const int p = site[(size_t)b];

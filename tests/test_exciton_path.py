@@ -52,14 +52,19 @@ def test_oracle_closed_forms():
     assert abs(triplets / n - 0.75) < 4 * np.sqrt(0.75 * 0.25 / n)               # molecule.py:93
 
 
-@pytest.mark.parametrize("dims,cutoff,seed", [((12, 12, 6), 4.0, 5), ((9, 10, 5), 3.0, 6), ((8, 8, 8), 1.5, 7)])
-def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed):
+@pytest.mark.parametrize("dims,cutoff,seed,B,generic", [
+    ((12, 12, 6), 4.0, 5, 32, False),      # register-table variant, 8 full slots; every site needs the periodic wrap
+    ((24, 22, 7), 4.0, 8, 27, False),      # ... with wrap-free sites too, and a ragged last block of trajectories
+    ((9, 10, 5), 3.0, 6, 32, False),       # 3 full slots + a tail slot that mixes transfer and on-site channels
+    ((9, 10, 5), 3.0, 6, 5, True),         # the generic shared-memory variant on the same model
+    ((8, 8, 8), 1.5, 7, 32, False)])       # M = 18 < 32: generic variant
+def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, generic):
     """hfx_spawn_kernel + hfx_run_kernel run lane by lane on the host (tests/emu): identical event
     sequences, channels, spins, waiting times, final states and tallies for 32 trajectories."""
     p = dict(xo.default_params(), cutoff=cutoff)
     o, _ = _oracle(dims, seed, p, props=(0.6, 0.3, 0.1))
-    B, n = 32, 250
-    dev = emu.x_run(o, seed * 1000 + 1, 40, B, n // 2, n_calls=2)
+    n = 250
+    dev = emu.x_run(o, seed * 1000 + 1, 40, B, n // 2, n_calls=2, generic=generic)
     tot = np.zeros(16, np.int64)
     for b in range(B):
         ref = o.run(seed * 1000 + 1, 40 + b, n)
