@@ -306,6 +306,15 @@ def ga_fitness_rate(rank, local_rank, world):
 X_L, X_TRAJ_PER_GPU, X_EVENTS, X_CUTOFF = 128, 1_000_000, 100, 4.0
 
 
+def exciton_traffic(events_per_launch):
+    """DRAM bytes of one exciton-kernel launch, scaled from the committed ncu capture (per event)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)["hfx_run_kernel"]["dram_bytes_per_event"]) * events_per_launch
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def exciton_rate(rank, local_rank, world):
     """The north_star's own target configuration for the exciton path (own model, parity unpinned:
     the reference has no exciton dynamics): 128^3 lattice, 10^6 concurrent single-exciton
@@ -344,7 +353,11 @@ def exciton_rate(rank, local_rank, world):
                        "model": "own (parity unpinned): DESIGN.md section 9, oracle/exciton_oracle.c"},
             "roofline": {"bound": "hbm", "bytes_per_event": bytes_per_event,
                          "achieved": rate * bytes_per_event / world / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel"},
+                         "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel",
+                         "traffic": exciton_traffic(X_TRAJ_PER_GPU * X_EVENTS),
+                         "note": "the 2 x 17 MB of Boltzmann weights of a 128^3 lattice are L2-resident (ncu: L2 hit 99.9 %, "
+                                 "DRAM ~1.5 B/event), so the algorithmic-bytes fraction is not an HBM utilisation; the kernel is "
+                                 "bound by the L1 data pipe (75 %) and instruction issue (profiles/r01f_*)"},
             "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
 
 

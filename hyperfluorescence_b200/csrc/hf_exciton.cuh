@@ -131,28 +131,37 @@ __global__ void hfx_spawn_kernel(const HfxParams P) {
     atomicAdd(P.totals + (local / P.traj_per_real) * HFX_T_N + HFX_T_GENERATED, 1ull);
 }
 
-struct __align__(16) HfxRec {         // phase A's view of one exciton (written by its lane, read by the whole warp)
-    const double *wp;                 // &w[site] in the exciton's spin manifold (realisation and halo included)
-    double inv_wi;                    // 1 / w[site]
-    int32_t site;                     // packed x, y, z
-    int32_t meta;                     // bit 0: singlet; bits 1-2: donor species; bit 3: no periodic wrap within the cutoff
-    double onsite[3];                 // channels M, M+1, M+2
-    double pad;
-};
-
+// Per-warp shared memory (one block of 32 trajectories), struct-of-arrays so that lane e writes and the
+// warp broadcasts without bank conflicts:
+//   L[32][33] f64 prefix sums | wp[32] u64 | inv[32] f64 | onsite[3][32] f64 | sm[32] int2 (site, meta) |
+//   tallies[HFX_T_N][32] u32 | nz[32] u32
 #define HFX_L_STRIDE 33               // doubles per exciton row of prefix sums (odd: conflict-free column reads)
 #define HFX_N_K 36                    // kf[9] kd[9] k_isc[3] k_risc[3] k_rad[6] k_nonrad[6]
+#define HFX_W_L 0
+#define HFX_W_WP (8 * 32 * HFX_L_STRIDE)
+#define HFX_W_INV (HFX_W_WP + 8 * 32)
+#define HFX_W_ON (HFX_W_INV + 8 * 32)
+#define HFX_W_SM (HFX_W_ON + 8 * 96)
+#define HFX_W_CNT (HFX_W_SM + 8 * 32)
+#define HFX_W_NZ (HFX_W_CNT + 4 * 32 * HFX_T_N)
+#define HFX_W_BYTES (HFX_W_NZ + 4 * 32)
 
 __host__ __device__ inline size_t hfx_smem_bytes(int M, int warps) {
-    // g6, gd, rate constants (f64) | per-warp prefix sums (f64) | per-warp exciton records | lin, off (i32) |
-    // per-warp tallies [HFX_T_N][32] (u32) | per-warp non-zero masks (u32)
-    return 8 * (2 * (size_t)M + HFX_N_K + (size_t)warps * 32 * HFX_L_STRIDE) + sizeof(HfxRec) * 32 * (size_t)warps +
-           4 * (2 * (size_t)M + (size_t)warps * (HFX_T_N * 32 + 32));
+    // CTA-wide tables: g6, gd, rate constants (f64), lin, off (i32, M rounded up to even) | per-warp blocks
+    return 8 * (2 * (size_t)M + HFX_N_K) + 4 * 2 * (size_t)((M + 1) & ~1) + (size_t)warps * HFX_W_BYTES;
 }
+
+// Keep a value in a register: under register pressure nvcc otherwise rematerialises shared-memory
+// bases (S2R + LEA chains) inside the event loop, which costs more issue slots than the register.
+#if defined(__CUDA_ARCH__)
+#define HFX_PIN32(x) asm volatile("" : "+r"(x))
+#else
+#define HFX_PIN32(x) (void)0
+#endif
 
 __device__ __forceinline__ double hfx_min1(double v) { return v < 1.0 ? v : 1.0; }
 
-// Offset (in sites) from an exciton on (px, py, pz) to the neighbour of packed offset o: periodic in
+// Offset (in sites) from an exciton on (px, py, .) to the neighbour of packed offset o: periodic in
 // x and y, straight through in z (the halo absorbs z outside [0, Z)).
 __device__ __forceinline__ int hfx_delta(int o, int px, int py, int dim_x, int dim_y, int plane) {
     const int dx = (o & 255) - 128, dy = ((o >> 8) & 255) - 128, dz = ((o >> 16) & 255) - 128;
@@ -167,51 +176,63 @@ __device__ __forceinline__ double hfx_rate(const double *pref, double g, double 
     return __dmul_rn(__dmul_rn(pref[hfx_tag_of(wj)], g), hfx_min1(__dmul_rn(wj, inv_wi)));
 }
 
+// inclusive Kogge-Stone scan over the 32 lane sums
+__device__ __forceinline__ double hfx_scan(double S, int lane) {
+    double L = S;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double up = __shfl_up_sync(HF_FULL, L, off);
+        if (lane >= off) L = __dadd_rn(L, up);
+    }
+    return L;
+}
+
 template <int KF>
 struct HfxLaneTables {                // this lane's channels of the KF full slots, in registers
-    int32_t lin[KF > 0 ? KF : 1];
-    double g6[KF > 0 ? KF : 1], gd[KF > 0 ? KF : 1];
+    int32_t lin[KF > 0 ? KF : 1];     // linear site offsets (valid when no periodic wrap is needed)
+    double gd[KF > 0 ? KF : 1];       // Dexter distance factors: triplets are the bulk of the events (they live 10^3 x longer)
 };
 
-// Phase A, loads: the weights of exciton `rec`'s neighbours on this lane's channels of the full slots.
+// Phase A, loads: the weights of the neighbours on this lane's channels of the full slots.
 template <int KF>
-__device__ __forceinline__ void hfx_gather(const HfxRec *rec, const HfxLaneTables<KF> &T, const int32_t *s_off_lane,
-                                           int dim_x, int dim_y, int plane, double (&buf)[KF > 0 ? KF : 1]) {
-    const double *wp = rec->wp;
-    if (rec->meta & 8) {
+__device__ __forceinline__ void hfx_gather(const double *wp, int site, int meta, const HfxLaneTables<KF> &T,
+                                           const int32_t *s_off_lane, int dim_x, int dim_y, int plane,
+                                           double (&buf)[KF > 0 ? KF : 1]) {
+    if (meta & 8) {
 #pragma unroll
         for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + T.lin[k]);
     } else {
-        const int site = rec->site, px = hf_px(site), py = hf_py(site);
+        const int px = hf_px(site), py = hf_py(site);
 #pragma unroll
         for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + hfx_delta(s_off_lane[32 * k], px, py, dim_x, dim_y, plane));
     }
 }
 
-template <int KF, bool kSinglet>
-__device__ __forceinline__ double hfx_lane_sum(const HfxLaneTables<KF> &T, const double *pref, double inv_wi,
-                                               const double (&buf)[KF > 0 ? KF : 1]) {
-    double S = 0.0;
-#pragma unroll
-    for (int k = 0; k < KF; ++k) S = __dadd_rn(S, hfx_rate(pref, kSinglet ? T.g6[k] : T.gd[k], buf[k], inv_wi));
-    return S;
-}
-
-// KF > 0: M / 32 == KF full slots with register-resident tables and prefetch; KF == 0: any M, tables in shared memory.
-template <int kWarps, int KF, int kMinBlocks>
+// KF > 0: M = 32 * KF + kTail neighbours, known at compile time: register-resident tables, prefetched
+// gathers (kRegG: the Dexter factors too, else they are read from shared memory).  KF == 0: any M (P.M),
+// tables in shared memory.
+template <int kWarps, int KF, int kTail, int kMinBlocks, bool kRegG>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const HfxParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = P.M, K = (int)(hfx_padded_channels(M) >> 5), Kfull = M >> 5;
+    const int M = KF > 0 ? 32 * KF + kTail : P.M;
+    const int K = (M + 3 + 31) >> 5;
+    constexpr int KB = KF > 0 ? KF : 1;
     double *s_g6 = reinterpret_cast<double *>(hf_smem);
     double *s_gd = s_g6 + M;
     double *s_k = s_gd + M;
-    double *s_L = s_k + HFX_N_K + (size_t)warp * (32 * HFX_L_STRIDE);
-    HfxRec *s_rec = reinterpret_cast<HfxRec *>(s_k + HFX_N_K + (size_t)kWarps * (32 * HFX_L_STRIDE)) + 32 * warp;
-    int32_t *s_lin = reinterpret_cast<int32_t *>(s_rec - 32 * warp + 32 * kWarps);
-    int32_t *s_off = s_lin + M;
-    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_off + M) + warp * (HFX_T_N * 32);
-    unsigned *s_nz = reinterpret_cast<unsigned *>(s_off + M) + kWarps * (HFX_T_N * 32) + warp * 32;
+    int32_t *s_lin = reinterpret_cast<int32_t *>(s_k + HFX_N_K);
+    int32_t *s_off = s_lin + ((M + 1) & ~1);
+    unsigned wofs = (unsigned)(8 * (2 * M + HFX_N_K) + 8 * ((M + 1) & ~1)) + (unsigned)warp * HFX_W_BYTES;
+    HFX_PIN32(wofs);
+    unsigned char *const wsm = hf_smem + wofs;                                  // this warp's block
+    double *const s_L = reinterpret_cast<double *>(wsm + HFX_W_L);
+    const double **const s_wp = reinterpret_cast<const double **>(wsm + HFX_W_WP);
+    double *const s_inv = reinterpret_cast<double *>(wsm + HFX_W_INV);
+    double *const s_on = reinterpret_cast<double *>(wsm + HFX_W_ON);
+    int2 *const s_sm = reinterpret_cast<int2 *>(wsm + HFX_W_SM);
+    unsigned *const s_cnt = reinterpret_cast<unsigned *>(wsm + HFX_W_CNT);
+    unsigned *const s_nz = reinterpret_cast<unsigned *>(wsm + HFX_W_NZ);
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = P.g6[m]; s_gd[m] = P.gd[m]; s_lin[m] = P.lin[m]; s_off[m] = P.offsets[m]; }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = P.kf[threadIdx.x]; s_k[9 + threadIdx.x] = P.kd[threadIdx.x]; }
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = P.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = P.k_risc[threadIdx.x]; }
@@ -220,8 +241,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
     const int plane = P.X * P.Y, dim_x = P.X, dim_y = P.Y;
     HfxLaneTables<KF> T;
 #pragma unroll
-    for (int k = 0; k < KF; ++k) { T.lin[k] = s_lin[32 * k + lane]; T.g6[k] = s_g6[32 * k + lane]; T.gd[k] = s_gd[32 * k + lane]; }
+    for (int k = 0; k < KF; ++k) { T.lin[k] = s_lin[32 * k + lane]; T.gd[k] = kRegG ? s_gd[32 * k + lane] : 0.0; }
     const int32_t *s_off_lane = s_off + lane;
+    const double *s_g6_lane = s_g6 + lane, *s_gd_lane = s_gd + lane;
 
     const int64_t n_blocks = (P.B + 31) >> 5;
     for (int64_t blk = (int64_t)blockIdx.x * kWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarps) {
@@ -233,91 +255,99 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
         const double *ws1 = P.ws1 + r * P.w_stride + P.w_halo, *wt1 = P.wt1 + r * P.w_stride + P.w_halo;
         int site = 0, spin = HFX_SINGLET;
         double time = 0.0, lifetime = 0.0;
-        uint64_t draws = 0, trace_at = 0;
-        bool traced = false;
-        if (active) {
-            site = P.site[local]; spin = P.spin[local]; time = P.time[local]; lifetime = P.lifetime[local]; draws = P.draws[local];
-            traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
-            if (traced) trace_at = P.trace_len[local - P.trace_first];
-        }
+        uint64_t draws = 0;
+        if (active) { site = P.site[local]; spin = P.spin[local]; time = P.time[local]; lifetime = P.lifetime[local]; draws = P.draws[local]; }
+        const bool traced = active && P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
 #pragma unroll
         for (int t = 0; t < HFX_T_N; ++t) s_cnt[t * 32 + lane] = 0;
 
         for (int64_t ev = 0; ev < P.n_events; ++ev) {
-            // ---- this lane's exciton: its record for phase A and its random numbers ----
-            const bool singlet = spin == HFX_SINGLET;
-            const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-            const int64_t i = (int64_t)pz * plane + py * dim_x + px;
-            const double *wp = (singlet ? ws1 : wt1) + i;
-            double inv_wi = 0.0, r_flip = 0.0, r_rad = 0.0, r_nonrad = 0.0, u_sel = 0.0, u_time = 0.0;
-            int a = 0;
-            const double *pref = s_k;
+            // ---- this lane's exciton: what phase A needs to know about it ----
             if (active) {
+                const bool singlet = spin == HFX_SINGLET;
+                const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+                const int64_t i = (int64_t)pz * plane + py * dim_x + px;
+                const double *wp = (singlet ? ws1 : wt1) + i;
                 const double wi = __ldg(wp);
-                a = hfx_tag_of(wi);
-                inv_wi = __ddiv_rn(1.0, wi);
-                pref = s_k + (singlet ? 0 : 9) + 3 * a;
-                r_flip = singlet ? s_k[18 + a] : __dmul_rn(s_k[21 + a], hfx_min1(__dmul_rn(__ldg(ws1 + i), inv_wi)));   // inv_wi = 1/wt1[i] for a triplet
-                r_rad = s_k[24 + 2 * a + (singlet ? 0 : 1)];
-                r_nonrad = s_k[30 + 2 * a + (singlet ? 0 : 1)];
+                const int a = hfx_tag_of(wi);
+                const double inv_wi = __ddiv_rn(1.0, wi);
                 const bool nowrap = px >= P.R && px < dim_x - P.R && py >= P.R && py < dim_y - P.R;
-                HfxRec rec;
-                rec.wp = wp; rec.inv_wi = inv_wi; rec.site = site; rec.meta = (singlet ? 1 : 0) | (a << 1) | (nowrap ? 8 : 0);
-                rec.onsite[0] = r_flip; rec.onsite[1] = r_rad; rec.onsite[2] = r_nonrad; rec.pad = 0.0;
-                s_rec[lane] = rec;
-                const HfPhiloxBlock rnd = hf_philox_block(P.k0, P.k1, HF_STREAM_XTRAJ, ident, draws >> 1);
-                draws += 2;
-                u_sel = hf_block_uniform(rnd, 0); u_time = hf_block_uniform(rnd, 1);
+                s_wp[lane] = wp;
+                s_inv[lane] = inv_wi;
+                s_sm[lane] = make_int2(site, (singlet ? 1 : 0) | (a << 1) | (nowrap ? 8 : 0));
+                s_on[lane] = singlet ? s_k[18 + a] : __dmul_rn(s_k[21 + a], hfx_min1(__dmul_rn(__ldg(ws1 + i), inv_wi)));   // inv_wi = 1/wt1[i] for a triplet
+                s_on[32 + lane] = s_k[24 + 2 * a + (singlet ? 0 : 1)];
+                s_on[64 + lane] = s_k[30 + 2 * a + (singlet ? 0 : 1)];
             }
             __syncwarp();
 
-            // ---- phase A: the warp evaluates one exciton at a time ----
-            double buf0[KF > 0 ? KF : 1], buf1[KF > 0 ? KF : 1];
-            if (KF > 0) hfx_gather<KF>(s_rec, T, s_off_lane, dim_x, dim_y, plane, buf0);
-            for (int e = 0; e < count; ++e) {
-                const HfxRec *rec = s_rec + e;
-                const int meta = rec->meta;
-                const double e_inv = rec->inv_wi;
-                const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);
-                double S;
-                if (KF > 0) {
-                    // the next exciton's gathers go out before this one's are consumed (two register buffers, swapped by parity)
-                    if (e & 1) {
-                        if (e + 1 < count) hfx_gather<KF>(rec + 1, T, s_off_lane, dim_x, dim_y, plane, buf0);
-                        S = (meta & 1) ? hfx_lane_sum<KF, true>(T, e_pref, e_inv, buf1) : hfx_lane_sum<KF, false>(T, e_pref, e_inv, buf1);
-                    } else {
-                        if (e + 1 < count) hfx_gather<KF>(rec + 1, T, s_off_lane, dim_x, dim_y, plane, buf1);
-                        S = (meta & 1) ? hfx_lane_sum<KF, true>(T, e_pref, e_inv, buf0) : hfx_lane_sum<KF, false>(T, e_pref, e_inv, buf0);
-                    }
-                } else {
-                    S = 0.0;
-                }
-                {   // slots not covered above: the remaining transfer channels and the three on-site ones
-                    const int site_e = rec->site, ex = hf_px(site_e), ey = hf_py(site_e);
-                    const double *g = (meta & 1) ? s_g6 : s_gd;
-                    for (int k = (KF > 0 ? KF : 0); k < K; ++k) {
-                        const int c = (k << 5) + lane;
-                        double rate = 0.0;
-                        if (c < M) rate = hfx_rate(e_pref, g[c], __ldg(rec->wp + hfx_delta(s_off[c], ex, ey, dim_x, dim_y, plane)), e_inv);
-                        else if (c < M + 3) rate = rec->onsite[c - M];
-                        S = __dadd_rn(S, rate);
-                    }
-                }
-                // one inclusive Kogge-Stone scan over the 32 lane sums
-                double L = S;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double up = __shfl_up_sync(HF_FULL, L, off);
-                    if (lane >= off) L = __dadd_rn(L, up);
-                }
-                s_L[e * HFX_L_STRIDE + lane] = L;
-                const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
-                if (lane == 0) s_nz[e] = nonzero;
+            // ---- phase A: the warp evaluates one exciton at a time; the scan of exciton e - 1 is issued
+            //      together with the rates of exciton e (independent chains), the gathers of e + 1 before both ----
+            double buf0[KB], buf1[KB];
+            double S_prev = 0.0;
+            if (KF > 0) { const int2 sm0 = s_sm[0]; hfx_gather<KF>(s_wp[0], sm0.x, sm0.y, T, s_off_lane, dim_x, dim_y, plane, buf0); }
+            // one exciton: `cur` holds its gathered weights, the next exciton's go into `nxt`
+#define HFX_PHASE_A(e, cur, nxt)                                                                                              \
+            {                                                                                                                 \
+                const int2 sm = s_sm[e];                                                                                      \
+                const int meta = sm.y;                                                                                        \
+                const double e_inv = s_inv[e];                                                                                \
+                const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);                                    \
+                if (KF > 0 && (e) + 1 < count) {                                                                              \
+                    const int2 smn = s_sm[(e) + 1];                                                                           \
+                    hfx_gather<KF>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt);                     \
+                }                                                                                                             \
+                double S = 0.0, L_prev;                                                                                       \
+                if (meta & 1) {                                                                                               \
+                    _Pragma("unroll") for (int k = 0; k < KF; ++k) S = __dadd_rn(S, hfx_rate(e_pref, s_g6_lane[32 * k], cur[k], e_inv)); \
+                    L_prev = hfx_scan(S_prev, lane);                                                                          \
+                } else {                                                                                                      \
+                    _Pragma("unroll") for (int k = 0; k < KF; ++k) S = __dadd_rn(S, hfx_rate(e_pref, kRegG ? T.gd[k] : s_gd_lane[32 * k], cur[k], e_inv)); \
+                    L_prev = hfx_scan(S_prev, lane);                                                                          \
+                }                                                                                                             \
+                if ((e) > 0) {                                                                                                \
+                    s_L[((e) - 1) * HFX_L_STRIDE + lane] = L_prev;                                                            \
+                    const unsigned nonzero = __ballot_sync(HF_FULL, S_prev > 0.0);                                            \
+                    if (lane == 0) s_nz[(e) - 1] = nonzero;                                                                   \
+                }                                                                                                             \
+                if (K > KF) {   /* slots not covered above: the remaining transfer channels and the three on-site ones */    \
+                    const double *g = (meta & 1) ? s_g6 : s_gd;                                                               \
+                    const double *e_wp = s_wp[e];                                                                             \
+                    const int ex = hf_px(sm.x), ey = hf_py(sm.x);                                                             \
+                    for (int k = KF; k < K; ++k) {                                                                            \
+                        const int c = (k << 5) + lane;                                                                        \
+                        double rate = 0.0;                                                                                    \
+                        if (c < M) rate = hfx_rate(e_pref, g[c], __ldg(e_wp + hfx_delta(s_off[c], ex, ey, dim_x, dim_y, plane)), e_inv); \
+                        else if (c < M + 3) rate = s_on[(c - M) * 32 + (e)];                                                  \
+                        S = __dadd_rn(S, rate);                                                                               \
+                    }                                                                                                         \
+                }                                                                                                             \
+                S_prev = S;                                                                                                   \
+            }
+            for (int e = 0; e < count; e += 2) {
+                HFX_PHASE_A(e, buf0, buf1)
+                if (e + 1 < count) HFX_PHASE_A(e + 1, buf1, buf0)
+            }
+#undef HFX_PHASE_A
+            {
+                const double L_last = hfx_scan(S_prev, lane);
+                s_L[(count - 1) * HFX_L_STRIDE + lane] = L_last;
+                const unsigned nonzero = __ballot_sync(HF_FULL, S_prev > 0.0);
+                if (lane == 0) s_nz[count - 1] = nonzero;
             }
             __syncwarp();
 
             // ---- phase B: every lane selects and applies its own exciton's event ----
             if (active) {
+                const bool singlet = spin == HFX_SINGLET;
+                const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+                const double *wp = s_wp[lane];
+                const double inv_wi = s_inv[lane];
+                const int a = (s_sm[lane].y >> 1) & 3;
+                const double *pref = s_k + (singlet ? 0 : 9) + 3 * a;
+                const HfPhiloxBlock rnd = hf_philox_block(P.k0, P.k1, HF_STREAM_XTRAJ, ident, draws >> 1);
+                draws += 2;
+                const double u_sel = hf_block_uniform(rnd, 0), u_time = hf_block_uniform(rnd, 1);
                 const double *row = s_L + lane * HFX_L_STRIDE;
                 const double R = row[31];
                 const double target = __dmul_rn(u_sel, R);
@@ -332,9 +362,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                     const int c = (k << 5) + lstar;
                     double rate = 0.0;
                     if (c < M) rate = hfx_rate(pref, g[c], __ldg(wp + hfx_delta(s_off[c], px, py, dim_x, dim_y, plane)), inv_wi);
-                    else if (c == M) rate = r_flip;
-                    else if (c == M + 1) rate = r_rad;
-                    else if (c == M + 2) rate = r_nonrad;
+                    else if (c < M + 3) rate = s_on[(c - M) * 32 + lane];
                     acc = __dadd_rn(acc, rate);
                     if (rate > 0.0) last_live = k;
                     if (slot < 0 && acc > target) slot = k;
@@ -369,23 +397,21 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                     s_cnt[HFX_T_GENERATED * 32 + lane] += 1;
                 }
                 if (traced) {
-                    if (trace_at < (uint64_t)P.trace_cap) {
+                    const uint64_t at = P.trace_len[local - P.trace_first];
+                    if (at < (uint64_t)P.trace_cap) {
                         HfTraceRec rec;
-                        rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
+                        rec.initial = (int32_t)hf_site(P.X, P.Y, site); rec.final_ = (int32_t)hf_site(P.X, P.Y, fin);
                         rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
                         rec.pad[0] = (uint8_t)spin; rec.pad[1] = 0;     // spin of the trajectory's exciton after the step
                         rec.spins = (uint32_t)chosen; rec.draws = draws;
-                        P.trace[(local - P.trace_first) * P.trace_cap + trace_at] = rec;
+                        P.trace[(local - P.trace_first) * P.trace_cap + at] = rec;
                     }
-                    trace_at += 1;
+                    P.trace_len[local - P.trace_first] = at + 1;
                 }
                 site = site_after;
             }
         }
-        if (active) {
-            P.site[local] = site; P.spin[local] = spin; P.time[local] = time; P.lifetime[local] = lifetime; P.draws[local] = draws;
-            if (traced) P.trace_len[local - P.trace_first] = trace_at;
-        }
+        if (active) { P.site[local] = site; P.spin[local] = spin; P.time[local] = time; P.lifetime[local] = lifetime; P.draws[local] = draws; }
         // tallies: one atomic per counter and warp when the 32 trajectories share a realisation
         const int64_t r_first = __shfl_sync(HF_FULL, r, 0), r_last = __shfl_sync(HF_FULL, r, 31);
         const bool uniform = r_first == r_last;

@@ -193,11 +193,11 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 typedef void (*hfx_kernel_fn)(const HfxParams);
 constexpr int kXWarps = 8;
 static hfx_kernel_fn x_pick_kernel(int M) {
-    switch (M >> 5) {
-        case 3: return hfx_run_kernel<kXWarps, 3, 2>;
-        case 8: return hfx_run_kernel<kXWarps, 8, 2>;
-        case 16: return hfx_run_kernel<kXWarps, 16, 1>;
-        default: return hfx_run_kernel<kXWarps, 0, 2>;
+    switch (M) {
+        case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true>;                         // cutoff 3
+        case 256: return hfx_run_kernel<kXWarps, 8, 0, 2, true>;                          // cutoff 4
+        case 514: return hfx_run_kernel<kXWarps, 16, 2, 1, true>;                         // cutoff 5
+        default: return hfx_run_kernel<kXWarps, 0, 0, 2, false>;
     }
 }
 

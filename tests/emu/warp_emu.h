@@ -30,6 +30,8 @@
 #define __restrict__
 
 struct emu_dim3 { unsigned x, y, z; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 v = {x, y}; return v; }
 static emu_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDim = {32, 1, 1}, gridDim = {1, 1, 1};
 alignas(16) unsigned char hf_smem[1 << 20];
 
