@@ -65,6 +65,9 @@ HF_XT_N = 16
 XT_NAMES = ("generated", "events", "forster", "dexter", "isc", "risc", "rad_host", "rad_tadf", "rad_fluo",
             "nonrad_s_host", "nonrad_s_tadf", "nonrad_s_fluo", "nonrad_t_host", "nonrad_t_tadf", "nonrad_t_fluo")
 
+HF_XDT_N = 24
+XDT_NAMES = XT_NAMES + ("_15", "ann_ss", "ann_st", "ann_ts", "ann_tt", "tta_up", "_21", "_22", "_23")
+
 INFO_DTYPE = np.dtype([(n, "<i4") for n in ("n_electrons", "n_holes", "n_eflags", "n_hflags", "n_move_e", "n_move_h",
                                              "special_kind", "special_particule", "special_site", "exciton_state",
                                              "status", "cache_count")] +
@@ -111,6 +114,13 @@ SIGNATURES = {
     "hf_x_download_weights": (C.c_int, [P, I32, P, P]),
     "hf_x_read_state": (C.c_int, [P, I64, I64, P, P, P, P, P]),
     "hf_x_read_trace": (C.c_int, [P, I64, P, C.POINTER(I64)]),
+    "hf_xd_configure": (C.c_int, [P, I32, P, F64]),
+    "hf_xd_spawn": (C.c_int, [P]),
+    "hf_xd_run": (C.c_int, [P, I64]),
+    "hf_xd_read_tallies": (C.c_int, [P, P]),
+    "hf_xd_read_realisation_tallies": (C.c_int, [P, P]),
+    "hf_xd_read_device": (C.c_int, [P, I64, P, P, P, P, P]),
+    "hf_xd_read_occupancy": (C.c_int, [P, I64, P]),
 }
 
 _lib = None
@@ -344,6 +354,40 @@ class Sim:
         n = I64(out.size)
         check(load().hf_x_read_trace(self._h, int(trajectory), ptr(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+    # -- high-density exciton devices (Path XD) ---------------------------------------------------
+    def xd_configure(self, n_excitons, annihilation=((1.0, 1.0), (1.0, 1.0)), p_tta=0.25):
+        ann = np.ascontiguousarray(annihilation, np.float64).reshape(4)
+        self.xd_n = int(n_excitons)
+        check(load().hf_xd_configure(self._h, self.xd_n, ptr(ann), float(p_tta)))
+
+    def xd_spawn(self):
+        check(load().hf_xd_spawn(self._h))
+
+    def xd_run(self, n_events):
+        check(load().hf_xd_run(self._h, int(n_events)))
+
+    def xd_tallies(self):
+        out = np.zeros(HF_XDT_N, np.uint64)
+        check(load().hf_xd_read_tallies(self._h, ptr(out)))
+        return {k: int(out[i]) for i, k in enumerate(XDT_NAMES) if not k.startswith("_")}
+
+    def xd_realisation_tallies(self):
+        out = np.zeros((self.n_realisations, HF_XDT_N), np.uint64)
+        check(load().hf_xd_read_realisation_tallies(self._h, ptr(out)))
+        return {k: out[:, i].astype(np.int64) for i, k in enumerate(XDT_NAMES) if not k.startswith("_")}
+
+    def xd_device(self, device=0):
+        n = self.xd_n
+        site, spin, tot, birth, scal = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n), np.zeros(n), np.zeros(3)
+        check(load().hf_xd_read_device(self._h, int(device), ptr(site), ptr(spin), ptr(tot), ptr(birth), ptr(scal)))
+        return dict(site=site, spin=spin, total_rate=tot, birth=birth, time=scal[0], lifetime_sum=scal[1], draws=int(scal[2]))
+
+    def xd_occupancy(self, device=0):
+        codes = np.zeros(self.N, np.uint8)
+        check(load().hf_xd_read_occupancy(self._h, int(device), ptr(codes)))
+        return codes
 
 
 def x_default_params() -> HfXParams:

@@ -1,0 +1,346 @@
+// High-density exciton devices ("Path XD", SURVEY.md §8 f4, BASELINE configs[3]): n interacting excitons
+// per device, a 2-bit-per-site occupancy mask, annihilation on occupied acceptors, one warp per device.
+//
+// PARITY UNPINNED: the reference has neither exciton dynamics nor annihilation; its only occupancy
+// rule is same-type charge blocking (reseau.py:385, 394).  The model is specified by
+// oracle/exciton_dense_oracle.c (read its header first: channels, canonical sums, selection rule,
+// replacement rule); this kernel is tested against it bit for bit.
+//
+// Device state lives in global memory between launches and in the warp's shared memory during one:
+//   pos[n_pad]   u32  packed x | y << 10 | z << 20 | spin << 30 (spin code 1 singlet / 3 triplet, molecule.py:16-21)
+//   T[n_pad]     f64  cached total rate of every exciton (0 for the padding slots)
+//   birth[n_pad] f64  device clock when the exciton was created
+//   occ[]        u32  16 sites per word, 2 bits per site, with the same R-plane halo as the weights
+// Per event the warp (1) scans the cached totals to pick an exciton, (2) evaluates that exciton's
+// M + 3 channels (lane = channel % 32; each lane also fetches the acceptor's occupancy code) and scans
+// them to pick the channel, (3) applies it — lane 0 edits the occupancy words — and (4) re-evaluates the
+// totals of the excitons that can see a changed site (at most three sites change per event).
+#pragma once
+#include "hf_exciton.cuh"
+
+#define HF_STREAM_XDENSE 5u
+#define HFXD_K_ANNIHILATION 6          // the `unbound` slot of event.py:49
+#define HFXD_T_ANN 16                  // + 2 * donor spin index + acceptor spin index
+#define HFXD_T_TTA_UP 20
+#define HFXD_T_N 24
+#define HFXD_MAX_EXCITONS 1024
+
+struct HfxdParams {
+    HfxParams X;                       // lattice, tables, rate constants, Philox key; B = devices, first_traj = first device id
+    int32_t n, n_pad;                  // excitons per device, rounded up to 32
+    double ann[4];                     // [donor spin index][acceptor spin index]
+    double p_tta, rc2;                 // triplet-triplet promotion probability; cutoff^2
+    uint32_t *pos;                     // [B][n_pad]
+    double *T, *birth;                 // [B][n_pad]
+    uint32_t *occ;                     // [B][occ_words]
+    int64_t occ_words;
+    double *time, *life;               // [B] device clock, summed lifetimes of the lost excitons
+    uint64_t *draws;                   // [B]
+    unsigned long long *totals;        // [n_real][HFXD_T_N]
+    int32_t fill;                      // 1: (re)fill the devices before running (hf_xd_spawn)
+};
+
+__host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
+    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T, birth (f64) | rates (f64) | pos (u32) | counters (u32)
+    return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 2 * (size_t)((M + 1) & ~1) +
+           (size_t)warps * (8 * (2 * (size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 32));
+}
+
+__device__ __forceinline__ int hfxd_occ_get(const uint32_t *occ, int64_t idx) {
+    return (int)((occ[idx >> 4] >> (2 * (int)(idx & 15))) & 3u);
+}
+__device__ __forceinline__ void hfxd_occ_set(uint32_t *occ, int64_t idx, int code) {
+    const int sh = 2 * (int)(idx & 15);
+    occ[idx >> 4] = (occ[idx >> 4] & ~(3u << sh)) | ((uint32_t)code << sh);
+}
+
+struct HfxdWarp {                      // one warp's view of its device
+    const HfxdParams *P;
+    const double *s_g6, *s_gd, *s_k, *s_ann;
+    const int32_t *s_lin, *s_off;
+    double *s_T, *s_birth, *s_rates;
+    uint32_t *s_pos, *s_cnt;
+    const double *ws1, *wt1;           // this device's realisation, site 0
+    uint32_t *occ;                     // this device's mask (index = site + halo)
+    int lane, K, M;
+};
+
+// Lane sums of the channel rates of an exciton (packed site + spin); kStore: also leave the rates in s_rates.
+template <bool kStore>
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps) {
+    const HfxParams &X = W.P->X;
+    const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
+    const bool singlet = spin == HFX_SINGLET;
+    const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+    const int plane = X.X * X.Y;
+    const int64_t i = (int64_t)pz * plane + py * X.X + px;
+    const double *w = (singlet ? W.ws1 : W.wt1) + i;
+    const double wi = __ldg(w);
+    const int a = hfx_tag_of(wi);
+    const double inv_wi = __ddiv_rn(1.0, wi);
+    const double *pref = W.s_k + (singlet ? 0 : 9) + 3 * a;
+    const double *g = singlet ? W.s_g6 : W.s_gd;
+    const double *ann = W.s_ann + (singlet ? 0 : 2);
+    const bool nowrap = px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
+    const int64_t oi = i + X.w_halo;
+    double S = 0.0;
+    for (int k = 0; k < W.K; ++k) {
+        const int c = (k << 5) + W.lane;
+        double rate = 0.0;
+        if (c < W.M) {
+            const int delta = nowrap ? W.s_lin[c] : hfx_delta(W.s_off[c], px, py, X.X, X.Y, plane);
+            const double wj = __ldg(w + delta);
+            rate = hfx_rate(pref, g[c], wj, inv_wi);
+            const int o = hfxd_occ_get(W.occ, oi + delta);
+            if (o) rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]);
+        } else if (c == W.M) {
+            rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
+        } else if (c == W.M + 1) {
+            rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
+        } else if (c == W.M + 2) {
+            rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+        }
+        if (kStore) W.s_rates[c] = rate;
+        S = __dadd_rn(S, rate);
+    }
+    return S;
+}
+
+// The canonical pick (oracle: pick()): v[n_slots][32] in shared memory, S = this lane's sum, L = its scan.
+// Returns the chosen index (slot * 32 + lane) and the running sum before it; warp-uniform.
+__device__ __forceinline__ int hfxd_pick(const double *v, int n_slots, double S, double L, double target, int lane, double &base) {
+    const unsigned over = __ballot_sync(HF_FULL, L > target);
+    const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
+    const int lstar = over ? __ffs(over) - 1 : (nonzero ? 31 - __clz(nonzero) : 0);
+    const double below = __shfl_sync(HF_FULL, L, (lstar + 31) & 31);
+    double acc = lstar > 0 ? below : 0.0, b_slot = acc, b_last = acc;
+    int slot = -1, last = -1;
+    for (int q = 0; q < n_slots; ++q) {
+        const double r = v[(q << 5) + lstar], before = acc;
+        acc = __dadd_rn(acc, r);
+        if (r > 0.0) { last = q; b_last = before; }
+        if (slot < 0 && acc > target) { slot = q; b_slot = before; }
+    }
+    if (slot < 0) { slot = last < 0 ? n_slots - 1 : last; b_slot = b_last; }
+    base = b_slot;
+    return (slot << 5) + lstar;
+}
+
+// A new exciton for slot k: the first empty interior site along the device's stream (oracle: replace()).
+__device__ __forceinline__ uint32_t hfxd_replace(const HfxdWarp &W, uint32_t ident, uint64_t &draws) {
+    const HfxParams &X = W.P->X;
+    const int64_t n_interior = (int64_t)X.X * X.Y * (X.Z - 2);
+    for (;;) {
+        const HfPhiloxBlock blk = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+        draws += 2;
+        const double ua = hf_block_uniform(blk, 0), ub = hf_block_uniform(blk, 1);
+        int64_t q = (int64_t)floor(ua * (double)n_interior);
+        if (q >= n_interior) q = n_interior - 1;
+        const int x = (int)(q % X.X), y = (int)((q / X.X) % X.Y), z = 1 + (int)(q / ((int64_t)X.X * X.Y));
+        const int64_t oi = ((int64_t)z * X.Y + y) * X.X + x + X.w_halo;
+        if (hfxd_occ_get(W.occ, oi)) continue;                                   // same word for every lane: uniform
+        const int spin = ub < X.singlet_fraction ? HFX_SINGLET : HFX_TRIPLET;
+        __syncwarp();
+        if (W.lane == 0) hfxd_occ_set(W.occ, oi, spin);
+        __syncwarp();
+        return (uint32_t)hf_pack(x, y, z) | ((uint32_t)spin << 30);
+    }
+}
+
+// does an exciton on packed site p see packed site c inside its cutoff sphere, or sit on it? (oracle: sees())
+__device__ __forceinline__ bool hfxd_sees(const HfxdParams &P, int p, int c) {
+    int dx = hf_px(c) - hf_px(p), dy = hf_py(c) - hf_py(p);
+    const int dz = hf_pz(c) - hf_pz(p);
+    const int hx = P.X.X / 2, hy = P.X.Y / 2;
+    if (dx > hx) dx -= P.X.X; else if (dx < -hx) dx += P.X.X;
+    if (dy > hy) dy -= P.X.Y; else if (dy < -hy) dy += P.X.Y;
+    if ((P.X.X & 1) == 0 && (dx == hx || dx == -hx)) return false;
+    if ((P.X.Y & 1) == 0 && (dy == hy || dy == -hy)) return false;
+    return (double)(dx * dx + dy * dy + dz * dz) <= P.rc2;
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams P) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const HfxParams &X = P.X;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int M = X.M, padded = (int)hfx_padded_channels(M), K = padded >> 5, n_pad = P.n_pad, n_slots = n_pad >> 5;
+    double *s_g6 = reinterpret_cast<double *>(hf_smem);
+    double *s_gd = s_g6 + M;
+    double *s_k = s_gd + M;
+    double *s_ann = s_k + HFX_N_K;
+    int32_t *s_lin = reinterpret_cast<int32_t *>(s_ann + 4);
+    int32_t *s_off = s_lin + ((M + 1) & ~1);
+    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 1) & ~1)) +
+                         (size_t)warp * (8 * (2 * (size_t)n_pad + padded) + 4 * ((size_t)n_pad + 32));
+    HfxdWarp W;
+    W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_lin = s_lin; W.s_off = s_off;
+    W.s_T = reinterpret_cast<double *>(wsm); W.s_birth = W.s_T + n_pad; W.s_rates = W.s_birth + n_pad;
+    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad;
+    W.lane = lane; W.K = K; W.M = M;
+    for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
+    if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
+    if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = X.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = X.k_risc[threadIdx.x]; }
+    if (threadIdx.x < 6) { s_k[24 + threadIdx.x] = X.k_rad[threadIdx.x]; s_k[30 + threadIdx.x] = X.k_nonrad[threadIdx.x]; }
+    if (threadIdx.x < 4) s_ann[threadIdx.x] = P.ann[threadIdx.x];
+    __syncthreads();
+
+    for (int64_t dev = (int64_t)blockIdx.x * kWarps + warp; dev < X.B; dev += (int64_t)gridDim.x * kWarps) {
+        const uint32_t ident = X.first_traj + (uint32_t)dev;
+        const int64_t r = dev / X.traj_per_real;
+        W.ws1 = X.ws1 + r * X.w_stride + X.w_halo; W.wt1 = X.wt1 + r * X.w_stride + X.w_halo;
+        W.occ = P.occ + dev * P.occ_words;
+        uint32_t *g_pos = P.pos + dev * n_pad;
+        double *g_T = P.T + dev * n_pad, *g_birth = P.birth + dev * n_pad;
+        double time, life;
+        uint64_t draws;
+        if (lane < 32) W.s_cnt[lane] = 0;
+        if (P.fill) {
+            // hf_xd_spawn: an empty mask (memset by the host), slots filled in order, then every total
+            time = 0.0; life = 0.0; draws = 0;
+            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = 0; W.s_T[q] = 0.0; W.s_birth[q] = 0.0; }
+            __syncwarp();
+            for (int k = 0; k < P.n; ++k) {
+                const uint32_t ps = hfxd_replace(W, ident, draws);
+                if (lane == 0) { W.s_pos[k] = ps; W.s_cnt[HFX_T_GENERATED] += 1; }
+            }
+            __syncwarp();
+            for (int k = 0; k < P.n; ++k) {
+                const double S = hfxd_lane_sum<false>(W, W.s_pos[k]);
+                const double tot = __shfl_sync(HF_FULL, hfx_scan(S, lane), 31);
+                if (lane == 0) W.s_T[k] = tot;
+            }
+        } else {
+            time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
+            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; W.s_birth[q] = g_birth[q]; }
+        }
+        __syncwarp();
+        const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
+        uint64_t trace_at = traced ? X.trace_len[dev - X.trace_first] : 0;
+
+        for (int64_t ev = 0; ev < X.n_events; ++ev) {
+            // (1) the exciton: canonical scan over the cached totals
+            double A = 0.0;
+            for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
+            const double G = hfx_scan(A, lane);
+            const double R = __shfl_sync(HF_FULL, G, 31);
+            const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+            draws += 2;
+            const double u_sel = hf_block_uniform(rnd, 0), u_time = hf_block_uniform(rnd, 1);
+            const double target = __dmul_rn(u_sel, R);
+            double base;
+            const int kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
+            // (2) its channel
+            const uint32_t ps = W.s_pos[kx];
+            const double S = hfxd_lane_sum<true>(W, ps);
+            const double L = hfx_scan(S, lane);
+            __syncwarp();
+            double base2;
+            const int chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
+            const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
+            time = __dadd_rn(time, dt);
+            // (3) apply
+            const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
+            const bool singlet = spin == HFX_SINGLET;
+            const int sidx = singlet ? 0 : 1;
+            const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+            const int64_t i = hf_site(X.X, X.Y, site);
+            const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
+            int changed[3], n_changed = 1, kind, tally, fin = site;
+            changed[0] = site; changed[1] = site; changed[2] = site;
+            bool lost = false;
+            uint32_t ps_after = ps;
+            if (chosen < M) {
+                const int o = W.s_off[chosen];
+                int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+                if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+                fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
+                changed[n_changed++] = fin;
+                const int64_t oj = hf_site(X.X, X.Y, fin) + X.w_halo;
+                const int occ_j = hfxd_occ_get(W.occ, oj);
+                __syncwarp();
+                if (occ_j == 0) {
+                    if (lane == 0) { hfxd_occ_set(W.occ, i + X.w_halo, 0); hfxd_occ_set(W.occ, oj, spin); }
+                    ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
+                    kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
+                    tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+                } else {
+                    const int oidx = occ_j == HFX_SINGLET ? 0 : 1;
+                    kind = HFXD_K_ANNIHILATION;
+                    tally = HFXD_T_ANN + 2 * sidx + oidx;
+                    if (sidx == 1 && oidx == 1) {                               // triplet on triplet: the survivor may be promoted
+                        const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+                        draws += 2;
+                        if (hf_block_uniform(b2, 0) < P.p_tta) {
+                            for (int q = lane; q < P.n; q += 32)
+                                if (q != kx && (int)(W.s_pos[q] & 0x3fffffffu) == fin) W.s_pos[q] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
+                            if (lane == 0) { hfxd_occ_set(W.occ, oj, HFX_SINGLET); W.s_cnt[HFXD_T_TTA_UP] += 1; }
+                        }
+                    }
+                    lost = true;
+                }
+            } else if (chosen == M) {
+                kind = HFX_K_ISC;                                               // molecule.py:299-307
+                tally = singlet ? HFX_T_ISC : HFX_T_RISC;
+                const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
+                ps_after = (uint32_t)site | ((uint32_t)flipped << 30);
+                if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, flipped);
+            } else {
+                kind = HFX_K_DECAY;
+                tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
+                lost = true;
+            }
+            if (lost) {
+                if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, 0);
+                life = __dadd_rn(life, __dsub_rn(time, W.s_birth[kx]));
+                __syncwarp();
+                ps_after = hfxd_replace(W, ident, draws);
+                changed[n_changed++] = (int)(ps_after & 0x3fffffffu);
+                if (lane == 0) { W.s_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
+            }
+            if (lane == 0) {
+                W.s_pos[kx] = ps_after;
+                W.s_cnt[HFX_T_EVENTS] += 1;
+                W.s_cnt[tally] += 1;
+                if (traced && trace_at < (uint64_t)X.trace_cap) {
+                    HfTraceRec rec;
+                    rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(X.X, X.Y, fin);
+                    rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
+                    rec.pad[0] = (uint8_t)(ps_after >> 30); rec.pad[1] = 0;
+                    rec.spins = (uint32_t)chosen | ((uint32_t)kx << 16); rec.draws = draws;
+                    X.trace[(dev - X.trace_first) * X.trace_cap + trace_at] = rec;
+                }
+            }
+            trace_at += 1;
+            __syncwarp();
+            // (4) refresh the cached totals of every exciton that sees a changed site
+            for (int q0 = 0; q0 < P.n; q0 += 32) {
+                const int q = q0 + lane;
+                bool dirty = false;
+                if (q < P.n) {
+                    const int p = (int)(W.s_pos[q] & 0x3fffffffu);
+                    dirty = q == kx;
+                    for (int c = 0; c < n_changed; ++c) dirty = dirty || hfxd_sees(P, p, changed[c]);
+                }
+                unsigned todo = __ballot_sync(HF_FULL, dirty);
+                while (todo) {
+                    const int b = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const double Sq = hfxd_lane_sum<false>(W, W.s_pos[q0 + b]);
+                    const double tot = __shfl_sync(HF_FULL, hfx_scan(Sq, lane), 31);
+                    if (lane == 0) W.s_T[q0 + b] = tot;
+                }
+            }
+            __syncwarp();
+        }
+        for (int q = lane; q < n_pad; q += 32) { g_pos[q] = W.s_pos[q]; g_T[q] = W.s_T[q]; g_birth[q] = W.s_birth[q]; }
+        if (lane == 0) {
+            P.time[dev] = time; P.life[dev] = life; P.draws[dev] = draws;
+            if (traced) X.trace_len[dev - X.trace_first] = trace_at;
+        }
+        __syncwarp();
+        if (lane < HFXD_T_N && W.s_cnt[lane]) atomicAdd(P.totals + r * HFXD_T_N + lane, (unsigned long long)W.s_cnt[lane]);
+        __syncwarp();
+    }
+}

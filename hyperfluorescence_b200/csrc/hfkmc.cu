@@ -15,6 +15,7 @@
 #include "hf_frm.cuh"
 #include "hf_frm_c1.cuh"
 #include "hf_exciton.cuh"
+#include "hf_exciton_dense.cuh"
 
 static_assert(sizeof(HfTraceRec) == sizeof(hf_event), "trace record must match hf_event");
 static_assert(sizeof(hf_event) == 32, "hf_event is 32 bytes");
@@ -78,6 +79,15 @@ struct hf_sim {
     unsigned long long *d_x_totals = nullptr;
     int x_warps = 8, x_grid = 1;
     size_t x_smem = 0;
+    // high-density exciton devices (hf_xd_*)
+    bool xd_configured = false, xd_spawned = false;
+    HfxdParams XD;
+    uint32_t *d_xd_pos = nullptr, *d_xd_occ = nullptr;
+    double *d_xd_T = nullptr, *d_xd_birth = nullptr, *d_xd_time = nullptr, *d_xd_life = nullptr;
+    uint64_t *d_xd_draws = nullptr;
+    unsigned long long *d_xd_totals = nullptr;
+    int xd_grid = 1;
+    size_t xd_smem = 0;
     // timing of hf_run launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -331,6 +341,8 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HF_OK;
@@ -892,6 +904,7 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if ((rc = x_configure_launch(s))) return rc;
     s->x_configured = true;
     s->x_spawned = false;
+    s->xd_configured = false; s->xd_spawned = false;      // the dense devices share these tables and weights
     return HF_OK;
 }
 
@@ -993,6 +1006,163 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
     if (lifetime_sum) HF_CUDA(cudaMemcpyAsync(lifetime_sum, s->d_x_life + first, 8 * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
     HF_CUDA(cudaStreamSynchronize(s->stream));
     if (site) for (int64_t i = 0; i < n; ++i) site[i] = unpack_site(s, packed[(size_t)i]);
+    return HF_OK;
+}
+
+// ---- high-density exciton devices (Path XD; model specified by oracle/exciton_dense_oracle.c) ------------
+
+constexpr int kXdWarps = 4;
+
+static void xd_free(hf_sim *s) {
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
+    s->d_xd_pos = nullptr; s->d_xd_occ = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_time = nullptr;
+    s->d_xd_life = nullptr; s->d_xd_draws = nullptr; s->d_xd_totals = nullptr;
+}
+
+int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, double p_tta) {
+    if (!s || !annihilation) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "hf_xd_configure before hf_x_configure");
+    if (n_excitons < 1 || n_excitons > HFXD_MAX_EXCITONS)
+        return fail(HF_ERR_BAD_ARG, "excitons per device must be in [1, %d]", HFXD_MAX_EXCITONS);
+    const int64_t n_interior = (int64_t)s->P.X * s->P.Y * (s->P.Z - 2);
+    if ((int64_t)n_excitons * 2 > n_interior) return fail(HF_ERR_BAD_ARG, "more excitons than half the interior sites");
+    if (!(p_tta >= 0.0 && p_tta <= 1.0)) return fail(HF_ERR_BAD_ARG, "p_tta must be a probability");
+    for (int k = 0; k < 4; ++k)
+        if (!(annihilation[k] >= 0.0)) return fail(HF_ERR_BAD_ARG, "annihilation factors must be >= 0");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    xd_free(s);
+    HfxdParams &D = s->XD;
+    memset(&D, 0, sizeof(D));
+    D.X = s->X;
+    D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
+    for (int k = 0; k < 4; ++k) D.ann[k] = annihilation[k];
+    D.p_tta = p_tta;
+    D.rc2 = s->x_params.cutoff * s->x_params.cutoff;
+    D.occ_words = (s->X.w_stride + 15) / 16;
+    const size_t B = (size_t)s->P.B, np = (size_t)D.n_pad;
+    if ((rc = dev_alloc(&s->d_xd_pos, B * np))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_T, B * np))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_birth, B * np))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_occ, B * (size_t)D.occ_words))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_time, B))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_life, B))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_draws, B))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_totals, (size_t)s->n_real * HFXD_T_N))) return rc;
+    D.pos = s->d_xd_pos; D.T = s->d_xd_T; D.birth = s->d_xd_birth; D.occ = s->d_xd_occ;
+    D.time = s->d_xd_time; D.life = s->d_xd_life; D.draws = s->d_xd_draws; D.totals = s->d_xd_totals;
+    const size_t smem = hfxd_smem_bytes(s->X.M, D.n_pad, kXdWarps);
+    if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "%d excitons per device need %zu B of shared memory", n_excitons, smem);
+    if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hfxd_run_kernel<kXdWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfxd_run_kernel<kXdWarps>, kXdWarps * 32, smem));
+    if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "dense exciton kernel does not fit an SM");
+    const int64_t need = ((int64_t)B + kXdWarps - 1) / kXdWarps, cap = (int64_t)s->sm_count * per_sm;
+    s->xd_smem = smem; s->xd_grid = (int)(need < cap ? need : cap);
+    if (s->xd_grid < 1) s->xd_grid = 1;
+    s->xd_configured = true; s->xd_spawned = false;
+    return HF_OK;
+}
+
+static int xd_launch(hf_sim *s, int64_t n_events, int fill) {
+    HfxdParams &D = s->XD;
+    D.fill = fill;
+    D.X.n_events = n_events;
+    D.X.trace = s->d_trace; D.X.trace_first = s->P.trace_first; D.X.trace_n = s->P.trace_n; D.X.trace_cap = s->P.trace_cap;
+    D.X.trace_len = s->d_x_trace_len;
+    if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
+    cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+    HF_CUDA(cudaEventRecord(e0, s->stream));
+    hfxd_run_kernel<kXdWarps><<<s->xd_grid, kXdWarps * 32, s->xd_smem, s->stream>>>(D);
+    HF_CUDA(cudaEventRecord(e1, s->stream));
+    if (!fill) s->timing.emplace_back(e0, e1);
+    else { s->event_pool.push_back(e0); s->event_pool.push_back(e1); }
+    HF_CUDA(cudaGetLastError());
+    return HF_OK;
+}
+
+int hf_xd_spawn(hf_sim *s) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->xd_configured) return fail(HF_ERR_STATE, "hf_xd_spawn before hf_xd_configure");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaMemsetAsync(s->d_xd_occ, 0, 4 * (size_t)s->P.B * (size_t)s->XD.occ_words, s->stream));
+    HF_CUDA(cudaMemsetAsync(s->d_xd_totals, 0, sizeof(unsigned long long) * (size_t)s->n_real * HFXD_T_N, s->stream));
+    if (s->d_x_trace_len) HF_CUDA(cudaMemsetAsync(s->d_x_trace_len, 0, sizeof(uint64_t) * (size_t)s->P.trace_n, s->stream));
+    if ((rc = xd_launch(s, 0, 1))) return rc;
+    s->xd_spawned = true;
+    return HF_OK;
+}
+
+int hf_xd_run(hf_sim *s, int64_t n_events) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->xd_spawned) return fail(HF_ERR_STATE, "hf_xd_run before hf_xd_spawn");
+    if (n_events < 0) return fail(HF_ERR_BAD_ARG, "n_events must be >= 0");
+    int rc = use_device(s);
+    if (rc) return rc;
+    return xd_launch(s, n_events, 0);
+}
+
+int hf_xd_read_realisation_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->xd_spawned) return fail(HF_ERR_STATE, "no dense exciton devices yet");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaMemcpyAsync(out, s->d_xd_totals, sizeof(uint64_t) * (size_t)s->n_real * HFXD_T_N, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    return HF_OK;
+}
+
+int hf_xd_read_tallies(hf_sim *s, uint64_t *out) {
+    if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
+    std::vector<uint64_t> all((size_t)s->n_real * HFXD_T_N);
+    int rc = hf_xd_read_realisation_tallies(s, all.data());
+    if (rc) return rc;
+    for (int k = 0; k < HFXD_T_N; ++k) out[k] = 0;
+    for (int r = 0; r < s->n_real; ++r)
+        for (int k = 0; k < HFXD_T_N; ++k) out[k] += all[(size_t)r * HFXD_T_N + k];
+    return HF_OK;
+}
+
+int hf_xd_read_device(hf_sim *s, int64_t device, int32_t *site, int32_t *spin, double *total_rate, double *birth, double *scalars) {
+    int rc = check_traj(s, device);
+    if (rc) return rc;
+    if (!s->xd_spawned) return fail(HF_ERR_STATE, "no dense exciton devices yet");
+    if ((rc = use_device(s))) return rc;
+    const size_t n = (size_t)s->XD.n, np = (size_t)s->XD.n_pad;
+    std::vector<uint32_t> pos(n);
+    HF_CUDA(cudaMemcpyAsync(pos.data(), s->d_xd_pos + (size_t)device * np, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (total_rate) HF_CUDA(cudaMemcpyAsync(total_rate, s->d_xd_T + (size_t)device * np, 8 * n, cudaMemcpyDeviceToHost, s->stream));
+    if (birth) HF_CUDA(cudaMemcpyAsync(birth, s->d_xd_birth + (size_t)device * np, 8 * n, cudaMemcpyDeviceToHost, s->stream));
+    uint64_t draws = 0;
+    double tl[2] = {0.0, 0.0};
+    HF_CUDA(cudaMemcpyAsync(&tl[0], s->d_xd_time + device, 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(&tl[1], s->d_xd_life + device, 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(&draws, s->d_xd_draws + device, 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t k = 0; k < n; ++k) {
+        if (site) site[k] = unpack_site(s, (int32_t)(pos[k] & 0x3fffffffu));
+        if (spin) spin[k] = (int32_t)(pos[k] >> 30);
+    }
+    if (scalars) { scalars[0] = tl[0]; scalars[1] = tl[1]; scalars[2] = (double)draws; }
+    return HF_OK;
+}
+
+int hf_xd_read_occupancy(hf_sim *s, int64_t device, uint8_t *codes) {
+    int rc = check_traj(s, device);
+    if (rc) return rc;
+    if (!codes) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->xd_spawned) return fail(HF_ERR_STATE, "no dense exciton devices yet");
+    if ((rc = use_device(s))) return rc;
+    std::vector<uint32_t> words((size_t)s->XD.occ_words);
+    HF_CUDA(cudaMemcpyAsync(words.data(), s->d_xd_occ + (size_t)device * (size_t)s->XD.occ_words, 4 * words.size(), cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < s->P.N; ++i) {
+        const int64_t idx = i + s->X.w_halo;
+        codes[i] = (uint8_t)((words[(size_t)(idx >> 4)] >> (2 * (int)(idx & 15))) & 3u);
+    }
     return HF_OK;
 }
 

@@ -76,3 +76,63 @@ class ExcitonEnsemble:
 
     def close(self):
         self._sim.close()
+
+
+class DenseExcitonEnsemble:
+    """``devices`` independent devices, each holding ``excitons_per_device`` INTERACTING excitons on one
+    of ``realisations`` lattices: a 2-bit-per-site occupancy mask, transfers towards occupied sites
+    are annihilation channels (``annihilation[donor spin][acceptor spin]`` scales their rate, 0 =
+    pure blocking; spin index 0 singlet, 1 triplet), a triplet hit by a triplet is promoted to a
+    singlet with probability ``p_tta``.  Lost excitons are replaced at once on a random empty
+    interior site, so the exciton density stays at excitons_per_device / sites.
+
+    BASELINE configs[3] ("high-density excitons with occupancy blocking and exciton-exciton
+    annihilation").  The reference has nothing of the kind — its only occupancy rule is same-type
+    charge blocking (``reseau.py:385, 394``) — so the model is this package's own (DESIGN.md §10;
+    specification: ``oracle/exciton_dense_oracle.c``)."""
+
+    def __init__(self, dimension, proportions=(0.84, 0.15, 0.01), devices=1, excitons_per_device=32, realisations=1,
+                 parameters=None, annihilation=((1.0, 1.0), (1.0, 1.0)), p_tta=0.25, seed=None, device=0,
+                 first_device=0, first_realisation=0):
+        if not isinstance(dimension, tuple) or len(dimension) != 3:
+            raise TypeError("dimension must be a 3-tuple")
+        if dimension[-1] < 3:
+            raise ValueError(f"Expected the last component of dimension to be > 2, got {dimension[-1]}.")
+        if not 1 <= excitons_per_device <= 1024 or 2 * excitons_per_device > dimension[0] * dimension[1] * (dimension[2] - 2):
+            raise ValueError("excitons_per_device must be in [1, 1024] and at most half the interior sites")
+        if sum(proportions) != 1.:                                          # quirk Q1, reseau.py:143-145
+            norm = sum(dimension)
+            proportions = tuple(d / norm for d in dimension)
+        self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        self.parameters = nat.x_params_from_dict(parameters or {})
+        self.excitons_per_device = int(excitons_per_device)
+        self._sim = nat.Sim(dimension, proportions, 0.1, 1, 1, devices, realisations, self.seed, first_device,
+                            first_realisation, device)
+        self._sim.generate_lattice()
+        self._sim.x_configure(self.parameters)
+        self._sim.xd_configure(self.excitons_per_device, annihilation, p_tta)
+        self._sim.xd_spawn()
+
+    def run(self, n_events: int) -> None:
+        """n_events KMC events per device."""
+        self._sim.xd_run(n_events)
+        self._sim.sync()
+
+    def tallies(self) -> dict:
+        return self._sim.xd_tallies()
+
+    def device(self, index=0) -> dict:
+        return self._sim.xd_device(index)
+
+    def summary(self) -> dict:
+        t = self.tallies()
+        rad = t["rad_host"] + t["rad_tadf"] + t["rad_fluo"]
+        ann = t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]
+        lost = rad + ann + sum(t[k] for k in t if k.startswith("nonrad_"))
+        frac = (lambda v: v / lost) if lost else (lambda v: 0.0)
+        return dict(excitons_lost=lost, annihilated=ann, annihilation_fraction=frac(ann), iqe=frac(rad),
+                    eqe=self.parameters.outcoupling * frac(rad), tta_up=t["tta_up"], events=t["events"],
+                    channels={k: frac(t[k]) for k in t if k.startswith(("rad_", "nonrad_", "ann_"))})
+
+    def close(self):
+        self._sim.close()

@@ -272,6 +272,41 @@ int hf_x_read_state(hf_sim *sim, int64_t first, int64_t n, int32_t *site, int32_
  * index, pad[0] = spin of the trajectory's exciton after the step (the new one after a decay). */
 int hf_x_read_trace(hf_sim *sim, int64_t trajectory, hf_event *out, int64_t *n);
 
+/* =====================================================================================================
+ * High-density exciton devices ("Path XD", BASELINE configs[3]: occupancy blocking and exciton-exciton
+ * annihilation).  The reference has NO implementation of this either (parity unpinned): its only
+ * occupancy rule is same-type charge blocking (reseau.py:385, 394).  The model is this library's
+ * own, specified by oracle/exciton_dense_oracle.c and DESIGN.md section 10.
+ * Every trajectory of the handle becomes a DEVICE holding n_excitons interacting excitons on its
+ * lattice realisation, with a 2-bit-per-site occupancy mask (0 empty, HF_X_SINGLET, HF_X_TRIPLET).
+ * A transfer towards an occupied site is an annihilation channel (rate x annihilation[donor spin
+ * index][acceptor spin index]; 0 = pure blocking): the donor is lost, a triplet acceptor hit by a
+ * triplet becomes a singlet with probability p_tta; lost excitons are replaced at once on a random
+ * empty interior site.  Needs hf_x_configure first (tables, rate constants, Boltzmann weights).
+ * ===================================================================================================== */
+enum {
+    HF_XDT_ANN_SS = 16, HF_XDT_ANN_ST = 17, HF_XDT_ANN_TS = 18, HF_XDT_ANN_TT = 19,   /* donor, acceptor */
+    HF_XDT_TTA_UP = 20,               /* triplet acceptors promoted to singlets                          */
+    HF_XDT_N = 24                     /* indices 0..14 as HF_XT_*                                         */
+};
+#define HF_EV_ANNIHILATION 6          /* reported in the `unbound` slot of event.py:49                   */
+#define HF_XD_MAX_EXCITONS 1024
+int hf_xd_configure(hf_sim *sim, int32_t n_excitons, const double *annihilation /* [2][2] */, double p_tta);
+/* Empty the masks and fill every device with n_excitons new excitons. */
+int hf_xd_spawn(hf_sim *sim);
+/* n_events rejection-free KMC events for every device (one event = one channel of one exciton). */
+int hf_xd_run(hf_sim *sim, int64_t n_events);
+int hf_xd_read_tallies(hf_sim *sim, uint64_t *out /* [HF_XDT_N] */);
+int hf_xd_read_realisation_tallies(hf_sim *sim, uint64_t *out /* [n_realisations][HF_XDT_N] */);
+/* One device: site / spin / cached total rate / birth time of its n_excitons slots; scalars[3] =
+ * device clock, summed lifetimes of the lost excitons, XDENSE draws consumed.  Any pointer may be NULL. */
+int hf_xd_read_device(hf_sim *sim, int64_t device, int32_t *site, int32_t *spin, double *total_rate, double *birth,
+                      double *scalars);
+/* codes[N]: the occupancy code of every site of one device. */
+int hf_xd_read_occupancy(hf_sim *sim, int64_t device, uint8_t *codes);
+/* Traces of dense devices are read with hf_x_read_trace: kind as there plus HF_EV_ANNIHILATION,
+ * spins = channel | exciton slot << 16, pad[0] = spin of that slot after the event. */
+
 #ifdef __cplusplus
 }
 #endif

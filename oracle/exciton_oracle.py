@@ -14,6 +14,10 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libexciton_oracle.so")
+DENSE_LIB_PATH = os.path.join(HERE, "libexciton_dense_oracle.so")
+XDT_NAMES = ("generated", "events", "forster", "dexter", "isc", "risc", "rad_host", "rad_tadf", "rad_fluo",
+             "nonrad_s_host", "nonrad_s_tadf", "nonrad_s_fluo", "nonrad_t_host", "nonrad_t_tadf", "nonrad_t_fluo", "_15",
+             "ann_ss", "ann_st", "ann_ts", "ann_tt", "tta_up", "_21", "_22", "_23")
 XT_NAMES = ("generated", "events", "forster", "dexter", "isc", "risc", "rad_host", "rad_tadf", "rad_fluo",
             "nonrad_s_host", "nonrad_s_tadf", "nonrad_s_fluo", "nonrad_t_host", "nonrad_t_tadf", "nonrad_t_fluo", "_pad")
 KT = 8.617333262 * 10.**(-5) * 300.
@@ -33,6 +37,20 @@ def lib():
     if _lib is None:
         _lib = C.CDLL(build())
     return _lib
+
+
+_dense = None
+
+
+def dense_lib():
+    global _dense
+    if _dense is None:
+        src = os.path.join(HERE, "exciton_dense_oracle.c")
+        if not os.path.exists(DENSE_LIB_PATH) or os.path.getmtime(DENSE_LIB_PATH) < os.path.getmtime(src):
+            subprocess.run(["make", "-C", HERE, "-B", "libexciton_dense_oracle.so"], check=True, capture_output=True)
+        _dense = C.CDLL(DENSE_LIB_PATH)
+        _dense.hfxd_run.restype = C.c_int64
+    return _dense
 
 
 def _p(a):
@@ -130,3 +148,38 @@ class ExcitonOracle:
         lib().hfx_run_batch(*self._model_args(), C.c_uint64(seed), C.c_int64(first), C.c_int64(n), C.c_int64(n_events),
                             C.c_int(n_threads), _p(tallies))
         return {k: int(v) for k, v in zip(XT_NAMES, tallies) if not k.startswith("_")}
+
+
+class DenseExcitonOracle(ExcitonOracle):
+    """The high-density model (oracle/exciton_dense_oracle.c): n interacting excitons per device."""
+
+    def __init__(self, dims, species, ws1, wt1, params, tab=None, annihilation=((1.0, 1.0), (1.0, 1.0)), p_tta=0.25):
+        super().__init__(dims, species, ws1, wt1, params, tab)
+        self.ann = np.ascontiguousarray(annihilation, np.float64).reshape(4)
+        self.p_tta = float(p_tta)
+
+    def _dense_args(self):
+        X, Y, Z = self.dims
+        return [C.c_int(X), C.c_int(Y), C.c_int(Z), _p(self.ws1), _p(self.wt1), C.c_int(len(self.g6)), _p(self.off),
+                _p(self.g6), _p(self.gd), _p(self.kf), _p(self.kd), _p(self.k_isc), _p(self.k_risc), _p(self.k_rad),
+                _p(self.k_nonrad), C.c_double(self.params["singlet_fraction"]), C.c_double(self.params["cutoff"]),
+                _p(self.ann), C.c_double(self.p_tta)]
+
+    def run_device(self, seed, device, n_excitons, n_events, verify=False):
+        n, m = int(n_events), int(n_excitons)
+        tr = dict(kind=np.zeros(n, np.uint8), exciton=np.zeros(n, np.int32), initial=np.zeros(n, np.int32),
+                  final=np.zeros(n, np.int32), channel=np.zeros(n, np.int32), dt=np.zeros(n), spin=np.zeros(n, np.uint8))
+        tallies = np.zeros(24, np.uint64)
+        pos, spin, tot, scal = np.zeros(m, np.int32), np.zeros(m, np.int32), np.zeros(m), np.zeros(3)
+        bad = dense_lib().hfxd_run(*self._dense_args(), C.c_uint64(seed), C.c_uint32(device), C.c_int(m), C.c_int64(n),
+                                   C.c_int(int(verify)), _p(tr["kind"]), _p(tr["exciton"]), _p(tr["initial"]), _p(tr["final"]),
+                                   _p(tr["channel"]), _p(tr["dt"]), _p(tr["spin"]), _p(tallies), _p(pos), _p(spin), _p(tot), _p(scal))
+        return dict(trace=tr, tallies={k: int(v) for k, v in zip(XDT_NAMES, tallies) if not k.startswith("_")},
+                    site=pos, spin=spin, total_rate=tot, time=scal[0], lifetime_sum=scal[1], draws=int(scal[2]),
+                    cache_mismatches=int(bad))
+
+    def run_devices(self, seed, first, n_devices, n_excitons, n_events, n_threads=1):
+        tallies = np.zeros(24, np.uint64)
+        dense_lib().hfxd_run_batch(*self._dense_args(), C.c_uint64(seed), C.c_int64(first), C.c_int64(n_devices),
+                                   C.c_int(int(n_excitons)), C.c_int64(n_events), C.c_int(n_threads), _p(tallies))
+        return {k: int(v) for k, v in zip(XDT_NAMES, tallies) if not k.startswith("_")}

@@ -165,3 +165,24 @@ def x_run(oracle, seed, first_traj, B, n_events, n_calls=1, generic=False):
     if rc:
         raise RuntimeError(f"emu_x_run failed ({rc})")
     return dict(trace=trace, site=site, spin=spin, time=time, lifetime_sum=life, draws=draws, totals=totals)
+
+
+def xd_run(oracle, seed, device, n_excitons, n_events, n_calls=1):
+    """The high-density kernel (one device = one warp) under emulation, model held by a DenseExcitonOracle."""
+    o = oracle
+    cap = max(n_events * n_calls, 1)
+    trace = np.zeros(cap, EVENT_DTYPE)
+    n = int(n_excitons)
+    site, spin, tot, scal = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n), np.zeros(3)
+    totals = np.zeros(24, np.uint64)
+    occ = np.zeros(int(np.prod(o.dims)), np.uint8)
+    d = (C.c_int32 * 3)(*o.dims)
+    rc = lib().emu_xd_run(d, _p(o.ws1), _p(o.wt1), C.c_int32(len(o.g6)), _p(o.off), _p(o.g6), _p(o.gd), _p(o.kf), _p(o.kd),
+                          _p(o.k_isc), _p(o.k_risc), _p(o.k_rad), _p(o.k_nonrad), C.c_double(o.params["singlet_fraction"]),
+                          C.c_double(o.params["cutoff"]), _p(o.ann), C.c_double(o.p_tta), C.c_uint64(seed), C.c_uint32(device),
+                          C.c_int32(n), C.c_int64(n_events), C.c_int32(n_calls), _p(trace), C.c_int64(cap), _p(site), _p(spin),
+                          _p(tot), _p(scal), _p(totals), _p(occ))
+    if rc:
+        raise RuntimeError(f"emu_xd_run failed ({rc})")
+    return dict(trace=trace, site=site, spin=spin, total_rate=tot, time=scal[0], lifetime_sum=scal[1], draws=int(scal[2]),
+                totals=totals, occupancy=occ)

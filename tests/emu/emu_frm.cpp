@@ -6,6 +6,7 @@
 #include "../../hyperfluorescence_b200/csrc/hf_frm.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_frm_c1.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_exciton.cuh"
+#include "../../hyperfluorescence_b200/csrc/hf_exciton_dense.cuh"
 
 #include <vector>
 
@@ -257,6 +258,73 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
         spin_out[b] = spin[(size_t)b]; time_out[b] = time[(size_t)b]; life_out[b] = life[(size_t)b]; draws_out[b] = draws[(size_t)b];
     }
     memcpy(totals_out, totals.data(), sizeof(unsigned long long) * HFX_T_N);
+    return 0;
+}
+
+static void xd_run_body(void *a) { hfxd_run_kernel<1>(*(const HfxdParams *)a); }
+
+// High-density devices: ONE device (one warp), fill + n_calls x hfxd_run(n_events).
+int emu_xd_run(const int32_t dims[3], const double *ws1, const double *wt1, int32_t M, const int8_t *offsets, const double *g6,
+               const double *gd, const double *kf, const double *kd, const double *k_isc, const double *k_risc,
+               const double *k_rad, const double *k_nonrad, double singlet_fraction, double cutoff, const double *ann,
+               double p_tta, uint64_t seed, uint32_t device, int32_t n_excitons, int64_t n_events, int32_t n_calls,
+               HfTraceRec *trace_out, int64_t trace_cap, int32_t *site_out, int32_t *spin_out, double *total_out,
+               double *scalars_out, unsigned long long *totals_out, uint8_t *occ_out) {
+    HfxdParams D;
+    memset(&D, 0, sizeof(D));
+    HfxParams &P = D.X;
+    P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z; P.B = 1; P.traj_per_real = 1;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = device;
+    P.M = M;
+    std::vector<int32_t> packed((size_t)M), lin((size_t)M);
+    int maxr = 0;
+    for (int m = 0; m < M; ++m) {
+        packed[(size_t)m] = (offsets[3 * m] + 128) | ((offsets[3 * m + 1] + 128) << 8) | ((offsets[3 * m + 2] + 128) << 16);
+        lin[(size_t)m] = (int32_t)((int64_t)offsets[3 * m + 2] * P.X * P.Y + (int64_t)offsets[3 * m + 1] * P.X + offsets[3 * m]);
+        for (int k = 0; k < 3; ++k) { const int v = offsets[3 * m + k] < 0 ? -offsets[3 * m + k] : offsets[3 * m + k]; if (v > maxr) maxr = v; }
+    }
+    P.R = maxr; P.lin = lin.data(); P.offsets = packed.data(); P.g6 = g6; P.gd = gd;
+    memcpy(P.kf, kf, sizeof(P.kf)); memcpy(P.kd, kd, sizeof(P.kd));
+    memcpy(P.k_isc, k_isc, sizeof(P.k_isc)); memcpy(P.k_risc, k_risc, sizeof(P.k_risc));
+    memcpy(P.k_rad, k_rad, sizeof(P.k_rad)); memcpy(P.k_nonrad, k_nonrad, sizeof(P.k_nonrad));
+    P.singlet_fraction = singlet_fraction;
+    P.w_halo = (int64_t)maxr * P.X * P.Y; P.w_stride = P.N + 2 * P.w_halo;
+    std::vector<double> hs1((size_t)P.w_stride, 0.0), ht1((size_t)P.w_stride, 0.0);
+    memcpy(hs1.data() + P.w_halo, ws1, sizeof(double) * (size_t)P.N);
+    memcpy(ht1.data() + P.w_halo, wt1, sizeof(double) * (size_t)P.N);
+    P.ws1 = hs1.data(); P.wt1 = ht1.data();
+    D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
+    memcpy(D.ann, ann, sizeof(D.ann));
+    D.p_tta = p_tta; D.rc2 = cutoff * cutoff;
+    D.occ_words = (P.w_stride + 15) / 16;
+    std::vector<uint32_t> pos((size_t)D.n_pad, 0), occ((size_t)D.occ_words, 0);
+    std::vector<double> T((size_t)D.n_pad, 0.0), birth((size_t)D.n_pad, 0.0);
+    double time = 0.0, life = 0.0;
+    uint64_t draws = 0, tlen = 0;
+    std::vector<unsigned long long> totals(HFXD_T_N, 0);
+    std::vector<HfTraceRec> trace((size_t)(trace_cap + 1));
+    D.pos = pos.data(); D.T = T.data(); D.birth = birth.data(); D.occ = occ.data();
+    D.time = &time; D.life = &life; D.draws = &draws; D.totals = totals.data();
+    P.trace = trace.data(); P.trace_first = 0; P.trace_n = 1; P.trace_cap = trace_cap; P.trace_len = &tlen;
+    if (hfxd_smem_bytes(M, D.n_pad, 1) > sizeof(hf_smem)) return 2;
+    blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
+    D.fill = 1; P.n_events = 0;
+    emu_run_warp(xd_run_body, &D);
+    D.fill = 0;
+    for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(xd_run_body, &D); }
+    memcpy(trace_out, trace.data(), sizeof(HfTraceRec) * (size_t)trace_cap);
+    for (int k = 0; k < n_excitons; ++k) {
+        const int p = (int)(pos[(size_t)k] & 0x3fffffffu);
+        site_out[k] = (int32_t)((((int64_t)(p >> 20)) * P.Y + ((p >> 10) & 1023)) * P.X + (p & 1023));
+        spin_out[k] = (int32_t)(pos[(size_t)k] >> 30);
+        total_out[k] = T[(size_t)k];
+    }
+    scalars_out[0] = time; scalars_out[1] = life; scalars_out[2] = (double)draws;
+    memcpy(totals_out, totals.data(), sizeof(unsigned long long) * HFXD_T_N);
+    for (int64_t i = 0; i < P.N; ++i) {
+        const int64_t idx = i + P.w_halo;
+        occ_out[i] = (uint8_t)((occ[(size_t)(idx >> 4)] >> (2 * (int)(idx & 15))) & 3u);
+    }
     return 0;
 }
 
