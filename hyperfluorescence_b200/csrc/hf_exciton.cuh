@@ -67,6 +67,7 @@ struct HfxParams {
     uint32_t k0, k1, first_traj;
     int32_t M;                        // neighbour offsets
     int32_t R;                        // ceil(cutoff): sites at least R away from the x / y seams need no wrap
+    int32_t block;                    // trajectories a warp owns at a time (1..32)
     const int32_t *offsets;           // [M] packed (dx+128) | (dy+128) << 8 | (dz+128) << 16
     const int32_t *lin;               // [M] dz*X*Y + dy*X + dx
     const double *g6, *gd;            // [M]
@@ -245,13 +246,14 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
     const int32_t *s_off_lane = s_off + lane;
     const double *s_g6_lane = s_g6 + lane, *s_gd_lane = s_gd + lane;
 
-    const int64_t n_blocks = (P.B + 31) >> 5;
+    const int bs = P.block;
+    const int64_t n_blocks = (P.B + bs - 1) / bs;
     for (int64_t blk = (int64_t)blockIdx.x * kWarps + warp; blk < n_blocks; blk += (int64_t)gridDim.x * kWarps) {
-        const int64_t local = (blk << 5) + lane;
-        const int count = (int)(P.B - (blk << 5) < 32 ? P.B - (blk << 5) : 32);
+        const int64_t local = blk * bs + lane;
+        const int count = (int)(P.B - blk * bs < bs ? P.B - blk * bs : bs);
         const bool active = lane < count;
         const uint32_t ident = P.first_traj + (uint32_t)local;
-        const int64_t r = (active ? local : (blk << 5)) / P.traj_per_real;
+        const int64_t r = (active ? local : blk * bs) / P.traj_per_real;
         const double *ws1 = P.ws1 + r * P.w_stride + P.w_halo, *wt1 = P.wt1 + r * P.w_stride + P.w_halo;
         int site = 0, spin = HFX_SINGLET;
         double time = 0.0, lifetime = 0.0;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
         }
         if (active) { P.site[local] = site; P.spin[local] = spin; P.time[local] = time; P.lifetime[local] = lifetime; P.draws[local] = draws; }
         // tallies: one atomic per counter and warp when the 32 trajectories share a realisation
-        const int64_t r_first = __shfl_sync(HF_FULL, r, 0), r_last = __shfl_sync(HF_FULL, r, 31);
+        const int64_t r_first = __shfl_sync(HF_FULL, r, 0), r_last = __shfl_sync(HF_FULL, r, count - 1);
         const bool uniform = r_first == r_last;
         for (int t = 0; t < HFX_T_N; ++t) {
             unsigned v = s_cnt[t * 32 + lane];

@@ -11,8 +11,9 @@ ap.add_argument("--B", type=int, default=1_000_000)
 ap.add_argument("--events", type=int, default=100)
 ap.add_argument("--cutoff", type=float, default=4.0)
 ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--real", type=int, default=1, help="disorder realisations (trajectories are split evenly over them)")
 a = ap.parse_args()
-sim = nat.Sim((a.L, a.L, a.L), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=a.B, seed=1)
+sim = nat.Sim((a.L, a.L, a.L), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=a.B, n_realisations=a.real, seed=1)
 sim.generate_lattice()
 sim.x_configure(nat.x_params_from_dict(dict(cutoff=a.cutoff)))
 sim.x_spawn()
@@ -24,7 +25,7 @@ t = sim.x_tallies()
 M = sim.x_tables()["g6"].size
 ev = a.B * a.events * n
 bytes_per_event = M * 9 + (M + 7) // 8 + 2 * 21 + 16
-print(json.dumps(dict(L=a.L, B=a.B, cutoff=a.cutoff, M=int(M), events_per_s=ev / (ms * 1e-3), ms_per_launch=ms / n,
+print(json.dumps(dict(L=a.L, B=a.B, realisations=a.real, cutoff=a.cutoff, M=int(M), events_per_s=ev / (ms * 1e-3), ms_per_launch=ms / n,
                       bytes_per_event=bytes_per_event, algorithmic_GBs=ev * bytes_per_event / (ms * 1e-3) / 1e9,
                       iqe=(t["rad_tadf"] + t["rad_fluo"]) / max(1, t["generated"] - a.B))))
 sim.close()

@@ -216,7 +216,7 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     memset(&P, 0, sizeof(P));
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z; P.B = B; P.traj_per_real = B;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = first_traj;
-    P.M = M;
+    P.M = M; P.block = 32;
     std::vector<int32_t> packed((size_t)M);
     for (int m = 0; m < M; ++m) packed[(size_t)m] = (offsets[3 * m] + 128) | ((offsets[3 * m + 1] + 128) << 8) | ((offsets[3 * m + 2] + 128) << 16);
     std::vector<int32_t> lin((size_t)M);

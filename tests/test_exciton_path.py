@@ -132,6 +132,30 @@ def test_gpu_exciton_path_equals_specification():
 
 
 @pytest.mark.gpu
+def test_gpu_exciton_results_do_not_depend_on_the_warp_batch(monkeypatch):
+    """The number of trajectories a warp owns at a time (32, or fewer when the weights exceed the L2:
+    hf_x_configure) is a scheduling choice: states and tallies must not change with it."""
+    from hyperfluorescence_b200 import _native as nat
+    out = []
+    for block in ("32", "3", "7"):
+        monkeypatch.setenv("HF_X_BLOCK", block)
+        sim = nat.Sim((20, 20, 10), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=1000, n_realisations=2, seed=3)
+        sim.generate_lattice()
+        sim.x_configure()
+        sim.x_spawn()
+        sim.x_run(150)
+        sim.sync()
+        st = sim.x_state()
+        out.append((st["site"].copy(), st["spin"].copy(), st["draws"].copy(), st["lifetime_sum"].copy(), sim.x_realisation_tallies()))
+        sim.close()
+    for o in out[1:]:
+        for a, b in zip(out[0][:4], o[:4]):
+            assert np.array_equal(a, b)
+        for k in out[0][4]:
+            assert np.array_equal(out[0][4][k], o[4][k]), k
+
+
+@pytest.mark.gpu
 def test_gpu_exciton_ensemble_api():
     from hyperfluorescence_b200.excitons import ExcitonEnsemble
     ens = ExcitonEnsemble((20, 20, 20), trajectories=4096, seed=5)
