@@ -255,7 +255,9 @@ def run_ours(args):
     }
     if not args.no_ga:
         line["ga"] = ga_fitness_rate(rank, local_rank, world)
-        line["exciton_path"] = exciton_rate(rank, local_rank, world)
+        line["exciton_path"] = exciton_rate(rank, local_rank, world, cpu=not args.no_cpu)
+        line["disorder_sweep"] = exciton_rate(rank, local_rank, world, lattice=256, realisations_total=64, label="disorder_sweep")
+        line["high_density"] = dense_rate(rank, local_rank, world)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_sample(cores, 2500)
@@ -315,15 +317,18 @@ def exciton_traffic(events_per_launch):
         return None
 
 
-def exciton_rate(rank, local_rank, world):
-    """The north_star's own target configuration for the exciton path (own model, parity unpinned:
-    the reference has no exciton dynamics): 128^3 lattice, 10^6 concurrent single-exciton
+def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, label="north_star", cpu=False):
+    """The exciton path (own model, parity unpinned: the reference has no exciton dynamics).
+    north_star: the north_star's target configuration — 128^3 lattice, 10^6 concurrent single-exciton
     trajectories per GPU, cutoff 4 lattice constants (256 transfer channels + 3 on-site), rejection-free
-    selection; events/s over all ranks and the algorithmic-bytes roofline fraction of SURVEY.md 8(d)."""
+    selection.  disorder_sweep: BASELINE configs[4] — 256^3, 64 disorder realisations sharded over the ranks,
+    10^6 trajectories per GPU.  Events/s over all ranks and the algorithmic-bytes roofline fraction of
+    SURVEY.md 8(d)."""
     import torch
     from hyperfluorescence_b200 import _native as nat
-    sim = nat.Sim((X_L, X_L, X_L), PROPS, FIELD, 1, 1, n_trajectories=X_TRAJ_PER_GPU, seed=SEED,
-                  first_trajectory=rank * X_TRAJ_PER_GPU, device=local_rank)
+    n_real = max(1, realisations_total // world)
+    sim = nat.Sim((lattice,) * 3, PROPS, FIELD, 1, 1, n_trajectories=X_TRAJ_PER_GPU, n_realisations=n_real, seed=SEED,
+                  first_trajectory=rank * X_TRAJ_PER_GPU, first_realisation=rank * n_real, device=local_rank)
     sim.generate_lattice()
     sim.x_configure(nat.x_params_from_dict(dict(cutoff=X_CUTOFF)))
     sim.x_spawn()
@@ -334,8 +339,12 @@ def exciton_rate(rank, local_rank, world):
     for _ in range(3):
         sim.x_run(X_EVENTS)
     ms, n = sim.run_timing()
-    m = int(sim.x_tables()["g6"].size)
+    tab = sim.x_tables()
+    m = int(tab["g6"].size)
     t = sim.x_tallies()
+    cpu_line = None
+    if cpu and world == 1 and rank == 0:
+        cpu_line = exciton_cpu_sample(sim, lattice, tab)
     sim.close()
     if world > 1:
         import torch.distributed as dist
@@ -347,18 +356,82 @@ def exciton_rate(rank, local_rank, world):
     peak, _ = hbm_peak()
     rate = events / (ms * 1e-3)
     decayed = max(1, t["generated"] - X_TRAJ_PER_GPU)
-    return {"metric": "KMC exciton events/sec (box), exciton path", "value": rate, "unit": "events/s",
-            "config": {"lattice": [X_L] * 3, "trajectories_per_gpu": X_TRAJ_PER_GPU, "cutoff": X_CUTOFF,
-                       "channels": m + 3, "events_per_trajectory_per_launch": X_EVENTS,
-                       "model": "own (parity unpinned): DESIGN.md section 9, oracle/exciton_oracle.c"},
-            "roofline": {"bound": "hbm", "bytes_per_event": bytes_per_event,
-                         "achieved": rate * bytes_per_event / world / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel",
-                         "traffic": exciton_traffic(X_TRAJ_PER_GPU * X_EVENTS),
-                         "note": "the 2 x 17 MB of Boltzmann weights of a 128^3 lattice are L2-resident (ncu: L2 hit 99.9 %, "
+    l2_resident = n_real * lattice ** 3 * 8 < 60e6
+    out = {"metric": "KMC exciton events/sec (box), exciton path", "value": rate, "unit": "events/s",
+           "config": {"workload": label, "lattice": [lattice] * 3, "realisations_per_gpu": n_real,
+                      "trajectories_per_gpu": X_TRAJ_PER_GPU, "cutoff": X_CUTOFF,
+                      "channels": m + 3, "events_per_trajectory_per_launch": X_EVENTS,
+                      "model": "own (parity unpinned): DESIGN.md section 9, oracle/exciton_oracle.c"},
+           "roofline": {"bound": "hbm", "bytes_per_event": bytes_per_event,
+                        "achieved": rate * bytes_per_event / world / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel",
+                        "traffic": exciton_traffic(X_TRAJ_PER_GPU * X_EVENTS) if l2_resident else None,
+                        "note": ("the 2 x 17 MB of Boltzmann weights of a 128^3 lattice are L2-resident (ncu: L2 hit 99.9 %, "
                                  "DRAM ~1.5 B/event), so the algorithmic-bytes fraction is not an HBM utilisation; the kernel is "
-                                 "bound by the L1 data pipe (75 %) and instruction issue (profiles/r01f_*)"},
-            "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
+                                 "bound by the L1 data pipe (75 %) and instruction issue (profiles/r01f_*)") if l2_resident else
+                                ("weights exceed the L2: with 32 trajectories per warp the kernel moves 7.9 KB/event from DRAM at "
+                                 "4.2 TB/s = 65 % of the HBM peak (profiles/r01g_*); the adaptive warp batch trades that for L2 "
+                                 "hits (82 %, 0.5 KB/event from DRAM, profiles/r01h_*)")},
+           "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
+    if cpu_line:
+        out["cpu_baseline"] = cpu_line
+    return out
+
+
+def exciton_cpu_sample(sim, lattice, tab):
+    """The exciton specification (oracle/exciton_oracle.c, POSIX threads over trajectories) on this box's host
+    cores, on the device's own lattice: a bounded sample of the same workload."""
+    from hyperfluorescence_b200 import _native as nat
+    from oracle import exciton_oracle as xo
+    lat = sim.download_lattice(0)
+    ws1, wt1 = sim.x_weights(0)
+    params = dict(nat.x_params_to_dict(nat.x_default_params()), cutoff=X_CUTOFF)
+    o = xo.ExcitonOracle((lattice,) * 3, lat["species"], ws1, wt1, params, tab)
+    cores = os.cpu_count() or 1
+    n_traj = 1500 * cores
+    o.run_batch(SEED, 0, max(cores, 64), 10, n_threads=cores)                  # warm the page cache / threads
+    t0 = time.perf_counter()
+    o.run_batch(SEED, 0, n_traj, X_EVENTS, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n_traj * X_EVENTS / dt, "unit": "events/s", "cores": cores, "kind": "port",
+            "sample": f"{n_traj} of the {X_TRAJ_PER_GPU} trajectories x {X_EVENTS} events on the same {lattice}^3 lattice, {cores} threads"}
+
+
+XD_L, XD_DEVICES_PER_GPU, XD_EXCITONS, XD_EVENTS = 128, 4096, 256, 200
+
+
+def dense_rate(rank, local_rank, world):
+    """BASELINE configs[3]: high-density excitons on a 128^3 lattice with occupancy blocking and
+    exciton-exciton annihilation (own model, parity unpinned: DESIGN.md section 10).  4096 devices per GPU x
+    256 interacting excitons each (10^6 excitons per GPU); one event = one channel of one exciton."""
+    import torch
+    from hyperfluorescence_b200 import _native as nat
+    sim = nat.Sim((XD_L,) * 3, PROPS, FIELD, 1, 1, n_trajectories=XD_DEVICES_PER_GPU, seed=SEED,
+                  first_trajectory=rank * XD_DEVICES_PER_GPU, device=local_rank)
+    sim.generate_lattice()
+    sim.x_configure(nat.x_params_from_dict(dict(cutoff=X_CUTOFF)))
+    sim.xd_configure(XD_EXCITONS)
+    sim.xd_spawn()
+    sim.xd_run(XD_EVENTS)
+    sim.sync()
+    sim.run_timing()
+    for _ in range(3):
+        sim.xd_run(XD_EVENTS)
+    ms, n = sim.run_timing()
+    t = sim.xd_tallies()
+    sim.close()
+    if world > 1:
+        import torch.distributed as dist
+        v = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        ms = float(v.item())
+    lost = max(1, sum(v for k, v in t.items() if k.startswith(("rad_", "nonrad_", "ann_"))))
+    return {"metric": "KMC exciton events/sec (box), high-density devices", "value": world * XD_DEVICES_PER_GPU * XD_EVENTS * n / (ms * 1e-3),
+            "unit": "events/s",
+            "config": {"lattice": [XD_L] * 3, "devices_per_gpu": XD_DEVICES_PER_GPU, "excitons_per_device": XD_EXCITONS,
+                       "cutoff": X_CUTOFF, "events_per_device_per_launch": XD_EVENTS, "kernel": "hfxd_run_kernel",
+                       "model": "own (parity unpinned): DESIGN.md section 10, oracle/exciton_dense_oracle.c"},
+            "annihilation_fraction": (t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]) / lost}
 
 
 def main():
@@ -368,7 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep and exciton-path legs")
+    ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep, exciton-path, disorder-sweep and high-density legs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.no_cpu:
         args.warmup = 3
