@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: NCCL's own banner / debug output (stdout by default) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
