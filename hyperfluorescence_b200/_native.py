@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhfkmc.so")
+LIB_PATH = os.environ.get("HFKMC_LIB") or os.path.join(HERE, "libhfkmc.so")   # HFKMC_LIB: kernel-variant experiments
 
 HF_N_TALLIES = 20
 TALLY_NAMES = ("emission", "recombination", "injection", "steps", "fired", "move_e", "move_h", "bound", "decay",

@@ -68,7 +68,12 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
     return HF_ST_OK;
 }
 
+#ifndef HF_C1_THREADS
 #define HF_C1_THREADS 128
+#endif
+#ifndef HF_C1_MIN_BLOCKS
+#define HF_C1_MIN_BLOCKS 6
+#endif
 #define HF_C1_MAXCAND 27
 // relative half-width of the "could be the minimum" window of the screening pass, see hf_c1_gen
 #define HF_C1_WINDOW 0x1p-9f
@@ -348,7 +353,7 @@ __device__ __forceinline__ void hf_c1_store(const HfParams &P, const HfC1 &s, co
 }
 
 // Lattice.operations(stop) for charges == 1: one thread per trajectory.
-__global__ void __launch_bounds__(HF_C1_THREADS, 6) hf_run_c1_kernel(const HfParams P) {
+__global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_kernel(const HfParams P) {
     __shared__ float approx_all[HF_C1_MAXCAND * HF_C1_THREADS];
     float *approx = approx_all + threadIdx.x;
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
