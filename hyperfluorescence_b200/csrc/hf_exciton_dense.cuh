@@ -14,7 +14,10 @@
 // Per event the warp (1) scans the cached totals to pick an exciton, (2) evaluates that exciton's
 // M + 3 channels (lane = channel % 32; each lane also fetches the acceptor's occupancy code) and scans
 // them to pick the channel, (3) applies it — lane 0 edits the occupancy words — and (4) re-evaluates the
-// totals of the excitons that can see a changed site (at most three sites change per event).
+// totals of the excitons that can see a changed site.  Those are found without scanning the device: every
+// evaluation of an exciton ON a changed site (the chosen exciton before the event, the same slot after it,
+// a promoted acceptor) already fetches the occupancy codes of all sites in its cutoff sphere, so the lanes
+// that met an occupied site name the neighbours; only those are looked up in the position list.
 #pragma once
 #include "hf_exciton.cuh"
 
@@ -43,7 +46,7 @@ struct HfxdParams {
 __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
     // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T, birth (f64) | rates (f64) | pos (u32) | counters (u32)
     return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 2 * (size_t)((M + 1) & ~1) +
-           (size_t)warps * (8 * (2 * (size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 32));
+           (size_t)warps * (8 * (2 * (size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64));
 }
 
 __device__ __forceinline__ int hfxd_occ_get(const uint32_t *occ, int64_t idx) {
@@ -59,15 +62,17 @@ struct HfxdWarp {                      // one warp's view of its device
     const double *s_g6, *s_gd, *s_k, *s_ann;
     const int32_t *s_lin, *s_off;
     double *s_T, *s_birth, *s_rates;
-    uint32_t *s_pos, *s_cnt;
+    uint32_t *s_pos, *s_cnt, *s_dirty;
     const double *ws1, *wt1;           // this device's realisation, site 0
     uint32_t *occ;                     // this device's mask (index = site + halo)
     int lane, K, M;
 };
 
 // Lane sums of the channel rates of an exciton (packed site + spin); kStore: also leave the rates in s_rates.
+// `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  Four slots are
+// gathered (weight + occupancy word) before any of them is consumed.
 template <bool kStore>
-__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps) {
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
     const bool singlet = spin == HFX_SINGLET;
@@ -84,26 +89,77 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps) 
     const bool nowrap = px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
     const int64_t oi = i + X.w_halo;
     double S = 0.0;
-    for (int k = 0; k < W.K; ++k) {
-        const int c = (k << 5) + W.lane;
-        double rate = 0.0;
-        if (c < W.M) {
-            const int delta = nowrap ? W.s_lin[c] : hfx_delta(W.s_off[c], px, py, X.X, X.Y, plane);
-            const double wj = __ldg(w + delta);
-            rate = hfx_rate(pref, g[c], wj, inv_wi);
-            const int o = hfxd_occ_get(W.occ, oi + delta);
-            if (o) rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]);
-        } else if (c == W.M) {
-            rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
-        } else if (c == W.M + 1) {
-            rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
-        } else if (c == W.M + 2) {
-            rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+    seen = 0;
+    for (int k0 = 0; k0 < W.K; k0 += 4) {
+        double wj[4];
+        uint32_t ow[4];
+        int sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = ((k0 + u) << 5) + W.lane;
+            wj[u] = 0.0; ow[u] = 0; sh[u] = 0;
+            if (c < W.M) {
+                const int delta = nowrap ? W.s_lin[c] : hfx_delta(W.s_off[c], px, py, X.X, X.Y, plane);
+                wj[u] = __ldg(w + delta);
+                const int64_t oj = oi + delta;
+                ow[u] = W.occ[oj >> 4];
+                sh[u] = 2 * (int)(oj & 15);
+            }
         }
-        if (kStore) W.s_rates[c] = rate;
-        S = __dadd_rn(S, rate);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int k = k0 + u, c = (k << 5) + W.lane;
+            if (k < W.K) {
+                double rate = 0.0;
+                if (c < W.M) {
+                    rate = hfx_rate(pref, g[c], wj[u], inv_wi);
+                    const int o = (int)((ow[u] >> sh[u]) & 3u);
+                    if (o) { rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]); seen |= 1u << k; }
+                } else if (c == W.M) {
+                    rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
+                } else if (c == W.M + 1) {
+                    rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
+                } else if (c == W.M + 2) {
+                    rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+                }
+                if (kStore) W.s_rates[c] = rate;
+                S = __dadd_rn(S, rate);
+            }
+        }
     }
     return S;
+}
+
+// Slot of the exciton sitting on packed site `nb` (-1 if none); warp-uniform.
+__device__ __forceinline__ int hfxd_find(const HfxdWarp &W, int nb) {
+    for (int q0 = 0; q0 < W.P->n; q0 += 32) {
+        const int q = q0 + W.lane;
+        const unsigned hit = __ballot_sync(HF_FULL, q < W.P->n && (int)(W.s_pos[q] & 0x3fffffffu) == nb);
+        if (hit) return q0 + __ffs(hit) - 1;
+    }
+    return -1;
+}
+
+// Mark as dirty the excitons on the occupied sites an evaluation at packed site `site` has met.
+__device__ __forceinline__ void hfxd_mark_seen(const HfxdWarp &W, int site, unsigned seen) {
+    const HfxParams &X = W.P->X;
+    unsigned any = __ballot_sync(HF_FULL, seen != 0);
+    while (any) {
+        const int src = __ffs(any) - 1;
+        any &= any - 1;
+        unsigned m = __shfl_sync(HF_FULL, seen, src);
+        while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const int o = W.s_off[(k << 5) + src];
+            int xx = hf_px(site) + (o & 255) - 128, yy = hf_py(site) + ((o >> 8) & 255) - 128;
+            if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+            if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+            const int q = hfxd_find(W, hf_pack(xx, yy, hf_pz(site) + ((o >> 16) & 255) - 128));
+            if (q >= 0 && W.lane == 0) W.s_dirty[q >> 5] |= 1u << (q & 31);
+        }
+    }
+    __syncwarp();
 }
 
 // The canonical pick (oracle: pick()): v[n_slots][32] in shared memory, S = this lane's sum, L = its scan.
@@ -147,18 +203,6 @@ __device__ __forceinline__ uint32_t hfxd_replace(const HfxdWarp &W, uint32_t ide
     }
 }
 
-// does an exciton on packed site p see packed site c inside its cutoff sphere, or sit on it? (oracle: sees())
-__device__ __forceinline__ bool hfxd_sees(const HfxdParams &P, int p, int c) {
-    int dx = hf_px(c) - hf_px(p), dy = hf_py(c) - hf_py(p);
-    const int dz = hf_pz(c) - hf_pz(p);
-    const int hx = P.X.X / 2, hy = P.X.Y / 2;
-    if (dx > hx) dx -= P.X.X; else if (dx < -hx) dx += P.X.X;
-    if (dy > hy) dy -= P.X.Y; else if (dy < -hy) dy += P.X.Y;
-    if ((P.X.X & 1) == 0 && (dx == hx || dx == -hx)) return false;
-    if ((P.X.Y & 1) == 0 && (dy == hy || dy == -hy)) return false;
-    return (double)(dx * dx + dy * dy + dz * dz) <= P.rc2;
-}
-
 template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
@@ -172,11 +216,11 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
     int32_t *s_lin = reinterpret_cast<int32_t *>(s_ann + 4);
     int32_t *s_off = s_lin + ((M + 1) & ~1);
     unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 1) & ~1)) +
-                         (size_t)warp * (8 * (2 * (size_t)n_pad + padded) + 4 * ((size_t)n_pad + 32));
+                         (size_t)warp * (8 * (2 * (size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64));
     HfxdWarp W;
     W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_lin = s_lin; W.s_off = s_off;
     W.s_T = reinterpret_cast<double *>(wsm); W.s_birth = W.s_T + n_pad; W.s_rates = W.s_birth + n_pad;
-    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad;
+    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
     W.lane = lane; W.K = K; W.M = M;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
@@ -194,7 +238,8 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
         double *g_T = P.T + dev * n_pad, *g_birth = P.birth + dev * n_pad;
         double time, life;
         uint64_t draws;
-        if (lane < 32) W.s_cnt[lane] = 0;
+        W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
+        unsigned seen;
         if (P.fill) {
             // hf_xd_spawn: an empty mask (memset by the host), slots filled in order, then every total
             time = 0.0; life = 0.0; draws = 0;
@@ -206,7 +251,7 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
             }
             __syncwarp();
             for (int k = 0; k < P.n; ++k) {
-                const double S = hfxd_lane_sum<false>(W, W.s_pos[k]);
+                const double S = hfxd_lane_sum<false>(W, W.s_pos[k], seen);
                 const double tot = __shfl_sync(HF_FULL, hfx_scan(S, lane), 31);
                 if (lane == 0) W.s_T[k] = tot;
             }
@@ -232,9 +277,10 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
             const int kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
             // (2) its channel
             const uint32_t ps = W.s_pos[kx];
-            const double S = hfxd_lane_sum<true>(W, ps);
+            const double S = hfxd_lane_sum<true>(W, ps, seen);
             const double L = hfx_scan(S, lane);
             __syncwarp();
+            hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), seen);                   // the neighbours of the site that is about to change
             double base2;
             const int chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
             const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
@@ -246,8 +292,7 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
             const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
             const int64_t i = hf_site(X.X, X.Y, site);
             const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
-            int changed[3], n_changed = 1, kind, tally, fin = site;
-            changed[0] = site; changed[1] = site; changed[2] = site;
+            int kind, tally, fin = site, promoted = -1;
             bool lost = false;
             uint32_t ps_after = ps;
             if (chosen < M) {
@@ -256,7 +301,6 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
                 if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
                 if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
                 fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
-                changed[n_changed++] = fin;
                 const int64_t oj = hf_site(X.X, X.Y, fin) + X.w_halo;
                 const int occ_j = hfxd_occ_get(W.occ, oj);
                 __syncwarp();
@@ -273,9 +317,12 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
                         const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
                         draws += 2;
                         if (hf_block_uniform(b2, 0) < P.p_tta) {
-                            for (int q = lane; q < P.n; q += 32)
-                                if (q != kx && (int)(W.s_pos[q] & 0x3fffffffu) == fin) W.s_pos[q] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
-                            if (lane == 0) { hfxd_occ_set(W.occ, oj, HFX_SINGLET); W.s_cnt[HFXD_T_TTA_UP] += 1; }
+                            promoted = hfxd_find(W, fin);
+                            if (lane == 0) {
+                                if (promoted >= 0) W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
+                                hfxd_occ_set(W.occ, oj, HFX_SINGLET);
+                                W.s_cnt[HFXD_T_TTA_UP] += 1;
+                            }
                         }
                     }
                     lost = true;
@@ -296,7 +343,6 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
                 life = __dadd_rn(life, __dsub_rn(time, W.s_birth[kx]));
                 __syncwarp();
                 ps_after = hfxd_replace(W, ident, draws);
-                changed[n_changed++] = (int)(ps_after & 0x3fffffffu);
                 if (lane == 0) { W.s_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
             }
             if (lane == 0) {
@@ -314,22 +360,32 @@ __global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams 
             }
             trace_at += 1;
             __syncwarp();
-            // (4) refresh the cached totals of every exciton that sees a changed site
-            for (int q0 = 0; q0 < P.n; q0 += 32) {
-                const int q = q0 + lane;
-                bool dirty = false;
-                if (q < P.n) {
-                    const int p = (int)(W.s_pos[q] & 0x3fffffffu);
-                    dirty = q == kx;
-                    for (int c = 0; c < n_changed; ++c) dirty = dirty || hfxd_sees(P, p, changed[c]);
-                }
-                unsigned todo = __ballot_sync(HF_FULL, dirty);
+            // (4) refresh the cached totals: the slot itself in its new state (its evaluation names the neighbours of
+            //     the site it now occupies), a promoted acceptor (whose neighbours see a different spin), then everybody marked
+            {
+                const double Sk = hfxd_lane_sum<false>(W, ps_after, seen);
+                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sk, lane), 31);
+                if (lane == 0) W.s_T[kx] = tot;
+                hfxd_mark_seen(W, (int)(ps_after & 0x3fffffffu), seen);
+            }
+            if (promoted >= 0) {
+                const double Sa = hfxd_lane_sum<false>(W, W.s_pos[promoted], seen);
+                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sa, lane), 31);
+                if (lane == 0) { W.s_T[promoted] = tot; W.s_dirty[promoted >> 5] &= ~(1u << (promoted & 31)); }
+                hfxd_mark_seen(W, fin, seen);
+            }
+            for (int wq = 0; wq < n_slots; ++wq) {
+                unsigned todo = W.s_dirty[wq];
+                if (wq == (kx >> 5)) todo &= ~(1u << (kx & 31));                 // done above
+                __syncwarp();
+                if (lane == 0) W.s_dirty[wq] = 0;
                 while (todo) {
-                    const int b = __ffs(todo) - 1;
+                    const int q = (wq << 5) + __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const double Sq = hfxd_lane_sum<false>(W, W.s_pos[q0 + b]);
+                    unsigned unused;
+                    const double Sq = hfxd_lane_sum<false>(W, W.s_pos[q], unused);
                     const double tot = __shfl_sync(HF_FULL, hfx_scan(Sq, lane), 31);
-                    if (lane == 0) W.s_T[q0 + b] = tot;
+                    if (lane == 0) W.s_T[q] = tot;
                 }
             }
             __syncwarp();

@@ -51,7 +51,8 @@ def test_oracle_cache_is_exact_and_model_properties():
     ((10, 9, 6), 2.0, 4, 40, ((1.0, 1.0), (1.0, 1.0)), 0.25),      # crowded: many annihilations, wrap on every site
     ((12, 11, 7), 3.0, 5, 33, ((0.5, 2.0), (0.0, 1.0)), 0.6),       # two slots of excitons, mixed factors, TS blocked
     ((9, 9, 5), 1.5, 6, 7, ((0.0, 0.0), (0.0, 0.0)), 0.0),          # pure blocking
-    ((22, 20, 6), 4.0, 7, 64, ((1.0, 1.0), (1.0, 1.0)), 0.25)])     # the cutoff-4 table, wrap-free sites exist
+    ((22, 20, 6), 4.0, 7, 64, ((1.0, 1.0), (1.0, 1.0)), 0.25),      # the cutoff-4 table, wrap-free sites exist
+    ((11, 10, 6), 3.0, 8, 96, ((1.0, 1.0), (1.0, 3.0)), 1.0)])      # very crowded, every TT annihilation promotes the survivor
 def test_emulated_dense_kernel_equals_specification(dims, cutoff, seed, n, ann, p_tta):
     p = dict(xo.default_params(), cutoff=cutoff)
     o, _ = _oracle(dims, seed, p, annihilation=ann, p_tta=p_tta)
