@@ -142,6 +142,37 @@ class DeviceFitness:
             self._sim = None
 
 
+class ExcitonFitness(DeviceFitness):
+    """EQE (percent) of a population of compositions from the exciton path: photons per decayed exciton
+    times the outcoupling, for ``trajectories_per_candidate`` single-exciton trajectories of ``steps`` KMC
+    events on each candidate's own lattice (``excitons.ExcitonEnsemble``'s model, DESIGN.md section 9 — this
+    package's own: the reference has no exciton dynamics and therefore no EQE)."""
+
+    def __init__(self, dims, parameters=None, cfg: GAConfig | None = None, seed=0, device=0, rank=0, world=1):
+        super().__init__(dims, 1, 0.1, cfg, seed, device, rank, world)
+        self.parameters = parameters or {}
+
+    def __call__(self, counts):
+        from . import _native as nat
+        counts = np.asarray(counts, dtype=np.int64)
+        if len(counts) != self.cfg.population:
+            raise ValueError("population size mismatch")
+        sim = self._handle()
+        mine = counts[self.rank * self.local:(self.rank + 1) * self.local]
+        sim.generate_lattice_mixed(self.comps.proportions(mine))
+        params = nat.x_params_from_dict(self.parameters)
+        sim.x_configure(params)
+        sim.x_spawn()
+        sim.x_run(self.cfg.steps)
+        t = sim.x_realisation_tallies()
+        self.last_tallies = t
+        rad = (t["rad_host"] + t["rad_tadf"] + t["rad_fluo"]).astype(np.float64)
+        decayed = rad + sum(t[k] for k in t if k.startswith("nonrad_")).astype(np.float64)
+        local = 100.0 * params.outcoupling * rad / np.maximum(decayed, 1.0)
+        self.generation += 1
+        return all_gather_fitness(local, self.world)
+
+
 def all_gather_fitness(local, world):
     """Concatenate the per-rank fitness blocks (identity for one rank)."""
     local = np.ascontiguousarray(local, dtype=np.float64)

@@ -69,3 +69,34 @@ def test_device_fitness_equals_oracle_per_candidate():
     out = ga.run(3)
     assert len(out["history"]) == 3 and out["best_fitness"] >= 0.0
     fit_fn.close()
+
+
+@pytest.mark.gpu
+def test_exciton_fitness_ranks_compositions_and_equals_specification():
+    """EQE fitness from the exciton path: per-candidate photons / decayed excitons equal the specification run
+    on each candidate's own lattice."""
+    from hyperfluorescence_b200 import _native as nat
+    from hyperfluorescence_b200.evolution import ExcitonFitness, GAConfig
+    from oracle import exciton_oracle as xo
+    dims = (16, 16, 8)
+    cfg = GAConfig(population=4, trajectories_per_candidate=256, steps=400)
+    fit = ExcitonFitness(dims, parameters=dict(cutoff=3.0), cfg=cfg, seed=21)
+    counts = fit.comps.clip(np.array([[1, 1], [300, 20], [600, 60], [150, 150]]))
+    f = fit(counts)
+    assert f.shape == (4,) and np.all(f >= 0) and np.all(f <= 20.0)                 # outcoupling 0.2
+    assert len(set(np.round(f, 9))) == 4                                             # four different devices
+    sim = fit._handle()
+    per = fit.last_tallies
+    params = dict(nat.x_params_to_dict(nat.x_default_params()), cutoff=3.0)
+    tab = sim.x_tables()
+    for r in (0, 2):
+        lat = sim.download_lattice(r)
+        ws1, wt1 = sim.x_weights(r)
+        o = xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params, tab)
+        ref = o.run_batch(21, r * 256, 256, 400, n_threads=4)
+        for k in xo.XT_NAMES[:15]:
+            assert int(per[k][r]) == ref[k], (r, k)
+        rad = ref["rad_host"] + ref["rad_tadf"] + ref["rad_fluo"]
+        lost = rad + sum(v for k, v in ref.items() if k.startswith("nonrad_"))
+        assert abs(f[r] - 100.0 * 0.2 * rad / lost) < 1e-12
+    fit.close()
