@@ -151,3 +151,37 @@ def test_gpu_dense_ensemble_api():
     with pytest.raises(ValueError):
         DenseExcitonEnsemble((8, 8, 4), devices=1, excitons_per_device=2000)
     ens.close(); blk.close()
+
+
+@pytest.mark.gpu
+def test_gpu_dense_full_size_properties():
+    """BASELINE configs[3] at size (128^3, 2048 devices x 256 excitons): conservation laws, mask == list on
+    sampled devices, and two sampled devices against the specification (with its cache verification)."""
+    from hyperfluorescence_b200 import _native as nat
+    dims, B, n, n_events = (128, 128, 128), 2048, 256, 150
+    sim = nat.Sim(dims, (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=B, seed=13)
+    try:
+        sim.generate_lattice()
+        sim.x_configure()
+        sim.xd_configure(n)
+        sim.xd_spawn()
+        sim.xd_run(n_events)
+        sim.sync()
+        t = sim.xd_tallies()
+        lost = sum(v for k, v in t.items() if k.startswith(("rad_", "nonrad_", "ann_")))
+        assert t["events"] == B * n_events and t["generated"] == B * n + lost
+        assert t["forster"] + t["dexter"] + t["isc"] + t["risc"] + lost == t["events"]
+        assert t["tta_up"] <= t["ann_tt"]
+        lat = sim.download_lattice(0)
+        ws1, wt1 = sim.x_weights(0)
+        o = xo.DenseExcitonOracle(dims, lat["species"], ws1, wt1, nat.x_params_to_dict(nat.x_default_params()), sim.x_tables())
+        for d in (0, B - 1):
+            got = sim.xd_device(d)
+            occ = sim.xd_occupancy(d)
+            assert int((occ != 0).sum()) == n and np.array_equal(occ[got["site"]], got["spin"].astype(np.uint8))
+            ref = o.run_device(13, d, n, n_events, verify=(d == 0))
+            assert ref["cache_mismatches"] == 0
+            assert np.array_equal(got["site"], ref["site"]) and np.array_equal(got["spin"], ref["spin"])
+            assert np.array_equal(got["total_rate"], ref["total_rate"]) and got["draws"] == ref["draws"]
+    finally:
+        sim.close()

@@ -169,3 +169,39 @@ def test_gpu_exciton_ensemble_api():
     with pytest.raises(ValueError):
         ExcitonEnsemble((20, 20, 2))
     ens.close()
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_full_size_properties():
+    """The north_star's own size (128^3, 10^6 trajectories, cutoff 4), where the oracle cannot follow:
+    conservation laws of the tallies, the draw accounting of every trajectory and a sampled comparison
+    of 24 trajectories with the specification."""
+    from hyperfluorescence_b200 import _native as nat
+    B, n = 1_000_000, 60
+    sim = nat.Sim((128, 128, 128), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=B, seed=11)
+    try:
+        sim.generate_lattice()
+        sim.x_configure()
+        sim.x_spawn()
+        sim.x_run(n // 2)
+        sim.x_run(n - n // 2)
+        sim.sync()
+        t = sim.x_tallies()
+        decays = sum(v for k, v in t.items() if k.startswith(("rad_", "nonrad_")))
+        assert t["events"] == B * n
+        assert t["generated"] == B + decays
+        assert t["forster"] + t["dexter"] + t["isc"] + t["risc"] + decays == t["events"]
+        assert t["rad_host"] == 0                                                  # hosts never emit (molecule.py:396-400)
+        st = sim.x_state()
+        assert int(st["draws"].sum()) == 2 * (B + t["events"] + decays)            # spawn + event + respawn blocks
+        assert st["site"].min() >= 0 and st["site"].max() < 128 ** 3
+        assert set(np.unique(st["spin"])) <= {1, 3}
+        assert np.all(st["time"] >= 0) and np.all(np.isfinite(st["time"]))
+        lat = sim.download_lattice(0)
+        ws1, wt1 = sim.x_weights(0)
+        o = xo.ExcitonOracle((128, 128, 128), lat["species"], ws1, wt1, nat.x_params_to_dict(nat.x_default_params()), sim.x_tables())
+        for b in list(range(0, 8)) + list(range(499_990, 499_998)) + list(range(B - 8, B)):
+            ref = o.run(11, b, n)
+            assert (st["site"][b], st["spin"][b], int(st["draws"][b])) == (ref["site"], ref["spin"], ref["draws"]), b
+    finally:
+        sim.close()
