@@ -853,6 +853,19 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if (s->P.X < 2 * R + 1 || s->P.Y < 2 * R + 1)
         return fail(HF_ERR_BAD_ARG, "x and y must be >= 2*cutoff+1 = %d for unique periodic images", 2 * R + 1);
     if (!(p->dexter_length > 0.0)) return fail(HF_ERR_BAD_ARG, "dexter_length must be positive");
+    if (!(p->singlet_fraction >= 0.0 && p->singlet_fraction <= 1.0)) return fail(HF_ERR_BAD_ARG, "singlet_fraction must be a probability");
+    for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b)
+            if (!(p->forster_radius[a][b] >= 0.0) || !(p->dexter_prefactor[a][b] >= 0.0))
+                return fail(HF_ERR_BAD_ARG, "transfer parameters must be >= 0");
+        if (!(p->k_isc[a] >= 0.0) || !(p->k_risc[a] >= 0.0)) return fail(HF_ERR_BAD_ARG, "spin-flip rates must be >= 0");
+        for (int sp = 0; sp < 2; ++sp) {
+            if (!(p->k_rad[a][sp] >= 0.0) || !(p->k_nonrad[a][sp] >= 0.0)) return fail(HF_ERR_BAD_ARG, "decay rates must be >= 0");
+            // every exciton must be able to end: with no decay channel the total rate of an isolated site can be 0
+            if (!(p->k_rad[a][sp] + p->k_nonrad[a][sp] > 0.0))
+                return fail(HF_ERR_BAD_ARG, "species %d needs a non-zero decay rate for spin index %d", a, sp);
+        }
+    }
     int rc = use_device(s);
     if (rc) return rc;
     HF_CUDA(cudaStreamSynchronize(s->stream));

@@ -205,3 +205,45 @@ def test_gpu_exciton_full_size_properties():
             assert (st["site"][b], st["spin"][b], int(st["draws"][b])) == (ref["site"], ref["spin"], ref["draws"]), b
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_api_errors():
+    """Misuse of the hf_x_* / hf_xd_* entry points fails with a status and a message, never with a crash."""
+    from hyperfluorescence_b200 import _native as nat
+    sim = nat.Sim((12, 12, 6), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=64, seed=1)
+    try:
+        with pytest.raises(nat.HfError, match="before a lattice"):
+            sim.x_configure()
+        sim.generate_lattice()
+        with pytest.raises(nat.HfError, match="before hf_x_configure"):
+            sim.x_spawn()
+        with pytest.raises(nat.HfError, match="before hf_x_configure"):
+            sim.xd_configure(8)
+        for bad in (dict(cutoff=0.5), dict(cutoff=7.0), dict(dexter_length=0.0), dict(singlet_fraction=1.5),
+                    dict(k_nonrad=np.zeros((3, 2)), k_rad=np.zeros((3, 2))), dict(k_isc=np.array([-1.0, 0, 0]))):
+            with pytest.raises(nat.HfError):
+                sim.x_configure(nat.x_params_from_dict(bad))
+        with pytest.raises(nat.HfError, match="unique periodic images"):
+            sim.x_configure(nat.x_params_from_dict(dict(cutoff=6.0)))              # 12 < 2 * 6 + 1
+        sim.x_configure()
+        with pytest.raises(nat.HfError, match="before hf_x_spawn"):
+            sim.x_run(10)
+        with pytest.raises(nat.HfError, match="before hf_xd_spawn"):
+            sim.xd_configure(8); sim.xd_run(10)
+        for bad_n in (0, 2000, 400):                                               # 400 > half of the 576 interior sites
+            with pytest.raises(nat.HfError):
+                sim.xd_configure(bad_n)
+        with pytest.raises(nat.HfError):
+            sim.xd_configure(8, ((1.0, -1.0), (1.0, 1.0)))
+        with pytest.raises(nat.HfError):
+            sim.xd_configure(8, p_tta=1.5)
+        sim.x_spawn(); sim.x_run(0); sim.x_run(5); sim.sync()
+        assert sim.x_tallies()["events"] == 64 * 5
+        with pytest.raises(nat.HfError):
+            sim.x_run(-1)
+        sim.x_configure(nat.x_params_from_dict(dict(cutoff=2.0)))                  # reconfiguring drops the dense devices
+        with pytest.raises(nat.HfError, match="before hf_xd_configure"):
+            sim.xd_spawn()
+    finally:
+        sim.close()
