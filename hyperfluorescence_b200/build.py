@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhfkmc.so")
 SOURCES = [os.path.join(CSRC, "hfkmc.cu")]
-HEADERS = [os.path.join(CSRC, "hf_frm.cuh"), os.path.join(CSRC, "hf_frm_c1.cuh"), os.path.join(CSRC, "hf_exciton.cuh"), os.path.join(CSRC, "hf_exciton_dense.cuh"), os.path.join(CSRC, "hf_philox.cuh"),
+HEADERS = [os.path.join(CSRC, "hf_frm.cuh"), os.path.join(CSRC, "hf_frm_c1.cuh"), os.path.join(CSRC, "hf_frm_small.cuh"), os.path.join(CSRC, "hf_exciton.cuh"), os.path.join(CSRC, "hf_exciton_dense.cuh"), os.path.join(CSRC, "hf_philox.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "hfkmc.h")]
 
 NVCC_FLAGS = [

@@ -102,6 +102,7 @@ struct HfWarp {
     int64_t local;                 // local trajectory index
     const uint8_t *species;        // this trajectory's realisation
     const double *lumo, *homo;
+    float *approx;                 // thread-per-trajectory kernel only: this thread's screening column (27 floats)
     unsigned c_move_e, c_move_h, c_bound, c_decay, c_capture_e, c_capture_h;
     unsigned c_recomb_host, c_recomb_tadf, c_recomb_fluo, c_emit_tadf, c_emit_fluo;
 
@@ -182,35 +183,59 @@ __device__ __forceinline__ int64_t hf_randbelow(const HfParams &P, HfWarp &w, in
     return (int64_t)floor(r * 0x1p53) % n;
 }
 
+// ---- lanes per trajectory ---------------------------------------------------------------------
+// The bookkeeping below is written once for L lanes cooperating on one trajectory: L = 32 is the
+// warp-per-trajectory kernel (hf_run_kernel), L = 1 the thread-per-trajectory kernel for small `charges`
+// (hf_frm_small.cuh), where every collective degenerates to the identity and every strided loop to a
+// serial one.  Same statements, same order, same results.
+template <int L> __device__ __forceinline__ unsigned hf_ballot(bool p) {
+    if constexpr (L == 32) return __ballot_sync(HF_FULL, p); else return p ? 1u : 0u;
+}
+template <int L, typename T> __device__ __forceinline__ T hf_shfl(T v, int src) {
+    if constexpr (L == 32) return __shfl_sync(HF_FULL, v, src); else return v;
+}
+template <int L, typename T> __device__ __forceinline__ T hf_shfl_xor(T v, int off) {
+    if constexpr (L == 32) return __shfl_xor_sync(HF_FULL, v, off); else return v;
+}
+template <int L> __device__ __forceinline__ void hf_sync() {
+    if constexpr (L == 32) __syncwarp();
+}
+// thread-per-trajectory candidate loop (hf_frm_small.cuh)
+__device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags);
+
 // ---- ordered-list primitives (warp-cooperative, n is warp-uniform) ---------------------------
+template <int L = 32>
 __device__ __forceinline__ int hf_find_first(const int32_t *a, int n, int v, int lane) {
-    for (int base = 0; base < n; base += 32) {
+    for (int base = 0; base < n; base += L) {
         const int i = base + lane;
-        const unsigned m = __ballot_sync(HF_FULL, i < n && a[i] == v);
+        const unsigned m = hf_ballot<L>(i < n && a[i] == v);
         if (m) return base + __ffs(m) - 1;
     }
     return -1;
 }
 
+template <int L = 32>
 __device__ __forceinline__ bool hf_contains(const int32_t *a, int n, int v, int lane) {
-    return hf_find_first(a, n, v, lane) >= 0;
+    return hf_find_first<L>(a, n, v, lane) >= 0;
 }
 
 // list.remove(a[idx]) keeping the order of the rest
+template <int L = 32>
 __device__ __forceinline__ void hf_remove_at(int32_t *a, int n, int idx, int lane) {
-    for (int base = idx; base < n - 1; base += 32) {
+    for (int base = idx; base < n - 1; base += L) {
         const int i = base + lane;
         int v = 0;
         if (i < n - 1) v = a[i + 1];
-        __syncwarp();
+        hf_sync<L>();
         if (i < n - 1) a[i] = v;
-        __syncwarp();
+        hf_sync<L>();
     }
 }
 
 // Molecule.switch_electron / switch_hole (molecule.py:78-86) on the flag SET
+template <int L = 32>
 __device__ __forceinline__ bool hf_toggle_flag(const HfParams &P, HfWarp &w, int t, int site, int lane) {
-    const int idx = hf_find_first(w.flag(t), w.n_flag(t), site, lane);
+    const int idx = hf_find_first<L>(w.flag(t), w.n_flag(t), site, lane);
     if (idx >= 0) {
         if (lane == 0) w.flag(t)[idx] = w.flag(t)[w.n_flag(t) - 1];
         w.set_n_flag(t, w.n_flag(t) - 1);
@@ -219,25 +244,27 @@ __device__ __forceinline__ bool hf_toggle_flag(const HfParams &P, HfWarp &w, int
         if (lane == 0) w.flag(t)[w.n_flag(t)] = site;
         w.set_n_flag(t, w.n_flag(t) + 1);
     }
-    __syncwarp();
+    hf_sync<L>();
     return true;
 }
 
+template <int L = 32>
 __device__ __forceinline__ void hf_clear_flag(HfWarp &w, int t, int site, int lane) {
-    const int idx = hf_find_first(w.flag(t), w.n_flag(t), site, lane);
+    const int idx = hf_find_first<L>(w.flag(t), w.n_flag(t), site, lane);
     if (idx >= 0) {
         if (lane == 0) w.flag(t)[idx] = w.flag(t)[w.n_flag(t) - 1];
         w.set_n_flag(t, w.n_flag(t) - 1);
     }
-    __syncwarp();
+    hf_sync<L>();
 }
 
 // _remove_move_*_events (reseau.py:352-364) under Event.__eq__ (event.py:141-147): drop every
 // event of type t whose initial == a OR final == b (quirk Q4), keeping the order of the rest.
+template <int L = 32>
 __device__ __forceinline__ void hf_remove_events(HfWarp &w, int t, int a, int b, int lane) {
     const int n = w.n_ev(t);
     int out = 0;
-    for (int base = 0; base < n; base += 32) {
+    for (int base = 0; base < n; base += L) {
         const int i = base + lane;
         int ini = 0, fin = 0;
         double tau = 0.0;
@@ -246,22 +273,23 @@ __device__ __forceinline__ void hf_remove_events(HfWarp &w, int t, int a, int b,
             ini = w.ev_init(t)[i]; fin = w.ev_final(t)[i]; tau = w.ev_tau(t)[i];
             keep = !(ini == a || fin == b);
         }
-        const unsigned m = __ballot_sync(HF_FULL, keep);
+        const unsigned m = hf_ballot<L>(keep);
         const int dst = out + __popc(m & ((1u << lane) - 1u));
-        __syncwarp();
+        hf_sync<L>();
         if (keep) { w.ev_init(t)[dst] = ini; w.ev_final(t)[dst] = fin; w.ev_tau(t)[dst] = tau; }
-        __syncwarp();
+        hf_sync<L>();
         out += __popc(m);
     }
     w.set_n_ev(t, out);
 }
 
 // _update_events (reseau.py:564-578): tau -= time on every pending move event
+template <int L = 32>
 __device__ __forceinline__ void hf_update_events(HfWarp &w, double time, int lane) {
 #pragma unroll
     for (int t = 0; t < 2; ++t)
-        for (int i = lane; i < w.n_ev(t); i += 32) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
-    __syncwarp();
+        for (int i = lane; i < w.n_ev(t); i += L) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
+    hf_sync<L>();
 }
 
 // ---- neighbour table: reseau.py:184-205 for charge_tranfer_distance == 1 (quirk Q3) ----------
@@ -318,24 +346,27 @@ __device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w
 
 // 1/|loc_j - initial| for both lists, computed once per regenerated event instead of once per
 // candidate (the reference recomputes it 26 times: SURVEY.md §8a2); same bits.
+template <int L = 32>
 __device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, int lane) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int32_t *list = s == 0 ? w.pos(t) : w.pos(1 - t);
         const int n = s == 0 ? w.n_pos(t) : w.n_pos(1 - t);
-        for (int j = lane; j < n; j += 32) {
+        for (int j = lane; j < n; j += L) {
             const int d2 = hf_dist2(list[j], initial);
             w.inv_old(s)[j] = d2 == 0 ? 0.0 : __ddiv_rn(1.0, __dsqrt_rn((double)d2));
         }
     }
-    __syncwarp();
+    hf_sync<L>();
 }
 
 // _new_move_electron_events / _new_move_hole_events (reseau.py:380-396; use_flags = true) and the
 // per-charge body of _init_move_*_events (reseau.py:240-276; use_flags = false: membership in
 // the position list).  Lanes = candidates in the reference's x-major neighbour order; one TRAJ
 // uniform per unblocked candidate in that order; first minimum wins.  Returns a status.
+template <int L = 32>
 __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags, int lane) {
+    if constexpr (L == 1) return hf_gen_move_event_serial(P, w, t, pos, use_flags);
     const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
     const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
     const int total = 9 * nz;
@@ -348,9 +379,9 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
     bool blocked = false;
     for (int j = 0; j < nb; ++j) blocked |= (blk[j] == cand);                    // 385 / 394 ; 249 / 268
     const bool active = valid && !blocked;
-    const unsigned mask = __ballot_sync(HF_FULL, active);
+    const unsigned mask = hf_ballot<L>(active);
     if (mask == 0) return HF_ST_VALUE_ERROR;                                     // min() of an empty sequence
-    hf_fill_inv_old(w, t, pos, lane);
+    hf_fill_inv_old<L>(w, t, pos, lane);
     double tau = INFINITY, rate = 0.0;
     bool zero_div = false, exhausted = false;
     if (active) {
@@ -358,8 +389,8 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
         const double u = hf_traj_uniform(P, w, w.draws + (uint64_t)rank, &exhausted);
         tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
     }
-    if (__ballot_sync(HF_FULL, exhausted)) return HF_ST_REPLAY_EXHAUSTED;
-    const unsigned zmask = __ballot_sync(HF_FULL, active && zero_div);
+    if (hf_ballot<L>(exhausted)) return HF_ST_REPLAY_EXHAUSTED;
+    const unsigned zmask = hf_ballot<L>(active && zero_div);
     if (zmask) {                                   // draws up to and including the failing candidate
         const int f = __ffs(zmask) - 1;
         w.draws += (uint64_t)__popc(mask & (f == 31 ? HF_FULL : ((2u << f) - 1u)));
@@ -369,35 +400,36 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
     // min(events): first minimum in candidate order (387 / 396)
     int best = active ? lane : 99;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const double otau = __shfl_xor_sync(HF_FULL, tau, off);
-        const int obest = __shfl_xor_sync(HF_FULL, best, off);
+    for (int off = L / 2; off > 0; off >>= 1) {
+        const double otau = hf_shfl_xor<L>(tau, off);
+        const int obest = hf_shfl_xor<L>(best, off);
         if (otau < tau || (otau == tau && obest < best)) { tau = otau; best = obest; }
     }
-    const int fin = __shfl_sync(HF_FULL, cand, best & 31);
+    const int fin = hf_shfl<L>(cand, best & 31);
     if (w.n_ev(t) >= P.cap_c) return HF_ST_CAPACITY;
     if (lane == 0) { w.ev_init(t)[w.n_ev(t)] = pos; w.ev_final(t)[w.n_ev(t)] = fin; w.ev_tau(t)[w.n_ev(t)] = tau; }
     w.set_n_ev(t, w.n_ev(t) + 1);
-    __syncwarp();
+    hf_sync<L>();
     return HF_ST_OK;
 }
 
 // _electron_reinjection / _hole_reinjection (reseau.py:448-470): choice() over the free sites of
 // the injection face in x-major order, append, toggle the flag, _injection += 1.
+template <int L = 32>
 __device__ __forceinline__ int hf_reinject(const HfParams &P, HfWarp &w, int t, int lane) {
     const int zf = t == 0 ? P.Z - 1 : 0;
     const int n = w.n_pos(t);
     const int32_t *list = w.pos(t);
     // distinct occupied face sites
     int n_occ = 0;
-    for (int base = 0; base < n; base += 32) {
+    for (int base = 0; base < n; base += L) {
         const int j = base + lane;
         bool first = false;
         if (j < n && hf_pz(list[j]) == zf) {
             first = true;
             for (int q = 0; q < j; ++q) first &= (list[q] != list[j]);
         }
-        n_occ += __popc(__ballot_sync(HF_FULL, first));
+        n_occ += __popc(hf_ballot<L>(first));
     }
     const int64_t n_free = (int64_t)P.X * P.Y - n_occ;
     if (n_free <= 0) return HF_ST_VALUE_ERROR;                                   // choice() of an empty sequence
@@ -408,14 +440,14 @@ __device__ __forceinline__ int hf_reinject(const HfParams &P, HfWarp &w, int t, 
     int64_t f = k;
     for (;;) {
         int c = 0;
-        for (int base = 0; base < n; base += 32) {
+        for (int base = 0; base < n; base += L) {
             const int j = base + lane;
             bool hit = false;
             if (j < n && hf_pz(list[j]) == zf && (int64_t)hf_px(list[j]) * P.Y + hf_py(list[j]) <= f) {
                 hit = true;
                 for (int q = 0; q < j; ++q) hit &= (list[q] != list[j]);
             }
-            c += __popc(__ballot_sync(HF_FULL, hit));
+            c += __popc(hf_ballot<L>(hit));
         }
         const int64_t f2 = k + c;
         if (f2 == f) break;
@@ -425,13 +457,14 @@ __device__ __forceinline__ int hf_reinject(const HfParams &P, HfWarp &w, int t, 
     if (n >= P.cap_c) return HF_ST_CAPACITY;
     if (lane == 0) w.pos(t)[n] = site;
     w.set_n_pos(t, n + 1);
-    __syncwarp();
-    if (!hf_toggle_flag(P, w, t, site, lane)) return HF_ST_CAPACITY;
+    hf_sync<L>();
+    if (!hf_toggle_flag<L>(P, w, t, site, lane)) return HF_ST_CAPACITY;
     w.injection += 1;
     return HF_ST_OK;
 }
 
 // ---- state load / store ------------------------------------------------------------------------
+template <int L = 32>
 __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int64_t local, int lane) {
     const HfScalars sc = P.sc[local];
     w.local = local;
@@ -448,43 +481,44 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
     w.homo = P.homo + r * P.N;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-        for (int i = lane; i < w.n_pos(t); i += 32) w.pos(t)[i] = P.pos[t][local * P.cap_c + i];
-        for (int i = lane; i < w.n_flag(t); i += 32) w.flag(t)[i] = P.flag[t][local * P.cap_f + i];
-        for (int i = lane; i < w.n_ev(t); i += 32) {
+        for (int i = lane; i < w.n_pos(t); i += L) w.pos(t)[i] = P.pos[t][local * P.cap_c + i];
+        for (int i = lane; i < w.n_flag(t); i += L) w.flag(t)[i] = P.flag[t][local * P.cap_f + i];
+        for (int i = lane; i < w.n_ev(t); i += L) {
             w.ev_init(t)[i] = P.ev_init[t][local * P.cap_c + i];
             w.ev_final(t)[i] = P.ev_final[t][local * P.cap_c + i];
             w.ev_tau(t)[i] = P.ev_tau[t][local * P.cap_c + i];
         }
     }
-    if (lane < HF_CACHE) {                 // ring stored slot-major: [slot][trajectory]
-        w.cache_init[lane] = P.cache_init[lane * P.B + local];
-        w.cache_final[lane] = P.cache_final[lane * P.B + local];
-        w.cache_kp[lane] = P.cache_kp[lane * P.B + local];
-        w.cache_tau[lane] = P.cache_tau[lane * P.B + local];
+    for (int c = lane; c < HF_CACHE; c += L) {   // ring stored slot-major: [slot][trajectory]
+        w.cache_init[c] = P.cache_init[c * P.B + local];
+        w.cache_final[c] = P.cache_final[c * P.B + local];
+        w.cache_kp[c] = P.cache_kp[c * P.B + local];
+        w.cache_tau[c] = P.cache_tau[c * P.B + local];
     }
     w.c_move_e = w.c_move_h = w.c_bound = w.c_decay = w.c_capture_e = w.c_capture_h = 0;
     w.c_recomb_host = w.c_recomb_tadf = w.c_recomb_fluo = w.c_emit_tadf = w.c_emit_fluo = 0;
-    __syncwarp();
+    hf_sync<L>();
 }
 
+template <int L = 32>
 __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int lane) {
     const int64_t local = w.local;
-    __syncwarp();
+    hf_sync<L>();
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-        for (int i = lane; i < w.n_pos(t); i += 32) P.pos[t][local * P.cap_c + i] = w.pos(t)[i];
-        for (int i = lane; i < w.n_flag(t); i += 32) P.flag[t][local * P.cap_f + i] = w.flag(t)[i];
-        for (int i = lane; i < w.n_ev(t); i += 32) {
+        for (int i = lane; i < w.n_pos(t); i += L) P.pos[t][local * P.cap_c + i] = w.pos(t)[i];
+        for (int i = lane; i < w.n_flag(t); i += L) P.flag[t][local * P.cap_f + i] = w.flag(t)[i];
+        for (int i = lane; i < w.n_ev(t); i += L) {
             P.ev_init[t][local * P.cap_c + i] = w.ev_init(t)[i];
             P.ev_final[t][local * P.cap_c + i] = w.ev_final(t)[i];
             P.ev_tau[t][local * P.cap_c + i] = w.ev_tau(t)[i];
         }
     }
-    if (lane < HF_CACHE) {
-        P.cache_init[lane * P.B + local] = w.cache_init[lane];
-        P.cache_final[lane * P.B + local] = w.cache_final[lane];
-        P.cache_kp[lane * P.B + local] = w.cache_kp[lane];
-        P.cache_tau[lane * P.B + local] = w.cache_tau[lane];
+    for (int c = lane; c < HF_CACHE; c += L) {
+        P.cache_init[c * P.B + local] = w.cache_init[c];
+        P.cache_final[c * P.B + local] = w.cache_final[c];
+        P.cache_kp[c * P.B + local] = w.cache_kp[c];
+        P.cache_tau[c * P.B + local] = w.cache_tau[c];
     }
     if (lane == 0) {
         HfScalars sc;
@@ -505,6 +539,7 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
 
 // ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
 // Returns HF_ST_OK when an event fired; ev_* describe it (packed coordinates).
+template <int L = 32>
 __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                        int *ev_init, int *ev_final, double *ev_tau) {
     int kind, part, ini, fin;
@@ -519,7 +554,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         if (total == 0) return HF_ST_NO_EVENTS;                                  // 487-488
         double btau = INFINITY;
         int bidx = -1;
-        for (int base = 0; base < total; base += 32) {
+        for (int base = 0; base < total; base += L) {
             const int i = base + lane;
             if (i < total) {
                 const double ti = i < ne ? w.ev_tau(0)[i] : w.ev_tau(1)[i - ne];
@@ -527,9 +562,9 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
             }
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ot = __shfl_xor_sync(HF_FULL, btau, off);
-            const int oi = __shfl_xor_sync(HF_FULL, bidx, off);
+        for (int off = L / 2; off > 0; off >>= 1) {
+            const double ot = hf_shfl_xor<L>(btau, off);
+            const int oi = hf_shfl_xor<L>(bidx, off);
             if (oi >= 0 && (bidx < 0 || ot < btau || (ot == btau && oi > bidx))) { btau = ot; bidx = oi; }
         }
         const int t = bidx < ne ? 0 : 1, i = bidx - (t ? ne : 0);
@@ -547,25 +582,25 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
 
     if (kind == HF_K_MOVE) {                                                     // 492-524
         const int t = part - 1, o = 1 - t;
-        hf_remove_events(w, t, ini, fin, lane);                                  // 495 / 511 (Q4)
-        if (!hf_toggle_flag(P, w, t, ini, lane)) return HF_ST_CAPACITY;          // 423-424 / 429-430
-        if (!hf_toggle_flag(P, w, t, fin, lane)) return HF_ST_CAPACITY;
-        const int idx = hf_find_first(w.pos(t), w.n_pos(t), ini, lane);          // 425-426 / 431-432
+        hf_remove_events<L>(w, t, ini, fin, lane);                                  // 495 / 511 (Q4)
+        if (!hf_toggle_flag<L>(P, w, t, ini, lane)) return HF_ST_CAPACITY;          // 423-424 / 429-430
+        if (!hf_toggle_flag<L>(P, w, t, fin, lane)) return HF_ST_CAPACITY;
+        const int idx = hf_find_first<L>(w.pos(t), w.n_pos(t), ini, lane);          // 425-426 / 431-432
         if (idx < 0) return HF_ST_VALUE_ERROR;
-        hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+        hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
         if (lane == 0) w.pos(t)[w.n_pos(t) - 1] = fin;
-        __syncwarp();
-        const bool opposite_here = hf_contains(w.flag(o), w.n_flag(o), fin, lane);
+        hf_sync<L>();
+        const bool opposite_here = hf_contains<L>(w.flag(o), w.n_flag(o), fin, lane);
         const int capture_z = t == 0 ? 0 : P.Z - 1;
         if (!opposite_here && hf_pz(fin) != capture_z) {                         // 498-500 / 514-516
-            hf_update_events(w, tau, lane);
-            return hf_gen_move_event(P, w, t, fin, true, lane);
+            hf_update_events<L>(w, tau, lane);
+            return hf_gen_move_event<L>(P, w, t, fin, true, lane);
         } else if (opposite_here) {                                              // 501-505 / 517-521
-            hf_remove_events(w, o, fin, fin, lane);
+            hf_remove_events<L>(w, o, fin, fin, lane);
             // _update_events(0.) leaves every tau unchanged (Q5)
             w.special = HF_K_BOUND | (HF_PART_EXCITON << 8); w.special_site = fin;
         } else {                                                                 // 506-508 / 522-524
-            hf_update_events(w, tau, lane);
+            hf_update_events<L>(w, tau, lane);
             w.special = HF_K_CAPTURE | (part << 8); w.special_site = fin;
         }
         return HF_ST_OK;
@@ -573,7 +608,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     const int site = w.special_site;
     w.special = 0;                                                               // _remove_*_event
     if (kind == HF_K_BOUND) {                                                    // 529-533
-        const bool both = hf_contains(w.flag(0), w.n_flag(0), site, lane) && hf_contains(w.flag(1), w.n_flag(1), site, lane);
+        const bool both = hf_contains<L>(w.flag(0), w.n_flag(0), site, lane) && hf_contains<L>(w.flag(1), w.n_flag(1), site, lane);
         if (both) {                                                              // molecule.py:88-96
             const double r = hf_philox_uniform(P.k0, P.k1, HF_STREAM_SPIN, w.ident, w.spins);
             w.spins += 1;
@@ -581,9 +616,9 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         }
 #pragma unroll
         for (int t = 0; t < 2; ++t) {                                            // 434-438
-            const int idx = hf_find_first(w.pos(t), w.n_pos(t), site, lane);
+            const int idx = hf_find_first<L>(w.pos(t), w.n_pos(t), site, lane);
             if (idx < 0) return HF_ST_VALUE_ERROR;
-            hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+            hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
             w.set_n_pos(t, w.n_pos(t) - 1);
         }
         w.special = HF_K_DECAY | (HF_PART_EXCITON << 8); w.special_site = site;
@@ -595,30 +630,30 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         if (w.xstate) {                                                          // molecule.py:185-199, 283-297, 387-400
             photon = sp != HF_SPECIES_HOST && w.xstate == HF_XS_SINGLET;
             w.xstate = 0;
-            hf_clear_flag(w, 0, site, lane);
-            hf_clear_flag(w, 1, site, lane);
+            hf_clear_flag<L>(w, 0, site, lane);
+            hf_clear_flag<L>(w, 1, site, lane);
         }
         w.recombination += 1;                                                    // 472-476
         w.c_recomb_host += sp == 0; w.c_recomb_tadf += sp == 1; w.c_recomb_fluo += sp == 2;
         if (photon) { w.emission += 1; w.c_emit_tadf += sp == 1; w.c_emit_fluo += sp == 2; }
-        int st = hf_reinject(P, w, 0, lane);
+        int st = hf_reinject<L>(P, w, 0, lane);
         if (st != HF_ST_OK) return st;
-        st = hf_gen_move_event(P, w, 0, w.pos(0)[w.n_pos(0) - 1], true, lane);
+        st = hf_gen_move_event<L>(P, w, 0, w.pos(0)[w.n_pos(0) - 1], true, lane);
         if (st != HF_ST_OK) return st;
-        st = hf_reinject(P, w, 1, lane);
+        st = hf_reinject<L>(P, w, 1, lane);
         if (st != HF_ST_OK) return st;
-        return hf_gen_move_event(P, w, 1, w.pos(1)[w.n_pos(1) - 1], true, lane);
+        return hf_gen_move_event<L>(P, w, 1, w.pos(1)[w.n_pos(1) - 1], true, lane);
     }
     // capture (551-561)
     const int t = part - 1;
-    if (!hf_toggle_flag(P, w, t, site, lane)) return HF_ST_CAPACITY;             // 440-446
-    const int idx = hf_find_first(w.pos(t), w.n_pos(t), site, lane);
+    if (!hf_toggle_flag<L>(P, w, t, site, lane)) return HF_ST_CAPACITY;             // 440-446
+    const int idx = hf_find_first<L>(w.pos(t), w.n_pos(t), site, lane);
     if (idx < 0) return HF_ST_VALUE_ERROR;
-    hf_remove_at(w.pos(t), w.n_pos(t), idx, lane);
+    hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
     w.set_n_pos(t, w.n_pos(t) - 1);
-    const int st = hf_reinject(P, w, t, lane);
+    const int st = hf_reinject<L>(P, w, t, lane);
     if (st != HF_ST_OK) return st;
-    return hf_gen_move_event(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
+    return hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
 }
 
 // ---- kernels -------------------------------------------------------------------------------------

@@ -1,0 +1,188 @@
+// Thread-per-trajectory First-Reaction-Method kernel for SMALL `charges` (2 <= C <= 8): the
+// reference's own driver configuration (OLED.py:6-10: charges = 4) and the GA fitness sweeps.
+//
+// ncu on the warp-per-trajectory kernel (profiles/r01a_*): 1174 warp instructions per event, half of
+// them bookkeeping on lists of <= 2C entries that 32 lanes cannot share, the other half ONE candidate's
+// rate arithmetic (the 26 candidates run in parallel lanes).  With a handful of charges it is cheaper to
+// give every lane its own trajectory: the bookkeeping is hf_step<1> — the SAME statements as the warp
+// kernel, instantiated with one lane per trajectory (hf_frm.cuh) — on per-thread shared-memory lists,
+// and the candidate loop below screens the 17-26 candidates in fp32 before verifying the possible
+// minima exactly, like hf_frm_c1.cuh does for C = 1.
+#pragma once
+#include "hf_frm.cuh"
+#include "hf_frm_c1.cuh"
+
+#define HF_SMALL_MAX_CHARGES 8
+#define HF_SMALL_THREADS 64
+
+// bytes of shared memory per trajectory: the lists of hf_carve + the screening column, an odd number of
+// 8-byte words so that the threads of a warp spread over the banks
+__host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
+    size_t b = hf_warp_smem_bytes(cap_c, cap_f) + 4u * 28u;
+    b = (b + 7u) & ~(size_t)7u;
+    if (((b >> 3) & 1u) == 0) b += 8;
+    return b;
+}
+
+// _new_move_*_events (reseau.py:380-396) and the per-charge body of _init_move_*_events (240-276) for
+// one thread's trajectory: min() over the unblocked candidates, first minimum wins, one TRAJ uniform
+// per unblocked candidate in neighbour order.
+//
+// Screen-then-verify as in hf_c1_gen, with these differences: candidates can be blocked (they draw
+// nothing), and the Coulomb sum has up to 2C - 1 terms.  The fp32 estimate still ignores it: every
+// term is |1/r' - 1/r| <= 1 times HF_ELECTROSTATIC = 4.8e-7 eV, so <= 15 terms shift dE / kT by
+// <= 2.8e-4 and the estimate of 1e13 * tau by a relative 2.8e-4 on top of hf_c1_gen's 4e-5: candidates
+// outside a window of 1 + 2^-9 around the best estimate still cannot win or tie
+// ((1 + 2^-9)(1 - 3.2e-4) > 1 + 3.2e-4).  Whenever the reference could raise ZeroDivisionError for
+// geometric reasons (a same-type charge on a candidate: the flag/list desynchronisation of DESIGN.md §0;
+// an opposite charge on the moving charge's own site) every candidate is evaluated exactly, in order,
+// as the warp kernel does.
+__device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags) {
+    const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
+    const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
+    const int total = 9 * nz;
+    const int32_t *blk = use_flags ? w.flag(t) : w.pos(t);
+    const int nb = use_flags ? w.n_flag(t) : w.n_pos(t);
+    const int ns = w.n_pos(t), no = w.n_pos(1 - t);
+    const double *__restrict__ E = w.energy(t);
+    float *approx = w.approx;
+    const double e_init = __ldg(E + hf_site(P, pos));
+    const double fz = t == 0 ? -P.field : P.field;
+    const int64_t plane = (int64_t)P.X * P.Y;
+    // ---- pass 0: which candidates are active, their dE in fp32, and whether a geometric ZeroDivisionError is possible
+    unsigned amask = 0;
+    bool slow = false;
+    for (int j = 0; j < no; ++j) slow |= w.pos(1 - t)[j] == pos;                 // 1 / |loc - initial| with loc == initial
+    {
+        int l = 0;
+        for (int ix = 0; ix < 3; ++ix) {
+            const int cx = hf_bvk_xy(px, P.X, ix);
+            for (int iy = 0; iy < 3; ++iy) {
+                const int cy = hf_bvk_xy(py, P.Y, iy);
+                const double *row = E + ((int64_t)cy * P.X + cx);
+                for (int iz = 0; iz < nz; ++iz, ++l) {
+                    const int cz = hf_bvk_z(pz, P.Z, iz);
+                    const int cand = hf_pack(cx, cy, cz);
+                    bool active = cand != pos;
+                    for (int j = 0; j < nb; ++j) active &= blk[j] != cand;       // 385 / 394 ; 249 / 268
+                    if (!active) continue;
+                    amask |= 1u << l;
+                    bool onto_opposite = false;
+                    for (int j = 0; j < no; ++j) onto_opposite |= w.pos(1 - t)[j] == cand;
+                    for (int j = 0; j < ns; ++j) slow |= (w.pos(t)[j] != pos && w.pos(t)[j] == cand);
+                    const double dE = (__ldg(row + cz * plane) - e_init) + fz * (double)(cz - pz);
+                    approx[l] = onto_opposite ? -INFINITY : (float)dE;           // onto an opposite charge: k = 1e13
+                }
+            }
+        }
+    }
+    const int n = __popc(amask);
+    if (n == 0) return HF_ST_VALUE_ERROR;                                        // min() of an empty sequence
+    hf_fill_inv_old<1>(w, t, pos, 0);
+    const uint64_t d0 = w.draws;
+    bool exhausted = false;
+    double best = 0.0;
+    int32_t bfin = -1;
+    unsigned verify = amask;
+    if (!slow) {
+        // ---- pass 1: fp32 estimates of 1e13 * tau; uniform d0 + r is half (p + r) & 1 of Philox block (d0 >> 1) + ((p + r) >> 1)
+        const int p = (int)(d0 & 1);
+        const float inv_kt = (float)(1.0 / HF_KT);
+        float amin = INFINITY, amin2 = INFINITY;
+        int lmin = 0;
+        unsigned forced = 0, rem = amask;
+        for (int j = 0; 2 * j < n + p; ++j) {
+            HfPhiloxBlock rnd = {0, 0, 0, 0};
+            if (!P.replay) rnd = hf_philox_block(P.k0, P.k1, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = 2 * j + h - p;
+                if (r < 0 || r >= n) continue;
+                const int l = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const double u = P.replay ? hf_traj_uniform(P, w, d0 + (uint64_t)r, &exhausted) : hf_block_uniform(rnd, (uint64_t)h);
+                float t0;
+                if (u < 0x1p-6) {
+                    const float uf = (float)u;
+                    t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                } else {
+                    t0 = -__logf((float)(1.0 - u));
+                }
+                float a = t0;
+                const float x = approx[l] * inv_kt;
+                if (x > 0.0f) a = t0 * __expf(x);
+                if (x > 700.0f) forced |= 1u << l;
+                if (t0 == 0.0f) a = 0.0f;                                        // 0 * inf
+                approx[l] = a;
+                if (a < amin) { amin2 = amin; amin = a; lmin = l; }
+                else if (!(a >= amin2)) amin2 = a;                               // also catches NaN
+            }
+        }
+        if (exhausted) { w.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
+        const float thr = amin * (1.0f + HF_C1_WINDOW);
+        verify = forced | (1u << lmin);
+        if (!(amin2 > thr)) {
+            for (unsigned m = amask; m; m &= m - 1) {
+                const int i = __ffs(m) - 1;
+                if (!(approx[i] > thr)) verify |= 1u << i;
+            }
+        }
+    }
+    // ---- pass 2: exact evaluation in candidate order, first minimum (387 / 396)
+    for (unsigned m = verify; m; m &= m - 1) {
+        const int i = __ffs(m) - 1;
+        const int ix = i / (3 * nz), iy = (i / nz) % 3, iz = i % nz;
+        const int cand = hf_pack(hf_bvk_xy(px, P.X, ix), hf_bvk_xy(py, P.Y, iy), hf_bvk_z(pz, P.Z, iz));
+        const int rank = __popc(amask & ((1u << i) - 1u));
+        const double u = hf_traj_uniform(P, w, d0 + (uint64_t)rank, &exhausted);
+        if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
+        double rate = 0.0;
+        bool zero_div = false;
+        const double tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
+        if (zero_div) { w.draws = d0 + (uint64_t)rank + 1; return HF_ST_ZERO_DIVISION; }   // draws up to and including the failing candidate
+        if (bfin < 0 || tau < best) { best = tau; bfin = cand; }
+    }
+    w.draws = d0 + (uint64_t)n;
+    if (w.n_ev(t) >= P.cap_c) return HF_ST_CAPACITY;
+    w.ev_init(t)[w.n_ev(t)] = pos; w.ev_final(t)[w.n_ev(t)] = bfin; w.ev_tau(t)[w.n_ev(t)] = best;
+    w.set_n_ev(t, w.n_ev(t) + 1);
+    return HF_ST_OK;
+}
+
+// Lattice.operations(stop) for 2 <= charges <= HF_SMALL_MAX_CHARGES: one thread per trajectory.
+__global__ void __launch_bounds__(HF_SMALL_THREADS) hf_run_small_kernel(const HfParams P) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= P.B) return;
+    const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f);
+    HfWarp w;
+    hf_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f);
+    w.approx = reinterpret_cast<float *>(hf_smem + threadIdx.x * stride + hf_warp_smem_bytes(P.cap_c, P.cap_f));
+    hf_load_state<1>(P, w, local, 0);
+    if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;   // reseau.py:587-589
+    const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
+    HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+    if (w.status == HF_ST_OK) {
+        for (int64_t i = 0; i < P.n_steps; ++i) {
+            w.steps += 1;                                                        // 582
+            int kind, part, ini, fin;
+            double tau;
+            const int st = hf_step<1>(P, w, 0, &kind, &part, &ini, &fin, &tau);
+            if (st != HF_ST_OK) { w.status = st; break; }                        // 587-591
+            if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
+            else if (kind == HF_K_BOUND) w.c_bound += 1;
+            else if (kind == HF_K_DECAY) w.c_decay += 1;
+            else { if (part == 1) w.c_capture_e += 1; else w.c_capture_h += 1; }
+            if (traced && w.fired < (uint64_t)P.trace_cap) {
+                HfTraceRec rec;
+                rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
+                rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
+                rec.pad[0] = rec.pad[1] = 0;
+                rec.spins = (uint32_t)w.spins; rec.draws = w.draws;
+                trace[w.fired] = rec;
+            }
+            w.fired += 1;
+        }
+    }
+    hf_store_state<1>(P, w, 0);
+}

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include "hf_frm.cuh"
 #include "hf_frm_c1.cuh"
+#include "hf_frm_small.cuh"
 #include "hf_exciton.cuh"
 #include "hf_exciton_dense.cuh"
 
@@ -583,6 +584,12 @@ int hf_run(hf_sim *s, int64_t stop) {
         const int threads = HF_C1_THREADS;
         const int64_t blocks = (s->P.B + threads - 1) / threads;
         hf_run_c1_kernel<<<(unsigned)blocks, threads, 0, s->stream>>>(s->P);
+    } else if (s->P.C <= HF_SMALL_MAX_CHARGES && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
+        // one thread per trajectory, lists in per-thread shared memory (hf_frm_small.cuh)
+        const size_t smem = hf_small_thread_bytes(s->P.cap_c, s->P.cap_f) * HF_SMALL_THREADS;
+        if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_run_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t blocks = (s->P.B + HF_SMALL_THREADS - 1) / HF_SMALL_THREADS;
+        hf_run_small_kernel<<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(s->P);
     } else {
         switch (s->warps) {
             case 8: launch_run<8>(s); break;

@@ -60,7 +60,7 @@ def generate(dims, props, seed, realisation=0):
     return out
 
 
-def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_calls=1, replay=None):
+def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_calls=1, replay=None, small_kernel=False):
     dims = tuple(int(v) for v in dims)
     cap, cap_f = charges, (2 if charges == 1 else 2 * charges + 8)
     trace_cap = stop * n_calls
@@ -84,7 +84,7 @@ def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_cal
     rc = lib().emu_run(d, C.c_double(field), C.c_int32(charges), C.c_uint64(seed), C.c_uint32(trajectory),
                        _p(species), _p(homo), _p(lumo), None if rp is None else _p(rp),
                        C.c_int64(0 if rp is None else rp.size), C.c_int64(stop), C.c_int32(n_calls),
-                       _p(trace), C.c_int64(trace_cap), _p(ints), _p(u64), _p(lists), _p(flags), _p(taus),
+                       C.c_int32(int(small_kernel)), _p(trace), C.c_int64(trace_cap), _p(ints), _p(u64), _p(lists), _p(flags), _p(taus),
                        _p(totals), _p(cache_i), _p(cache_tau), _p(init_lists), _p(init_taus), _p(init_counts))
     if rc:
         raise RuntimeError(f"emu_run failed ({rc})")

@@ -5,6 +5,7 @@
 
 #include "../../hyperfluorescence_b200/csrc/hf_frm.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_frm_c1.cuh"
+#include "../../hyperfluorescence_b200/csrc/hf_frm_small.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_exciton.cuh"
 #include "../../hyperfluorescence_b200/csrc/hf_exciton_dense.cuh"
 
@@ -46,6 +47,7 @@ struct InjectArgs { const HfParams *P; int32_t *pool; };
 void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P, x->pool); }
 void run_body(void *a) { hf_run_kernel<1>(*(const HfParams *)a); }
 void run_c1_body(void *a) { hf_run_c1_kernel(*(const HfParams *)a); }
+void run_small_body(void *a) { hf_run_small_kernel(*(const HfParams *)a); }
 
 struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
 void shuffle_body(void *a) { auto *x = (ShuffleArgs *)a; hf_species_shuffle(*x->P, x->pool, x->total, &x->n_host, &x->n_tadf, x->layer, 0); }
@@ -96,7 +98,7 @@ int emu_generate(const int32_t dims[3], const double props[3], uint64_t seed, ui
 //            me_final, mh_final; flags_out: 2 blocks of cap_f; taus_out: 2 blocks of cap doubles.
 int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed, uint32_t trajectory,
             const uint8_t *species, const double *homo, const double *lumo,
-            const double *replay, int64_t n_replay, int64_t stop, int32_t n_calls,
+            const double *replay, int64_t n_replay, int64_t stop, int32_t n_calls, int32_t small_kernel,
             HfTraceRec *trace_out, int64_t trace_cap,
             int32_t *ints_out, uint64_t *u64_out, int32_t *lists_out, int32_t *flags_out, double *taus_out,
             unsigned long long *totals_out, int32_t *cache_i_out, double *cache_tau_out,
@@ -129,9 +131,10 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
             init_lists_out[(4 + t) * cap + i] = P.ev_final[t][i];
             init_taus_out[t * cap + i] = P.ev_tau[t][i];
         }
+    if (small_kernel && (charges < 2 || charges > HF_SMALL_MAX_CHARGES || hf_small_thread_bytes(P.cap_c, P.cap_f) * 32 > sizeof(hf_smem))) return 4;
     for (int c = 0; c < n_calls; ++c) {
         P.n_steps = stop;
-        emu_run_warp(run_body, &P);
+        emu_run_warp(small_kernel ? run_small_body : run_body, &P);      // thread kernel: lane 0 owns the trajectory
     }
     const HfScalars &sc = b.sc[0];
     const int32_t ints[12] = {sc.n_pos[0], sc.n_pos[1], sc.n_flag[0], sc.n_flag[1], sc.n_ev[0], sc.n_ev[1],

@@ -222,14 +222,18 @@ def test_batch_matches_oracle_per_trajectory(nat):
         sim.close()
 
 
-@pytest.mark.parametrize("name,steps", [("tiny333_s5", 1500), ("c1_s1", 2000)])
-def test_thread_kernel_equals_warp_kernel(nat, name, steps):
-    """charges == 1 has two step kernels (thread-per-trajectory by default, warp-per-trajectory with
-    HF_FLAG_WARP_KERNEL): 4096 trajectories must end in exactly the same state under both."""
+@pytest.mark.parametrize("name,steps,charges", [("tiny333_s5", 1500, 1), ("c1_s1", 2000, 1),
+                                                ("d0_s1", 1500, 4), ("d0_s2", 1200, 2), ("rag456_s6", 1000, 8),
+                                                ("dense_s8", 1500, 6), ("tiny333_s5", 1500, 3)])
+def test_thread_kernel_equals_warp_kernel(nat, name, steps, charges):
+    """charges <= 8 has two step kernels (thread-per-trajectory by default: hf_frm_c1.cuh for one charge,
+    hf_frm_small.cuh for 2..8; warp-per-trajectory with HF_FLAG_WARP_KERNEL): 4096 trajectories must end in
+    exactly the same state under both — including the ones the reference's quirks stop (ZeroDivisionError,
+    ValueError) on crowded little lattices."""
     g = load_golden(name)
     B = 4096
     def run(flags):
-        sim = nat.Sim(g["dims"], tuple(float(p) for p in g["props"]), g["field_f"], 1, 1, n_trajectories=B,
+        sim = nat.Sim(g["dims"], tuple(float(p) for p in g["props"]), g["field_f"], charges, 1, n_trajectories=B,
                       seed=977, first_trajectory=10, flags=flags)
         sim.upload_lattice(0, g["species"], g["homo"], g["lumo"])
         sim.inject()
@@ -254,8 +258,10 @@ def test_thread_kernel_equals_warp_kernel(nat, name, steps):
     assert thread["pos"] == warp["pos"]
     for a, b in zip(thread["traces"], warp["traces"]):
         assert np.array_equal(a, b)                      # same device libm: bit-identical, tau included
-    if name == "tiny333_s5":
+    if name == "tiny333_s5" and charges == 1:
         assert thread["tallies"]["recombination"] > 100_000 and thread["tallies"]["capture_e"] > 1000
+    if charges > 1:
+        assert thread["tallies"]["recombination"] > 1000
 
 
 def test_sharding_is_invisible(nat):
