@@ -94,6 +94,8 @@ struct HfWarp {
     double *ev_tau_b, *inv_old_b, *cache_tau;
     int32_t *pos_b, *flag_b, *ev_init_b, *ev_final_b, *cache_init, *cache_final, *cache_kp;
     int32_t cap_c, cap_f;
+    int64_t cache_stride;          // 1: the ring lives in shared memory (warp kernel); B: it is written straight to the
+                                   // slot-major global arrays (thread-per-trajectory kernel: coalesced across the warp)
     // warp-uniform scalars (kept as named fields so that nothing is dynamically indexed)
     int32_t n_pos0, n_pos1, n_flag0, n_flag1, n_ev0, n_ev1;
     int32_t special, special_site, xstate, status, cache_head, cache_n;
@@ -127,7 +129,7 @@ __host__ __device__ inline size_t hf_warp_smem_bytes(int cap_c, int cap_f) {
 }
 
 __device__ __forceinline__ void hf_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f) {
-    w.cap_c = cap_c; w.cap_f = cap_f;
+    w.cap_c = cap_c; w.cap_f = cap_f; w.cache_stride = 1;
     double *d = reinterpret_cast<double *>(base);
     w.ev_tau_b = d; d += 2 * cap_c;
     w.inv_old_b = d; d += 2 * cap_c;
@@ -489,6 +491,11 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
             w.ev_tau(t)[i] = P.ev_tau[t][local * P.cap_c + i];
         }
     }
+    if constexpr (L == 1) {                        // the ring is used in place: [slot][trajectory] in global memory
+        w.cache_stride = P.B;
+        w.cache_init = P.cache_init + local; w.cache_final = P.cache_final + local;
+        w.cache_kp = P.cache_kp + local; w.cache_tau = P.cache_tau + local;
+    } else
     for (int c = lane; c < HF_CACHE; c += L) {   // ring stored slot-major: [slot][trajectory]
         w.cache_init[c] = P.cache_init[c * P.B + local];
         w.cache_final[c] = P.cache_final[c * P.B + local];
@@ -514,6 +521,7 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
             P.ev_tau[t][local * P.cap_c + i] = w.ev_tau(t)[i];
         }
     }
+    if constexpr (L == 32)
     for (int c = lane; c < HF_CACHE; c += L) {
         P.cache_init[c * P.B + local] = w.cache_init[c];
         P.cache_final[c * P.B + local] = w.cache_final[c];
@@ -573,8 +581,9 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     }
     // _cache.popleft(); _cache.append(event)  (489-490)
     if (lane == 0) {
-        w.cache_init[w.cache_head] = ini; w.cache_final[w.cache_head] = fin;
-        w.cache_kp[w.cache_head] = kind | (part << 8); w.cache_tau[w.cache_head] = tau;
+        const int64_t at = w.cache_head * w.cache_stride;
+        w.cache_init[at] = ini; w.cache_final[at] = fin;
+        w.cache_kp[at] = kind | (part << 8); w.cache_tau[at] = tau;
     }
     w.cache_head = w.cache_head + 1 == HF_CACHE ? 0 : w.cache_head + 1;
     if (w.cache_n < HF_CACHE) w.cache_n += 1;

@@ -17,8 +17,25 @@
 
 // bytes of shared memory per trajectory: the lists of hf_carve + the screening column, an odd number of
 // 8-byte words so that the threads of a warp spread over the banks
+// lists of one trajectory without the _cache ring (written straight to global memory by hf_step<1>)
+__host__ __device__ inline size_t hf_small_list_bytes(int cap_c, int cap_f) {
+    return 8u * (4u * (size_t)cap_c) + 4u * (6u * (size_t)cap_c + 2u * (size_t)cap_f);
+}
+__device__ __forceinline__ void hf_small_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f) {
+    w.cap_c = cap_c; w.cap_f = cap_f; w.cache_stride = 1;
+    double *d = reinterpret_cast<double *>(base);
+    w.ev_tau_b = d; d += 2 * cap_c;
+    w.inv_old_b = d; d += 2 * cap_c;
+    int32_t *i = reinterpret_cast<int32_t *>(d);
+    w.pos_b = i; i += 2 * cap_c;
+    w.ev_init_b = i; i += 2 * cap_c;
+    w.ev_final_b = i; i += 2 * cap_c;
+    w.flag_b = i; i += 2 * cap_f;
+    w.approx = reinterpret_cast<float *>(i);
+    w.cache_init = w.cache_final = w.cache_kp = nullptr; w.cache_tau = nullptr;   // set by hf_load_state<1>
+}
 __host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
-    size_t b = hf_warp_smem_bytes(cap_c, cap_f) + 4u * 28u;
+    size_t b = hf_small_list_bytes(cap_c, cap_f) + 4u * 28u;
     b = (b + 7u) & ~(size_t)7u;
     if (((b >> 3) & 1u) == 0) b += 8;
     return b;
@@ -49,10 +66,32 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
     const double e_init = __ldg(E + hf_site(P, pos));
     const double fz = t == 0 ? -P.field : P.field;
     const int64_t plane = (int64_t)P.X * P.Y;
-    // ---- pass 0: which candidates are active, their dE in fp32, and whether a geometric ZeroDivisionError is possible
-    unsigned amask = 0;
+    // ---- pass 0: which candidates are blocked, lead onto an opposite charge or onto a same-type charge (the
+    //      flag / list desynchronisation of DESIGN.md §0: ZeroDivisionError in the reference) — found from the
+    //      short lists, not by testing every candidate against every entry; then the candidates' dE in fp32
+    unsigned blocked = 0, onto_opp = 0, onto_same = 0;
     bool slow = false;
-    for (int j = 0; j < no; ++j) slow |= w.pos(1 - t)[j] == pos;                 // 1 / |loc - initial| with loc == initial
+    {
+        int xs[3], ys[3], zs[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { xs[i] = hf_bvk_xy(px, P.X, i); ys[i] = hf_bvk_xy(py, P.Y, i); zs[i] = i < nz ? hf_bvk_z(pz, P.Z, i) : -1; }
+        // bit mask of the candidates (ix, iy, iz) whose coordinates equal the packed site q
+        auto cand_bits = [&](int q) -> unsigned {
+            const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
+            unsigned bx = 0, by = 0, bz = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { bx |= (xs[i] == qx) << i; by |= (ys[i] == qy) << i; bz |= (zs[i] == qz) << i; }
+            unsigned m = 0;
+            if (bx && by && bz)
+                for (int ix = 0; ix < 3; ++ix) for (int iy = 0; iy < 3; ++iy) for (int iz = 0; iz < nz; ++iz)
+                    if ((bx >> ix & 1u) && (by >> iy & 1u) && (bz >> iz & 1u)) m |= 1u << ((ix * 3 + iy) * nz + iz);
+            return m;
+        };
+        for (int j = 0; j < nb; ++j) blocked |= cand_bits(blk[j]);               // 385 / 394 ; 249 / 268
+        for (int j = 0; j < no; ++j) { const int q = w.pos(1 - t)[j]; onto_opp |= cand_bits(q); slow |= q == pos; }   // 1 / |loc - initial| = 1 / 0
+        for (int j = 0; j < ns; ++j) { const int q = w.pos(t)[j]; if (q != pos) onto_same |= cand_bits(q); }
+    }
+    unsigned amask = ((1u << total) - 1u) & ~blocked;                           // total <= 27; the charge's own site is cleared below
     {
         int l = 0;
         for (int ix = 0; ix < 3; ++ix) {
@@ -62,20 +101,15 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
                 const double *row = E + ((int64_t)cy * P.X + cx);
                 for (int iz = 0; iz < nz; ++iz, ++l) {
                     const int cz = hf_bvk_z(pz, P.Z, iz);
-                    const int cand = hf_pack(cx, cy, cz);
-                    bool active = cand != pos;
-                    for (int j = 0; j < nb; ++j) active &= blk[j] != cand;       // 385 / 394 ; 249 / 268
-                    if (!active) continue;
-                    amask |= 1u << l;
-                    bool onto_opposite = false;
-                    for (int j = 0; j < no; ++j) onto_opposite |= w.pos(1 - t)[j] == cand;
-                    for (int j = 0; j < ns; ++j) slow |= (w.pos(t)[j] != pos && w.pos(t)[j] == cand);
+                    if (hf_pack(cx, cy, cz) == pos) { amask &= ~(1u << l); continue; }
+                    if (!(amask >> l & 1u)) continue;
                     const double dE = (__ldg(row + cz * plane) - e_init) + fz * (double)(cz - pz);
-                    approx[l] = onto_opposite ? -INFINITY : (float)dE;           // onto an opposite charge: k = 1e13
+                    approx[l] = (onto_opp >> l & 1u) ? -INFINITY : (float)dE;    // onto an opposite charge: k = 1e13
                 }
             }
         }
     }
+    slow |= (onto_same & amask) != 0;
     const int n = __popc(amask);
     if (n == 0) return HF_ST_VALUE_ERROR;                                        // min() of an empty sequence
     hf_fill_inv_old<1>(w, t, pos, 0);
@@ -156,8 +190,7 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS) hf_run_small_kernel(const Hf
     if (local >= P.B) return;
     const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f);
     HfWarp w;
-    hf_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f);
-    w.approx = reinterpret_cast<float *>(hf_smem + threadIdx.x * stride + hf_warp_smem_bytes(P.cap_c, P.cap_f));
+    hf_small_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f);
     hf_load_state<1>(P, w, local, 0);
     if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;   // reseau.py:587-589
     const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
