@@ -208,6 +208,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
 // ---- ordered-list primitives (warp-cooperative, n is warp-uniform) ---------------------------
 template <int L = 32>
 __device__ __forceinline__ int hf_find_first(const int32_t *a, int n, int v, int lane) {
+#pragma unroll 1
     for (int base = 0; base < n; base += L) {
         const int i = base + lane;
         const unsigned m = hf_ballot<L>(i < n && a[i] == v);
@@ -224,6 +225,7 @@ __device__ __forceinline__ bool hf_contains(const int32_t *a, int n, int v, int 
 // list.remove(a[idx]) keeping the order of the rest
 template <int L = 32>
 __device__ __forceinline__ void hf_remove_at(int32_t *a, int n, int idx, int lane) {
+#pragma unroll 1
     for (int base = idx; base < n - 1; base += L) {
         const int i = base + lane;
         int v = 0;
@@ -266,6 +268,7 @@ template <int L = 32>
 __device__ __forceinline__ void hf_remove_events(HfWarp &w, int t, int a, int b, int lane) {
     const int n = w.n_ev(t);
     int out = 0;
+#pragma unroll 1
     for (int base = 0; base < n; base += L) {
         const int i = base + lane;
         int ini = 0, fin = 0;
@@ -290,6 +293,7 @@ template <int L = 32>
 __device__ __forceinline__ void hf_update_events(HfWarp &w, double time, int lane) {
 #pragma unroll
     for (int t = 0; t < 2; ++t)
+#pragma unroll 1
         for (int i = lane; i < w.n_ev(t); i += L) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
     hf_sync<L>();
 }
@@ -308,11 +312,22 @@ __device__ __forceinline__ int hf_bvk_z(int p, int size, int i) {
     return p - 1 + i;                                        // [size-2, size-1]
 }
 
+// 1 / sqrt(d2), exp and -log(rng) / k as the reference computes them.  kCompact routes them through single
+// out-of-line copies: the thread-per-trajectory kernel is bound by instruction fetch (ncu: stall_no_inst 60 %
+// with every fp64 division, square root, exp and log expanded inline at each use), the warp kernel is not.
+__device__ __noinline__ double hf_inv_dist_call(int d2) { return __ddiv_rn(1.0, __dsqrt_rn((double)d2)); }
+__device__ __noinline__ double hf_boltzmann_call(double dE) { return exp(__ddiv_rn(-dE, HF_KT)); }
+__device__ __noinline__ double hf_wait_call(double rng, double k) { return __ddiv_rn(-log(rng), k); }
+template <bool kCompact> __device__ __forceinline__ double hf_inv_dist(int d2) {
+    if constexpr (kCompact) return hf_inv_dist_call(d2); else return __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+}
+
 // One candidate hop of a charge of type t from `initial` to `cand` given its uniform u:
 // _time_move_electron / _time_move_hole (reseau.py:283-292, 315-324) with the Coulomb term of
 // reseau.py:297-313 / 329-345.  inv_old[0][j] / inv_old[1][j] hold 1/|loc_j - initial| for the
 // same-type / opposite-type lists (0 where the distance is 0).  Returns tau; *rate gets k;
 // *zero_div is set where the reference would raise ZeroDivisionError.
+template <bool kCompact = false>
 __device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w, int t, int initial, int cand,
                                               double u, double *rate, bool *zero_div) {
     const double rng = __dsub_rn(1.0, u);                                        // 284 / 316
@@ -327,7 +342,7 @@ __device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w
         if (loc == initial) continue;
         const int d2 = hf_dist2(loc, cand);
         if (d2 == 0) { *zero_div = true; return 0.0; }
-        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+        const double inv_new = hf_inv_dist<kCompact>(d2);
         out = __dadd_rn(out, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, w.inv_old(0)[j])));
     }
     for (int j = 0; j < no; ++j) {                                               // 305-312 / 337-344
@@ -335,15 +350,15 @@ __device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w
         if (loc == cand) { out = -INFINITY; break; }
         const double io = w.inv_old(1)[j];
         if (io == 0.0) { *zero_div = true; return 0.0; }
-        const double inv_new = __ddiv_rn(1.0, __dsqrt_rn((double)hf_dist2(loc, cand)));
+        const double inv_new = hf_inv_dist<kCompact>(hf_dist2(loc, cand));
         out = __dsub_rn(out, __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(inv_new, io)));
     }
     dE = __dadd_rn(dE, out);                                                     // 288 / 320
     double k = HF_RATE0;                                                         // 289 / 321
-    if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));                   // 290-291 / 322-323
+    if (dE >= 0) k = __dmul_rn(k, kCompact ? hf_boltzmann_call(dE) : exp(__ddiv_rn(-dE, HF_KT)));   // 290-291 / 322-323
     *rate = k;
     if (k == 0.0) { *zero_div = true; return 0.0; }                              // float division by zero
-    return __ddiv_rn(-log(rng), k);                                              // 292 / 324
+    return kCompact ? hf_wait_call(rng, k) : __ddiv_rn(-log(rng), k);            // 292 / 324
 }
 
 // 1/|loc_j - initial| for both lists, computed once per regenerated event instead of once per
@@ -356,7 +371,7 @@ __device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, i
         const int n = s == 0 ? w.n_pos(t) : w.n_pos(1 - t);
         for (int j = lane; j < n; j += L) {
             const int d2 = hf_dist2(list[j], initial);
-            w.inv_old(s)[j] = d2 == 0 ? 0.0 : __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+            w.inv_old(s)[j] = d2 == 0 ? 0.0 : hf_inv_dist<L == 1>(d2);
         }
     }
     hf_sync<L>();
@@ -483,8 +498,11 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
     w.homo = P.homo + r * P.N;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
+#pragma unroll 1
         for (int i = lane; i < w.n_pos(t); i += L) w.pos(t)[i] = P.pos[t][local * P.cap_c + i];
+#pragma unroll 1
         for (int i = lane; i < w.n_flag(t); i += L) w.flag(t)[i] = P.flag[t][local * P.cap_f + i];
+#pragma unroll 1
         for (int i = lane; i < w.n_ev(t); i += L) {
             w.ev_init(t)[i] = P.ev_init[t][local * P.cap_c + i];
             w.ev_final(t)[i] = P.ev_final[t][local * P.cap_c + i];
@@ -513,8 +531,11 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
     hf_sync<L>();
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
+#pragma unroll 1
         for (int i = lane; i < w.n_pos(t); i += L) P.pos[t][local * P.cap_c + i] = w.pos(t)[i];
+#pragma unroll 1
         for (int i = lane; i < w.n_flag(t); i += L) P.flag[t][local * P.cap_f + i] = w.flag(t)[i];
+#pragma unroll 1
         for (int i = lane; i < w.n_ev(t); i += L) {
             P.ev_init[t][local * P.cap_c + i] = w.ev_init(t)[i];
             P.ev_final[t][local * P.cap_c + i] = w.ev_final(t)[i];
@@ -545,11 +566,29 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
     }
 }
 
+// Re-inject (optionally) and regenerate the move event of the LAST charge of type t.  The warp kernel does it
+// on the spot; the thread-per-trajectory kernel queues it (4 bits per request: 8 | 4 * reinject | t, at most two
+// per event) and runs the queue in ONE place after hf_step, so that the lanes of a warp — each with its own
+// trajectory, most of them regenerating one event per step — execute the candidate loop together.
+template <int L>
+__device__ __forceinline__ int hf_regen(const HfParams &P, HfWarp &w, int t, bool reinject, int lane, int *queue) {
+    if constexpr (L == 1) {
+        *queue |= (8 | (reinject ? 4 : 0) | t) << (*queue ? 4 : 0);
+        return HF_ST_OK;
+    } else {
+        if (reinject) {
+            const int st = hf_reinject<L>(P, w, t, lane);
+            if (st != HF_ST_OK) return st;
+        }
+        return hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
+    }
+}
+
 // ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
 // Returns HF_ST_OK when an event fired; ev_* describe it (packed coordinates).
 template <int L = 32>
 __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
-                                       int *ev_init, int *ev_final, double *ev_tau) {
+                                       int *ev_init, int *ev_final, double *ev_tau, int *queue = nullptr) {
     int kind, part, ini, fin;
     double tau;
     if (w.special) {
@@ -603,7 +642,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         const int capture_z = t == 0 ? 0 : P.Z - 1;
         if (!opposite_here && hf_pz(fin) != capture_z) {                         // 498-500 / 514-516
             hf_update_events<L>(w, tau, lane);
-            return hf_gen_move_event<L>(P, w, t, fin, true, lane);
+            return hf_regen<L>(P, w, t, false, lane, queue);                    // the moved charge is the last of its list
         } else if (opposite_here) {                                              // 501-505 / 517-521
             hf_remove_events<L>(w, o, fin, fin, lane);
             // _update_events(0.) leaves every tau unchanged (Q5)
@@ -645,13 +684,9 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
         w.recombination += 1;                                                    // 472-476
         w.c_recomb_host += sp == 0; w.c_recomb_tadf += sp == 1; w.c_recomb_fluo += sp == 2;
         if (photon) { w.emission += 1; w.c_emit_tadf += sp == 1; w.c_emit_fluo += sp == 2; }
-        int st = hf_reinject<L>(P, w, 0, lane);
+        const int st = hf_regen<L>(P, w, 0, true, lane, queue);
         if (st != HF_ST_OK) return st;
-        st = hf_gen_move_event<L>(P, w, 0, w.pos(0)[w.n_pos(0) - 1], true, lane);
-        if (st != HF_ST_OK) return st;
-        st = hf_reinject<L>(P, w, 1, lane);
-        if (st != HF_ST_OK) return st;
-        return hf_gen_move_event<L>(P, w, 1, w.pos(1)[w.n_pos(1) - 1], true, lane);
+        return hf_regen<L>(P, w, 1, true, lane, queue);
     }
     // capture (551-561)
     const int t = part - 1;
@@ -660,9 +695,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     if (idx < 0) return HF_ST_VALUE_ERROR;
     hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
     w.set_n_pos(t, w.n_pos(t) - 1);
-    const int st = hf_reinject<L>(P, w, t, lane);
-    if (st != HF_ST_OK) return st;
-    return hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
+    return hf_regen<L>(P, w, t, true, lane, queue);
 }
 
 // ---- kernels -------------------------------------------------------------------------------------

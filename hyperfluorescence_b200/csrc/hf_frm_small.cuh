@@ -41,6 +41,26 @@ __host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
     return b;
 }
 
+// Bit mask of the candidates (ix, iy, iz), numbered (ix * 3 + iy) * nz + iz like the reference's neighbour list,
+// whose coordinates equal the packed site q.  xs / ys / zs: the coordinates of the three neighbour columns,
+// rows and planes, 10 bits each.  (More than one bit only on lattices so small that a periodic image repeats.)
+__device__ __noinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, int q) {
+    const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
+    unsigned m = 0;
+#pragma unroll 1
+    for (int ix = 0; ix < 3; ++ix) {
+        if (((xs >> (10 * ix)) & 1023) != qx) continue;
+#pragma unroll 1
+        for (int iy = 0; iy < 3; ++iy) {
+            if (((ys >> (10 * iy)) & 1023) != qy) continue;
+#pragma unroll 1
+            for (int iz = 0; iz < nz; ++iz)
+                if (((zs >> (10 * iz)) & 1023) == qz) m |= 1u << ((ix * 3 + iy) * nz + iz);
+        }
+    }
+    return m;
+}
+
 // _new_move_*_events (reseau.py:380-396) and the per-charge body of _init_move_*_events (240-276) for
 // one thread's trajectory: min() over the unblocked candidates, first minimum wins, one TRAJ uniform
 // per unblocked candidate in neighbour order.
@@ -72,24 +92,18 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
     unsigned blocked = 0, onto_opp = 0, onto_same = 0;
     bool slow = false;
     {
-        int xs[3], ys[3], zs[3];
+        int xs = 0, ys = 0, zs = 0;                                              // the three columns / rows / planes, 10 bits each
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { xs[i] = hf_bvk_xy(px, P.X, i); ys[i] = hf_bvk_xy(py, P.Y, i); zs[i] = i < nz ? hf_bvk_z(pz, P.Z, i) : -1; }
-        // bit mask of the candidates (ix, iy, iz) whose coordinates equal the packed site q
-        auto cand_bits = [&](int q) -> unsigned {
-            const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
-            unsigned bx = 0, by = 0, bz = 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { bx |= (xs[i] == qx) << i; by |= (ys[i] == qy) << i; bz |= (zs[i] == qz) << i; }
-            unsigned m = 0;
-            if (bx && by && bz)
-                for (int ix = 0; ix < 3; ++ix) for (int iy = 0; iy < 3; ++iy) for (int iz = 0; iz < nz; ++iz)
-                    if ((bx >> ix & 1u) && (by >> iy & 1u) && (bz >> iz & 1u)) m |= 1u << ((ix * 3 + iy) * nz + iz);
-            return m;
-        };
-        for (int j = 0; j < nb; ++j) blocked |= cand_bits(blk[j]);               // 385 / 394 ; 249 / 268
-        for (int j = 0; j < no; ++j) { const int q = w.pos(1 - t)[j]; onto_opp |= cand_bits(q); slow |= q == pos; }   // 1 / |loc - initial| = 1 / 0
-        for (int j = 0; j < ns; ++j) { const int q = w.pos(t)[j]; if (q != pos) onto_same |= cand_bits(q); }
+        for (int i = 0; i < 3; ++i) {
+            xs |= hf_bvk_xy(px, P.X, i) << (10 * i); ys |= hf_bvk_xy(py, P.Y, i) << (10 * i);
+            zs |= (i < nz ? hf_bvk_z(pz, P.Z, i) : 1023) << (10 * i);             // 1023: no such plane (z < 1023 on any lattice)
+        }
+#pragma unroll 1
+        for (int j = 0; j < nb; ++j) blocked |= hf_cand_bits(xs, ys, zs, nz, blk[j]);   // 385 / 394 ; 249 / 268
+#pragma unroll 1
+        for (int j = 0; j < no; ++j) { const int q = w.pos(1 - t)[j]; onto_opp |= hf_cand_bits(xs, ys, zs, nz, q); slow |= q == pos; }   // 1 / |loc - initial| = 1 / 0
+#pragma unroll 1
+        for (int j = 0; j < ns; ++j) { const int q = w.pos(t)[j]; if (q != pos) onto_same |= hf_cand_bits(xs, ys, zs, nz, q); }
     }
     unsigned amask = ((1u << total) - 1u) & ~blocked;                           // total <= 27; the charge's own site is cleared below
     {
@@ -172,7 +186,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
         if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
         double rate = 0.0;
         bool zero_div = false;
-        const double tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
+        const double tau = hf_hop_time<true>(P, w, t, pos, cand, u, &rate, &zero_div);
         if (zero_div) { w.draws = d0 + (uint64_t)rank + 1; return HF_ST_ZERO_DIVISION; }   // draws up to and including the failing candidate
         if (bfin < 0 || tau < best) { best = tau; bfin = cand; }
     }
@@ -200,7 +214,14 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS) hf_run_small_kernel(const Hf
             w.steps += 1;                                                        // 582
             int kind, part, ini, fin;
             double tau;
-            const int st = hf_step<1>(P, w, 0, &kind, &part, &ini, &fin, &tau);
+            int queue = 0;
+            int st = hf_step<1>(P, w, 0, &kind, &part, &ini, &fin, &tau, &queue);
+            // common tail: the regenerations the step asked for (one after a move or a capture, two after a decay)
+            for (; st == HF_ST_OK && queue; queue >>= 4) {
+                const int t = queue & 1;
+                if (queue & 4) st = hf_reinject<1>(P, w, t, 0);
+                if (st == HF_ST_OK) st = hf_gen_move_event_serial(P, w, t, w.pos(t)[w.n_pos(t) - 1], true);
+            }
             if (st != HF_ST_OK) { w.status = st; break; }                        // 587-591
             if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
             else if (kind == HF_K_BOUND) w.c_bound += 1;
