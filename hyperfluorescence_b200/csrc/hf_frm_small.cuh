@@ -13,7 +13,12 @@
 #include "hf_frm_c1.cuh"
 
 #define HF_SMALL_MAX_CHARGES 8
+#ifndef HF_SMALL_THREADS
 #define HF_SMALL_THREADS 64
+#endif
+#ifndef HF_SMALL_MIN_BLOCKS
+#define HF_SMALL_MIN_BLOCKS 7
+#endif
 
 // bytes of shared memory per trajectory: the lists of hf_carve + the screening column, an odd number of
 // 8-byte words so that the threads of a warp spread over the banks
@@ -198,7 +203,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
 }
 
 // Lattice.operations(stop) for 2 <= charges <= HF_SMALL_MAX_CHARGES: one thread per trajectory.
-__global__ void __launch_bounds__(HF_SMALL_THREADS) hf_run_small_kernel(const HfParams P) {
+__global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_small_kernel(const HfParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= P.B) return;
