@@ -91,7 +91,7 @@ struct HfParams {
 
 struct HfWarp {
     // shared-memory lists; the two particle types are adjacent: list(t) = base + t * capacity
-    double *ev_tau_b, *inv_old_b, *cache_tau;
+    double *ev_tau_b, *inv_old_b, *term_b, *cache_tau;
     int32_t *pos_b, *flag_b, *ev_init_b, *ev_final_b, *cache_init, *cache_final, *cache_kp;
     int32_t cap_c, cap_f;
     int64_t cache_stride;          // 1: the ring lives in shared memory (warp kernel); B: it is written straight to the
@@ -114,6 +114,7 @@ struct HfWarp {
     __device__ __forceinline__ int32_t *ev_final(int t) const { return ev_final_b + t * cap_c; }
     __device__ __forceinline__ double *ev_tau(int t) const { return ev_tau_b + t * cap_c; }
     __device__ __forceinline__ double *inv_old(int s) const { return inv_old_b + s * cap_c; }
+    __device__ __forceinline__ double *term(int s) const { return term_b + s * cap_c; }
     __device__ __forceinline__ const double *energy(int t) const { return t ? homo : lumo; }
     __device__ __forceinline__ int n_pos(int t) const { return t ? n_pos1 : n_pos0; }
     __device__ __forceinline__ int n_flag(int t) const { return t ? n_flag1 : n_flag0; }
@@ -124,7 +125,7 @@ struct HfWarp {
 };
 
 __host__ __device__ inline size_t hf_warp_smem_bytes(int cap_c, int cap_f) {
-    size_t b = 8u * (4u * cap_c + HF_CACHE) + 4u * (6u * cap_c + 2u * cap_f + 3u * HF_CACHE);
+    size_t b = 8u * (6u * cap_c + HF_CACHE) + 4u * (6u * cap_c + 2u * cap_f + 3u * HF_CACHE);
     return (b + 15u) & ~(size_t)15u;
 }
 
@@ -133,6 +134,7 @@ __device__ __forceinline__ void hf_carve(HfWarp &w, unsigned char *base, int cap
     double *d = reinterpret_cast<double *>(base);
     w.ev_tau_b = d; d += 2 * cap_c;
     w.inv_old_b = d; d += 2 * cap_c;
+    w.term_b = d; d += 2 * cap_c;
     w.cache_tau = d; d += HF_CACHE;
     int32_t *i = reinterpret_cast<int32_t *>(d);
     w.pos_b = i; i += 2 * cap_c;
@@ -377,6 +379,67 @@ __device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, i
     hf_sync<L>();
 }
 
+// Bit mask of the candidates (ix, iy, iz), numbered (ix * 3 + iy) * nz + iz like the reference's neighbour list,
+// whose coordinates equal the packed site q.  xs / ys / zs: the coordinates of the three neighbour columns,
+// rows and planes, 10 bits each (1023 = no such plane).  More than one bit only on lattices so small that a
+// periodic image repeats.
+__device__ __noinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, int q) {
+    const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
+    unsigned m = 0;
+#pragma unroll 1
+    for (int ix = 0; ix < 3; ++ix) {
+        if (((xs >> (10 * ix)) & 1023) != qx) continue;
+#pragma unroll 1
+        for (int iy = 0; iy < 3; ++iy) {
+            if (((ys >> (10 * iy)) & 1023) != qy) continue;
+#pragma unroll 1
+            for (int iz = 0; iz < nz; ++iz)
+                if (((zs >> (10 * iz)) & 1023) == qz) m |= 1u << ((ix * 3 + iy) * nz + iz);
+        }
+    }
+    return m;
+}
+
+// hf_hop_time for ONE candidate with the L lanes sharing the Coulomb sum: the terms
+// C_e (1/|loc - cand| - 1/|loc - initial|) — a division and a square root each, 96 % of the reference's run
+// time — are computed lane-parallel into shared memory, then added in list order exactly like reseau.py:299-312
+// (same operands, same order, same bits).  Only valid when no ZeroDivisionError is geometrically possible
+// (no same-type charge on the candidate, no opposite charge on `initial`): the caller checks.
+template <int L>
+__device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWarp &w, int t, int initial, int cand,
+                                                   double u, int lane, bool *zero_div) {
+    const double rng = __dsub_rn(1.0, u);                                        // 284 / 316
+    const double *E = w.energy(t);
+    double dE = __dsub_rn(__ldg(E + hf_site(P, cand)), __ldg(E + hf_site(P, initial)));   // 286 / 318
+    const double fz = t == 0 ? -P.field : P.field;
+    dE = __dadd_rn(dE, __dmul_rn(fz, (double)(hf_pz(cand) - hf_pz(initial))));   // 287 / 319
+    const int ns = w.n_pos(t), no = w.n_pos(1 - t);
+    for (int j = lane; j < ns; j += L) {
+        const int loc = w.pos(t)[j];
+        w.term(0)[j] = loc == initial ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist<false>(hf_dist2(loc, cand)), w.inv_old(0)[j]));
+    }
+    for (int j = lane; j < no; j += L) {
+        const int loc = w.pos(1 - t)[j];
+        w.term(1)[j] = loc == cand ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist<false>(hf_dist2(loc, cand)), w.inv_old(1)[j]));
+    }
+    hf_sync<L>();
+    double out = 0.0;
+    for (int j = 0; j < ns; ++j) {                                               // 299-304 / 331-336
+        if (w.pos(t)[j] == initial) continue;
+        out = __dadd_rn(out, w.term(0)[j]);
+    }
+    for (int j = 0; j < no; ++j) {                                               // 305-312 / 337-344
+        if (w.pos(1 - t)[j] == cand) { out = -INFINITY; break; }
+        out = __dsub_rn(out, w.term(1)[j]);
+    }
+    hf_sync<L>();
+    dE = __dadd_rn(dE, out);                                                     // 288 / 320
+    double k = HF_RATE0;
+    if (dE >= 0) k = __dmul_rn(k, exp(__ddiv_rn(-dE, HF_KT)));                   // 290-291 / 322-323
+    if (k == 0.0) { *zero_div = true; return 0.0; }                              // float division by zero
+    return __ddiv_rn(-log(rng), k);                                              // 292 / 324
+}
+
 // _new_move_electron_events / _new_move_hole_events (reseau.py:380-396; use_flags = true) and the
 // per-charge body of _init_move_*_events (reseau.py:240-276; use_flags = false: membership in
 // the position list).  Lanes = candidates in the reference's x-major neighbour order; one TRAJ
@@ -389,39 +452,106 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
     const int total = 9 * nz;
     const int ix = lane / (3 * nz), iy = (lane / nz) % 3, iz = lane % nz;
     const int cx = hf_bvk_xy(px, P.X, ix < 3 ? ix : 0), cy = hf_bvk_xy(py, P.Y, iy), cz = hf_bvk_z(pz, P.Z, iz);
-    const bool valid = lane < total && !(cx == px && cy == py && cz == pz);
     const int cand = hf_pack(cx, cy, cz);
     const int32_t *blk = use_flags ? w.flag(t) : w.pos(t);
     const int nb = use_flags ? w.n_flag(t) : w.n_pos(t);
-    bool blocked = false;
-    for (int j = 0; j < nb; ++j) blocked |= (blk[j] == cand);                    // 385 / 394 ; 249 / 268
-    const bool active = valid && !blocked;
+    const int ns = w.n_pos(t), no = w.n_pos(1 - t);
+    // which candidates are blocked (385 / 394 ; 249 / 268), lead onto an opposite charge, or onto a same-type
+    // charge (flag / list desynchronisation: ZeroDivisionError in the reference): from the lists, lane-strided
+    unsigned blocked_m = 0, opp_m = 0, same_m = 0;
+    bool opp_on_pos = false;
+    {
+        int xs = 0, ys = 0, zs = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            xs |= hf_bvk_xy(px, P.X, i) << (10 * i); ys |= hf_bvk_xy(py, P.Y, i) << (10 * i);
+            zs |= (i < nz ? hf_bvk_z(pz, P.Z, i) : 1023) << (10 * i);
+        }
+        for (int j = lane; j < nb; j += L) blocked_m |= hf_cand_bits(xs, ys, zs, nz, blk[j]);
+        for (int j = lane; j < no; j += L) { const int q = w.pos(1 - t)[j]; opp_m |= hf_cand_bits(xs, ys, zs, nz, q); opp_on_pos |= q == pos; }
+        for (int j = lane; j < ns; j += L) { const int q = w.pos(t)[j]; if (q != pos) same_m |= hf_cand_bits(xs, ys, zs, nz, q); }
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) {
+            blocked_m |= hf_shfl_xor<L>(blocked_m, off); opp_m |= hf_shfl_xor<L>(opp_m, off); same_m |= hf_shfl_xor<L>(same_m, off);
+        }
+    }
+    const bool active = lane < total && cand != pos && !(blocked_m >> lane & 1u);
     const unsigned mask = hf_ballot<L>(active);
     if (mask == 0) return HF_ST_VALUE_ERROR;                                     // min() of an empty sequence
     hf_fill_inv_old<L>(w, t, pos, lane);
-    double tau = INFINITY, rate = 0.0;
-    bool zero_div = false, exhausted = false;
-    if (active) {
-        const int rank = __popc(mask & ((1u << lane) - 1u));
-        const double u = hf_traj_uniform(P, w, w.draws + (uint64_t)rank, &exhausted);
-        tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
-    }
+    bool exhausted = false;
+    const int rank = __popc(mask & ((1u << lane) - 1u));
+    double u = 0.5;
+    if (active) u = hf_traj_uniform(P, w, w.draws + (uint64_t)rank, &exhausted);
     if (hf_ballot<L>(exhausted)) return HF_ST_REPLAY_EXHAUSTED;
-    const unsigned zmask = hf_ballot<L>(active && zero_div);
-    if (zmask) {                                   // draws up to and including the failing candidate
-        const int f = __ffs(zmask) - 1;
-        w.draws += (uint64_t)__popc(mask & (f == 31 ? HF_FULL : ((2u << f) - 1u)));
-        return HF_ST_ZERO_DIVISION;
+    double tau = INFINITY;
+    int best = 99;
+    if (hf_ballot<L>(opp_on_pos) != 0 || (same_m & mask) != 0) {
+        // a ZeroDivisionError is geometrically possible: every candidate exactly, the first failing one decides
+        double rate = 0.0;
+        bool zero_div = false;
+        if (active) tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
+        const unsigned zmask = hf_ballot<L>(active && zero_div);
+        if (zmask) {                               // draws up to and including the failing candidate
+            const int f = __ffs(zmask) - 1;
+            w.draws += (uint64_t)__popc(mask & (f == 31 ? HF_FULL : ((2u << f) - 1u)));
+            return HF_ST_ZERO_DIVISION;
+        }
+        // min(events): first minimum in candidate order (387 / 396)
+        best = active ? lane : 99;
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) {
+            const double otau = hf_shfl_xor<L>(tau, off);
+            const int obest = hf_shfl_xor<L>(best, off);
+            if (otau < tau || (otau == tau && obest < best)) { tau = otau; best = obest; }
+        }
+    } else {
+        // Screen-then-verify (cf. hf_c1_gen): an fp32 estimate of 1e13 * tau without the Coulomb sum for every
+        // candidate (lanes), exact evaluation — the lanes then share the O(charges) Coulomb sum — only of the
+        // candidates whose estimate lies within 1 + W of the smallest.  The estimate's relative error is
+        // <= eps = 4e-5 (hf_c1_gen) + C_e (ns + no) / kT (every neglected term is |1/r' - 1/r| <= 1); a candidate
+        // outside W = 4 eps (>= 2^-9) has tau >= a (1 - eps) > a_min (1 + W)(1 - eps) > a_min (1 + eps) >= tau of
+        // the best estimate: it can neither win nor tie.
+        float a = INFINITY;
+        bool forced = false;
+        if (active) {
+            const double *E = w.energy(t);
+            const double fz = t == 0 ? -P.field : P.field;
+            const double dE = (__ldg(E + hf_site(P, cand)) - __ldg(E + hf_site(P, pos))) + fz * (double)(cz - pz);
+            const float x = (opp_m >> lane & 1u) ? -INFINITY : (float)dE * (float)(1.0 / HF_KT);
+            float t0;
+            if (u < 0x1p-6) {
+                const float uf = (float)u;
+                t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+            } else {
+                t0 = -__logf((float)(1.0 - u));
+            }
+            a = t0;
+            if (x > 0.0f) a = t0 * __expf(x);
+            if (x > 700.0f) forced = true;                                       // the rate may underflow: ZeroDivisionError
+            if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
+        }
+        float amin = a;
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) amin = fminf(amin, hf_shfl_xor<L>(amin, off));
+        const float eps = 4e-5f + (float)(HF_ELECTROSTATIC / HF_KT) * (float)(ns + no);
+        const float window = fmaxf(0x1p-9f, 4.0f * eps);
+        const float thr = amin * (1.0f + window);
+        const unsigned verify = hf_ballot<L>(active && (forced || !(a > thr)));
+        for (unsigned m = verify; m; m &= m - 1) {
+            const int i = __ffs(m) - 1;
+            const int cand_i = hf_shfl<L>(cand, i);
+            const double u_i = hf_shfl<L>(u, i);
+            bool zero_div = false;
+            const double tau_i = hf_hop_time_coop<L>(P, w, t, pos, cand_i, u_i, lane, &zero_div);
+            if (zero_div) {                                                      // draws up to and including the failing candidate
+                w.draws += (uint64_t)__popc(mask & (i == 31 ? HF_FULL : ((2u << i) - 1u)));
+                return HF_ST_ZERO_DIVISION;
+            }
+            if (best == 99 || tau_i < tau) { tau = tau_i; best = i; }            // first minimum in candidate order
+        }
     }
     w.draws += (uint64_t)__popc(mask);
-    // min(events): first minimum in candidate order (387 / 396)
-    int best = active ? lane : 99;
-#pragma unroll
-    for (int off = L / 2; off > 0; off >>= 1) {
-        const double otau = hf_shfl_xor<L>(tau, off);
-        const int obest = hf_shfl_xor<L>(best, off);
-        if (otau < tau || (otau == tau && obest < best)) { tau = otau; best = obest; }
-    }
     const int fin = hf_shfl<L>(cand, best & 31);
     if (w.n_ev(t) >= P.cap_c) return HF_ST_CAPACITY;
     if (lane == 0) { w.ev_init(t)[w.n_ev(t)] = pos; w.ev_final(t)[w.n_ev(t)] = fin; w.ev_tau(t)[w.n_ev(t)] = tau; }

@@ -31,6 +31,7 @@ __device__ __forceinline__ void hf_small_carve(HfWarp &w, unsigned char *base, i
     double *d = reinterpret_cast<double *>(base);
     w.ev_tau_b = d; d += 2 * cap_c;
     w.inv_old_b = d; d += 2 * cap_c;
+    w.term_b = nullptr;                                                          // only the warp kernel shares a Coulomb sum
     int32_t *i = reinterpret_cast<int32_t *>(d);
     w.pos_b = i; i += 2 * cap_c;
     w.ev_init_b = i; i += 2 * cap_c;
@@ -44,26 +45,6 @@ __host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
     b = (b + 7u) & ~(size_t)7u;
     if (((b >> 3) & 1u) == 0) b += 8;
     return b;
-}
-
-// Bit mask of the candidates (ix, iy, iz), numbered (ix * 3 + iy) * nz + iz like the reference's neighbour list,
-// whose coordinates equal the packed site q.  xs / ys / zs: the coordinates of the three neighbour columns,
-// rows and planes, 10 bits each.  (More than one bit only on lattices so small that a periodic image repeats.)
-__device__ __noinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, int q) {
-    const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
-    unsigned m = 0;
-#pragma unroll 1
-    for (int ix = 0; ix < 3; ++ix) {
-        if (((xs >> (10 * ix)) & 1023) != qx) continue;
-#pragma unroll 1
-        for (int iy = 0; iy < 3; ++iy) {
-            if (((ys >> (10 * iy)) & 1023) != qy) continue;
-#pragma unroll 1
-            for (int iz = 0; iz < nz; ++iz)
-                if (((zs >> (10 * iz)) & 1023) == qz) m |= 1u << ((ix * 3 + iy) * nz + iz);
-        }
-    }
-    return m;
 }
 
 // _new_move_*_events (reseau.py:380-396) and the per-charge body of _init_move_*_events (240-276) for

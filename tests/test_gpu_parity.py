@@ -222,6 +222,42 @@ def test_batch_matches_oracle_per_trajectory(nat):
         sim.close()
 
 
+@pytest.mark.parametrize("dims,charges,steps", [((16, 16, 8), 40, 400), ((12, 10, 6), 24, 600), ((20, 20, 20), 100, 150)])
+def test_many_charges_match_oracle(nat, dims, charges, steps):
+    """charges > 8 run on the warp kernel, whose candidate loop screens in fp32 and shares the O(charges) Coulomb
+    sum of the few candidates it verifies among the lanes: every trajectory must still equal the C restatement of
+    the reference (pinned to the golden vectors) event for event, also where the reference's quirks stop it."""
+    from oracle import frm_oracle as fo
+    props, seed, B = (0.84, 0.15, 0.01), 4242, 24
+    olat = fo.OracleLattice.generate(dims, props, seed)
+    sim = nat.Sim(dims, props, 0.1, charges, 1, n_trajectories=B, seed=seed, first_trajectory=7)
+    try:
+        sim.generate_lattice()
+        sim.inject()
+        sim.set_trace(0, B, steps)
+        sim.run(steps)
+        sim.sync()
+        stopped = 0
+        for t in range(B):
+            o = fo.OracleTrajectory(olat, charges, seed, 7 + t, 0.1)
+            n, otr = o.run(steps)
+            info = sim.info(t)
+            ot = o.tallies()
+            assert info.fired == n, t
+            assert [info.emission, info.recombination, info.injection, info.steps, info.draws, info.spins] == \
+                [ot["emission"], ot["recombination"], ot["injection"], ot["step"], ot["draws"], ot["spins"]], t
+            assert info.status == {"ok": 0, "no_events": 1, "ZeroDivisionError": 2, "ValueError": 3}[o.status]
+            stopped += o.status != "ok"
+            tr = sim.trace(t, steps)
+            assert np.array_equal(tr["initial"], otr["initial"]) and np.array_equal(tr["final"], otr["final"])
+            assert np.array_equal(tr["kind"], otr["kind"])
+            _assert_tau(tr["tau"], otr["tau"], np.cumsum(otr["tau"]))
+            assert np.array_equal(sim.positions(t, 0), o.positions("electrons"))
+            assert np.array_equal(sim.positions(t, 1), o.positions("holes"))
+    finally:
+        sim.close()
+
+
 @pytest.mark.parametrize("name,steps,charges", [("tiny333_s5", 1500, 1), ("c1_s1", 2000, 1),
                                                 ("d0_s1", 1500, 4), ("d0_s2", 1200, 2), ("rag456_s6", 1000, 8),
                                                 ("dense_s8", 1500, 6), ("tiny333_s5", 1500, 3)])
