@@ -383,21 +383,29 @@ __device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, i
 // whose coordinates equal the packed site q.  xs / ys / zs: the coordinates of the three neighbour columns,
 // rows and planes, 10 bits each (1023 = no such plane).  More than one bit only on lattices so small that a
 // periodic image repeats.
-__device__ __noinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, int q) {
-    const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
+__device__ __noinline__ unsigned hf_cand_bits_hit(unsigned bx, unsigned by, unsigned bz, int nz) {
     unsigned m = 0;
 #pragma unroll 1
     for (int ix = 0; ix < 3; ++ix) {
-        if (((xs >> (10 * ix)) & 1023) != qx) continue;
+        if (!(bx >> ix & 1u)) continue;
 #pragma unroll 1
         for (int iy = 0; iy < 3; ++iy) {
-            if (((ys >> (10 * iy)) & 1023) != qy) continue;
+            if (!(by >> iy & 1u)) continue;
 #pragma unroll 1
             for (int iz = 0; iz < nz; ++iz)
-                if (((zs >> (10 * iz)) & 1023) == qz) m |= 1u << ((ix * 3 + iy) * nz + iz);
+                if (bz >> iz & 1u) m |= 1u << ((ix * 3 + iy) * nz + iz);
         }
     }
     return m;
+}
+__device__ __forceinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, int q) {
+    const int qx = hf_px(q), qy = hf_py(q), qz = hf_pz(q);
+    const unsigned bx = (unsigned)((xs & 1023) == qx) | (unsigned)(((xs >> 10) & 1023) == qx) << 1 | (unsigned)(((xs >> 20) & 1023) == qx) << 2;
+    if (!bx) return 0;                                                           // not in a neighbouring column: the usual case
+    const unsigned by = (unsigned)((ys & 1023) == qy) | (unsigned)(((ys >> 10) & 1023) == qy) << 1 | (unsigned)(((ys >> 20) & 1023) == qy) << 2;
+    const unsigned bz = (unsigned)((zs & 1023) == qz) | (unsigned)(((zs >> 10) & 1023) == qz) << 1 | (unsigned)(((zs >> 20) & 1023) == qz) << 2;
+    if (!by || !bz) return 0;
+    return hf_cand_bits_hit(bx, by, bz, nz);
 }
 
 // hf_hop_time for ONE candidate with the L lanes sharing the Coulomb sum: the terms
@@ -407,7 +415,7 @@ __device__ __noinline__ unsigned hf_cand_bits(int xs, int ys, int zs, int nz, in
 // (no same-type charge on the candidate, no opposite charge on `initial`): the caller checks.
 template <int L>
 __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWarp &w, int t, int initial, int cand,
-                                                   double u, int lane, bool *zero_div) {
+                                                   double u, bool onto_opposite, int lane, bool *zero_div) {
     const double rng = __dsub_rn(1.0, u);                                        // 284 / 316
     const double *E = w.energy(t);
     double dE = __dsub_rn(__ldg(E + hf_site(P, cand)), __ldg(E + hf_site(P, initial)));   // 286 / 318
@@ -423,14 +431,18 @@ __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWa
         w.term(1)[j] = loc == cand ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist<false>(hf_dist2(loc, cand)), w.inv_old(1)[j]));
     }
     hf_sync<L>();
+    // the sum itself, in list order.  A skipped entry (the moving charge itself, reseau.py:300 / 332) holds +0.0,
+    // and x + 0.0 == x bit for bit (out is never -0.0: it starts at +0.0 and round-to-nearest never produces -0.0
+    // from a cancellation), so the loops carry no test; a candidate ON an opposite charge ends at -inf whatever
+    // came before (reseau.py:305-308).
     double out = 0.0;
-    for (int j = 0; j < ns; ++j) {                                               // 299-304 / 331-336
-        if (w.pos(t)[j] == initial) continue;
-        out = __dadd_rn(out, w.term(0)[j]);
-    }
-    for (int j = 0; j < no; ++j) {                                               // 305-312 / 337-344
-        if (w.pos(1 - t)[j] == cand) { out = -INFINITY; break; }
-        out = __dsub_rn(out, w.term(1)[j]);
+    if (onto_opposite) {
+        out = -INFINITY;
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < ns; ++j) out = __dadd_rn(out, w.term(0)[j]);         // 299-304 / 331-336
+#pragma unroll 4
+        for (int j = 0; j < no; ++j) out = __dsub_rn(out, w.term(1)[j]);         // 309-312 / 341-344
     }
     hf_sync<L>();
     dE = __dadd_rn(dE, out);                                                     // 288 / 320
@@ -543,7 +555,7 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
             const int cand_i = hf_shfl<L>(cand, i);
             const double u_i = hf_shfl<L>(u, i);
             bool zero_div = false;
-            const double tau_i = hf_hop_time_coop<L>(P, w, t, pos, cand_i, u_i, lane, &zero_div);
+            const double tau_i = hf_hop_time_coop<L>(P, w, t, pos, cand_i, u_i, (opp_m >> i & 1u) != 0, lane, &zero_div);
             if (zero_div) {                                                      // draws up to and including the failing candidate
                 w.draws += (uint64_t)__popc(mask & (i == 31 ? HF_FULL : ((2u << i) - 1u)));
                 return HF_ST_ZERO_DIVISION;
