@@ -1,4 +1,4 @@
-// Thread-per-trajectory First-Reaction-Method kernel for SMALL `charges` (2 <= C <= 8): the
+// Thread-per-trajectory First-Reaction-Method kernel for SMALL `charges` (2 <= C <= 12): the
 // reference's own driver configuration (OLED.py:6-10: charges = 4) and the GA fitness sweeps.
 //
 // ncu on the warp-per-trajectory kernel (profiles/r01a_*): 1174 warp instructions per event, half of
@@ -12,7 +12,9 @@
 #include "hf_frm.cuh"
 #include "hf_frm_c1.cuh"
 
-#define HF_SMALL_MAX_CHARGES 8
+#ifndef HF_SMALL_MAX_CHARGES
+#define HF_SMALL_MAX_CHARGES 12
+#endif
 #ifndef HF_SMALL_THREADS
 #define HF_SMALL_THREADS 64
 #endif
@@ -53,10 +55,10 @@ __host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
 //
 // Screen-then-verify as in hf_c1_gen, with these differences: candidates can be blocked (they draw
 // nothing), and the Coulomb sum has up to 2C - 1 terms.  The fp32 estimate still ignores it: every
-// term is |1/r' - 1/r| <= 1 times HF_ELECTROSTATIC = 4.8e-7 eV, so <= 15 terms shift dE / kT by
-// <= 2.8e-4 and the estimate of 1e13 * tau by a relative 2.8e-4 on top of hf_c1_gen's 4e-5: candidates
-// outside a window of 1 + 2^-9 around the best estimate still cannot win or tie
-// ((1 + 2^-9)(1 - 3.2e-4) > 1 + 3.2e-4).  Whenever the reference could raise ZeroDivisionError for
+// term is |1/r' - 1/r| <= 1 times HF_ELECTROSTATIC = 4.8e-7 eV, so n terms shift dE / kT by <= 1.86e-5 n
+// and the estimate of 1e13 * tau by the same relative amount on top of hf_c1_gen's 4e-5 =: eps; candidates
+// outside a window of 1 + max(2^-9, 4 eps) around the best estimate cannot win or tie
+// ((1 + 4 eps)(1 - eps) > 1 + eps).  (Measured: faster than the warp kernel up to 12 charges of each type.)  Whenever the reference could raise ZeroDivisionError for
 // geometric reasons (a same-type charge on a candidate: the flag/list desynchronisation of DESIGN.md §0;
 // an opposite charge on the moving charge's own site) every candidate is evaluated exactly, in order,
 // as the warp kernel does.
@@ -153,7 +155,8 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
             }
         }
         if (exhausted) { w.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
-        const float thr = amin * (1.0f + HF_C1_WINDOW);
+        // window: 4 x the estimate's error bound, 4e-5 + C_e (ns + no) / kT (2^-9 up to 8 charges of each type)
+        const float thr = amin * (1.0f + fmaxf(HF_C1_WINDOW, 4.0f * (4e-5f + (float)(HF_ELECTROSTATIC / HF_KT) * (float)(ns + no))));
         verify = forced | (1u << lmin);
         if (!(amin2 > thr)) {
             for (unsigned m = amask; m; m &= m - 1) {

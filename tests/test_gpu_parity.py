@@ -224,7 +224,7 @@ def test_batch_matches_oracle_per_trajectory(nat):
 
 @pytest.mark.parametrize("dims,charges,steps", [((16, 16, 8), 40, 400), ((12, 10, 6), 24, 600), ((20, 20, 20), 100, 150)])
 def test_many_charges_match_oracle(nat, dims, charges, steps):
-    """charges > 8 run on the warp kernel, whose candidate loop screens in fp32 and shares the O(charges) Coulomb
+    """charges > 12 run on the warp kernel, whose candidate loop screens in fp32 and shares the O(charges) Coulomb
     sum of the few candidates it verifies among the lanes: every trajectory must still equal the C restatement of
     the reference (pinned to the golden vectors) event for event, also where the reference's quirks stop it."""
     from oracle import frm_oracle as fo
@@ -260,10 +260,11 @@ def test_many_charges_match_oracle(nat, dims, charges, steps):
 
 @pytest.mark.parametrize("name,steps,charges", [("tiny333_s5", 1500, 1), ("c1_s1", 2000, 1),
                                                 ("d0_s1", 1500, 4), ("d0_s2", 1200, 2), ("rag456_s6", 1000, 8),
-                                                ("dense_s8", 1500, 6), ("tiny333_s5", 1500, 3)])
+                                                ("dense_s8", 1500, 6), ("tiny333_s5", 1500, 3),
+                                                ("c10_s1", 600, 10), ("dense_s8", 800, 12)])
 def test_thread_kernel_equals_warp_kernel(nat, name, steps, charges):
-    """charges <= 8 has two step kernels (thread-per-trajectory by default: hf_frm_c1.cuh for one charge,
-    hf_frm_small.cuh for 2..8; warp-per-trajectory with HF_FLAG_WARP_KERNEL): 4096 trajectories must end in
+    """charges <= 12 has two step kernels (thread-per-trajectory by default: hf_frm_c1.cuh for one charge,
+    hf_frm_small.cuh for 2..12; warp-per-trajectory with HF_FLAG_WARP_KERNEL): 4096 trajectories must end in
     exactly the same state under both — including the ones the reference's quirks stop (ZeroDivisionError,
     ValueError) on crowded little lattices."""
     g = load_golden(name)
@@ -296,7 +297,7 @@ def test_thread_kernel_equals_warp_kernel(nat, name, steps, charges):
         assert np.array_equal(a, b)                      # same device libm: bit-identical, tau included
     if name == "tiny333_s5" and charges == 1:
         assert thread["tallies"]["recombination"] > 100_000 and thread["tallies"]["capture_e"] > 1000
-    if charges > 1:
+    if charges > 1 and name != "c10_s1":                  # (20^3 with 10 charges: hardly any meeting in 600 steps)
         assert thread["tallies"]["recombination"] > 1000
 
 

@@ -44,11 +44,11 @@ def _check_prefix(g, out, n):
 
 @pytest.mark.parametrize("small_kernel", [False, True])
 def test_emulated_kernel_matches_reference(golden, small_kernel):
-    """small_kernel: the thread-per-trajectory kernel for 2 <= charges <= 8 (hf_frm_small.cuh): hf_step<1>
+    """small_kernel: the thread-per-trajectory kernel for 2 <= charges <= 12 (hf_frm_small.cuh): hf_step<1>
     and the screened candidate loop must reproduce the same golden trajectories."""
     g = golden
-    if small_kernel and not 2 <= g["charges"] <= 8:
-        pytest.skip("the thread-per-trajectory kernel of hf_frm_small.cuh covers 2 <= charges <= 8")
+    if small_kernel and not 2 <= g["charges"] <= 12:
+        pytest.skip("the thread-per-trajectory kernel of hf_frm_small.cuh covers 2 <= charges <= 12")
     total = len(g["trace_kind"])
     complete = total <= _step_cap(g) or bool(g["error_s"])
     stop = g["n_steps"] if complete else _step_cap(g)
