@@ -366,7 +366,8 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
     ms, n = sim.run_timing()
     tab = sim.x_tables()
     m = int(tab["g6"].size)
-    t = sim.x_tallies()
+    from hyperfluorescence_b200 import distributed as hd
+    t = hd.all_reduce_named(sim.x_tallies())                                    # the one collective of the path
     cpu_line = None
     if cpu and world == 1 and rank == 0:
         cpu_line = exciton_cpu_sample(sim, lattice, tab)
@@ -380,7 +381,7 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
     bytes_per_event = m * (1 + 8) + (m + 7) // 8 + 2 * 21 + 16                  # SURVEY.md 8(d), Path X
     peak, _ = hbm_peak()
     rate = events / (ms * 1e-3)
-    decayed = max(1, t["generated"] - X_TRAJ_PER_GPU)
+    decayed = max(1, t["generated"] - world * X_TRAJ_PER_GPU)
     l2_resident = n_real * lattice ** 3 * 8 < 60e6
     out = {"metric": "KMC exciton events/sec (box), exciton path", "value": rate, "unit": "events/s",
            "config": {"workload": label, "lattice": [lattice] * 3, "realisations_per_gpu": n_real,
@@ -443,7 +444,8 @@ def dense_rate(rank, local_rank, world):
     for _ in range(3):
         sim.xd_run(XD_EVENTS)
     ms, n = sim.run_timing()
-    t = sim.xd_tallies()
+    from hyperfluorescence_b200 import distributed as hd
+    t = hd.all_reduce_named(sim.xd_tallies())                                   # the one collective of the path
     sim.close()
     if world > 1:
         import torch.distributed as dist

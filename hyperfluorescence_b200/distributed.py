@@ -103,3 +103,13 @@ def all_reduce_tallies(sim) -> dict:
         local = sim.tallies()
         vec = all_reduce_vector(np.array([local[k] for k in TALLY_NAMES] + [0] * (HF_N_TALLIES - len(TALLY_NAMES))))
     return {k: int(vec[i]) for i, k in enumerate(TALLY_NAMES)}
+
+
+def all_reduce_named(local: dict) -> dict:
+    """SUM all-reduce of a dict of integer tallies (``Sim.x_tallies()``, ``Sim.xd_tallies()``: emission
+    and quenching channels of the exciton extensions) over the default process group: the one collective of
+    those paths, like ``all_reduce_tallies`` for the reference's counters.  Key order must agree on all ranks
+    (it is the order of the C-ABI's HF_XT_* / HF_XDT_* enums)."""
+    keys = list(local)
+    vec = all_reduce_vector(np.array([int(local[k]) for k in keys], dtype=np.int64))
+    return {k: int(v) for k, v in zip(keys, vec)}

@@ -204,6 +204,16 @@ tot = hd.all_reduce_vector(vec)
 whole = lat.run_batch(3, 0.1, seed, 0, total, 400)
 assert tot.tolist() == [whole["emission"], whole["recombination"], whole["injection"], whole["events"]], (tot, whole)
 assert whole["recombination"] > 0
+# the exciton extension: each rank runs its shard of global trajectory ids with the specification oracle,
+# the named tallies are summed with the product's all-reduce and equal the unsharded run
+from oracle import exciton_oracle as xo
+arr = lat.arrays()
+ws1, wt1 = xo.weights(arr["s1"], arr["t1"], arr["species"])
+o = xo.ExcitonOracle(dims, arr["species"], ws1, wt1, dict(xo.default_params(), cutoff=1.5))
+mine = o.run_batch(seed, sh.first_trajectory, sh.n_trajectories, 120, n_threads=2)
+summed = hd.all_reduce_named(mine)
+assert summed == o.run_batch(seed, 0, total, 120, n_threads=2), summed
+assert summed["events"] == total * 120
 print("rank", rank, "ok", tot.tolist())
 '''
 
