@@ -25,8 +25,17 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: NCCL's own banner / debug output (stdout by default) goes to stderr
+# stdout carries exactly one JSON line.  Libraries write there too (NCCL prints its version banner with a
+# plain printf whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run
+# and the JSON line is written to a private duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -140,7 +149,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -268,7 +277,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample,
                                 "one_core_value": v1}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
@@ -470,6 +479,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-ga", action="store_true", help="skip the GA fitness-sweep, exciton-path, disorder-sweep and high-density legs")
     args = ap.parse_args()
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.warmup < 3 and args.impl == "ours" and not args.no_cpu:
         args.warmup = 3
     if args.impl == "reference":
