@@ -269,7 +269,7 @@ def run_ours(args):
         line["ga"] = ga_fitness_rate(rank, local_rank, world)
         line["exciton_path"] = exciton_rate(rank, local_rank, world, cpu=not args.no_cpu)
         line["disorder_sweep"] = exciton_rate(rank, local_rank, world, lattice=256, realisations_total=64, label="disorder_sweep")
-        line["high_density"] = dense_rate(rank, local_rank, world)
+        line["high_density"] = dense_rate(rank, local_rank, world, cpu=not args.no_cpu)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_sample(cores, 2500)
@@ -435,7 +435,26 @@ def exciton_cpu_sample(sim, lattice, tab):
 XD_L, XD_DEVICES_PER_GPU, XD_EXCITONS, XD_EVENTS = 128, 4096, 256, 200
 
 
-def dense_rate(rank, local_rank, world):
+def dense_cpu_sample(sim, tab):
+    """The high-density specification (oracle/exciton_dense_oracle.c, POSIX threads over devices) on this box's
+    host cores, on the device's own lattice: a bounded sample of the same workload (fill included)."""
+    from hyperfluorescence_b200 import _native as nat
+    from oracle import exciton_oracle as xo
+    lat = sim.download_lattice(0)
+    ws1, wt1 = sim.x_weights(0)
+    params = dict(nat.x_params_to_dict(nat.x_default_params()), cutoff=X_CUTOFF)
+    o = xo.DenseExcitonOracle((XD_L,) * 3, lat["species"], ws1, wt1, params, tab)
+    cores = os.cpu_count() or 1
+    n_dev = XD_DEVICES_PER_GPU // 4
+    t0 = time.perf_counter()
+    o.run_devices(SEED, 0, n_dev, XD_EXCITONS, XD_EVENTS, n_threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": n_dev * XD_EVENTS / dt, "unit": "events/s", "cores": cores, "kind": "port",
+            "sample": f"{n_dev} of the {XD_DEVICES_PER_GPU} devices x {XD_EXCITONS} excitons x {XD_EVENTS} events "
+                      f"(initial fill and totals included) on the same {XD_L}^3 lattice, {cores} threads"}
+
+
+def dense_rate(rank, local_rank, world, cpu=False):
     """BASELINE configs[3]: high-density excitons on a 128^3 lattice with occupancy blocking and
     exciton-exciton annihilation (own model, parity unpinned: DESIGN.md section 10).  4096 devices per GPU x
     256 interacting excitons each (10^6 excitons per GPU); one event = one channel of one exciton."""
@@ -455,6 +474,7 @@ def dense_rate(rank, local_rank, world):
     ms, n = sim.run_timing()
     from hyperfluorescence_b200 import distributed as hd
     t = hd.all_reduce_named(sim.xd_tallies())                                   # the one collective of the path
+    cpu_line = dense_cpu_sample(sim, sim.x_tables()) if (cpu and world == 1 and rank == 0) else None
     sim.close()
     if world > 1:
         import torch.distributed as dist
@@ -467,7 +487,8 @@ def dense_rate(rank, local_rank, world):
             "config": {"lattice": [XD_L] * 3, "devices_per_gpu": XD_DEVICES_PER_GPU, "excitons_per_device": XD_EXCITONS,
                        "cutoff": X_CUTOFF, "events_per_device_per_launch": XD_EVENTS, "kernel": "hfxd_run_kernel",
                        "model": "own (parity unpinned): DESIGN.md section 10, oracle/exciton_dense_oracle.c"},
-            "annihilation_fraction": (t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]) / lost}
+            "annihilation_fraction": (t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]) / lost,
+            **({"cpu_baseline": cpu_line} if cpu_line else {})}
 
 
 def main():
