@@ -380,6 +380,34 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
     cpu_line = None
     if cpu and world == 1 and rank == 0:
         cpu_line = exciton_cpu_sample(sim, lattice, tab)
+    e2e = None
+    if label == "north_star":
+        # end to end through the C-ABI with HOST buffers every step: lattice arrays from pinned host memory ->
+        # hf_upload_lattice (H2D), hf_x_configure (tables + Boltzmann weights), hf_x_spawn, hf_x_run, hf_x_read_tallies (D2H)
+        host = sim.download_lattice(0)
+        pinned = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in host.items()}
+        xp = nat.x_params_from_dict(dict(cutoff=X_CUTOFF))
+        def e2e_step():
+            sim.upload_lattice(0, pinned["species"], pinned["homo"], pinned["lumo"], pinned["s1"], pinned["t1"])
+            sim.x_configure(xp)
+            sim.x_spawn()
+            sim.x_run(X_EVENTS)
+            return sim.x_tallies()
+        e2e_step()
+        sim.sync()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            e2e_step()
+        sim.sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            import torch.distributed as dist
+            v = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            dt = float(v.item())
+        e2e = {"value": world * X_TRAJ_PER_GPU * X_EVENTS * 2 / dt, "unit": "events/s",
+               "h2d_bytes_per_step": int(sum(v.nbytes for v in pinned.values())), "d2h_bytes_per_step": 16 * 8, "steps": 2,
+               "path": "hf_upload_lattice(pinned host) + hf_x_configure + hf_x_spawn + hf_x_run + hf_x_read_tallies"}
     sim.close()
     if world > 1:
         import torch.distributed as dist
@@ -410,6 +438,8 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
            "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
     if cpu_line:
         out["cpu_baseline"] = cpu_line
+    if e2e:
+        out["e2e"] = e2e
     return out
 
 
