@@ -32,7 +32,7 @@ struct HfxdParams {
     HfxParams X;                       // lattice, tables, rate constants, Philox key; B = devices, first_traj = first device id
     int32_t n, n_pad;                  // excitons per device, rounded up to 32
     double ann[4];                     // [donor spin index][acceptor spin index]
-    double p_tta, rc2;                 // triplet-triplet promotion probability; cutoff^2
+    double p_tta;                      // triplet-triplet promotion probability
     uint32_t *pos;                     // [B][n_pad]
     double *T, *birth;                 // [B][n_pad]
     uint32_t *occ;                     // [B][occ_words]

@@ -1085,7 +1085,6 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
     for (int k = 0; k < 4; ++k) D.ann[k] = annihilation[k];
     D.p_tta = p_tta;
-    D.rc2 = s->x_params.cutoff * s->x_params.cutoff;
     D.occ_words = (s->X.w_stride + 15) / 16;
     const size_t B = (size_t)s->P.B, np = (size_t)D.n_pad;
     if ((rc = dev_alloc(&s->d_xd_pos, B * np))) return rc;

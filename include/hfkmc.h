@@ -68,8 +68,8 @@ enum { HF_SP_HOST = 0, HF_SP_TADF = 1, HF_SP_FLUO = 2 };
 
 /* hf_config.flags */
 #define HF_FLAG_NONE 0u
-/* Step charges == 1 trajectories with the generic warp-per-trajectory kernel instead of the
- * thread-per-trajectory one (cross-checks; both give identical results). */
+/* Step trajectories with charges <= 12 with the generic warp-per-trajectory kernel instead of the
+ * thread-per-trajectory ones (cross-checks; all give identical results). */
 #define HF_FLAG_WARP_KERNEL 1u
 
 /* Replaces the arguments of Lattice.__init__ (reseau.py:109-111) plus the batch shape. */

@@ -298,7 +298,7 @@ int emu_xd_run(const int32_t dims[3], const double *ws1, const double *wt1, int3
     P.ws1 = hs1.data(); P.wt1 = ht1.data();
     D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
     memcpy(D.ann, ann, sizeof(D.ann));
-    D.p_tta = p_tta; D.rc2 = cutoff * cutoff;
+    D.p_tta = p_tta; (void)cutoff;
     D.occ_words = (P.w_stride + 15) / 16;
     std::vector<uint32_t> pos((size_t)D.n_pad, 0), occ((size_t)D.occ_words, 0);
     std::vector<double> T((size_t)D.n_pad, 0.0), birth((size_t)D.n_pad, 0.0);
