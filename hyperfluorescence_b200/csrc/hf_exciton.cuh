@@ -37,7 +37,7 @@
 //      the chosen channel (re-evaluating only that lane's K rates, bit-identically), advances the
 //      clock and applies the event.
 // Everything that is per-event overhead (Philox, log, the divisions, bookkeeping, tallies) thereby
-// costs one warp instruction per 32 events instead of one per event: ~1030 -> ~190 warp
+// costs one warp instruction per 32 events instead of one per event: 1033 -> 297 warp
 // instructions per event at M = 256 (profiles/r01e_* vs r01f_*).
 #pragma once
 #include "hf_frm.cuh"
