@@ -247,3 +247,41 @@ def test_gpu_exciton_api_errors():
             sim.xd_spawn()
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,cutoff,B,R", [((13, 13, 3), 1.0, 1, 1),       # one interior plane, 6 channels, one trajectory
+                                               ((13, 14, 4), 6.0, 33, 1),      # the largest cutoff (M = 924): generic kernel, ragged batch
+                                               ((16, 16, 9), 2.5, 70, 7),      # realisation boundaries inside a warp's batch
+                                               ((11, 12, 6), 5.0, 40, 2)])     # cutoff 5 (17 slots of channels)
+def test_gpu_exciton_edge_shapes(dims, cutoff, B, R):
+    """Extreme shapes of the exciton path against the specification: final state of every trajectory and the
+    per-realisation tallies."""
+    from hyperfluorescence_b200 import _native as nat
+    n = 120
+    sim = nat.Sim(dims, (0.7, 0.2, 0.1), 0.1, 1, 1, n_trajectories=B, n_realisations=R, seed=31, first_trajectory=3)
+    try:
+        sim.generate_lattice()
+        params = dict(nat.x_params_to_dict(nat.x_default_params()), cutoff=cutoff)
+        sim.x_configure(nat.x_params_from_dict(dict(cutoff=cutoff)))
+        sim.x_spawn()
+        sim.x_run(n)
+        sim.sync()
+        st = sim.x_state()
+        per_real = sim.x_realisation_tallies()
+        tab = sim.x_tables()
+        for r in range(R):
+            lat = sim.download_lattice(r)
+            ws1, wt1 = sim.x_weights(r)
+            o = xo.ExcitonOracle(dims, lat["species"], ws1, wt1, params, tab)
+            lo, hi = r * (B // R), (r + 1) * (B // R)
+            acc = {}
+            for b in range(lo, hi):
+                ref = o.run(31, 3 + b, n)
+                assert (st["site"][b], st["spin"][b], int(st["draws"][b])) == (ref["site"], ref["spin"], ref["draws"]), b
+                for k, v in ref["tallies"].items():
+                    acc[k] = acc.get(k, 0) + v
+            for k, v in acc.items():
+                assert int(per_real[k][r]) == v, (r, k)
+    finally:
+        sim.close()
