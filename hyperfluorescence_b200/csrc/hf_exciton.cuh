@@ -195,30 +195,33 @@ struct HfxLaneTables {                // this lane's channels of the KF full slo
 };
 
 // Phase A, loads: the weights of the neighbours on this lane's channels of the full slots.
-template <int KF>
+// (slots kBase .. kBase + CH - 1: a kernel whose KF slots do not fit two register buffers gathers them in chunks)
+template <int KF, int CH = KF, int kBase = 0>
 __device__ __forceinline__ void hfx_gather(const double *wp, int site, int meta, const HfxLaneTables<KF> &T,
                                            const int32_t *s_off_lane, int dim_x, int dim_y, int plane,
-                                           double (&buf)[KF > 0 ? KF : 1]) {
+                                           double (&buf)[CH > 0 ? CH : 1]) {
     if (meta & 8) {
 #pragma unroll
-        for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + T.lin[k]);
+        for (int k = 0; k < CH; ++k) buf[k] = __ldg(wp + T.lin[kBase + k]);
     } else {
         const int px = hf_px(site), py = hf_py(site);
 #pragma unroll
-        for (int k = 0; k < KF; ++k) buf[k] = __ldg(wp + hfx_delta(s_off_lane[32 * k], px, py, dim_x, dim_y, plane));
+        for (int k = 0; k < CH; ++k) buf[k] = __ldg(wp + hfx_delta(s_off_lane[32 * (kBase + k)], px, py, dim_x, dim_y, plane));
     }
 }
 
 // KF > 0: M = 32 * KF + kTail neighbours, known at compile time: register-resident tables, prefetched
 // gathers (kRegG: the Dexter factors too, else they are read from shared memory).  KF == 0: any M (P.M),
 // tables in shared memory.
-template <int kWarps, int KF, int kTail, int kMinBlocks, bool kRegG>
+// kChunk: slots gathered at a time (KF, or KF / 2 for the 16-slot variant: two register buffers of 16 would spill).
+template <int kWarps, int KF, int kTail, int kMinBlocks, bool kRegG, int kChunk = KF>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const HfxParams P) {
+    static_assert(kChunk == KF || 2 * kChunk == KF, "one or two chunks");
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int M = KF > 0 ? 32 * KF + kTail : P.M;
     const int K = (M + 3 + 31) >> 5;
-    constexpr int KB = KF > 0 ? KF : 1;
+    constexpr int KB = kChunk > 0 ? kChunk : 1;
     double *s_g6 = reinterpret_cast<double *>(hf_smem);
     double *s_gd = s_g6 + M;
     double *s_k = s_gd + M;
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
             //      together with the rates of exciton e (independent chains), the gathers of e + 1 before both ----
             double buf0[KB], buf1[KB];
             double S_prev = 0.0;
-            if (KF > 0) { const int2 sm0 = s_sm[0]; hfx_gather<KF>(s_wp[0], sm0.x, sm0.y, T, s_off_lane, dim_x, dim_y, plane, buf0); }
+            if (KF > 0) { const int2 sm0 = s_sm[0]; hfx_gather<KF, kChunk, 0>(s_wp[0], sm0.x, sm0.y, T, s_off_lane, dim_x, dim_y, plane, buf0); }
             // one exciton: `cur` holds its gathered weights, the next exciton's go into `nxt`
 #define HFX_PHASE_A(e, cur, nxt)                                                                                              \
             {                                                                                                                 \
@@ -326,11 +329,62 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 }                                                                                                             \
                 S_prev = S;                                                                                                   \
             }
-            for (int e = 0; e < count; e += 2) {
-                HFX_PHASE_A(e, buf0, buf1)
-                if (e + 1 < count) HFX_PHASE_A(e + 1, buf1, buf0)
+            // the 16-slot variant: two halves per exciton; the first half's sums overlap the scan of exciton e - 1, the
+            // second half of e (then the first half of e + 1) is in flight while a half is consumed
+#define HFX_HALF(e, kBase, cur, nxt)                                                                                          \
+            {                                                                                                                 \
+                const int2 sm = s_sm[e];                                                                                      \
+                const int meta = sm.y;                                                                                        \
+                const double e_inv = s_inv[e];                                                                                \
+                const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);                                    \
+                if (kBase == 0) {                                                                                             \
+                    hfx_gather<KF, kChunk, kChunk>(s_wp[e], sm.x, sm.y, T, s_off_lane, dim_x, dim_y, plane, nxt);             \
+                } else if ((e) + 1 < count) {                                                                                 \
+                    const int2 smn = s_sm[(e) + 1];                                                                           \
+                    hfx_gather<KF, kChunk, 0>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt);          \
+                }                                                                                                             \
+                double S = kBase == 0 ? 0.0 : S_half;                                                                         \
+                if (meta & 1) {                                                                                               \
+                    _Pragma("unroll") for (int k = 0; k < kChunk; ++k) S = __dadd_rn(S, hfx_rate(e_pref, s_g6_lane[32 * (kBase + k)], cur[k], e_inv)); \
+                } else {                                                                                                      \
+                    _Pragma("unroll") for (int k = 0; k < kChunk; ++k) S = __dadd_rn(S, hfx_rate(e_pref, kRegG ? T.gd[kBase + k] : s_gd_lane[32 * (kBase + k)], cur[k], e_inv)); \
+                }                                                                                                             \
+                if (kBase == 0) {                                                                                             \
+                    S_half = S;                                                                                               \
+                    const double L_prev = hfx_scan(S_prev, lane);                                                             \
+                    if ((e) > 0) {                                                                                            \
+                        s_L[((e) - 1) * HFX_L_STRIDE + lane] = L_prev;                                                        \
+                        const unsigned nonzero = __ballot_sync(HF_FULL, S_prev > 0.0);                                        \
+                        if (lane == 0) s_nz[(e) - 1] = nonzero;                                                               \
+                    }                                                                                                         \
+                } else {                                                                                                      \
+                    const double *g = (meta & 1) ? s_g6 : s_gd;                                                               \
+                    const double *e_wp = s_wp[e];                                                                             \
+                    const int ex = hf_px(sm.x), ey = hf_py(sm.x);                                                             \
+                    for (int k = KF; k < K; ++k) {                                                                            \
+                        const int c = (k << 5) + lane;                                                                        \
+                        double rate = 0.0;                                                                                    \
+                        if (c < M) rate = hfx_rate(e_pref, g[c], __ldg(e_wp + hfx_delta(s_off[c], ex, ey, dim_x, dim_y, plane)), e_inv); \
+                        else if (c < M + 3) rate = s_on[(c - M) * 32 + (e)];                                                  \
+                        S = __dadd_rn(S, rate);                                                                               \
+                    }                                                                                                         \
+                    S_prev = S;                                                                                               \
+                }                                                                                                             \
+            }
+            if constexpr (kChunk == KF) {
+                for (int e = 0; e < count; e += 2) {
+                    HFX_PHASE_A(e, buf0, buf1)
+                    if (e + 1 < count) HFX_PHASE_A(e + 1, buf1, buf0)
+                }
+            } else {
+                double S_half = 0.0;
+                for (int e = 0; e < count; ++e) {
+                    HFX_HALF(e, 0, buf0, buf1)
+                    HFX_HALF(e, kChunk, buf1, buf0)
+                }
             }
 #undef HFX_PHASE_A
+#undef HFX_HALF
             {
                 const double L_last = hfx_scan(S_prev, lane);
                 s_L[(count - 1) * HFX_L_STRIDE + lane] = L_last;

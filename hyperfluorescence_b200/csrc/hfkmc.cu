@@ -208,7 +208,7 @@ static hfx_kernel_fn x_pick_kernel(int M) {
     switch (M) {
         case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true>;                         // cutoff 3
         case 256: return hfx_run_kernel<kXWarps, 8, 0, 2, true>;                          // cutoff 4
-        case 514: return hfx_run_kernel<kXWarps, 16, 2, 1, true>;                         // cutoff 5
+        case 514: return hfx_run_kernel<kXWarps, 16, 2, 2, false, 8>;                     // cutoff 5: two halves of 8 slots, Dexter factors from shared memory
         default: return hfx_run_kernel<kXWarps, 0, 0, 2, false>;
     }
 }

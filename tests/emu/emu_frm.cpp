@@ -206,6 +206,7 @@ static void x_spawn_body(void *a) { hfx_spawn_kernel(*(const HfxParams *)a); }
 static void x_run_body_generic(void *a) { hfx_run_kernel<1, 0, 0, 1, false>(*(const HfxParams *)a); }
 static void x_run_body_k3(void *a) { hfx_run_kernel<1, 3, 26, 1, true>(*(const HfxParams *)a); }
 static void x_run_body_k8(void *a) { hfx_run_kernel<1, 8, 0, 1, true>(*(const HfxParams *)a); }
+static void x_run_body_k16(void *a) { hfx_run_kernel<1, 16, 2, 1, false, 8>(*(const HfxParams *)a); }
 
 // Exciton path: B <= 32 trajectories on one lattice, hfx_spawn + n_calls x hfx_run(n_events).
 int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, const double *wt1, int32_t M,
@@ -252,7 +253,7 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     if (hfx_smem_bytes(M, 1) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     emu_run_warp(x_spawn_body, &P);
-    void (*body)(void *) = generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : x_run_body_generic;
+    void (*body)(void *) = generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : M == 514 ? x_run_body_k16 : x_run_body_generic;
     for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(body, &P); }
     memcpy(trace_out, trace.data(), sizeof(HfTraceRec) * (size_t)(B * trace_cap));
     for (int b = 0; b < B; ++b) {

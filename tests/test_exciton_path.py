@@ -57,7 +57,8 @@ def test_oracle_closed_forms():
     ((24, 22, 7), 4.0, 8, 27, False),      # ... with wrap-free sites too, and a ragged last block of trajectories
     ((9, 10, 5), 3.0, 6, 32, False),       # 3 full slots + a tail slot that mixes transfer and on-site channels
     ((9, 10, 5), 3.0, 6, 5, True),         # the generic shared-memory variant on the same model
-    ((8, 8, 8), 1.5, 7, 32, False)])       # M = 18 < 32: generic variant
+    ((8, 8, 8), 1.5, 7, 32, False),        # M = 18 < 32: generic variant
+    ((26, 24, 7), 5.0, 9, 19, False)])     # cutoff 5: 16 full slots gathered in two halves, wrap-free sites exist
 def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, generic):
     """hfx_spawn_kernel + hfx_run_kernel run lane by lane on the host (tests/emu): identical event
     sequences, channels, spins, waiting times, final states and tallies for 32 trajectories."""
