@@ -79,7 +79,8 @@ struct hf_sim {
     double *d_x_g6 = nullptr, *d_x_gd = nullptr, *d_ws1 = nullptr, *d_wt1 = nullptr, *d_x_time = nullptr, *d_x_life = nullptr;
     uint64_t *d_x_draws = nullptr, *d_x_trace_len = nullptr;
     unsigned long long *d_x_totals = nullptr;
-    int x_warps = 8, x_grid = 1;
+    int x_warps = 8, x_grid = 1, x_per_sm = 1;
+    bool x_tune = false;               // pick the warp batch by measurement at the next hf_x_run
     size_t x_smem = 0;
     // high-density exciton devices (hf_xd_*)
     bool xd_configured = false, xd_spawned = false;
@@ -213,6 +214,68 @@ static hfx_kernel_fn x_pick_kernel(int M) {
     }
 }
 
+void x_set_block(hf_sim *s, int block) {
+    s->X.block = block;
+    const int64_t blocks = (s->X.B + block - 1) / block;
+    const int64_t need = (blocks + kXWarps - 1) / kXWarps, cap = (int64_t)s->sm_count * s->x_per_sm;
+    s->x_grid = (int)(need < cap ? need : cap);
+    if (s->x_grid < 1) s->x_grid = 1;
+}
+
+// Pick the warp batch by measurement: a few events per candidate, each from the same saved state, which is
+// restored afterwards (tallies included).  Only when the weights exceed half the L2 and nothing is traced.
+int x_autotune(hf_sim *s) {
+    const size_t B = (size_t)s->P.B, nt = (size_t)s->n_real * HFX_T_N;
+    int32_t *site = nullptr, *spin = nullptr;
+    double *time = nullptr, *life = nullptr;
+    uint64_t *draws = nullptr;
+    unsigned long long *totals = nullptr;
+    int rc;
+    if ((rc = dev_alloc(&site, B)) || (rc = dev_alloc(&spin, B)) || (rc = dev_alloc(&time, B)) || (rc = dev_alloc(&life, B)) ||
+        (rc = dev_alloc(&draws, B)) || (rc = dev_alloc(&totals, nt))) {
+        cudaFree(site); cudaFree(spin); cudaFree(time); cudaFree(life); cudaFree(draws); cudaFree(totals);
+        return rc;
+    }
+    auto copy = [&](bool save) {
+        const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+        cudaMemcpyAsync(save ? site : s->d_x_site, save ? s->d_x_site : site, 4 * B, k, s->stream);
+        cudaMemcpyAsync(save ? spin : s->d_x_spin, save ? s->d_x_spin : spin, 4 * B, k, s->stream);
+        cudaMemcpyAsync(save ? time : s->d_x_time, save ? s->d_x_time : time, 8 * B, k, s->stream);
+        cudaMemcpyAsync(save ? life : s->d_x_life, save ? s->d_x_life : life, 8 * B, k, s->stream);
+        cudaMemcpyAsync(save ? draws : s->d_x_draws, save ? s->d_x_draws : draws, 8 * B, k, s->stream);
+        cudaMemcpyAsync(save ? totals : s->d_x_totals, save ? s->d_x_totals : totals, 8 * nt, k, s->stream);
+    };
+    copy(true);
+    HfxParams X = s->X;
+    X.trace = nullptr; X.trace_n = 0; X.trace_len = nullptr;
+    X.n_events = 12;
+    const int candidates[] = {32, 16, 8, 4, 3, 2};
+    cudaEvent_t e0 = get_event(s), e1 = get_event(s);
+    int best = 32;
+    float best_ms = 0.f;
+    for (int c : candidates) {
+        x_set_block(s, c);
+        X.block = c;
+        float ms = 0.f;
+        for (int rep = 0; rep < 2; ++rep) {                                      // the first repetition warms the caches for this batch size
+            cudaEventRecord(e0, s->stream);
+            x_pick_kernel(X.M)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(X);
+            cudaEventRecord(e1, s->stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        copy(false);
+        if (best_ms == 0.f || ms < best_ms) { best_ms = ms; best = c; }
+    }
+    s->event_pool.push_back(e0); s->event_pool.push_back(e1);
+    x_set_block(s, best);
+    cudaError_t e = cudaStreamSynchronize(s->stream);
+    cudaFree(site); cudaFree(spin); cudaFree(time); cudaFree(life); cudaFree(draws); cudaFree(totals);
+    if (e != cudaSuccess || (e = cudaGetLastError()) != cudaSuccess) return fail(HF_ERR_CUDA, "exciton batch tuning failed: %s", cudaGetErrorString(e));
+    s->x_tune = false;
+    return HF_OK;
+}
+
 int x_configure_launch(hf_sim *s) {
     const size_t smem = hfx_smem_bytes(s->X.M, kXWarps);
     if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "cutoff too large: %zu B of shared memory", smem);
@@ -223,32 +286,21 @@ int x_configure_launch(hf_sim *s) {
     if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "exciton kernel does not fit an SM");
     // Trajectories a warp owns at a time.  32 amortises the per-event selection work best.  When the Boltzmann
     // weights do not fit the L2, consecutive events of one exciton (whose spheres overlap by ~3/4) only hit the L2
-    // if the spheres all resident trajectories touch in between fit it: shrink the batch so that they do
-    // (measured on 256^3 x 64 realisations: 5.3e8 -> 9.0e8 events/s).
-    s->X.block = 32;
+    // if the lines all resident trajectories touch in between fit it; fewer trajectories per warp make them fit
+    // at the price of less amortisation.  Where the optimum lies depends on the lattice size, the number of
+    // realisations and the exciton density (128^3 x 16 realisations: 8; 256^3 x 64: 3), so it
+    // is measured: the first hf_x_run after hf_x_spawn times a few events per candidate on a copy of the state
+    // (x_autotune).  Results do not depend on the choice.
+    s->x_per_sm = per_sm; s->x_warps = kXWarps; s->x_smem = smem;
+    s->x_tune = false;
     {
         int l2_bytes = 0;
         cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, s->device);
         const double footprint = 8.0 * (double)s->n_real * (double)s->X.w_stride;            // one spin manifold
-        if (l2_bytes > 0 && footprint > 0.5 * (double)l2_bytes) {
-            double sphere_bytes = 0.0;                                                      // 128-byte lines one evaluation touches
-            for (size_t m = 0; m < s->x_offsets.size() / 3;) {
-                size_t e = m;
-                while (e < s->x_offsets.size() / 3 && s->x_offsets[3 * e + 1] == s->x_offsets[3 * m + 1] &&
-                       s->x_offsets[3 * e + 2] == s->x_offsets[3 * m + 2]) ++e;
-                sphere_bytes += 128.0 * (1.0 + (double)(e - m - 1) / 16.0);
-                m = e;
-            }
-            const double resident_warps = (double)s->sm_count * per_sm * kXWarps;
-            int b = (int)(0.45 * (double)l2_bytes / (sphere_bytes * resident_warps));
-            s->X.block = b < 1 ? 1 : (b > 32 ? 32 : b);
-        }
+        s->x_tune = l2_bytes > 0 && footprint > 0.5 * (double)l2_bytes;
     }
-    if (const char *e = getenv("HF_X_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= 32) s->X.block = v; }
-    const int64_t blocks = (s->X.B + s->X.block - 1) / s->X.block;
-    const int64_t need = (blocks + kXWarps - 1) / kXWarps, cap = (int64_t)s->sm_count * per_sm;
-    s->x_warps = kXWarps; s->x_smem = smem; s->x_grid = (int)(need < cap ? need : cap);
-    if (s->x_grid < 1) s->x_grid = 1;
+    x_set_block(s, 32);
+    if (const char *e = getenv("HF_X_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= 32) { x_set_block(s, v); s->x_tune = false; } }
     return HF_OK;
 }
 
@@ -973,6 +1025,7 @@ int hf_x_run(hf_sim *s, int64_t n_events) {
     if (n_events < 0) return fail(HF_ERR_BAD_ARG, "n_events must be >= 0");
     int rc = use_device(s);
     if (rc) return rc;
+    if (s->x_tune && !s->d_trace && n_events > 0 && (rc = x_autotune(s))) return rc;
     s->X.n_events = n_events;
     s->X.trace = s->d_trace; s->X.trace_first = s->P.trace_first; s->X.trace_n = s->P.trace_n; s->X.trace_cap = s->P.trace_cap;
     s->X.trace_len = s->d_x_trace_len;

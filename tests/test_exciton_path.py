@@ -286,3 +286,32 @@ def test_gpu_exciton_edge_shapes(dims, cutoff, B, R):
                 assert int(per_real[k][r]) == v, (r, k)
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_batch_tuning_leaves_no_trace(monkeypatch):
+    """Weights larger than half the L2 (128^3 x 4 realisations): the first hf_x_run measures a few candidate
+    warp batches on a copy of the state.  States and tallies must equal those of an untuned run."""
+    from hyperfluorescence_b200 import _native as nat
+    out = []
+    for block in (None, "32"):
+        if block is None:
+            monkeypatch.delenv("HF_X_BLOCK", raising=False)
+        else:
+            monkeypatch.setenv("HF_X_BLOCK", block)
+        sim = nat.Sim((128, 128, 128), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=20_000, n_realisations=4, seed=17)
+        sim.generate_lattice()
+        sim.x_configure()
+        sim.x_spawn()
+        sim.x_run(40)
+        sim.x_run(25)
+        sim.sync()
+        st = sim.x_state()
+        out.append((st["site"].copy(), st["spin"].copy(), st["draws"].copy(), st["time"].copy(), st["lifetime_sum"].copy(),
+                    sim.x_realisation_tallies()))
+        sim.close()
+    for a, b in zip(out[0][:5], out[1][:5]):
+        assert np.array_equal(a, b)
+    for k in out[0][5]:
+        assert np.array_equal(out[0][5][k], out[1][5][k]), k
+    assert int(out[0][5]["events"].sum()) == 20_000 * 65
