@@ -210,16 +210,17 @@ __device__ __forceinline__ void hfx_gather(const double *wp, int site, int meta,
     }
 }
 
-// KF > 0: M = 32 * KF + kTail neighbours, known at compile time: register-resident tables, prefetched
-// gathers (kRegG: the Dexter factors too, else they are read from shared memory).  KF == 0: any M (P.M),
-// tables in shared memory.
-// kChunk: slots gathered at a time (KF, or KF / 2 for the 16-slot variant: two register buffers of 16 would spill).
+// KF: the first KF slots of 32 channels (KF <= M / 32) have register-resident tables and prefetched gathers
+// (kRegG: the Dexter factors too, else they are read from shared memory); the slots after them — the rest of
+// the transfer channels and the three on-site ones — go through the shared-memory tables.  KF == 0: everything
+// does.  kTail >= 0: M = 32 * KF + kTail is known at compile time (the default cutoffs 3, 4, 5); kTail < 0: M = P.M.
+// kChunk: slots gathered at a time (KF, or KF / 2 above 8 slots: two register buffers of 16 would spill).
 template <int kWarps, int KF, int kTail, int kMinBlocks, bool kRegG, int kChunk = KF>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const HfxParams P) {
     static_assert(kChunk == KF || 2 * kChunk == KF, "one or two chunks");
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int M = KF > 0 ? 32 * KF + kTail : P.M;
+    const int M = (KF > 0 && kTail >= 0) ? 32 * KF + kTail : P.M;
     const int K = (M + 3 + 31) >> 5;
     constexpr int KB = kChunk > 0 ? kChunk : 1;
     double *s_g6 = reinterpret_cast<double *>(hf_smem);

@@ -206,11 +206,26 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 typedef void (*hfx_kernel_fn)(const HfxParams);
 constexpr int kXWarps = 8;
 static hfx_kernel_fn x_pick_kernel(int M) {
-    switch (M) {
+    switch (M) {                                                                          // the default cutoffs: M at compile time
         case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true>;                         // cutoff 3
         case 256: return hfx_run_kernel<kXWarps, 8, 0, 2, true>;                          // cutoff 4
         case 514: return hfx_run_kernel<kXWarps, 16, 2, 2, false, 8>;                     // cutoff 5: two halves of 8 slots, Dexter factors from shared memory
-        default: return hfx_run_kernel<kXWarps, 0, 0, 2, false>;
+        default: break;
+    }
+    switch (M >> 5) {                                                                     // any other cutoff: full slots in registers, M at run time
+        case 0: return hfx_run_kernel<kXWarps, 0, -1, 2, false>;
+        case 1: return hfx_run_kernel<kXWarps, 1, -1, 2, true>;
+        case 2: return hfx_run_kernel<kXWarps, 2, -1, 2, true>;
+        case 3: return hfx_run_kernel<kXWarps, 3, -1, 2, true>;
+        case 4: return hfx_run_kernel<kXWarps, 4, -1, 2, true>;
+        case 5: return hfx_run_kernel<kXWarps, 5, -1, 2, true>;
+        case 6: return hfx_run_kernel<kXWarps, 6, -1, 2, true>;
+        case 7: return hfx_run_kernel<kXWarps, 7, -1, 2, true>;
+        case 8: case 9: return hfx_run_kernel<kXWarps, 8, -1, 2, true>;
+        case 10: case 11: return hfx_run_kernel<kXWarps, 10, -1, 2, false, 5>;
+        case 12: case 13: return hfx_run_kernel<kXWarps, 12, -1, 2, false, 6>;
+        case 14: case 15: return hfx_run_kernel<kXWarps, 14, -1, 2, false, 7>;
+        default: return hfx_run_kernel<kXWarps, 16, -1, 2, false, 8>;                     // 16 or more slots: the first 16 prefetched
     }
 }
 

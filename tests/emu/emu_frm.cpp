@@ -203,7 +203,11 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
 
 static void x_spawn_body(void *a) { hfx_spawn_kernel(*(const HfxParams *)a); }
 // the same two variants the library picks (x_pick_kernel): register tables when M / 32 is instantiated, generic otherwise
-static void x_run_body_generic(void *a) { hfx_run_kernel<1, 0, 0, 1, false>(*(const HfxParams *)a); }
+static void x_run_body_generic(void *a) { hfx_run_kernel<1, 0, -1, 1, false>(*(const HfxParams *)a); }
+static void x_run_body_r2(void *a) { hfx_run_kernel<1, 2, -1, 1, true>(*(const HfxParams *)a); }           // run-time M variants
+static void x_run_body_r5(void *a) { hfx_run_kernel<1, 5, -1, 1, true>(*(const HfxParams *)a); }
+static void x_run_body_r12(void *a) { hfx_run_kernel<1, 12, -1, 1, false, 6>(*(const HfxParams *)a); }
+static void x_run_body_r16(void *a) { hfx_run_kernel<1, 16, -1, 1, false, 8>(*(const HfxParams *)a); }
 static void x_run_body_k3(void *a) { hfx_run_kernel<1, 3, 26, 1, true>(*(const HfxParams *)a); }
 static void x_run_body_k8(void *a) { hfx_run_kernel<1, 8, 0, 1, true>(*(const HfxParams *)a); }
 static void x_run_body_k16(void *a) { hfx_run_kernel<1, 16, 2, 1, false, 8>(*(const HfxParams *)a); }
@@ -253,7 +257,9 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     if (hfx_smem_bytes(M, 1) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     emu_run_warp(x_spawn_body, &P);
-    void (*body)(void *) = generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : M == 514 ? x_run_body_k16 : x_run_body_generic;
+    void (*body)(void *) = generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : M == 514 ? x_run_body_k16 :
+                           (M >> 5) == 2 ? x_run_body_r2 : (M >> 5) == 5 ? x_run_body_r5 : (M >> 5) == 12 ? x_run_body_r12 :
+                           (M >> 5) >= 16 ? x_run_body_r16 : x_run_body_generic;
     for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(body, &P); }
     memcpy(trace_out, trace.data(), sizeof(HfTraceRec) * (size_t)(B * trace_cap));
     for (int b = 0; b < B; ++b) {
