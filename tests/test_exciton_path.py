@@ -321,3 +321,22 @@ def test_gpu_exciton_batch_tuning_leaves_no_trace(monkeypatch):
     for k in out[0][5]:
         assert np.array_equal(out[0][5][k], out[1][5][k]), k
     assert int(out[0][5]["events"].sum()) == 20_000 * 65
+
+
+@pytest.mark.gpu
+def test_gpu_exciton_ensemble_on_uploaded_lattices():
+    """ExcitonEnsemble on lattices supplied by the caller (one dict per realisation) equals the ensemble that
+    generated the same lattices on the device."""
+    from hyperfluorescence_b200.excitons import ExcitonEnsemble
+    dims = (18, 16, 9)
+    gen = ExcitonEnsemble(dims, trajectories=600, realisations=3, seed=44, parameters=dict(cutoff=3.0))
+    lats = [gen._sim.download_lattice(r) for r in range(3)]
+    up = ExcitonEnsemble(dims, trajectories=600, realisations=3, seed=44, parameters=dict(cutoff=3.0), lattice=lats)
+    gen.run(180); up.run(180)
+    assert gen.tallies() == up.tallies()
+    a, b = gen._sim.x_state(), up._sim.x_state()
+    for k in ("site", "spin", "draws", "time", "lifetime_sum"):
+        assert np.array_equal(a[k], b[k]), k
+    s = up.summary()
+    assert s["events"] == 600 * 180 and abs(sum(s["channels"].values()) - 1.0) < 1e-12
+    gen.close(); up.close()
