@@ -204,7 +204,10 @@ void launch_inject(hf_sim *s, int32_t *pool) {
 // The exciton step kernel for a neighbour count M: register-resident tables when M / 32 is one of the
 // instantiated slot counts (cutoff 3, 4, 5 lattice constants), the generic shared-memory variant otherwise.
 typedef void (*hfx_kernel_fn)(const HfxParams);
-constexpr int kXWarps = 8;
+#ifndef HF_X_WARPS
+#define HF_X_WARPS 8
+#endif
+constexpr int kXWarps = HF_X_WARPS;
 static hfx_kernel_fn x_pick_kernel(int M) {
     switch (M) {                                                                          // the default cutoffs: M at compile time
         case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true>;                         // cutoff 3
