@@ -185,3 +185,46 @@ def test_gpu_dense_full_size_properties():
             assert np.array_equal(got["total_rate"], ref["total_rate"]) and got["draws"] == ref["draws"]
     finally:
         sim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,cutoff,n,B,R", [((12, 12, 5), 2.0, 1, 5, 1),         # one exciton per device: never meets anybody
+                                                 ((40, 40, 12), 3.0, 1024, 3, 1),     # the largest device (32 slots of excitons)
+                                                 ((14, 13, 6), 4.0, 33, 9, 3),        # cutoff 4 with wrap everywhere, 3 devices per realisation
+                                                 ((16, 16, 8), 2.5, 100, 7, 7)])      # one device per realisation
+def test_gpu_dense_edge_shapes(dims, cutoff, n, B, R):
+    """Extreme shapes of the high-density devices against the specification (with its cache verification)."""
+    from hyperfluorescence_b200 import _native as nat
+    n_events = 150
+    sim = nat.Sim(dims, (0.7, 0.2, 0.1), 0.1, 1, 1, n_trajectories=B, n_realisations=R, seed=23, first_trajectory=11)
+    try:
+        sim.generate_lattice()
+        params = dict(nat.x_params_to_dict(nat.x_default_params()), cutoff=cutoff)
+        sim.x_configure(nat.x_params_from_dict(dict(cutoff=cutoff)))
+        ann = ((1.0, 2.0), (0.5, 1.0))
+        sim.xd_configure(n, ann, 0.4)
+        sim.xd_spawn()
+        sim.xd_run(n_events)
+        sim.sync()
+        tab = sim.x_tables()
+        per_real = sim.xd_realisation_tallies()
+        for r in range(R):
+            lat = sim.download_lattice(r)
+            ws1, wt1 = sim.x_weights(r)
+            o = xo.DenseExcitonOracle(dims, lat["species"], ws1, wt1, params, tab, annihilation=ann, p_tta=0.4)
+            acc = {}
+            for d in range(r * (B // R), (r + 1) * (B // R)):
+                ref = o.run_device(23, 11 + d, n, n_events, verify=(n <= 100))
+                assert ref["cache_mismatches"] == 0
+                got = sim.xd_device(d)
+                assert np.array_equal(got["site"], ref["site"]) and np.array_equal(got["spin"], ref["spin"]), d
+                assert np.array_equal(got["total_rate"], ref["total_rate"]) and got["draws"] == ref["draws"]
+                for k, v in ref["tallies"].items():
+                    acc[k] = acc.get(k, 0) + v
+            for k, v in acc.items():
+                assert int(per_real[k][r]) == v, (r, k)
+        if n == 1:
+            t = sim.xd_tallies()
+            assert t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"] == 0
+    finally:
+        sim.close()
