@@ -27,6 +27,9 @@
 #define HFXD_T_TTA_UP 20
 #define HFXD_T_N 24
 #define HFXD_MAX_EXCITONS 1024
+#ifndef HFXD_CHUNK
+#define HFXD_CHUNK 3                   // slots whose gathers (weight + occupancy word) are in flight together
+#endif
 
 struct HfxdParams {
     HfxParams X;                       // lattice, tables, rate constants, Philox key; B = devices, first_traj = first device id
@@ -69,7 +72,7 @@ struct HfxdWarp {                      // one warp's view of its device
 };
 
 // Lane sums of the channel rates of an exciton (packed site + spin); kStore: also leave the rates in s_rates.
-// `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  Four slots are
+// `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  HFXD_CHUNK slots are
 // gathered (weight + occupancy word) before any of them is consumed.
 template <bool kStore>
 __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen) {
@@ -90,12 +93,12 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     const int64_t oi = i + X.w_halo;
     double S = 0.0;
     seen = 0;
-    for (int k0 = 0; k0 < W.K; k0 += 4) {
-        double wj[4];
-        uint32_t ow[4];
-        int sh[4];
+    for (int k0 = 0; k0 < W.K; k0 += HFXD_CHUNK) {
+        double wj[HFXD_CHUNK];
+        uint32_t ow[HFXD_CHUNK];
+        int sh[HFXD_CHUNK];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < HFXD_CHUNK; ++u) {
             const int c = ((k0 + u) << 5) + W.lane;
             wj[u] = 0.0; ow[u] = 0; sh[u] = 0;
             if (c < W.M) {
@@ -107,7 +110,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < HFXD_CHUNK; ++u) {
             const int k = k0 + u, c = (k << 5) + W.lane;
             if (k < W.K) {
                 double rate = 0.0;
