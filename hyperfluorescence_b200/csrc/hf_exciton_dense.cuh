@@ -27,6 +27,9 @@
 #define HFXD_T_TTA_UP 20
 #define HFXD_T_N 24
 #define HFXD_MAX_EXCITONS 1024
+#ifndef HFXD_MIN_BLOCKS
+#define HFXD_MIN_BLOCKS 5
+#endif
 #ifndef HFXD_CHUNK
 #define HFXD_CHUNK 3                   // slots whose gathers (weight + occupancy word) are in flight together
 #endif
@@ -207,7 +210,7 @@ __device__ __forceinline__ uint32_t hfxd_replace(const HfxdWarp &W, uint32_t ide
 }
 
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32) hfxd_run_kernel(const HfxdParams P) {
+__global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(const HfxdParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const HfxParams &X = P.X;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
