@@ -54,6 +54,9 @@ CASES = [
     ("field3_s11", (8, 8, 6), DEFAULT_PROPS, 3, 11, 1500, {"electric_field": 0.3}),
     # non-zero realisation id
     ("real3_s12", (8, 8, 8), DEFAULT_PROPS, 2, 12, 1500, {"realisation": 3, "trajectory": 5}),
+    # 6 and 8 charges of each type: the upper half of the thread-per-trajectory kernel's range (hf_frm_small.cuh)
+    ("c6_s13", (9, 8, 5), DEFAULT_PROPS, 6, 13, 1500, {}),
+    ("c8_s14", (12, 10, 4), (0.7, 0.2, 0.1), 8, 14, 1500, {}),
 ]
 
 
@@ -103,6 +106,13 @@ def main():
         reference_statistics()
         return
     written = {}
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    if only:                                     # add cases without regenerating the committed ones
+        for name, dims, props, charges, seed, steps, kw in CASES:
+            if name in only:
+                out = rh.run_reference(dims, props, charges, seed, steps, **kw)
+                _write(name, out, dims, seed, kw.get("realisation", 0), written)
+        return
     for name, dims, props, charges, seed, steps, kw in CASES:
         out = rh.run_reference(dims, props, charges, seed, steps, **kw)
         _write(name, out, dims, seed, kw.get("realisation", 0), written)
