@@ -57,6 +57,8 @@ CASES = [
     # 6 and 8 charges of each type: the upper half of the thread-per-trajectory kernel's range (hf_frm_small.cuh)
     ("c6_s13", (9, 8, 5), DEFAULT_PROPS, 6, 13, 1500, {}),
     ("c8_s14", (12, 10, 4), (0.7, 0.2, 0.1), 8, 14, 1500, {}),
+    # 20 charges of each type: the warp kernel's screened candidate loop with the lanes sharing the Coulomb sums
+    ("c20_s15", (12, 12, 5), DEFAULT_PROPS, 20, 15, 800, {}),
 ]
 
 
