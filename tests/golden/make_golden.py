@@ -77,7 +77,7 @@ def replay_case():
     return u
 
 
-def reference_statistics(n_runs=400, dims=(3, 3, 3), props=(0.5, 0.3, 0.2), charges=2, steps=1500):
+def reference_statistics(n_runs=400, dims=(3, 3, 3), props=(0.5, 0.3, 0.2), charges=2, steps=1500, name="stats_tiny"):
     """Tallies of n_runs UNMODIFIED reference runs on their own Mersenne-Twister streams (the only
     change is that each `Random()` gets a deterministic seed so the file is reproducible): the
     statistical half of the parity contract (3 sigma on IQE and channel fractions)."""
@@ -95,10 +95,10 @@ def reference_statistics(n_runs=400, dims=(3, 3, 3), props=(0.5, 0.3, 0.2), char
             em.append(lat._emission); rec.append(lat._recombination); inj.append(lat._injection); stp.append(lat._step)
     finally:
         reseau.Random, molecule.Random = saved
-    np.savez_compressed(os.path.join(HERE, "stats_tiny.npz"), dims=np.array(dims), props=np.array(props),
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), dims=np.array(dims), props=np.array(props),
                         charges=np.array(charges), steps=np.array(steps), emission=np.array(em),
                         recombination=np.array(rec), injection=np.array(inj), step=np.array(stp))
-    print(f"stats_tiny: runs={n_runs} emission/run={np.mean(em):.2f} recombination/run={np.mean(rec):.2f} "
+    print(f"{name}: runs={n_runs} emission/run={np.mean(em):.2f} recombination/run={np.mean(rec):.2f} "
           f"photons/recombination={np.sum(em) / np.sum(rec):.4f}")
 
 
@@ -106,6 +106,9 @@ def main():
     os.makedirs(HERE, exist_ok=True)
     if "--stats-only" in sys.argv:
         reference_statistics()
+        return
+    if "--stats-d0" in sys.argv:                 # the reference driver's own device (OLED.py:6-10), 2000 operations
+        reference_statistics(n_runs=150, dims=(10, 10, 5), props=DEFAULT_PROPS, charges=4, steps=2000, name="stats_d0")
         return
     written = {}
     only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]

@@ -418,13 +418,15 @@ def test_full_size_properties(nat):
         assert o.positions("electrons").tolist() == e and o.positions("holes").tolist() == h
 
 
-def test_statistics_within_three_sigma_of_reference(nat):
+@pytest.mark.parametrize("stats", ["stats_tiny", "stats_d0"])
+def test_statistics_within_three_sigma_of_reference(nat, stats):
     """Photons per recombination, recombinations per run and IQE over 20 000 device trajectories
     against the UNMODIFIED reference run with its own Mersenne-Twister streams
-    (tests/golden/stats_tiny.npz, make_golden.py): within 3 sigma."""
+    (tests/golden/stats_tiny.npz: 400 runs on 3x3x3; stats_d0.npz: 150 runs of the reference driver's own
+    device, OLED.py:6-10, 2000 operations; make_golden.py): within 3 sigma."""
     import os
     from tests.conftest import GOLDEN_DIR
-    ref = np.load(os.path.join(GOLDEN_DIR, "stats_tiny.npz"))
+    ref = np.load(os.path.join(GOLDEN_DIR, stats + ".npz"))
     dims = tuple(int(v) for v in ref["dims"])
     props = tuple(float(v) for v in ref["props"])
     charges, steps = int(ref["charges"]), int(ref["steps"])
