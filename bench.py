@@ -74,6 +74,23 @@ def measured_traffic():
         return None
 
 
+def issue_roofline(events_per_s_per_gpu, key, clocks=None):
+    """What actually bounds these kernels (DESIGN.md sections 3, 9): instruction issue.  Warp instructions per
+    event come from the committed ncu capture (profiles/traffic.json), the rate is measured live, the peak is
+    4 schedulers x 148 SMs x the SM clock sampled during the run (else the nominal 1.965 GHz)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        wipe = float((t[key] if key else t)["warp_inst_per_event"])
+    except Exception:
+        return None
+    mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    peak = 148 * 4 * mhz * 1e6
+    achieved = events_per_s_per_gpu * wipe
+    return {"bound": "issue", "warp_inst_per_event": wipe, "achieved": achieved / 1e9, "peak": peak / 1e9,
+            "unit": "Gwarp-inst/s", "frac": achieved / peak}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU every 200 ms while the timed region runs."""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -260,6 +277,7 @@ def run_ours(args):
                              "see DESIGN.md section 3 and profiles/"},
         "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "path": "hf_upload_lattice(pinned host) + hf_inject + hf_run + hf_read_tallies"},
+        "issue": issue_roofline(value / world, None, clocks),
         "gpu_launches": K,
         "clocks": clocks,
         "tallies": dict({k: tallies[k] for k in ("emission", "recombination", "injection", "fired", "stopped")},
@@ -435,6 +453,7 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
                                 ("weights exceed the L2: with 32 trajectories per warp the kernel moves 7.9 KB/event from DRAM at "
                                  "4.2 TB/s = 65 % of the HBM peak (profiles/r01g_*); the adaptive warp batch trades that for L2 "
                                  "hits (82 %, 0.5 KB/event from DRAM, profiles/r01h_*)")},
+           "issue": issue_roofline(rate / world, "hfx_run_kernel") if l2_resident else None,
            "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
     if cpu_line:
         out["cpu_baseline"] = cpu_line
