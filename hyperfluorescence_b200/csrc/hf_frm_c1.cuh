@@ -69,10 +69,10 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
 }
 
 #ifndef HF_C1_THREADS
-#define HF_C1_THREADS 256
+#define HF_C1_THREADS 384
 #endif
 #ifndef HF_C1_MIN_BLOCKS
-#define HF_C1_MIN_BLOCKS 3
+#define HF_C1_MIN_BLOCKS 2
 #endif
 #define HF_C1_MAXCAND 27
 // relative half-width of the "could be the minimum" window of the screening pass, see hf_c1_gen
