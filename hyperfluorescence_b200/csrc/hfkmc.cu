@@ -1127,7 +1127,10 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
 
 // ---- high-density exciton devices (Path XD; model specified by oracle/exciton_dense_oracle.c) ------------
 
-constexpr int kXdWarps = 4;
+#ifndef HF_XD_WARPS
+#define HF_XD_WARPS 4
+#endif
+constexpr int kXdWarps = HF_XD_WARPS;
 
 static void xd_free(hf_sim *s) {
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
