@@ -59,6 +59,12 @@ CASES = [
     ("c8_s14", (12, 10, 4), (0.7, 0.2, 0.1), 8, 14, 1500, {}),
     # 20 charges of each type: the warp kernel's screened candidate loop with the lanes sharing the Coulomb sums
     ("c20_s15", (12, 12, 5), DEFAULT_PROPS, 20, 15, 800, {}),
+    # charges = 1 on lattices so small that the two carriers meet all the time: the thread-per-trajectory kernel's
+    # bound / decay / capture / re-injection branches (hf_frm_c1.cuh) against the reference itself
+    # (reseau.py:501-508, 529-561) — hundreds of recombinations and captures per case
+    ("c1_tiny333_s21", (3, 3, 3), (0.5, 0.3, 0.2), 1, 21, 3000, {}),
+    ("c1_rag443_s22", (4, 4, 3), (0.5, 0.3, 0.2), 1, 22, 3000, {}),
+    ("c1_rag554_s23", (5, 5, 4), (0.6, 0.3, 0.1), 1, 23, 3000, {"trajectory": 3}),
 ]
 
 
@@ -102,10 +108,63 @@ def reference_statistics(n_runs=400, dims=(3, 3, 3), props=(0.5, 0.3, 0.2), char
           f"photons/recombination={np.sum(em) / np.sum(rec):.4f}")
 
 
+def _channel_run(args):
+    """One UNMODIFIED reference run of the OLED.py device with its own Mersenne-Twister streams (seeded per run so
+    that the file is reproducible).  The channel tallies the reference does not keep — which species the exciton
+    decayed on and whether it emitted — are observed by wrapping the *instance's* ``_decay`` (reseau.py:472-476);
+    ``operations`` itself runs untouched, swallowed ZeroDivisionError and stale IQE included."""
+    run, dims, props, charges, steps = args
+    import itertools
+    import random
+    reseau, molecule, _, _ = rh.import_reference()
+    counter = itertools.count(1)
+    reseau.Random = molecule.Random = lambda: random.Random(0x5EED0000 + run * 100003 + next(counter))
+    import io
+    import contextlib
+    code = {molecule.Host: 0, molecule.TADF: 1, molecule.Fluorescent: 2}
+    lat = reseau.Lattice(dims, props, charges=charges)
+    ch = [0, 0, 0, 0, 0, 0]                       # recombinations on host / TADF / fluorescent, emissions on the same
+    inner = lat._decay
+    def observed(position):
+        sp = code[lat._get_molecule_type(position)]
+        before = lat._emission
+        inner(position)
+        ch[sp] += 1
+        ch[3 + sp] += lat._emission - before
+    lat._decay = observed
+    with contextlib.redirect_stdout(io.StringIO()):      # the _cache dump of a swallowed ZeroDivisionError
+        lat.operations(steps)
+    return (lat._emission, lat._recombination, lat._injection, lat._step, lat._IQE, *ch)
+
+
+def reference_channel_statistics(n_runs=100_000, dims=(10, 10, 5), props=DEFAULT_PROPS, charges=4, steps=100,
+                                 name="stats_d0_1e5", procs=None):
+    """The north_star's statistical gate: tallies AND channel counts of 10^5 unmodified runs of the reference
+    driver's own device (OLED.py:6-11: 10x10x5, charges = 4, operations(100))."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count()
+    with mp.Pool(procs) as pool:
+        rows = pool.map(_channel_run, [(r, dims, props, charges, steps) for r in range(n_runs)], chunksize=250)
+    a = np.array([r[:4] + r[5:] for r in rows], dtype=np.int32)
+    iqe = np.array([r[4] for r in rows], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), dims=np.array(dims), props=np.array(props),
+                        charges=np.array(charges), steps=np.array(steps),
+                        emission=a[:, 0].astype(np.int16), recombination=a[:, 1].astype(np.int16),
+                        injection=a[:, 2].astype(np.int16), step=a[:, 3].astype(np.int16), iqe=iqe.astype(np.float32),
+                        recomb_host=a[:, 4].astype(np.int8), recomb_tadf=a[:, 5].astype(np.int8), recomb_fluo=a[:, 6].astype(np.int8),
+                        emit_host=a[:, 7].astype(np.int8), emit_tadf=a[:, 8].astype(np.int8), emit_fluo=a[:, 9].astype(np.int8))
+    print(f"{name}: runs={n_runs} recombination/run={a[:, 1].mean():.4f} emission/run={a[:, 0].mean():.4f} "
+          f"recomb host/tadf/fluo={a[:, 4].sum()}/{a[:, 5].sum()}/{a[:, 6].sum()} "
+          f"emit host/tadf/fluo={a[:, 7].sum()}/{a[:, 8].sum()}/{a[:, 9].sum()} early stops={(a[:, 3] < steps).sum()}")
+
+
 def main():
     os.makedirs(HERE, exist_ok=True)
     if "--stats-only" in sys.argv:
         reference_statistics()
+        return
+    if "--stats-d0-1e5" in sys.argv:             # 10^5 runs of OLED.py's device as OLED.py runs it (100 operations), with channels
+        reference_channel_statistics()
         return
     if "--stats-d0" in sys.argv:                 # the reference driver's own device (OLED.py:6-10), 2000 operations
         reference_statistics(n_runs=150, dims=(10, 10, 5), props=DEFAULT_PROPS, charges=4, steps=2000, name="stats_d0")

@@ -134,6 +134,26 @@ def test_emulated_c1_thread_kernel_matches_reference_and_warp_kernel(name, first
         assert np.array_equal(tr["draws"][:n].astype(np.int64), gold["trace_draws"][:n])
 
 
+@pytest.mark.parametrize("name", ["c1_tiny333_s21", "c1_rag443_s22", "c1_rag554_s23"])
+def test_emulated_c1_thread_kernel_recombines_like_the_reference(name):
+    """charges == 1 on lattices so small that the carriers meet all the time: the thread kernel's bound / decay /
+    capture / re-injection branches (hf_frm_c1.cuh) against the UNMODIFIED reference's own trajectory
+    (reseau.py:501-508, 529-561), every event, tau and draw count, plus the final tallies."""
+    g = load_golden(name)
+    traj, stop = g["trajectory"], len(g["trace_kind"])
+    c1 = emu.run_batch_c1(g["dims"], g["field_f"], g["seed_int"], 0, 32, True, g["species"], g["homo"], g["lumo"],
+                          stop=stop // 3, n_calls=3)
+    tr = c1["trace"][traj]
+    for k in ("kind", "particule", "initial", "final", "tau"):
+        assert np.array_equal(tr[k][:stop], g["trace_" + k]), k
+    assert np.array_equal(tr["draws"][:stop].astype(np.int64), g["trace_draws"])
+    assert np.array_equal(tr["spins"][:stop].astype(np.int64), g["trace_spins"])
+    sc = c1["sc"]
+    assert [int(sc["emission"][traj]), int(sc["recombination"][traj]), int(sc["injection"][traj]), int(sc["steps"][traj])] == \
+        g["final_tallies"].tolist()
+    assert int(g["final_tallies"][1]) >= 100                             # the case does recombine
+
+
 def test_emulated_c1_thread_kernel_recombination_paths():
     """A tiny lattice where bound / decay / capture / re-injection fire constantly: the thread kernel
     must follow the warp kernel (itself pinned to the reference) through every rare branch."""
