@@ -5,15 +5,18 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): 10^5 independent trajectories per GPU on one 64^3 lattice
-(default 0.84/0.15/0.01 host/TADF/emitter composition, charges = 1: one electron and one hole in
-flight per trajectory, field 0.1 eV/nm).  One bench "step" = one `hf_run` launch that advances
-every trajectory by EVENTS_PER_STEP KMC events (`Lattice.operations(1000)`, reseau.py:580-595).
-An "event" is one fired `_first_reaction_method` call (reseau.py:483-562).  Weak scaling: every
-rank carries its own 10^5 trajectories (global Philox ids), no data-path collective; one NCCL
-all-reduce of the tally vector after the timed region closes the run.
+Headline workload — the shape the north_star target is quoted on: a 128^3 lattice with 10^6 concurrent
+trajectories per GPU on the parity path (the reference's own First Reaction Method, reseau.py:483-562: default
+0.84/0.15/0.01 host/TADF/emitter composition, charges = 1: one electron and one hole in flight per trajectory,
+field 0.1 eV/nm), the only path whose event sequences are bit-exact under replayed RNG.  One bench "step" = one
+`hf_run` launch that advances every trajectory by EVENTS_PER_STEP KMC events (`Lattice.operations`,
+reseau.py:580-595).  An "event" is one fired `_first_reaction_method` call.  Weak scaling: every rank carries
+its own 10^6 trajectories (global Philox ids) on the one shared lattice realisation, no data-path collective; the
+one NCCL all-reduce of the tally vector is inside every `e2e` step.  At N > 1 a second field, `strong`, splits
+10^6 trajectories in total over the ranks.  BASELINE configs[1] (64^3, 10^5 trajectories) stays as the leg
+`configs1`.
 
-One JSON line is printed by rank 0; see DESIGN.md §Measurement for how each field is obtained.
+One JSON line is printed by rank 0; see DESIGN.md section 5 for how each field is obtained.
 """
 from __future__ import annotations
 
@@ -41,19 +44,31 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-DIMS = (64, 64, 64)
+DIMS = (128, 128, 128)
 PROPS = (0.84, 0.15, 0.01)
 CHARGES = 1
 FIELD = 0.1
 SEED = 0x48464B4D43            # "HFKMC" 
-TRAJ_PER_GPU = 100_000
-EVENTS_PER_STEP = 1000         # KMC events per trajectory per bench step
+TRAJ_PER_GPU = 1_000_000
+EVENTS_PER_STEP = 200          # KMC events per trajectory per bench step
+C1_DIMS, C1_TRAJ_PER_GPU, C1_EVENTS = (64, 64, 64), 100_000, 1000     # BASELINE configs[1], the leg `configs1`
 NEIGHBOURS = 26
 # compulsory bytes per event, no caching credit
 BYTES_PER_EVENT = NEIGHBOURS * (8 + 1) + 2 * CHARGES * 4 + 2 * CHARGES * 16 + 24 + 2
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-WORKLOAD = (f"{TRAJ_PER_GPU} trajectories/GPU x {EVENTS_PER_STEP} KMC events per step on one {DIMS[0]}^3 lattice, "
-            f"charges={CHARGES}, props={PROPS}, field={FIELD} (BASELINE configs[1])")
+WORKLOAD = (f"north_star shape, parity path: {TRAJ_PER_GPU} concurrent trajectories/GPU x {EVENTS_PER_STEP} KMC events per "
+            f"step on one {DIMS[0]}^3 lattice, charges={CHARGES}, props={PROPS}, field={FIELD}")
+# the SAME dict in both arms (ours / --impl reference): what differs between them (the bounded CPU sample) is
+# stated in `cpu_baseline.sample`, not here
+CONFIG = {
+    "workload": WORKLOAD, "lattice": list(DIMS), "charges": CHARGES, "props": list(PROPS), "field": FIELD,
+    "trajectories_per_gpu": TRAJ_PER_GPU, "events_per_trajectory_per_step": EVENTS_PER_STEP,
+    "events_fired": "move events only: with one carrier of each type the +0.1 eV per step towards the collecting electrode "
+                    "(quirk Q8, reseau.py:287, 319) keeps both at their injection faces, so bound / decay / capture / "
+                    "re-injection do not occur in the timed region; that is what the reference does on this device too",
+    "l2": "flushed between timed steps (256 MiB memset); the 34 MB of HOMO / LUMO energies are L2-resident by nature",
+    "timing": "CUDA events around each hf_run on its stream, summed over steps, max over ranks",
+}
 
 
 def hbm_peak():
@@ -65,30 +80,42 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu capture, if any."""
+def _traffic_entry(key):
+    """An ncu-derived entry of profiles/traffic.json, or None when it is absent or was captured from other kernel
+    sources than the ones that are built now (each entry carries the sha256 of the files its kernel comes from)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("hf_run_kernel_dram_bytes_per_launch")
+            e = json.load(f)[key]
+        from hyperfluorescence_b200.build import source_hashes
+        stamp = e.get("sources")
+        if not stamp or source_hashes(stamp.keys()) != stamp:
+            return None
+        return e
     except Exception:
         return None
+
+
+def measured_traffic(key="hf_run_c1_kernel", events_per_launch=None):
+    """dram bytes per launch of a step kernel from the committed ncu capture (scaled per event), if still valid."""
+    e = _traffic_entry(key)
+    if not e or events_per_launch is None:
+        return None
+    return float(e["dram_bytes_per_event"]) * events_per_launch
 
 
 def issue_roofline(events_per_s_per_gpu, key, clocks=None):
     """What actually bounds these kernels (DESIGN.md sections 3, 9): instruction issue.  Warp instructions per
     event come from the committed ncu capture (profiles/traffic.json), the rate is measured live, the peak is
     4 schedulers x 148 SMs x the SM clock sampled during the run (else the nominal 1.965 GHz)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            t = json.load(f)
-        wipe = float((t[key] if key else t)["warp_inst_per_event"])
-    except Exception:
+    e = _traffic_entry(key)
+    if not e:
         return None
+    wipe = float(e["warp_inst_per_event"])
     mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
     peak = 148 * 4 * mhz * 1e6
     achieved = events_per_s_per_gpu * wipe
     return {"bound": "issue", "warp_inst_per_event": wipe, "achieved": achieved / 1e9, "peak": peak / 1e9,
-            "unit": "Gwarp-inst/s", "frac": achieved / peak}
+            "unit": "Gwarp-inst/s", "frac": achieved / peak, "source": e.get("source")}
 
 
 class ClockSampler(threading.Thread):
@@ -124,16 +151,21 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_sample(cores, per_core_trajectories=1250):
+_ORACLE_LATTICES = {}
+
+
+def cpu_sample(cores, per_core_trajectories=2000, dims=DIMS, events=EVENTS_PER_STEP, total=TRAJ_PER_GPU):
     """The CPU baseline: oracle port (oracle/frm_oracle.c, pinned bit-exactly to the unmodified
     reference) on `cores` host threads, a bounded sample of the same workload."""
     from oracle import frm_oracle as fo
-    lat = fo.OracleLattice.generate(DIMS, PROPS, SEED)
-    n_traj = cores * per_core_trajectories
+    if dims not in _ORACLE_LATTICES:
+        _ORACLE_LATTICES[dims] = fo.OracleLattice.generate(dims, PROPS, SEED)       # the device generates the same one
+    lat = _ORACLE_LATTICES[dims]
+    n_traj = min(total, cores * per_core_trajectories)
     t0 = time.perf_counter()
-    res = lat.run_batch(CHARGES, FIELD, SEED, 0, n_traj, EVENTS_PER_STEP, n_threads=cores)
+    res = lat.run_batch(CHARGES, FIELD, SEED, 0, n_traj, events, n_threads=cores)
     dt = time.perf_counter() - t0
-    sample = (f"{n_traj} of the {TRAJ_PER_GPU} trajectories x {EVENTS_PER_STEP} events on the same {DIMS[0]}^3 lattice "
+    sample = (f"the first {n_traj} of the {total} trajectories x {events} events on the same {dims[0]}^3 lattice "
               f"(charge injection and initial events included), {cores} threads")
     return res["events"] / dt, sample, res
 
@@ -146,8 +178,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    cpu_sample(cores, 16)                                                           # builds the 128^3 lattice (untimed)
     for _ in range(args.warmup):
-        cpu_sample(cores, 125)
+        cpu_sample(cores, 200)
     t0 = time.perf_counter()
     events = 0
     sample = ""
@@ -160,35 +193,37 @@ def run_reference(args):
         "impl": "reference", "metric": "KMC exciton events/sec (box)", "value": value, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "lattice": list(DIMS), "charges": CHARGES},
+        "config": CONFIG,
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": "port",
-                         "sample": "each step: " + sample},
+                         "sample": "each step: " + sample,
+                         "note": "C restatement of the reference (bit-pinned to it); the unmodified Python reference does "
+                                 "~1e3 events/s per core on this device (SURVEY.md section 6) and cannot build a 128^3 "
+                                 "lattice (~13 GB of Python objects)"},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
-def run_ours(args):
-    import numpy as np
+def max_over_ranks(x, world):
+    if world == 1:
+        return float(x)
     import torch
     import torch.distributed as dist
-    from hyperfluorescence_b200 import _native as nat
-    from hyperfluorescence_b200 import distributed as hd
+    t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
 
-    rank, local_rank, world = hd.init_process_group()
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: hyperfluorescence_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
+
+def path_p_leg(nat, hd, rank, local_rank, world, dims, B, S, K, W, first_trajectory, clocks_of=None, e2e_steps=2):
+    """K timed hf_run launches of B trajectories x S events on one `dims` lattice (Path P, charges = 1), then the
+    same work end to end through the C-ABI with host buffers.  Returns a dict of raw measurements."""
+    import torch
+    import torch.distributed as dist
     stream = torch.cuda.current_stream()
-    B, S, K, W = TRAJ_PER_GPU, EVENTS_PER_STEP, args.steps, args.warmup
-
-    # weak scaling: rank r owns global trajectories [r*B, (r+1)*B) of the one shared realisation 0
-    sim = nat.Sim(DIMS, PROPS, FIELD, CHARGES, 1, n_trajectories=B, n_realisations=1, seed=SEED,
-                  first_trajectory=rank * B, first_realisation=0, device=local_rank)
-    sim.set_stream(stream.cuda_stream)
+    sim = nat.Sim(dims, PROPS, FIELD, CHARGES, 1, n_trajectories=B, n_realisations=1, seed=SEED,
+                  first_trajectory=first_trajectory, first_realisation=0, device=local_rank)
+    sim.set_stream(stream.cuda_stream)            # timed with torch events: the launches must be on torch's stream
     sim.generate_lattice()
     sim.inject()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")          # > 126 MB L2
@@ -201,8 +236,9 @@ def run_ours(args):
         sim.run(S)
     torch.cuda.synchronize()
     sim.run_timing()                                                            # reset the lib's own event timers
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if clocks_of is not None else None
+    if sampler:
+        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     barrier()
@@ -216,32 +252,28 @@ def run_ours(args):
     torch.cuda.synchronize()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
-    total_ms = float(sum(step_ms))
+    clocks = sampler.stop() if sampler else None
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in zip(starts, stops)), world)
     lib_ms, lib_launches = sim.run_timing()                                     # same launches, timed inside the lib
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    events_total = world * B * S * K
-    value = events_total / (total_ms * 1e-3)
-    tallies = hd.all_reduce_tallies(sim)                                        # the one collective of the path
+    tallies = hd.all_reduce_tallies(sim)
     fired_expected = world * B * S * (K + W)
+    if tallies["fired"] != fired_expected or tallies["stopped"]:
+        raise SystemExit(f"bench: {tallies['fired']} events fired, {fired_expected} expected, {tallies['stopped']} "
+                         "trajectories stopped: the timed region did not do the work it is credited with")
 
-    # end to end through the C-ABI with HOST buffers: lattice arrays from pinned host memory ->
-    # hf_upload_lattice (H2D), hf_inject, hf_run, hf_read_tallies (D2H), every step, wall clock.
+    # end to end through the C-ABI with HOST buffers, every step: lattice arrays from pinned host memory ->
+    # hf_upload_lattice (H2D), hf_inject, hf_run, tally reduction on the device + NCCL all-reduce over the ranks
+    # (the one collective of the path), device -> host read of the result.  Wall clock, max over ranks.
     host = sim.download_lattice(0)
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
-    pinned_np = {k: v.numpy() for k, v in pinned.items()}
-    h2d = sum(v.nbytes for v in pinned_np.values())
+    pinned = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in host.items()}
+    h2d = sum(v.nbytes for v in pinned.values())
     d2h = nat.HF_N_TALLIES * 8
-    e2e_steps = max(2, min(K, 3))
+
     def e2e_step():
-        sim.upload_lattice(0, pinned_np["species"], pinned_np["homo"], pinned_np["lumo"], pinned_np["s1"], pinned_np["t1"])
+        sim.upload_lattice(0, pinned["species"], pinned["homo"], pinned["lumo"], pinned["s1"], pinned["t1"])
         sim.inject()
         sim.run(S)
-        return sim.tallies()
+        return hd.all_reduce_tallies(sim)
     e2e_step()
     torch.cuda.synchronize()
     barrier()
@@ -249,54 +281,90 @@ def run_ours(args):
     for _ in range(e2e_steps):
         got = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * S * e2e_steps / e2e_s
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    if got["fired"] != world * B * S:
+        raise SystemExit(f"bench e2e: {got['fired']} events fired, {world * B * S} expected")
+    sim.close()
+    del flush
+    return dict(total_ms=total_ms, lib_ms=lib_ms, lib_launches=lib_launches, wall_s=t_wall, clocks=clocks, tallies=tallies,
+                fired_expected=fired_expected, e2e_value=world * B * S * e2e_steps / e2e_s, e2e_steps=e2e_steps, h2d=h2d, d2h=d2h,
+                value=world * B * S * K / (total_ms * 1e-3))
 
+
+E2E_PATH = ("hf_upload_lattice(pinned host) + hf_inject + hf_run + hf_reduce_tallies_device + NCCL all-reduce of the tallies "
+            "(N > 1) + device-to-host read")
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hyperfluorescence_b200 import _native as nat
+    from hyperfluorescence_b200 import distributed as hd
+
+    rank, local_rank, world = hd.init_process_group()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: hyperfluorescence_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    B, S, K, W = TRAJ_PER_GPU, EVENTS_PER_STEP, args.steps, args.warmup
+
+    # weak scaling: rank r owns global trajectories [r*B, (r+1)*B) of the one shared realisation 0
+    m = path_p_leg(nat, hd, rank, local_rank, world, DIMS, B, S, K, W, rank * B, clocks_of=True, e2e_steps=max(2, min(K, 3)))
+    value, clocks, tallies = m["value"], m["clocks"], m["tallies"]
     peak, peak_src = hbm_peak()
-    launch_s = (lib_ms / max(lib_launches, 1)) * 1e-3
+    launch_s = (m["lib_ms"] / max(m["lib_launches"], 1)) * 1e-3
     achieved = B * S * BYTES_PER_EVENT / launch_s / 1e9
     line = {
         "metric": "KMC exciton events/sec (box)", "value": value, "unit": "events/s", "n_gpus": world,
-        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "steps": K, "warmup": W, "ms_per_step": m["total_ms"] / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "lattice": list(DIMS), "charges": CHARGES,
-                   "trajectories_per_gpu": B, "events_per_trajectory_per_step": S,
-                   "l2": "flushed between timed steps (256 MiB memset); the 4.4 MB lattice is L2-resident by nature",
-                   "timing": "CUDA events around each hf_run on its stream, summed over steps, max over ranks",
-                   "wall_s_bracket": t_wall},
+        "config": CONFIG,
+        "wall_s_bracket": m["wall_s"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "hf_run_c1_kernel",
+                     "traffic": measured_traffic("hf_run_c1_kernel", B * S), "peak_source": peak_src, "kernel": "hf_run_c1_kernel",
                      "bytes_per_event": BYTES_PER_EVENT, "events_per_launch": B * S,
-                     "avg_launch_ms": lib_ms / max(lib_launches, 1),
-                     "note": "not HBM-bound: the 4.4 MB lattice is L2-resident and trajectory state stays in registers "
-                             "for the whole launch (ncu: dram bytes per launch in `traffic`, issue slots 63 % busy); "
-                             "see DESIGN.md section 3 and profiles/"},
-        "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "path": "hf_upload_lattice(pinned host) + hf_inject + hf_run + hf_read_tallies"},
-        "issue": issue_roofline(value / world, None, clocks),
+                     "avg_launch_ms": m["lib_ms"] / max(m["lib_launches"], 1),
+                     "note": "not HBM-bound: the 34 MB of site energies are L2-resident and trajectory state stays in registers "
+                             "for the whole launch (ncu: dram bytes per launch in `traffic`); the binding unit is instruction "
+                             "issue, see `issue`, DESIGN.md section 3 and profiles/"},
+        "e2e": {"value": m["e2e_value"], "unit": "events/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                "steps": m["e2e_steps"], "path": E2E_PATH},
+        "issue": issue_roofline(value / world, "hf_run_c1_kernel", clocks),
         "gpu_launches": K,
         "clocks": clocks,
-        "tallies": dict({k: tallies[k] for k in ("emission", "recombination", "injection", "fired", "stopped")},
-                        fired_expected=fired_expected),
+        "tallies": dict({k: tallies[k] for k in ("emission", "recombination", "injection", "fired", "stopped", "move_e", "move_h")},
+                        fired_expected=m["fired_expected"]),
     }
+    if world > 1:
+        # strong scaling of the same workload: 10^6 trajectories IN TOTAL, split over the ranks
+        Bs = TRAJ_PER_GPU // world
+        ms = path_p_leg(nat, hd, rank, local_rank, world, DIMS, Bs, S, K, W, rank * Bs, e2e_steps=2)
+        line["strong"] = {"value": ms["value"], "unit": "events/s", "scaling": "strong", "trajectories_total": Bs * world,
+                          "trajectories_per_gpu": Bs, "ms_per_step": ms["total_ms"] / K,
+                          "e2e": {"value": ms["e2e_value"], "unit": "events/s", "h2d_bytes_per_step": ms["h2d"],
+                                  "d2h_bytes_per_step": ms["d2h"], "steps": ms["e2e_steps"]},
+                          "note": "hf_run_c1_kernel holds 148 SMs x 768 threads = 113 664 trajectories per wave; a shard that is not "
+                                  "a multiple of that pays for a partly filled last wave"}
     if not args.no_ga:
+        mc = path_p_leg(nat, hd, rank, local_rank, world, C1_DIMS, C1_TRAJ_PER_GPU, C1_EVENTS, 3, 2, rank * C1_TRAJ_PER_GPU, e2e_steps=2)
+        line["configs1"] = {"metric": "KMC exciton events/sec (box), BASELINE configs[1]", "value": mc["value"], "unit": "events/s",
+                            "config": {"lattice": list(C1_DIMS), "trajectories_per_gpu": C1_TRAJ_PER_GPU,
+                                       "events_per_trajectory_per_step": C1_EVENTS, "charges": CHARGES},
+                            "e2e": {"value": mc["e2e_value"], "unit": "events/s", "h2d_bytes_per_step": mc["h2d"],
+                                    "d2h_bytes_per_step": mc["d2h"], "steps": mc["e2e_steps"]}}
         line["ga"] = ga_fitness_rate(rank, local_rank, world)
         line["exciton_path"] = exciton_rate(rank, local_rank, world, cpu=not args.no_cpu)
         line["disorder_sweep"] = exciton_rate(rank, local_rank, world, lattice=256, realisations_total=64, label="disorder_sweep")
         line["high_density"] = dense_rate(rank, local_rank, world, cpu=not args.no_cpu)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, sample, _ = cpu_sample(cores, 2500)
-        v1, _, _ = cpu_sample(1, 1250)
+        v, sample, _ = cpu_sample(cores, 4000)
+        v1, _, _ = cpu_sample(1, 4000)
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample,
                                 "one_core_value": v1}
     if rank == 0:
         emit(line)
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -362,11 +430,7 @@ X_L, X_TRAJ_PER_GPU, X_EVENTS, X_CUTOFF = 128, 1_000_000, 100, 4.0
 
 def exciton_traffic(events_per_launch):
     """DRAM bytes of one exciton-kernel launch, scaled from the committed ncu capture (per event)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return float(json.load(f)["hfx_run_kernel"]["dram_bytes_per_event"]) * events_per_launch
-    except (OSError, KeyError, ValueError):
-        return None
+    return measured_traffic("hfx_run_kernel", events_per_launch)
 
 
 def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, label="north_star", cpu=False):

@@ -14,9 +14,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HFKMC_LIB") or os.path.join(HERE, "libhfkmc.so")   # HFKMC_LIB: kernel-variant experiments
 
-HF_N_TALLIES = 20
+HF_N_TALLIES = 24
 TALLY_NAMES = ("emission", "recombination", "injection", "steps", "fired", "move_e", "move_h", "bound", "decay",
-               "capture_e", "capture_h", "recomb_host", "recomb_tadf", "recomb_fluo", "emit_tadf", "emit_fluo", "stopped")
+               "capture_e", "capture_h", "recomb_host", "recomb_tadf", "recomb_fluo", "emit_tadf", "emit_fluo", "stopped",
+               "x_forster", "x_dexter", "x_isc", "x_risc")
 
 HF_OK, HF_ERR_BAD_ARG, HF_ERR_CUDA, HF_ERR_NO_DEVICE, HF_ERR_UNSUPPORTED, HF_ERR_STATE = range(6)
 TRAJ_OK, TRAJ_NO_EVENTS, TRAJ_ZERO_DIVISION, TRAJ_VALUE_ERROR, TRAJ_REPLAY_EXHAUSTED, TRAJ_CAPACITY = range(6)
@@ -98,6 +99,8 @@ SIGNATURES = {
     "hf_read_info": (C.c_int, [P, I64, C.POINTER(HfTrajInfo)]),
     "hf_read_positions": (C.c_int, [P, I64, I32, P, C.POINTER(I32)]),
     "hf_read_flags": (C.c_int, [P, I64, I32, P, C.POINTER(I32)]),
+    "hf_p_excitons": (C.c_int, [P, I32]),
+    "hf_read_excitons": (C.c_int, [P, I64, P, P, P, P, P, P, C.POINTER(I32), C.POINTER(C.c_uint64), C.POINTER(F64)]),
     "hf_read_move_events": (C.c_int, [P, I64, I32, P, P, P, C.POINTER(I32)]),
     "hf_read_last_events": (C.c_int, [P, I64, P, C.POINTER(I32)]),
     "hf_set_trace": (C.c_int, [P, I64, I64, I64]),
@@ -304,6 +307,24 @@ class Sim:
         check(load().hf_eval_hops(self._h, int(trajectory), int(particule), n, ptr(initial), ptr(final), ptr(u),
                                   ptr(tau), ptr(rate), ptr(zd)))
         return tau, rate, zd
+
+    # -- integrated excitons (own model in the reference's slots) ---------------------------------
+    def p_excitons(self, mode):
+        """0: off (the reference as it is); 1: decay at once through the exciton slots; 2: dynamics with the
+        parameters of ``x_configure`` (call it first).  Needs a new ``inject``."""
+        check(load().hf_p_excitons(self._h, int(mode)))
+        self.exciton_mode = int(mode)
+
+    def excitons(self, trajectory=0):
+        cap = max(self.charges, 1)
+        a = {k: np.zeros(cap, np.int32) for k in ("site", "spin", "kind", "final", "radiative")}
+        tau = np.zeros(cap, np.float64)
+        n, draws, clock = I32(cap), C.c_uint64(0), F64(0.0)
+        check(load().hf_read_excitons(self._h, int(trajectory), ptr(a["site"]), ptr(a["spin"]), ptr(a["kind"]), ptr(a["final"]),
+                                      ptr(tau), ptr(a["radiative"]), C.byref(n), C.byref(draws), C.byref(clock)))
+        out = {k: v[:n.value].copy() for k, v in a.items()}
+        out.update(tau=tau[:n.value].copy(), draws=int(draws.value), clock=float(clock.value))
+        return out
 
     # -- exciton trajectories (Path X) -----------------------------------------------------------
     def x_configure(self, params: "HfXParams | None" = None):

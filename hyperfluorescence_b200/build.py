@@ -48,9 +48,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libhfkmc.so")
-    with open(os.path.join(HERE, "libhfkmc.ptxas.log"), "w") as f:
+    # register / spill report of every kernel; build/ is git-ignored (a copy per round lives in profiles/)
+    os.makedirs(os.path.join(os.path.dirname(HERE), "build"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(HERE), "build", "libhfkmc.ptxas.log"), "w") as f:
         f.write(res.stdout + res.stderr)
     return LIB
+
+
+def source_hashes(names=None) -> dict:
+    """sha256 of the kernel sources (all of csrc/ by default).  profiles/traffic.json stamps each ncu-derived
+    counter with the hashes of the files its kernel is compiled from, and bench.py drops a counter whose stamp
+    no longer matches what is built."""
+    import hashlib
+    out = {}
+    for name in sorted(names or os.listdir(CSRC)):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            out[name] = hashlib.sha256(f.read()).hexdigest()[:16]
+    return out
 
 
 if __name__ == "__main__":

@@ -63,11 +63,34 @@ struct HfTraceRec {                // == hf_event in include/hfkmc.h
     uint64_t draws;
 };
 
+// ---- integrated exciton dynamics (own model; functions in hf_frm_x.cuh) ----------------------------------------
+#define HF_STREAM_PX 5u             /* the trajectory's exciton draws: never the TRAJ stream, whose count is pinned */
+#define HF_K_ISC 3
+#define HF_K_FORSTER 4
+#define HFI_SPIN(m) ((m) & 3)
+#define HFI_ONSITE 4
+#define HFI_RAD 8
+#define HFI_KIND(m) (((m) >> 4) & 15)
+
+struct HfIntegrated {
+    int32_t mode, M;
+    const int32_t *offsets;           // [M] packed (dx+128) | (dy+128) << 8 | (dz+128) << 16   (hf_x_configure)
+    const double *g6, *gd;            // [M]
+    double kf[9], kd[9], k_isc[3], k_risc[3], k_rad[6], k_nonrad[6];
+    const double *ws1, *wt1;          // [n_real][w_stride] tagged weights, zero halo of w_halo sites below and above
+    int64_t w_stride, w_halo;
+    // state [B][cap_c] / [B]
+    int32_t *x_site, *x_meta, *x_final, *x_n;
+    double *x_tau, *x_clock;
+    uint64_t *x_draws;
+};
+
 struct HfParams {
     int32_t X, Y, Z;
     int64_t N;
     double field;
     int32_t C, cap_c, cap_f;
+    int32_t dist;                  // charge_tranfer_distance (reseau.py:110): 1 = the 3x3x3 table, > 1 = hf_gen_move_event_far
     int64_t B, traj_per_real;
     uint32_t k0, k1, first_traj, first_real;
     int64_t setsize;               // random.sample's pool/set switch for k = C (random.py:421-424)
@@ -84,9 +107,11 @@ struct HfParams {
     const double *replay;
     int64_t n_replay;
     HfTraceRec *trace;
+    const uint64_t *trace_base;    // [trace_n] HfScalars.fired of each traced trajectory when hf_set_trace armed the trace
     int64_t trace_first, trace_n, trace_cap;
     unsigned long long *totals;    // channel counters, HF_N_TALLIES
     int64_t n_steps;
+    HfIntegrated xi;               // xi.mode == 0: the reference as it is
 };
 
 struct HfWarp {
@@ -105,6 +130,13 @@ struct HfWarp {
     const uint8_t *species;        // this trajectory's realisation
     const double *lumo, *homo;
     float *approx;                 // thread-per-trajectory kernel only: this thread's screening column (27 floats)
+    // integrated excitons (P.xi.mode != 0): slots in creation order, see hf_frm_x.cuh
+    int32_t *x_site, *x_meta, *x_final;
+    double *x_tau, *x_scratch;     // x_scratch: 32 lane sums (warp kernel) / 8 prefix checkpoints (thread kernel)
+    int32_t n_x;
+    uint64_t xdraws;
+    double clock;
+    unsigned c_x_forster, c_x_dexter, c_x_isc, c_x_risc;
     unsigned c_move_e, c_move_h, c_bound, c_decay, c_capture_e, c_capture_h;
     unsigned c_recomb_host, c_recomb_tadf, c_recomb_fluo, c_emit_tadf, c_emit_fluo;
 
@@ -124,19 +156,25 @@ struct HfWarp {
     __device__ __forceinline__ void set_n_ev(int t, int v) { if (t) n_ev1 = v; else n_ev0 = v; }
 };
 
-__host__ __device__ inline size_t hf_warp_smem_bytes(int cap_c, int cap_f) {
+__host__ __device__ inline int hf_xcap(const HfParams &P) { return P.xi.mode ? P.cap_c : 0; }
+// xcap: exciton slots (cap_c in the integrated modes, else 0)
+__host__ __device__ inline size_t hf_warp_smem_bytes(int cap_c, int cap_f, int xcap = 0) {
     size_t b = 8u * (6u * cap_c + HF_CACHE) + 4u * (6u * cap_c + 2u * cap_f + 3u * HF_CACHE);
+    if (xcap) b += 8u * ((size_t)xcap + 32u) + 4u * 3u * (((size_t)xcap + 1u) & ~(size_t)1u);
     return (b + 15u) & ~(size_t)15u;
 }
 
-__device__ __forceinline__ void hf_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f) {
+__device__ __forceinline__ void hf_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f, int xcap = 0) {
     w.cap_c = cap_c; w.cap_f = cap_f; w.cache_stride = 1;
     double *d = reinterpret_cast<double *>(base);
     w.ev_tau_b = d; d += 2 * cap_c;
     w.inv_old_b = d; d += 2 * cap_c;
     w.term_b = d; d += 2 * cap_c;
     w.cache_tau = d; d += HF_CACHE;
+    w.x_tau = w.x_scratch = nullptr; w.x_site = w.x_meta = w.x_final = nullptr;
+    if (xcap) { w.x_tau = d; d += xcap; w.x_scratch = d; d += 32; }
     int32_t *i = reinterpret_cast<int32_t *>(d);
+    if (xcap) { const int xc = (xcap + 1) & ~1; w.x_site = i; i += xc; w.x_meta = i; i += xc; w.x_final = i; i += xc; }
     w.pos_b = i; i += 2 * cap_c;
     w.ev_init_b = i; i += 2 * cap_c;
     w.ev_final_b = i; i += 2 * cap_c;
@@ -297,6 +335,11 @@ __device__ __forceinline__ void hf_update_events(HfWarp &w, double time, int lan
     for (int t = 0; t < 2; ++t)
 #pragma unroll 1
         for (int i = lane; i < w.n_ev(t); i += L) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
+    if (w.x_tau) {                                 // _move_exciton_events, _isc_events, _decay_events (reseau.py:569-576)
+        w.clock = __dadd_rn(w.clock, time);
+#pragma unroll 1
+        for (int i = lane; i < w.n_x; i += L) w.x_tau[i] = __dsub_rn(w.x_tau[i], time);
+    }
     hf_sync<L>();
 }
 
@@ -312,6 +355,23 @@ __device__ __forceinline__ int hf_bvk_z(int p, int size, int i) {
     if (p - 1 > -1 && p + 1 < size) return p - 1 + i;
     if (p - 1 < 0) return i;                                 // [0, 1]
     return p - 1 + i;                                        // [size-2, size-1]
+}
+
+// ---- neighbour table for any charge_tranfer_distance: _born_von_karman verbatim (reseau.py:190-205) ----------
+// The three branches as written, including what they do away from distance 1 (quirk Q3): a position within
+// `distance` of the LOWER edge gets [0 .. d] + [size-d .. size-1] whatever the position is; one within `distance`
+// of the UPPER edge gets [p-d .. size-1] + [0 .. d-1] (up to 3d entries); z is never wrapped.  Duplicated and
+// asymmetric neighbours are part of the table: each entry is a candidate with its own uniform.
+__device__ __forceinline__ int hf_bvk_count(int p, int size, int d, bool is_z) {
+    if (p - d > -1 && p + d < size) return 2 * d + 1;
+    if (p - d < 0) return is_z ? d + 1 : 2 * d + 1;
+    return (size - (p - d)) + (is_z ? 0 : d);
+}
+__device__ __forceinline__ int hf_bvk_entry(int p, int size, int d, int i) {
+    if (p - d > -1 && p + d < size) return p - d + i;
+    if (p - d < 0) return i <= d ? i : size - d + (i - d - 1);
+    const int first = size - (p - d);
+    return i < first ? p - d + i : i - first;
 }
 
 // 1 / sqrt(d2), exp and -log(rng) / k as the reference computes them.  kCompact routes them through single
@@ -452,6 +512,65 @@ __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWa
     return __ddiv_rn(-log(rng), k);                                              // 292 / 324
 }
 
+// hf_gen_move_event for charge_tranfer_distance > 1: the neighbour list has up to 3d x 3d x (2d+1) entries
+// (reseau.py:184-205), taken 32 at a time in list order.  Every unblocked candidate is evaluated exactly (no
+// screening: this table is off every benchmark); uniforms are numbered in list order across
+// the chunks, the first minimum wins, the first failing candidate raises.
+template <int L>
+__device__ __forceinline__ int hf_gen_move_event_far(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags, int lane) {
+    const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos), d = P.dist;
+    const int nx = hf_bvk_count(px, P.X, d, false), ny = hf_bvk_count(py, P.Y, d, false), nz = hf_bvk_count(pz, P.Z, d, true);
+    const int total = nx * ny * nz;
+    const int32_t *blk = use_flags ? w.flag(t) : w.pos(t);
+    const int nb = use_flags ? w.n_flag(t) : w.n_pos(t);
+    hf_fill_inv_old<L>(w, t, pos, lane);
+    double btau = INFINITY;
+    int bfin = -1;
+    uint64_t drawn = 0;
+    for (int base = 0; base < total; base += L) {
+        const int i = base + lane;
+        int cand = pos;
+        bool active = false;
+        if (i < total) {
+            cand = hf_pack(hf_bvk_entry(px, P.X, d, i / (ny * nz)), hf_bvk_entry(py, P.Y, d, (i / nz) % ny), hf_bvk_entry(pz, P.Z, d, i % nz));
+            active = cand != pos;                                                // reseau.py:188
+            for (int j = 0; j < nb && active; ++j) active = blk[j] != cand;      // 385 / 394 ; 249 / 268
+        }
+        const unsigned mask = hf_ballot<L>(active);
+        if (mask == 0) continue;
+        bool exhausted = false, zero_div = false;
+        double tau = INFINITY, rate = 0.0;
+        if (active) {
+            const double u = hf_traj_uniform(P, w, w.draws + drawn + (uint64_t)__popc(mask & ((1u << lane) - 1u)), &exhausted);
+            if (!exhausted) tau = hf_hop_time(P, w, t, pos, cand, u, &rate, &zero_div);
+        }
+        if (hf_ballot<L>(exhausted)) return HF_ST_REPLAY_EXHAUSTED;
+        const unsigned zmask = hf_ballot<L>(active && zero_div);
+        if (zmask) {                               // draws up to and including the failing candidate
+            const int f = __ffs(zmask) - 1;
+            w.draws += drawn + (uint64_t)__popc(mask & (f == 31 ? HF_FULL : ((2u << f) - 1u)));
+            return HF_ST_ZERO_DIVISION;
+        }
+        int best = active ? lane : 99;
+#pragma unroll
+        for (int off = L / 2; off > 0; off >>= 1) {
+            const double otau = hf_shfl_xor<L>(tau, off);
+            const int obest = hf_shfl_xor<L>(best, off);
+            if (otau < tau || (otau == tau && obest < best)) { tau = otau; best = obest; }
+        }
+        const int fin = hf_shfl<L>(cand, best & 31);
+        if (bfin < 0 || tau < btau) { btau = tau; bfin = fin; }                  // first minimum across the chunks
+        drawn += (uint64_t)__popc(mask);
+    }
+    if (bfin < 0) return HF_ST_VALUE_ERROR;                                      // min() of an empty sequence
+    w.draws += drawn;
+    if (w.n_ev(t) >= P.cap_c) return HF_ST_CAPACITY;
+    if (lane == 0) { w.ev_init(t)[w.n_ev(t)] = pos; w.ev_final(t)[w.n_ev(t)] = bfin; w.ev_tau(t)[w.n_ev(t)] = btau; }
+    w.set_n_ev(t, w.n_ev(t) + 1);
+    hf_sync<L>();
+    return HF_ST_OK;
+}
+
 // _new_move_electron_events / _new_move_hole_events (reseau.py:380-396; use_flags = true) and the
 // per-charge body of _init_move_*_events (reseau.py:240-276; use_flags = false: membership in
 // the position list).  Lanes = candidates in the reference's x-major neighbour order; one TRAJ
@@ -459,6 +578,7 @@ __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWa
 template <int L = 32>
 __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, int t, int pos, bool use_flags, int lane) {
     if constexpr (L == 1) return hf_gen_move_event_serial(P, w, t, pos, use_flags);
+    if (P.dist != 1) return hf_gen_move_event_far<L>(P, w, t, pos, use_flags, lane);
     const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
     const int nz = (pz - 1 > -1 && pz + 1 < P.Z) ? 3 : 2;
     const int total = 9 * nz;
@@ -664,6 +784,16 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
     }
     w.c_move_e = w.c_move_h = w.c_bound = w.c_decay = w.c_capture_e = w.c_capture_h = 0;
     w.c_recomb_host = w.c_recomb_tadf = w.c_recomb_fluo = w.c_emit_tadf = w.c_emit_fluo = 0;
+    w.c_x_forster = w.c_x_dexter = w.c_x_isc = w.c_x_risc = 0;
+    w.n_x = 0; w.xdraws = 0; w.clock = 0.0;
+    if (P.xi.mode) {
+        w.n_x = P.xi.x_n[local]; w.xdraws = P.xi.x_draws[local]; w.clock = P.xi.x_clock[local];
+#pragma unroll 1
+        for (int i = lane; i < w.n_x; i += L) {
+            w.x_site[i] = P.xi.x_site[local * P.cap_c + i]; w.x_meta[i] = P.xi.x_meta[local * P.cap_c + i];
+            w.x_final[i] = P.xi.x_final[local * P.cap_c + i]; w.x_tau[i] = P.xi.x_tau[local * P.cap_c + i];
+        }
+    }
     hf_sync<L>();
 }
 
@@ -691,6 +821,19 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
         P.cache_kp[c * P.B + local] = w.cache_kp[c];
         P.cache_tau[c * P.B + local] = w.cache_tau[c];
     }
+    if (P.xi.mode) {
+#pragma unroll 1
+        for (int i = lane; i < w.n_x; i += L) {
+            P.xi.x_site[local * P.cap_c + i] = w.x_site[i]; P.xi.x_meta[local * P.cap_c + i] = w.x_meta[i];
+            P.xi.x_final[local * P.cap_c + i] = w.x_final[i]; P.xi.x_tau[local * P.cap_c + i] = w.x_tau[i];
+        }
+        if (lane == 0) {
+            P.xi.x_n[local] = w.n_x; P.xi.x_draws[local] = w.xdraws; P.xi.x_clock[local] = w.clock;
+            const unsigned cx[4] = {w.c_x_forster, w.c_x_dexter, w.c_x_isc, w.c_x_risc};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (cx[i]) atomicAdd(P.totals + 17 + i, (unsigned long long)cx[i]);
+        }
+    }
     if (lane == 0) {
         HfScalars sc;
 #pragma unroll
@@ -707,6 +850,8 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
         for (int i = 0; i < 11; ++i) if (c[i]) atomicAdd(P.totals + 5 + i, (unsigned long long)c[i]);
     }
 }
+
+#include "hf_frm_x.cuh"
 
 // Re-inject (optionally) and regenerate the move event of the LAST charge of type t.  The warp kernel does it
 // on the spot; the thread-per-trajectory kernel queues it (4 bits per request: 8 | 4 * reinject | t, at most two
@@ -740,7 +885,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
     } else {
         // min tau over move_e + move_h, LAST one in concatenation order on ties (Q6)
         const int ne = w.n_ev(0), total = ne + w.n_ev(1);
-        if (total == 0) return HF_ST_NO_EVENTS;                                  // 487-488
+        if (total == 0 && w.n_x == 0) return HF_ST_NO_EVENTS;                    // 487-488
         double btau = INFINITY;
         int bidx = -1;
         for (int base = 0; base < total; base += L) {
@@ -755,6 +900,40 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
             const double ot = hf_shfl_xor<L>(btau, off);
             const int oi = hf_shfl_xor<L>(bidx, off);
             if (oi >= 0 && (bidx < 0 || ot < btau || (ot == btau && oi > bidx))) { btau = ot; bidx = oi; }
+        }
+        // the excitons' events follow the carriers' in _get_all_events (reseau.py:608-612): move_x, isc, decay lists,
+        // slots in creation order inside each; equal taus -> the later one wins
+        int xsel = -1;
+        if (w.n_x > 0) {
+            double xt = INFINITY;
+            int xkey = -1;
+#pragma unroll 1
+            for (int i = lane; i < w.n_x; i += L) {
+                const double ti = w.x_tau[i];
+                const int key = (hfi_class(HFI_KIND(w.x_meta[i])) << 16) | i;
+                if (xkey < 0 || ti < xt || (ti == xt && key > xkey)) { xt = ti; xkey = key; }
+            }
+#pragma unroll
+            for (int off = L / 2; off > 0; off >>= 1) {
+                const double ot = hf_shfl_xor<L>(xt, off);
+                const int ok = hf_shfl_xor<L>(xkey, off);
+                if (ok >= 0 && (xkey < 0 || ot < xt || (ot == xt && ok > xkey))) { xt = ot; xkey = ok; }
+            }
+            if (bidx < 0 || xt <= btau) { xsel = xkey & 0xffff; btau = xt; }
+        }
+        if (xsel >= 0) {
+            kind = HFI_KIND(w.x_meta[xsel]); part = HF_PART_EXCITON; tau = btau;
+            ini = w.x_site[xsel]; fin = w.x_final[xsel];
+            hf_sync<L>();
+            if (lane == 0) {
+                const int64_t at = w.cache_head * w.cache_stride;
+                w.cache_init[at] = ini; w.cache_final[at] = fin;
+                w.cache_kp[at] = kind | (part << 8); w.cache_tau[at] = tau;
+            }
+            w.cache_head = w.cache_head + 1 == HF_CACHE ? 0 : w.cache_head + 1;
+            if (w.cache_n < HF_CACHE) w.cache_n += 1;
+            *ev_kind = kind; *ev_part = part; *ev_init = ini; *ev_final = fin; *ev_tau = tau;
+            return hfi_fire<L>(P, w, xsel, kind, fin, tau, lane, queue);
         }
         const int t = bidx < ne ? 0 : 1, i = bidx - (t ? ne : 0);
         kind = HF_K_MOVE; part = t + 1; tau = btau;
@@ -811,6 +990,17 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
             hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
             w.set_n_pos(t, w.n_pos(t) - 1);
         }
+        if (P.xi.mode) {                       // integrated: the exciton gets a slot and its first event (hf_frm_x.cuh)
+            if (w.n_x >= P.cap_c) return HF_ST_CAPACITY;
+            const int k = w.n_x;
+            hf_sync<L>();
+            if (lane == 0) { w.x_site[k] = site; w.x_meta[k] = both ? (w.xstate | HFI_ONSITE) : 0; }
+            w.n_x = k + 1;
+            w.xstate = 0;
+            hf_sync<L>();
+            hfi_new_event<L>(P, w, k, lane);
+            return HF_ST_OK;
+        }
         w.special = HF_K_DECAY | (HF_PART_EXCITON << 8); w.special_site = site;
         return HF_ST_OK;
     }
@@ -848,13 +1038,14 @@ __global__ void __launch_bounds__(kWarps * 32) hf_run_kernel(const HfParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HfWarp w;
-    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f), P.cap_c, P.cap_f);
+    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f, hf_xcap(P)), P.cap_c, P.cap_f, hf_xcap(P));
     for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
         hf_load_state(P, w, local, lane);
         // a ZeroDivisionError only ends the operations() call it happened in (reseau.py:587-589)
         if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;
         const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
         HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+        const uint64_t trace_base = traced ? P.trace_base[local - P.trace_first] : 0;   // events fired before the trace was armed
         if (w.status == HF_ST_OK) {
             for (int64_t i = 0; i < P.n_steps; ++i) {
                 w.steps += 1;                                                    // 582
@@ -862,17 +1053,18 @@ __global__ void __launch_bounds__(kWarps * 32) hf_run_kernel(const HfParams P) {
                 double tau;
                 const int st = hf_step(P, w, lane, &kind, &part, &ini, &fin, &tau);
                 if (st != HF_ST_OK) { w.status = st; break; }                    // 587-591
-                if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
-                else if (kind == HF_K_BOUND) w.c_bound += 1;
+                if (kind == HF_K_BOUND) w.c_bound += 1;
                 else if (kind == HF_K_DECAY) w.c_decay += 1;
+                else if (part == HF_PART_EXCITON) {}                             // transfers and spin flips: counted by hfi_fire
+                else if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
                 else { if (part == 1) w.c_capture_e += 1; else w.c_capture_h += 1; }
-                if (traced && lane == 0 && w.fired < (uint64_t)P.trace_cap) {
+                if (traced && lane == 0 && w.fired - trace_base < (uint64_t)P.trace_cap) {
                     HfTraceRec rec;
                     rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
                     rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
                     rec.pad[0] = rec.pad[1] = 0;
                     rec.spins = (uint32_t)w.spins; rec.draws = w.draws;
-                    trace[w.fired] = rec;
+                    trace[w.fired - trace_base] = rec;
                 }
                 w.fired += 1;
             }
@@ -889,7 +1081,7 @@ __global__ void __launch_bounds__(kWarps * 32) hf_inject_kernel(const HfParams P
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HfWarp w;
-    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f), P.cap_c, P.cap_f);
+    hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f, hf_xcap(P)), P.cap_c, P.cap_f, hf_xcap(P));
     const int64_t molecules = (int64_t)P.X * P.Y;
     for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
         hf_load_state(P, w, local, lane);      // zero-initialised by the host
@@ -941,7 +1133,7 @@ __global__ void hf_eval_hops_kernel(const HfParams P, int64_t local, int t, int 
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31;
     HfWarp w;
-    hf_carve(w, hf_smem, P.cap_c, P.cap_f);
+    hf_carve(w, hf_smem, P.cap_c, P.cap_f, hf_xcap(P));
     hf_load_state(P, w, local, lane);
     for (int i = 0; i < n; ++i) {
         const int ini = hf_pack_site(P, initial[i]), fin = hf_pack_site(P, final_[i]);

@@ -113,18 +113,23 @@ __device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, 
 // Screen-then-verify.  Evaluating exp(), log(), a square root and three divisions in fp64 for all
 // 26 candidates costs ~420 instructions per candidate (ncu, profiles/r01b_*), yet only the
 // minimum is kept.  Pass 1 computes a cheap fp32 estimate a_i of 1e13 * tau_i for every candidate
-// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by 4e-5:
+// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by eps = 6e-5:
 //   -log(rng): rng >= 2^-6 away from 1: __logf abs error 2^-21.41 on |log| >= 0.0157  -> 2.7e-5
 //              otherwise the series u + u^2/2 + u^3/3 (truncation u^3/4 <= 9.5e-7)      -> 1.3e-6
 //   exp(dE/kT): float rounding of x (6e-8 x) + __expf (2 + 1.173 x ulp), x <= 88        -> 1.2e-5
-//              neglected Coulomb term (<= 1e-9 eV -> 4e-8 in x)                         -> 4e-8
-// Every candidate whose estimate lies within a factor 1 + 2^-9 (50x that bound) of the smallest
-// estimate is then evaluated EXACTLY, in candidate order, by hf_c1_exact_tau; the first minimum
-// among those is the reference's min().  A candidate outside the window has
-// tau_i >= a_i (1 - 4e-5) > a_min (1 + 2^-9)(1 - 4e-5) > a_min (1 + 4e-5) >= tau of the best
+//              neglected Coulomb term of the one opposite charge: C_e |1/r' - 1/r| with r, r' >= 1 is below
+//              C_e = 4.8e-7 eV whatever the geometry (adjacent charges: C_e (1 - 1/2) = 2.4e-7 eV), i.e.
+//              below C_e / kT = 1.86e-5 in x                                            -> 1.9e-5
+//   sum 5.8e-5 < eps.
+// Every candidate whose estimate lies within a factor 1 + W, W = 2^-9 (16x the 2 eps / (1 - eps) = 1.2e-4 the
+// argument needs) of the smallest estimate is then evaluated EXACTLY, in candidate order, by hf_c1_exact_tau;
+// the first minimum among those is the reference's min().  A candidate outside the window has
+// tau_i >= a_i (1 - eps) > a_min (1 + W)(1 - eps) > a_min (1 + eps) >= tau of the best
 // estimate, so it can neither win nor tie.  Estimates that overflow (x > 88) are +inf and only
 // matter when all are (then every candidate is verified); candidates with x > 700 are always
 // verified because the reference raises ZeroDivisionError when any rate underflows to 0.
+// tests/test_gpu_parity.py::test_adjacent_charges_screening_is_exact keeps the two carriers on neighbouring sites
+// for > 10^6 regenerated events and compares every one with the all-exact C restatement.
 // Result: bit-identical events and taus at ~1.06 exact evaluations per event instead of 26.
 __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, const double *homo, int t, HfC1 &s,
                                          int64_t local, uint32_t ident, float *approx /* [l * HF_C1_THREADS] */) {
@@ -368,6 +373,7 @@ __global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_ker
     if (s.status == HF_ST_ZERO_DIVISION || s.status == HF_ST_NO_EVENTS) s.status = HF_ST_OK;
     const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
     HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+    const uint64_t trace_base = traced ? P.trace_base[local - P.trace_first] : 0;   // events fired before the trace was armed
     if (s.status == HF_ST_OK) {
         for (int64_t i = 0; i < P.n_steps; ++i) {
             s.steps += 1;                                                        // 582
@@ -385,13 +391,13 @@ __global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_ker
             else if (kind == HF_K_BOUND) c.bound += 1;
             else if (kind == HF_K_DECAY) c.decay += 1;
             else { if (part == 1) c.capture_e += 1; else c.capture_h += 1; }
-            if (traced && s.fired < (uint64_t)P.trace_cap) {
+            if (traced && s.fired - trace_base < (uint64_t)P.trace_cap) {
                 HfTraceRec rec;
                 rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
                 rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
                 rec.pad[0] = rec.pad[1] = 0;
                 rec.spins = (uint32_t)s.spins; rec.draws = s.draws;
-                trace[s.fired] = rec;
+                trace[s.fired - trace_base] = rec;
             }
             s.fired += 1;
         }

@@ -25,16 +25,21 @@
 // bytes of shared memory per trajectory: the lists of hf_carve + the screening column, an odd number of
 // 8-byte words so that the threads of a warp spread over the banks
 // lists of one trajectory without the _cache ring (written straight to global memory by hf_step<1>)
-__host__ __device__ inline size_t hf_small_list_bytes(int cap_c, int cap_f) {
-    return 8u * (4u * (size_t)cap_c) + 4u * (6u * (size_t)cap_c + 2u * (size_t)cap_f);
+// xcap: exciton slots of the integrated modes (hf_frm_x.cuh): taus + 8 prefix checkpoints, three int lists
+__host__ __device__ inline size_t hf_small_list_bytes(int cap_c, int cap_f, int xcap = 0) {
+    return 8u * (4u * (size_t)cap_c) + 4u * (6u * (size_t)cap_c + 2u * (size_t)cap_f) +
+           (xcap ? 8u * ((size_t)xcap + 8u) + 4u * 3u * (size_t)xcap : 0u);
 }
-__device__ __forceinline__ void hf_small_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f) {
+__device__ __forceinline__ void hf_small_carve(HfWarp &w, unsigned char *base, int cap_c, int cap_f, int xcap = 0) {
     w.cap_c = cap_c; w.cap_f = cap_f; w.cache_stride = 1;
     double *d = reinterpret_cast<double *>(base);
     w.ev_tau_b = d; d += 2 * cap_c;
     w.inv_old_b = d; d += 2 * cap_c;
     w.term_b = nullptr;                                                          // only the warp kernel shares a Coulomb sum
+    w.x_tau = w.x_scratch = nullptr; w.x_site = w.x_meta = w.x_final = nullptr;
+    if (xcap) { w.x_tau = d; d += xcap; w.x_scratch = d; d += 8; }
     int32_t *i = reinterpret_cast<int32_t *>(d);
+    if (xcap) { w.x_site = i; i += xcap; w.x_meta = i; i += xcap; w.x_final = i; i += xcap; }
     w.pos_b = i; i += 2 * cap_c;
     w.ev_init_b = i; i += 2 * cap_c;
     w.ev_final_b = i; i += 2 * cap_c;
@@ -42,8 +47,8 @@ __device__ __forceinline__ void hf_small_carve(HfWarp &w, unsigned char *base, i
     w.approx = reinterpret_cast<float *>(i);
     w.cache_init = w.cache_final = w.cache_kp = nullptr; w.cache_tau = nullptr;   // set by hf_load_state<1>
 }
-__host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f) {
-    size_t b = hf_small_list_bytes(cap_c, cap_f) + 4u * 28u;
+__host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f, int xcap = 0) {
+    size_t b = hf_small_list_bytes(cap_c, cap_f, xcap) + 4u * 28u;
     b = (b + 7u) & ~(size_t)7u;
     if (((b >> 3) & 1u) == 0) b += 8;
     return b;
@@ -191,13 +196,14 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= P.B) return;
-    const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f);
+    const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P));
     HfWarp w;
-    hf_small_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f);
+    hf_small_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f, hf_xcap(P));
     hf_load_state<1>(P, w, local, 0);
     if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;   // reseau.py:587-589
     const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
     HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
+    const uint64_t trace_base = traced ? P.trace_base[local - P.trace_first] : 0;   // events fired before the trace was armed
     if (w.status == HF_ST_OK) {
         for (int64_t i = 0; i < P.n_steps; ++i) {
             w.steps += 1;                                                        // 582
@@ -212,17 +218,18 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
                 if (st == HF_ST_OK) st = hf_gen_move_event_serial(P, w, t, w.pos(t)[w.n_pos(t) - 1], true);
             }
             if (st != HF_ST_OK) { w.status = st; break; }                        // 587-591
-            if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
-            else if (kind == HF_K_BOUND) w.c_bound += 1;
+            if (kind == HF_K_BOUND) w.c_bound += 1;
             else if (kind == HF_K_DECAY) w.c_decay += 1;
+            else if (part == HF_PART_EXCITON) {}                                 // transfers and spin flips: counted by hfi_fire
+            else if (kind == HF_K_MOVE) { if (part == 1) w.c_move_e += 1; else w.c_move_h += 1; }
             else { if (part == 1) w.c_capture_e += 1; else w.c_capture_h += 1; }
-            if (traced && w.fired < (uint64_t)P.trace_cap) {
+            if (traced && w.fired - trace_base < (uint64_t)P.trace_cap) {
                 HfTraceRec rec;
                 rec.initial = (int32_t)hf_site(P, ini); rec.final_ = (int32_t)hf_site(P, fin);
                 rec.tau = tau; rec.kind = (uint8_t)kind; rec.particule = (uint8_t)part;
                 rec.pad[0] = rec.pad[1] = 0;
                 rec.spins = (uint32_t)w.spins; rec.draws = w.draws;
-                trace[w.fired] = rec;
+                trace[w.fired - trace_base] = rec;
             }
             w.fired += 1;
         }

@@ -4,6 +4,7 @@
 // hf_create fails with HF_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -54,6 +55,7 @@ struct hf_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     bool have_lattice = false, injected = false;
+    std::vector<char> have_st;         // per realisation: S1 / T1 energies were generated or uploaded
     // lattice
     uint8_t *d_species = nullptr;
     double *d_homo = nullptr, *d_lumo = nullptr, *d_s1 = nullptr, *d_t1 = nullptr;
@@ -66,6 +68,8 @@ struct hf_sim {
     unsigned long long *d_totals = nullptr, *d_sum = nullptr;
     double *d_replay = nullptr;
     HfTraceRec *d_trace = nullptr;
+    uint64_t *d_trace_base = nullptr;
+    std::vector<uint64_t> trace_base;  // host copy of d_trace_base
     // launch shape of the step kernel
     int warps = 4, grid = 1;
     size_t smem = 0;
@@ -91,6 +95,10 @@ struct hf_sim {
     unsigned long long *d_xd_totals = nullptr;
     int xd_grid = 1;
     size_t xd_smem = 0;
+    // integrated excitons (hf_p_excitons)
+    int32_t *d_pi_site = nullptr, *d_pi_meta = nullptr, *d_pi_final = nullptr, *d_pi_n = nullptr;
+    double *d_pi_tau = nullptr, *d_pi_clock = nullptr;
+    uint64_t *d_pi_draws = nullptr;
     // timing of hf_run launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -102,7 +110,7 @@ namespace {
 
 template <int W>
 int configure_launch(hf_sim *s) {
-    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P));
     const size_t smem = per_warp * W;
     if (smem > 48 * 1024) {
         HF_CUDA(cudaFuncSetAttribute(hf_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -121,7 +129,7 @@ int configure_launch(hf_sim *s) {
 }
 
 int pick_launch(hf_sim *s) {
-    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P));
     const size_t limit = 200 * 1024;
     if (per_warp * 8 <= limit / 4) return configure_launch<8>(s);   // >= 4 CTAs of 8 warps per SM
     if (per_warp * 4 <= limit) return configure_launch<4>(s);
@@ -322,6 +330,17 @@ int x_configure_launch(hf_sim *s) {
     return HF_OK;
 }
 
+// HfParams.xi <- the tables, rate constants and weights of hf_x_configure (integrated mode 2)
+static void sync_integrated(hf_sim *s) {
+    HfIntegrated &I = s->P.xi;
+    const HfxParams &X = s->X;
+    I.M = X.M; I.offsets = X.offsets; I.g6 = X.g6; I.gd = X.gd;
+    memcpy(I.kf, X.kf, sizeof(I.kf)); memcpy(I.kd, X.kd, sizeof(I.kd));
+    memcpy(I.k_isc, X.k_isc, sizeof(I.k_isc)); memcpy(I.k_risc, X.k_risc, sizeof(I.k_risc));
+    memcpy(I.k_rad, X.k_rad, sizeof(I.k_rad)); memcpy(I.k_nonrad, X.k_nonrad, sizeof(I.k_nonrad));
+    I.ws1 = X.ws1; I.wt1 = X.wt1; I.w_stride = X.w_stride; I.w_halo = X.w_halo;
+}
+
 extern "C" {
 
 const char *hf_last_error(void) { return g_error; }
@@ -353,8 +372,13 @@ int hf_create(const hf_config *c, hf_sim **out) {
         return fail(HF_ERR_BAD_ARG, "Not enough molecules for current proportions and dimension.");
     if (c->charges < 1 || c->charges > (int64_t)X * Y)                                           // reseau.py:212-213
         return fail(HF_ERR_BAD_ARG, "Required %d charges but only %lld molecules available.", c->charges, (long long)X * Y);
-    if (c->distance != 1)
-        return fail(HF_ERR_UNSUPPORTED, "charge_tranfer_distance=%d: only 1 is supported (the reference's neighbour table is ill-defined beyond it, quirk Q3)", c->distance);
+    // reseau.py:190-205 for any distance (quirk Q3 reproduced verbatim).  The table indexes [0 .. distance] on every
+    // axis, so a lattice thinner than that is an IndexError in the reference.
+    if (c->distance < 1 || c->distance > 8)
+        return fail(HF_ERR_UNSUPPORTED, "charge_tranfer_distance=%d: supported range is 1..8", c->distance);
+    if (X < c->distance + 1 || Y < c->distance + 1 || Z < c->distance + 1)
+        return fail(HF_ERR_BAD_ARG, "charge_tranfer_distance=%d needs every dimension >= %d (list index out of range in the reference)",
+                    c->distance, c->distance + 1);
     if (c->n_trajectories < 1 || c->n_realisations < 1 || c->n_trajectories % c->n_realisations != 0)
         return fail(HF_ERR_BAD_ARG, "n_realisations (%d) must divide n_trajectories (%lld)", c->n_realisations, (long long)c->n_trajectories);
 
@@ -381,7 +405,9 @@ int hf_create(const hf_config *c, hf_sim **out) {
     P.field = c->electric_field;
     P.C = c->charges;
     P.cap_c = c->charges;
-    P.cap_f = c->charges == 1 ? 2 : 2 * c->charges + 8;
+    P.dist = c->distance;
+    // distance > 1 always runs the warp kernel, whose flag sets need their general capacity
+    P.cap_f = (c->charges == 1 && c->distance == 1) ? 2 : 2 * c->charges + 8;
     P.B = c->n_trajectories;
     P.traj_per_real = c->n_trajectories / c->n_realisations;
     P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
@@ -418,6 +444,10 @@ int hf_create(const hf_config *c, hf_sim **out) {
     if ((rc = dev_alloc(&s->d_cache_tau, (size_t)(B * HF_CACHE)))) return bail(rc);
     if ((rc = dev_alloc(&s->d_totals, (size_t)HF_N_TALLIES))) return bail(rc);
     if ((rc = dev_alloc(&s->d_sum, (size_t)HF_N_TALLIES))) return bail(rc);
+    // no array is ever read uninitialised (a lattice uploaded without S1 / T1 reads zeros through the facade)
+    cudaMemsetAsync(s->d_species, 0, (size_t)(R * N), s->stream);
+    for (double *p : {s->d_homo, s->d_lumo, s->d_s1, s->d_t1}) cudaMemsetAsync(p, 0, 8 * (size_t)(R * N), s->stream);
+    s->have_st.assign((size_t)R, 0);
     fill_params(s);
     if ((rc = pick_launch(s))) return bail(rc);
     *out = s;
@@ -433,12 +463,14 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_species); cudaFree(s->d_homo); cudaFree(s->d_lumo); cudaFree(s->d_s1); cudaFree(s->d_t1);
     cudaFree(s->d_pos); cudaFree(s->d_flag); cudaFree(s->d_ev_init); cudaFree(s->d_ev_final); cudaFree(s->d_ev_tau);
     cudaFree(s->d_sc); cudaFree(s->d_cache_i); cudaFree(s->d_cache_tau); cudaFree(s->d_totals); cudaFree(s->d_sum);
-    cudaFree(s->d_replay); cudaFree(s->d_trace);
+    cudaFree(s->d_replay); cudaFree(s->d_trace); cudaFree(s->d_trace_base);
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
+    cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
+    cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HF_OK;
@@ -506,6 +538,7 @@ static int generate_lattice_impl(hf_sim *s, const double *props /* [n_real][3] *
     if (e != cudaSuccess) return fail(HF_ERR_CUDA, "lattice generation failed: %s", cudaGetErrorString(e));
     HF_CUDA(cudaGetLastError());
     s->have_lattice = true;
+    std::fill(s->have_st.begin(), s->have_st.end(), 1);
     return HF_OK;
 }
 
@@ -571,6 +604,7 @@ int hf_upload_lattice(hf_sim *s, int32_t r, const uint8_t *species, const double
     if (s1) HF_CUDA(cudaMemcpyAsync(s->d_s1 + off, s1, N * 8, cudaMemcpyHostToDevice, s->stream));
     if (t1) HF_CUDA(cudaMemcpyAsync(s->d_t1 + off, t1, N * 8, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaStreamSynchronize(s->stream));      // the caller may free its buffers on return
+    s->have_st[(size_t)r] = (s1 && t1) ? 1 : 0;
     s->have_lattice = true;
     return HF_OK;
 }
@@ -622,6 +656,15 @@ int hf_inject(hf_sim *s) {
     HF_CUDA(cudaMemsetAsync(s->d_cache_i, 0, sizeof(int32_t) * 3 * (size_t)P.B * HF_CACHE, s->stream));
     HF_CUDA(cudaMemsetAsync(s->d_cache_tau, 0, sizeof(double) * (size_t)P.B * HF_CACHE, s->stream));
     HF_CUDA(cudaMemsetAsync(s->d_totals, 0, sizeof(unsigned long long) * HF_N_TALLIES, s->stream));
+    if (s->P.xi.mode) {
+        HF_CUDA(cudaMemsetAsync(s->d_pi_n, 0, sizeof(int32_t) * (size_t)P.B, s->stream));
+        HF_CUDA(cudaMemsetAsync(s->d_pi_draws, 0, sizeof(uint64_t) * (size_t)P.B, s->stream));
+        HF_CUDA(cudaMemsetAsync(s->d_pi_clock, 0, sizeof(double) * (size_t)P.B, s->stream));
+    }
+    if (s->d_trace_base) {                                                   // `fired` restarts at 0, so does the trace
+        HF_CUDA(cudaMemsetAsync(s->d_trace_base, 0, sizeof(uint64_t) * s->trace_base.size(), s->stream));
+        std::fill(s->trace_base.begin(), s->trace_base.end(), 0);
+    }
     int32_t *pool = nullptr;
     const int64_t molecules = (int64_t)P.X * P.Y;
     if (molecules <= P.setsize)
@@ -649,14 +692,15 @@ int hf_run(hf_sim *s, int64_t stop) {
     if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
     cudaEvent_t e0 = get_event(s), e1 = get_event(s);
     HF_CUDA(cudaEventRecord(e0, s->stream));
-    if (s->P.C == 1 && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
+    const bool thread_kernels = !(s->cfg.flags & HF_FLAG_WARP_KERNEL) && s->P.dist == 1;   // both are built on the 3x3x3 table
+    if (s->P.C == 1 && thread_kernels && s->P.xi.mode == 0) {
         // one thread per trajectory (hf_frm_c1.cuh)
         const int threads = HF_C1_THREADS;
         const int64_t blocks = (s->P.B + threads - 1) / threads;
         hf_run_c1_kernel<<<(unsigned)blocks, threads, 0, s->stream>>>(s->P);
-    } else if (s->P.C <= HF_SMALL_MAX_CHARGES && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
+    } else if (s->P.C <= HF_SMALL_MAX_CHARGES && thread_kernels) {
         // one thread per trajectory, lists in per-thread shared memory (hf_frm_small.cuh)
-        const size_t smem = hf_small_thread_bytes(s->P.cap_c, s->P.cap_f) * HF_SMALL_THREADS;
+        const size_t smem = hf_small_thread_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P)) * HF_SMALL_THREADS;
         if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_run_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t blocks = (s->P.B + HF_SMALL_THREADS - 1) / HF_SMALL_THREADS;
         hf_run_small_kernel<<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(s->P);
@@ -748,6 +792,12 @@ int hf_read_positions(hf_sim *s, int64_t t, int32_t which, int32_t *sites, int32
     if (rc) return rc;
     if (which == 0) return read_list(s, t, s->P.pos[0], s->P.cap_c, info.n_electrons, sites, n);
     if (which == 1) return read_list(s, t, s->P.pos[1], s->P.cap_c, info.n_holes, sites, n);
+    if (which == 2 && s->P.xi.mode) {   // integrated: the exciton slots, in creation order
+        int32_t cnt = 0;
+        HF_CUDA(cudaMemcpyAsync(&cnt, s->d_pi_n + t, 4, cudaMemcpyDeviceToHost, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+        return read_list(s, t, s->d_pi_site, s->P.cap_c, cnt, sites, n);
+    }
     if (which == 2) {   // _excitons_locations: the exciton lives between its bound and decay steps
         if (!sites || !n) return fail(HF_ERR_BAD_ARG, "null argument");
         if (info.special_kind == HF_EV_DECAY) {
@@ -760,6 +810,65 @@ int hf_read_positions(hf_sim *s, int64_t t, int32_t which, int32_t *sites, int32
         return HF_OK;
     }
     return fail(HF_ERR_BAD_ARG, "which must be 0, 1 or 2");
+}
+
+int hf_p_excitons(hf_sim *s, int32_t mode) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (mode < 0 || mode > 2) return fail(HF_ERR_BAD_ARG, "mode must be 0 (off), 1 (decay at once) or 2 (dynamics)");
+    if (mode == 2 && !s->x_configured) return fail(HF_ERR_STATE, "hf_p_excitons(2) before hf_x_configure: the dynamics use its tables and weights");
+    int rc = use_device(s);
+    if (rc) return rc;
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    const size_t B = (size_t)s->P.B, n = B * (size_t)s->P.cap_c;
+    if (mode && !s->d_pi_site) {
+        if ((rc = dev_alloc(&s->d_pi_site, n)) || (rc = dev_alloc(&s->d_pi_meta, n)) || (rc = dev_alloc(&s->d_pi_final, n)) ||
+            (rc = dev_alloc(&s->d_pi_tau, n)) || (rc = dev_alloc(&s->d_pi_n, B)) || (rc = dev_alloc(&s->d_pi_draws, B)) ||
+            (rc = dev_alloc(&s->d_pi_clock, B))) return rc;
+    }
+    HfIntegrated &I = s->P.xi;
+    memset(&I, 0, sizeof(I));
+    I.mode = mode;
+    I.x_site = s->d_pi_site; I.x_meta = s->d_pi_meta; I.x_final = s->d_pi_final; I.x_tau = s->d_pi_tau;
+    I.x_n = s->d_pi_n; I.x_draws = s->d_pi_draws; I.x_clock = s->d_pi_clock;
+    if (mode == 2) sync_integrated(s);
+    s->injected = false;                               // the event lists change shape: hf_inject starts the trajectories
+    return pick_launch(s);
+}
+
+int hf_read_excitons(hf_sim *s, int64_t t, int32_t *site, int32_t *spin, int32_t *kind, int32_t *final_, double *tau,
+                     int32_t *radiative, int32_t *n, uint64_t *draws, double *clock) {
+    int rc = check_traj(s, t);
+    if (rc) return rc;
+    if (!n) return fail(HF_ERR_BAD_ARG, "null argument");
+    if (!s->P.xi.mode) { *n = 0; if (draws) *draws = 0; if (clock) *clock = 0.0; return HF_OK; }
+    if ((rc = use_device(s))) return rc;
+    int32_t cnt = 0;
+    uint64_t d = 0;
+    double c = 0.0;
+    HF_CUDA(cudaMemcpyAsync(&cnt, s->d_pi_n + t, 4, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(&d, s->d_pi_draws + t, 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(&c, s->d_pi_clock + t, 8, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    if (draws) *draws = d;
+    if (clock) *clock = c;
+    if (*n < cnt) return fail(HF_ERR_BAD_ARG, "buffer too small: need %d", cnt);
+    *n = cnt;
+    if (cnt == 0) return HF_OK;
+    std::vector<int32_t> a((size_t)cnt), b((size_t)cnt), f((size_t)cnt);
+    const size_t off = (size_t)t * (size_t)s->P.cap_c;
+    HF_CUDA(cudaMemcpyAsync(a.data(), s->d_pi_site + off, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(b.data(), s->d_pi_meta + off, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaMemcpyAsync(f.data(), s->d_pi_final + off, 4 * (size_t)cnt, cudaMemcpyDeviceToHost, s->stream));
+    if (tau) HF_CUDA(cudaMemcpyAsync(tau, s->d_pi_tau + off, 8 * (size_t)cnt, cudaMemcpyDeviceToHost, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < cnt; ++i) {
+        if (site) site[i] = unpack_site(s, a[(size_t)i]);
+        if (final_) final_[i] = unpack_site(s, f[(size_t)i]);
+        if (spin) spin[i] = HFI_SPIN(b[(size_t)i]);
+        if (kind) kind[i] = HFI_KIND(b[(size_t)i]);
+        if (radiative) radiative[i] = (b[(size_t)i] & HFI_RAD) ? 1 : 0;
+    }
+    return HF_OK;
 }
 
 int hf_read_flags(hf_sim *s, int64_t t, int32_t which, int32_t *sites, int32_t *n) {
@@ -823,15 +932,28 @@ int hf_set_trace(hf_sim *s, int64_t first, int64_t n, int64_t capacity) {
     int rc = use_device(s);
     if (rc) return rc;
     HF_CUDA(cudaStreamSynchronize(s->stream));
-    cudaFree(s->d_trace);
-    s->d_trace = nullptr;
-    s->P.trace = nullptr;
+    cudaFree(s->d_trace); cudaFree(s->d_trace_base);
+    s->d_trace = nullptr; s->d_trace_base = nullptr;
+    s->P.trace = nullptr; s->P.trace_base = nullptr;
+    s->trace_base.clear();
     s->P.trace_first = s->P.trace_n = s->P.trace_cap = 0;
     if (n > 0) {
         if (first < 0 || first + n > s->P.B || capacity < 1) return fail(HF_ERR_BAD_ARG, "bad trace window");
         if ((rc = dev_alloc(&s->d_trace, (size_t)(n * capacity)))) return rc;
+        if ((rc = dev_alloc(&s->d_trace_base, (size_t)n))) return rc;
         HF_CUDA(cudaMemsetAsync(s->d_trace, 0, sizeof(HfTraceRec) * (size_t)(n * capacity), s->stream));
-        s->P.trace = s->d_trace;
+        // records are indexed from the events each trajectory has fired so far: arming the trace after earlier
+        // hf_run calls loses no slot (hf_inject restarts the count)
+        s->trace_base.assign((size_t)n, 0);
+        if (s->injected) {
+            std::vector<HfScalars> sc((size_t)n);
+            HF_CUDA(cudaMemcpyAsync(sc.data(), s->d_sc + first, sizeof(HfScalars) * (size_t)n, cudaMemcpyDeviceToHost, s->stream));
+            HF_CUDA(cudaStreamSynchronize(s->stream));
+            for (int64_t i = 0; i < n; ++i) s->trace_base[(size_t)i] = sc[(size_t)i].fired;
+        }
+        HF_CUDA(cudaMemcpyAsync(s->d_trace_base, s->trace_base.data(), sizeof(uint64_t) * (size_t)n, cudaMemcpyHostToDevice, s->stream));
+        HF_CUDA(cudaStreamSynchronize(s->stream));
+        s->P.trace = s->d_trace; s->P.trace_base = s->d_trace_base;
         s->P.trace_first = first; s->P.trace_n = n; s->P.trace_cap = capacity;
     }
     cudaFree(s->d_x_trace_len);
@@ -850,7 +972,8 @@ int hf_read_trace(hf_sim *s, int64_t t, hf_event *out, int64_t *n) {
     if (!out || !n) return fail(HF_ERR_BAD_ARG, "null argument");
     if (!s->d_trace || t < s->P.trace_first || t >= s->P.trace_first + s->P.trace_n)
         return fail(HF_ERR_STATE, "trajectory %lld is not traced", (long long)t);
-    int64_t count = (int64_t)info.fired < s->P.trace_cap ? (int64_t)info.fired : s->P.trace_cap;
+    const int64_t since = (int64_t)(info.fired - s->trace_base[(size_t)(t - s->P.trace_first)]);
+    int64_t count = since < s->P.trace_cap ? since : s->P.trace_cap;
     if (*n < count) return fail(HF_ERR_BAD_ARG, "buffer too small: need %lld", (long long)count);
     if (count > 0) {
         HF_CUDA(cudaMemcpyAsync(out, s->d_trace + (t - s->P.trace_first) * s->P.trace_cap, sizeof(hf_event) * (size_t)count,
@@ -879,7 +1002,7 @@ int hf_eval_hops(hf_sim *s, int64_t t, int32_t particule, int32_t n, const int32
     cudaMemcpyAsync(d_i, initial, 4 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
     cudaMemcpyAsync(d_i + n, final_, 4 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
     cudaMemcpyAsync(d_d, u, 8 * (size_t)n, cudaMemcpyHostToDevice, s->stream);
-    const size_t smem = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f);
+    const size_t smem = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P));
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(hf_eval_hops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) {
@@ -924,6 +1047,9 @@ int hf_x_default_params(hf_x_params *p) {
 int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if (!s || !p) return fail(HF_ERR_BAD_ARG, "null argument");
     if (!s->have_lattice) return fail(HF_ERR_STATE, "hf_x_configure before a lattice exists");
+    for (int r = 0; r < s->n_real; ++r)
+        if (!s->have_st[(size_t)r])
+            return fail(HF_ERR_STATE, "realisation %d was uploaded without S1 / T1 energies: the exciton rates need them", r);
     if (!(p->cutoff >= 1.0) || p->cutoff > 6.0)      // <= 32 slots per lane: (M + 3) <= 1024 channels
         return fail(HF_ERR_BAD_ARG, "cutoff must be in [1, 6] lattice constants");
     const int R = (int)std::floor(p->cutoff);
@@ -1019,6 +1145,7 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if ((rc = x_configure_launch(s))) return rc;
     s->x_configured = true;
     s->x_spawned = false;
+    if (s->P.xi.mode == 2) sync_integrated(s);             // the integrated mode reads these tables and weights
     s->xd_configured = false; s->xd_spawned = false;      // the dense devices share these tables and weights
     return HF_OK;
 }

@@ -95,8 +95,8 @@ def all_reduce_tallies(sim) -> dict:
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl":
         t = torch.zeros(HF_N_TALLIES, dtype=torch.int64, device="cuda")
-        sim.set_stream(torch.cuda.current_stream().cuda_stream)
-        sim.reduce_tallies_device(t.data_ptr())
+        sim.reduce_tallies_device(t.data_ptr())          # on the handle's own stream, which it keeps
+        sim.sync()                                       # ... finished before NCCL reads t on torch's stream
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         vec = t.cpu().numpy()
     else:

@@ -26,8 +26,8 @@ from .molecule import (EXCITON, SPECIES_CLASSES, Fluorescent, Host, Molecule, Pr
 
 
 def born_von_karman(position: int, distance: int, size: int, axe: str) -> list[int]:
-    """Neighbour coordinates along one axis, periodic in x and y, open in z, with the exact
-    (distance-1-only) edge behaviour of ``reseau.py:190-205`` (quirk Q3)."""
+    """Neighbour coordinates along one axis, periodic in x and y, open in z, with the exact edge
+    behaviour of ``reseau.py:190-205`` at any distance (quirk Q3: only distance 1 is symmetric)."""
     lower, upper = position - distance, position + distance
     if lower > -1 and upper < size:
         return list(range(lower, upper + 1))
@@ -108,7 +108,7 @@ class Lattice:
             architecture=NotImplemented)                                   # reseau.py:109-111
 
     Keyword-only extras (none changes the behaviour of a positional reference-style call):
-      seed            Philox key; default: fresh OS entropy (the reference is unseeded too)
+      seed            Philox key; default: $HF_SEED if set, else fresh OS entropy (the reference is unseeded too)
       trajectories    independent trajectories carried by this object (default 1).  Tallies and
                       IQE are then sums over all of them.
       realisations    independent lattice realisations shared by the trajectories (default 1)
@@ -129,11 +129,10 @@ class Lattice:
         molecules = self._dimension.x * self._dimension.y
         if self._charges > molecules:                                              # reseau.py:212-213
             raise ValueError(f"Required {self._charges} charges but only {molecules} molecules available.")
-        if charge_tranfer_distance != 1:
-            raise NotImplementedError(
-                "charge_tranfer_distance != 1 is not supported: the reference's neighbour table is only "
-                "well defined for distance 1 (reseau.py:190-205)")
+        # any distance: the device builds _born_von_karman's table verbatim, seams and duplicates included (Q3)
         self._distance = charge_tranfer_distance
+        if seed is None and os.environ.get("HF_SEED"):         # unmodified reference scripts cannot pass seed=
+            seed = int(os.environ["HF_SEED"], 0)
         self._seed_value = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self._trajectories = int(trajectories)
         self._sim = nat.Sim(dimension, (self._proportions.host, self._proportions.tadf, self._proportions.fluo),

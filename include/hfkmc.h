@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define HF_ABI_VERSION 1
+#define HF_ABI_VERSION 2
 
 typedef struct hf_sim hf_sim;
 
@@ -43,7 +43,7 @@ typedef enum hf_status {
     HF_ERR_BAD_ARG = 1,       /* TypeError / IndexError / ValueError of reseau.py:126-139, 212-213 */
     HF_ERR_CUDA = 2,          /* a CUDA runtime call failed; see hf_last_error()                   */
     HF_ERR_NO_DEVICE = 3,     /* no sm_100 device: the product has no CPU path                     */
-    HF_ERR_UNSUPPORTED = 4,   /* charge_tranfer_distance != 1 (quirk Q3), capacity limits          */
+    HF_ERR_UNSUPPORTED = 4,   /* capacity limits (dimensions > 1023, charge_tranfer_distance > 8)  */
     HF_ERR_STATE = 5          /* call order (e.g. hf_run before a lattice exists)                  */
 } hf_status;
 
@@ -78,7 +78,7 @@ typedef struct hf_config {
     double props[3];             /* (host, tadf, fluo) AFTER quirk Q1 (reseau.py:143-145)            */
     double electric_field;       /* eV/nm, default 0.1 (reseau.py:110)                               */
     int32_t charges;             /* electrons = holes = charges (reseau.py:152)                      */
-    int32_t distance;            /* charge_tranfer_distance; only 1 is supported (quirk Q3)          */
+    int32_t distance;            /* charge_tranfer_distance 1..8: reseau.py:190-205 verbatim (Q3)    */
     int64_t n_trajectories;      /* independent Lattice instances ("devices") held by this handle    */
     int32_t n_realisations;      /* lattice realisations; must divide n_trajectories; trajectory i   */
                                  /* runs on realisation i / (n_trajectories / n_realisations)        */
@@ -124,7 +124,8 @@ enum {
     HF_T_RECOMB_HOST = 11, HF_T_RECOMB_TADF = 12, HF_T_RECOMB_FLUO = 13,
     HF_T_EMIT_TADF = 14, HF_T_EMIT_FLUO = 15,
     HF_T_STOPPED = 16,           /* trajectories whose status != HF_TRAJ_OK                          */
-    HF_N_TALLIES = 20
+    HF_T_X_FORSTER = 17, HF_T_X_DEXTER = 18, HF_T_X_ISC = 19, HF_T_X_RISC = 20,   /* integrated excitons (hf_p_excitons)  */
+    HF_N_TALLIES = 24
 };
 
 const char *hf_last_error(void);
@@ -188,6 +189,22 @@ int hf_read_infos(hf_sim *sim, int64_t first, int64_t n, hf_traj_info *out);
 /* Lattice._electrons_locations / _holes_locations / _excitons_locations in list order
  * (which = 0 / 1 / 2; reseau.py:208-210, 617-621).  *n in: capacity, out: length. */
 int hf_read_positions(hf_sim *sim, int64_t trajectory, int32_t which, int32_t *sites, int32_t *n);
+/* Integrated exciton dynamics — the slots the reference reserves and leaves empty: _move_exciton_events /
+ * _isc_events / _decay_events (reseau.py:233-235), the `...` branches of the dispatcher (reseau.py:526-550, routing
+ * comment 533), TADF.intersystem_crossing (molecule.py:299-307).  OWN MODEL beyond mode 1 (specification: the
+ * "integrated excitons" block of oracle/frm_oracle.c).  mode 0: off, the reference as it is (the exciton decays at
+ * tau = 0 on the site it formed on, reseau.py:529-533); 1: the same behaviour routed through the exciton slots and
+ * lists (bit-identical to mode 0: the parity gate of the new code path); 2: the exciton formed by a `bound` event
+ * hops (Forster / Dexter), crosses (ISC / RISC) and decays (radiatively or not) in the SAME First Reaction Method as
+ * the carriers, with the parameters, tables and Boltzmann weights of hf_x_configure (call it first).  Changing the
+ * mode needs a new hf_inject. */
+int hf_p_excitons(hf_sim *sim, int32_t mode);
+/* Exciton slots of one trajectory in creation order: site, spin (HF_X_*), and the pending event of each — kind
+ * (HF_EV_FORSTER / HF_EV_MOVE transfer, HF_EV_ISC, HF_EV_DECAY), final site, residual tau, radiative flag: the
+ * contents of _move_exciton_events / _isc_events / _decay_events.  *n in: capacity, out: count.  draws: uniforms
+ * consumed on the trajectory's exciton stream; clock: simulated time (s).  Any output may be NULL. */
+int hf_read_excitons(hf_sim *sim, int64_t trajectory, int32_t *site, int32_t *spin, int32_t *kind, int32_t *final_,
+                     double *tau, int32_t *radiative, int32_t *n, uint64_t *draws, double *clock);
 /* Sites whose Molecule.electron (which=0) / .hole (which=1) flag is True (molecule.py:69-70). */
 int hf_read_flags(hf_sim *sim, int64_t trajectory, int32_t which, int32_t *sites, int32_t *n);
 /* Lattice._move_electron_events (which=0) / _move_hole_events (which=1) in list order
@@ -208,8 +225,9 @@ int hf_read_trace(hf_sim *sim, int64_t trajectory, hf_event *out, int64_t *n);
 int hf_eval_hops(hf_sim *sim, int64_t trajectory, int32_t particule, int32_t n, const int32_t *initial,
                  const int32_t *final_, const double *u, double *tau, double *rate, int32_t *zero_division);
 
-/* Timing helper for bench.py: average device time (ms) of the hf_run launches issued since the
- * last call, measured with CUDA events on the handle's stream, and their count. */
+/* Timing helper for bench.py: TOTAL device time (ms) of the hf_run / hf_x_run / hf_xd_run launches issued
+ * since the last call, measured with CUDA events on the handle's stream, and their count (the average is
+ * total_ms / launches).  Resets both. */
 int hf_run_timing(hf_sim *sim, double *total_ms, int64_t *launches);
 
 /* =====================================================================================================

@@ -59,6 +59,11 @@ def lib():
         L.hfo_neighbourhood.restype = i32
         L.hfo_neighbourhood.argtypes = [p, i32, C.c_int32, p, i32]
         L.hfo_run_batch.argtypes = [p, i32, f64, i32, u64, i64, i64, i64, i32, p]
+        L.hfo_traj_set_excitons.argtypes = [p, i32, i32] + [p] * 11
+        L.hfo_traj_excitons.restype = i32
+        L.hfo_traj_excitons.argtypes = [p] * 8
+        L.hfo_traj_channels.argtypes = [p, p, p]
+        L.hfo_run_batch_x.argtypes = [p, i32, f64, i32, u64, i64, i64, i64, i32, i32, i32] + [p] * 12
         L.hfo_contract_uniform.restype = f64
         L.hfo_contract_uniform.argtypes = [u64, u32, u32, u64]
         _lib = L
@@ -125,6 +130,15 @@ class OracleLattice:
             raise IndexError("neighbour outside the grid")
         return buf[:n].copy()
 
+    def run_batch_x(self, charges, field, seed, first_trajectory, n_trajectories, stop, model, n_threads=1, distance=1):
+        """run_batch with integrated excitons (own model): ``model`` is an ``ExcitonModel``."""
+        out = np.zeros(15, np.int64)
+        lib().hfo_run_batch_x(self._h, charges, float(field), distance, int(seed), int(first_trajectory),
+                              int(n_trajectories), int(stop), int(n_threads), *model.args(), _ptr(out))
+        names = ("emission", "recombination", "injection", "events", "stopped_early", "forster", "dexter", "isc", "risc",
+                 "recomb_host", "recomb_tadf", "recomb_fluo", "emit_host", "emit_tadf", "emit_fluo")
+        return {k: int(v) for k, v in zip(names, out)}
+
     def run_batch(self, charges, field, seed, first_trajectory, n_trajectories, stop, n_threads=1, distance=1):
         out = np.zeros(5, np.int64)
         lib().hfo_run_batch(self._h, charges, float(field), distance, int(seed), int(first_trajectory),
@@ -138,6 +152,28 @@ class OracleLattice:
             self._h = None
 
 
+class ExcitonModel:
+    """Integrated exciton dynamics (own model, frm_oracle.c header).  mode 1: decay at once through the exciton
+    slots (the reference's behaviour); mode 2: dynamics with the exciton path's parameters, tables and tagged
+    Boltzmann weights (the arrays of oracle/exciton_oracle.py or the device's own)."""
+
+    def __init__(self, mode, params=None, tables=None, ws1=None, wt1=None):
+        self.mode = int(mode)
+        if self.mode == 2:
+            f = lambda a, t=np.float64: np.ascontiguousarray(a, t)
+            self.off = f(tables["offsets"], np.int8)
+            self.g6, self.gd, self.kf, self.kd = f(tables["g6"]), f(tables["gd"]), f(tables["kf"]), f(tables["kd"])
+            self.k_isc, self.k_risc = f(params["k_isc"]), f(params["k_risc"])
+            self.k_rad, self.k_nonrad = f(params["k_rad"]), f(params["k_nonrad"])
+            self.ws1, self.wt1 = f(ws1), f(wt1)
+
+    def args(self):
+        if self.mode != 2:
+            return [self.mode, 0] + [None] * 11
+        return [self.mode, int(self.g6.size)] + [_ptr(a) for a in (self.off, self.g6, self.gd, self.kf, self.kd, self.k_isc,
+                                                                  self.k_risc, self.k_rad, self.k_nonrad, self.ws1, self.wt1)]
+
+
 class OracleTrajectory:
     """One reference ``Lattice`` instance's dynamic state on a given realisation."""
 
@@ -149,6 +185,30 @@ class OracleTrajectory:
                                         int(trajectory), None if self._replay is None else _ptr(self._replay),
                                         0 if self._replay is None else self._replay.size, C.byref(st))
         self.status = STATUS[st.value]
+        self._model = None
+
+    def set_excitons(self, model: "ExcitonModel"):
+        """Integrated excitons (own model); call before the first run."""
+        self._model = model                                   # keeps the arrays alive
+        lib().hfo_traj_set_excitons(self._h, *model.args())
+
+    def excitons(self):
+        n = lib().hfo_traj_excitons(self._h, None, None, None, None, None, None, None)
+        a = {k: np.zeros(n, np.int32) for k in ("site", "spin", "kind", "final", "rad", "onflags")}
+        a["tau"] = np.zeros(n, np.float64)
+        if n:
+            lib().hfo_traj_excitons(self._h, *(_ptr(a[k]) for k in ("site", "spin", "kind", "final", "tau", "rad", "onflags")))
+        return a
+
+    def channels(self):
+        out = np.zeros(12, np.int64)
+        clock = C.c_double(0)
+        lib().hfo_traj_channels(self._h, _ptr(out), C.byref(clock))
+        names = ("forster", "dexter", "isc", "risc", "recomb_host", "recomb_tadf", "recomb_fluo",
+                 "emit_host", "emit_tadf", "emit_fluo", "xdraws")
+        d = {k: int(v) for k, v in zip(names, out)}
+        d["clock"] = clock.value
+        return d
 
     def run(self, stop, trace=True):
         stop = int(stop)

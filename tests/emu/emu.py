@@ -60,9 +60,42 @@ def generate(dims, props, seed, realisation=0):
     return out
 
 
-def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_calls=1, replay=None, small_kernel=False):
+class EmuXModel(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("M", C.c_int32)] + [(k, C.c_void_p) for k in (
+        "offsets", "g6", "gd", "kf", "kd", "k_isc", "k_risc", "k_rad", "k_nonrad", "ws1", "wt1")] + \
+        [("w_stride", C.c_int64), ("w_halo", C.c_int64)]
+
+
+def xmodel(mode, dims=None, params=None, tables=None, ws1=None, wt1=None):
+    """The integrated exciton model as the device would hold it (P.xi): packed offsets, haloed tagged weights."""
+    m = EmuXModel()
+    m.mode = int(mode)
+    keep = []
+    if m.mode == 2:
+        import math
+        off = np.asarray(tables["offsets"], np.int32)
+        packed = np.ascontiguousarray((off[:, 0] + 128) | ((off[:, 1] + 128) << 8) | ((off[:, 2] + 128) << 16), np.int32)
+        halo = int(math.ceil(params["cutoff"])) * dims[0] * dims[1]
+        N = dims[0] * dims[1] * dims[2]
+        def haloed(w):
+            out = np.zeros(N + 2 * halo)
+            out[halo:halo + N] = w
+            return out
+        arrs = dict(offsets=packed, g6=tables["g6"], gd=tables["gd"], kf=tables["kf"], kd=tables["kd"], k_isc=params["k_isc"],
+                    k_risc=params["k_risc"], k_rad=params["k_rad"], k_nonrad=params["k_nonrad"], ws1=haloed(ws1), wt1=haloed(wt1))
+        for k, v in arrs.items():
+            a = v if k == "offsets" else np.ascontiguousarray(v, np.float64)
+            keep.append(a)
+            setattr(m, k, a.ctypes.data)
+        m.M, m.w_stride, m.w_halo = int(packed.size), N + 2 * halo, halo
+    m._keep = keep
+    return m
+
+
+def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_calls=1, replay=None, small_kernel=False,
+        distance=1, excitons=None):
     dims = tuple(int(v) for v in dims)
-    cap, cap_f = charges, (2 if charges == 1 else 2 * charges + 8)
+    cap, cap_f = charges, (2 if (charges == 1 and distance == 1) else 2 * charges + 8)
     trace_cap = stop * n_calls
     trace = np.zeros(max(trace_cap, 1), EVENT_DTYPE)
     ints = np.zeros(12, np.int32)
@@ -70,7 +103,8 @@ def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_cal
     lists = np.zeros(6 * cap, np.int32)
     flags = np.zeros(2 * cap_f, np.int32)
     taus = np.zeros(2 * cap, np.float64)
-    totals = np.zeros(20, np.uint64)
+    totals = np.zeros(24, np.uint64)
+    x_ints, x_tau, x_scal = np.zeros(3 * cap, np.int32), np.zeros(cap, np.float64), np.zeros(3, np.float64)
     cache_i = np.zeros(30, np.int32)
     cache_tau = np.zeros(10, np.float64)
     init_lists = np.zeros(6 * cap, np.int32)
@@ -84,8 +118,9 @@ def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_cal
     rc = lib().emu_run(d, C.c_double(field), C.c_int32(charges), C.c_uint64(seed), C.c_uint32(trajectory),
                        _p(species), _p(homo), _p(lumo), None if rp is None else _p(rp),
                        C.c_int64(0 if rp is None else rp.size), C.c_int64(stop), C.c_int32(n_calls),
-                       C.c_int32(int(small_kernel)), _p(trace), C.c_int64(trace_cap), _p(ints), _p(u64), _p(lists), _p(flags), _p(taus),
-                       _p(totals), _p(cache_i), _p(cache_tau), _p(init_lists), _p(init_taus), _p(init_counts))
+                       C.c_int32(int(small_kernel)), C.c_int32(int(distance)), _p(trace), C.c_int64(trace_cap), _p(ints), _p(u64), _p(lists), _p(flags), _p(taus),
+                       _p(totals), _p(cache_i), _p(cache_tau), _p(init_lists), _p(init_taus), _p(init_counts),
+                       None if excitons is None else C.byref(excitons), _p(x_ints), _p(x_tau), _p(x_scal))
     if rc:
         raise RuntimeError(f"emu_run failed ({rc})")
     n_e, n_h, n_fe, n_fh, n_me, n_mh = (int(v) for v in ints[:6])
@@ -104,6 +139,12 @@ def run(dims, field, charges, seed, trajectory, species, homo, lumo, stop, n_cal
         cache_init=unpack(cache_i[0:10], dims), cache_final=unpack(cache_i[10:20], dims), cache_kp=cache_i[20:30].copy(),
         cache_tau=cache_tau,
     )
+    if excitons is not None and excitons.mode:
+        nx = int(x_scal[0])
+        meta = x_ints[cap:cap + nx]
+        out.update(x_site=unpack(x_ints[:nx], dims), x_spin=meta & 3, x_onsite=(meta >> 2) & 1, x_rad=(meta >> 3) & 1,
+                   x_kind=(meta >> 4) & 15, x_final=unpack(x_ints[2 * cap:2 * cap + nx], dims), x_tau=x_tau[:nx].copy(),
+                   xdraws=int(x_scal[1]), clock=float(x_scal[2]))
     ne0, nh0, nme0, nmh0, st0 = (int(v) for v in init_counts)
     out.update(
         init_status=st0,

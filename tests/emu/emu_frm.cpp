@@ -19,7 +19,11 @@ struct Buffers {
     std::vector<HfScalars> sc;
     std::vector<unsigned long long> totals;
     std::vector<HfTraceRec> trace;
+    std::vector<uint64_t> trace_base;
     std::vector<int32_t> pool;
+    std::vector<int32_t> x_site, x_meta, x_final, x_n;
+    std::vector<double> x_tau, x_clock;
+    std::vector<uint64_t> x_draws;
 };
 
 void wire(HfParams &P, Buffers &b, int64_t trace_cap) {
@@ -40,7 +44,33 @@ void wire(HfParams &P, Buffers &b, int64_t trace_cap) {
     P.cache_init = b.cache_i.data(); P.cache_final = b.cache_i.data() + B * HF_CACHE; P.cache_kp = b.cache_i.data() + 2 * B * HF_CACHE;
     P.cache_tau = b.cache_tau.data();
     P.totals = b.totals.data();
+    b.trace_base.assign(B, 0); P.trace_base = b.trace_base.data();
     P.trace = b.trace.data(); P.trace_first = 0; P.trace_n = B; P.trace_cap = trace_cap;
+    if (P.xi.mode) {
+        b.x_site.assign(B * P.cap_c, 0); b.x_meta.assign(B * P.cap_c, 0); b.x_final.assign(B * P.cap_c, 0);
+        b.x_tau.assign(B * P.cap_c, 0.0); b.x_n.assign(B, 0); b.x_clock.assign(B, 0.0); b.x_draws.assign(B, 0);
+        P.xi.x_site = b.x_site.data(); P.xi.x_meta = b.x_meta.data(); P.xi.x_final = b.x_final.data();
+        P.xi.x_tau = b.x_tau.data(); P.xi.x_n = b.x_n.data(); P.xi.x_clock = b.x_clock.data(); P.xi.x_draws = b.x_draws.data();
+    }
+}
+
+// Integrated exciton model of an emulated run (P.xi): mode 0 / 1 need nothing else; mode 2 takes the tables and
+// the haloed, tagged weights exactly as hf_x_configure would have built them on the device.
+struct EmuXModel {
+    int32_t mode, M;
+    const int32_t *offsets; const double *g6, *gd, *kf, *kd, *k_isc, *k_risc, *k_rad, *k_nonrad, *ws1, *wt1;
+    int64_t w_stride, w_halo;
+};
+void apply_xmodel(HfParams &P, const EmuXModel *m) {
+    memset(&P.xi, 0, sizeof(P.xi));
+    if (!m) return;
+    P.xi.mode = m->mode;
+    if (m->mode != 2) return;
+    P.xi.M = m->M; P.xi.offsets = m->offsets; P.xi.g6 = m->g6; P.xi.gd = m->gd;
+    memcpy(P.xi.kf, m->kf, sizeof(P.xi.kf)); memcpy(P.xi.kd, m->kd, sizeof(P.xi.kd));
+    memcpy(P.xi.k_isc, m->k_isc, sizeof(P.xi.k_isc)); memcpy(P.xi.k_risc, m->k_risc, sizeof(P.xi.k_risc));
+    memcpy(P.xi.k_rad, m->k_rad, sizeof(P.xi.k_rad)); memcpy(P.xi.k_nonrad, m->k_nonrad, sizeof(P.xi.k_nonrad));
+    P.xi.ws1 = m->ws1; P.xi.wt1 = m->wt1; P.xi.w_stride = m->w_stride; P.xi.w_halo = m->w_halo;
 }
 
 struct InjectArgs { const HfParams *P; int32_t *pool; };
@@ -98,15 +128,19 @@ int emu_generate(const int32_t dims[3], const double props[3], uint64_t seed, ui
 //            me_final, mh_final; flags_out: 2 blocks of cap_f; taus_out: 2 blocks of cap doubles.
 int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed, uint32_t trajectory,
             const uint8_t *species, const double *homo, const double *lumo,
-            const double *replay, int64_t n_replay, int64_t stop, int32_t n_calls, int32_t small_kernel,
+            const double *replay, int64_t n_replay, int64_t stop, int32_t n_calls, int32_t small_kernel, int32_t distance,
             HfTraceRec *trace_out, int64_t trace_cap,
             int32_t *ints_out, uint64_t *u64_out, int32_t *lists_out, int32_t *flags_out, double *taus_out,
             unsigned long long *totals_out, int32_t *cache_i_out, double *cache_tau_out,
-            int32_t *init_lists_out, double *init_taus_out, int32_t *init_counts_out) {
+            int32_t *init_lists_out, double *init_taus_out, int32_t *init_counts_out,
+            const EmuXModel *xmodel, int32_t *x_ints_out /* [3][cap]: site, meta, final */, double *x_tau_out /* [cap] */,
+            double *x_scalars_out /* n_x, draws, clock */) {
     HfParams P;
     memset(&P, 0, sizeof(P));
+    apply_xmodel(P, xmodel);
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
-    P.field = field; P.C = charges; P.cap_c = charges; P.cap_f = charges == 1 ? 2 : 2 * charges + 8;
+    P.field = field; P.C = charges; P.cap_c = charges; P.cap_f = (charges == 1 && distance == 1) ? 2 : 2 * charges + 8;
+    P.dist = distance;
     P.B = 1; P.traj_per_real = 1;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = trajectory; P.first_real = 0;
     P.setsize = sample_setsize(charges);
@@ -114,7 +148,7 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
     P.replay = replay; P.n_replay = n_replay;
     Buffers b;
     wire(P, b, trace_cap);
-    if (hf_warp_smem_bytes(P.cap_c, P.cap_f) > sizeof(hf_smem)) return 2;
+    if (hf_warp_smem_bytes(P.cap_c, P.cap_f, hf_xcap(P)) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     b.pool.assign((size_t)((int64_t)P.X * P.Y), 0);
     InjectArgs ia{&P, b.pool.data()};
@@ -131,7 +165,7 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
             init_lists_out[(4 + t) * cap + i] = P.ev_final[t][i];
             init_taus_out[t * cap + i] = P.ev_tau[t][i];
         }
-    if (small_kernel && (charges < 2 || charges > HF_SMALL_MAX_CHARGES || hf_small_thread_bytes(P.cap_c, P.cap_f) * 32 > sizeof(hf_smem))) return 4;
+    if (small_kernel && (charges < 1 || charges > HF_SMALL_MAX_CHARGES || hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P)) * 32 > sizeof(hf_smem))) return 4;
     for (int c = 0; c < n_calls; ++c) {
         P.n_steps = stop;
         emu_run_warp(small_kernel ? run_small_body : run_body, &P);      // thread kernel: lane 0 owns the trajectory
@@ -151,9 +185,16 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
         }
         for (int i = 0; i < P.cap_f; ++i) flags_out[t * P.cap_f + i] = P.flag[t][i];
     }
-    memcpy(totals_out, b.totals.data(), sizeof(unsigned long long) * 20);
+    memcpy(totals_out, b.totals.data(), sizeof(unsigned long long) * 24);
     memcpy(cache_i_out, b.cache_i.data(), sizeof(int32_t) * 3 * HF_CACHE);
     memcpy(cache_tau_out, b.cache_tau.data(), sizeof(double) * HF_CACHE);
+    if (P.xi.mode && x_ints_out) {
+        for (int i = 0; i < cap; ++i) {
+            x_ints_out[i] = b.x_site[i]; x_ints_out[cap + i] = b.x_meta[i]; x_ints_out[2 * cap + i] = b.x_final[i];
+            x_tau_out[i] = b.x_tau[i];
+        }
+        x_scalars_out[0] = (double)b.x_n[0]; x_scalars_out[1] = (double)b.x_draws[0]; x_scalars_out[2] = b.x_clock[0];
+    }
     const int64_t n = (int64_t)sc.fired < trace_cap ? (int64_t)sc.fired : trace_cap;
     memcpy(trace_out, b.trace.data(), sizeof(HfTraceRec) * (size_t)n);
     return 0;
@@ -173,7 +214,7 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
     HfParams P;
     memset(&P, 0, sizeof(P));
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
-    P.field = field; P.C = 1; P.cap_c = 1; P.cap_f = 2;
+    P.field = field; P.C = 1; P.cap_c = 1; P.cap_f = 2; P.dist = 1;
     P.B = B; P.traj_per_real = B;
     P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = first_traj; P.first_real = 0;
     P.setsize = sample_setsize(1);

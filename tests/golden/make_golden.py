@@ -65,6 +65,12 @@ CASES = [
     ("c1_tiny333_s21", (3, 3, 3), (0.5, 0.3, 0.2), 1, 21, 3000, {}),
     ("c1_rag443_s22", (4, 4, 3), (0.5, 0.3, 0.2), 1, 22, 3000, {}),
     ("c1_rag554_s23", (5, 5, 4), (0.6, 0.3, 0.1), 1, 23, 3000, {"trajectory": 3}),
+    # charge_tranfer_distance > 1: _born_von_karman's table as the reference builds it (reseau.py:190-205, quirk Q3):
+    # 124 neighbours in the bulk, asymmetric / duplicated entries near the seams, lattices thinner than 2d+1
+    ("dist2_s31", (10, 10, 6), DEFAULT_PROPS, 4, 31, 1500, {"distance": 2}),
+    ("dist2_thin_s32", (5, 4, 4), (0.5, 0.3, 0.2), 2, 32, 1200, {"distance": 2}),
+    ("dist3_s33", (9, 8, 7), DEFAULT_PROPS, 3, 33, 800, {"distance": 3}),
+    ("dist2_c1_s34", (8, 8, 5), DEFAULT_PROPS, 1, 34, 1500, {"distance": 2}),
 ]
 
 

@@ -368,6 +368,156 @@ def test_facade_matches_oracle_and_oled_driver(nat, capsys):
     test.close()
 
 
+@pytest.mark.parametrize("dims,props,seed", [((3, 3, 3), (0.5, 0.3, 0.2), 777), ((4, 4, 3), (0.5, 0.3, 0.2), 778)])
+def test_adjacent_charges_screening_is_exact(nat, dims, props, seed):
+    """The fp32 screening pass of hf_c1_gen neglects the Coulomb term of the opposite charge (hf_frm_c1.cuh: at most
+    C_e / kT = 1.9e-5 relative, most with the two carriers on neighbouring sites).  On these lattices the carriers
+    are neighbours most of the time: > 10^6 events regenerated next to the opposite charge, every trajectory compared
+    with the C restatement, which evaluates all candidates exactly (reseau.py:283-345, 380-396)."""
+    from oracle import frm_oracle as fo
+    B, steps = 8192, 800
+    sim = nat.Sim(dims, props, 0.1, 1, 1, n_trajectories=B, seed=seed)
+    try:
+        sim.generate_lattice()
+        sim.inject()
+        sim.run(steps)
+        sim.sync()
+        lat = sim.download_lattice(0)
+        infos = sim.infos(0, B)
+        pos = [(sim.positions(t, 0).tolist(), sim.positions(t, 1).tolist(), sim.move_events(t, 0), sim.move_events(t, 1))
+               for t in range(0, B, 64)]
+        tallies = sim.tallies()
+    finally:
+        sim.close()
+    olat = fo.OracleLattice.from_arrays(dims, lat["species"], lat["homo"], lat["lumo"])
+    X, Y = dims[0], dims[1]
+    near = moves = 0
+    for t in range(B):
+        o = fo.OracleTrajectory(olat, 1, seed, t, 0.1)
+        if t % 64 == 0 and t < 2048:
+            # how often the regenerated charge sits next to the opposite one (sampled on 32 trajectories)
+            for _ in range(steps):
+                n, tr = o.run(1)
+                if n and tr["kind"][0] == 1:
+                    e, h = o.positions("electrons"), o.positions("holes")
+                    if len(e) and len(h):
+                        moves += 1
+                        de = [abs(int(e[0]) % X - int(h[0]) % X), abs(int(e[0]) // X % Y - int(h[0]) // X % Y),
+                              abs(int(e[0]) // (X * Y) - int(h[0]) // (X * Y))]
+                        near += max(de) <= 1
+        else:
+            o.run(steps, trace=False)
+        ot, info = o.tallies(), infos[t]
+        assert [int(info[k]) for k in ("emission", "recombination", "injection", "steps", "draws", "spins", "status")] == \
+            [ot["emission"], ot["recombination"], ot["injection"], ot["step"], ot["draws"], ot["spins"], 0], t
+        if t % 64 == 0:
+            e, h, me, mh = pos[t // 64]
+            assert e == o.positions("electrons").tolist() and h == o.positions("holes").tolist()
+            for got, name in ((me, "move_e"), (mh, "move_h")):
+                ev = o.events(name)
+                assert np.array_equal(got[1], ev["final"])
+                _assert_tau(got[2], ev["tau"], 1e-9)
+    regenerated_near = near / max(moves, 1) * (tallies["move_e"] + tallies["move_h"])
+    assert regenerated_near > 1e6, (near, moves, regenerated_near)
+
+
+def test_channel_fractions_over_1e5_trajectories(nat):
+    """The north_star's statistical gate: EQE (here IQE, the only efficiency the reference defines, reseau.py:595)
+    and CHANNEL FRACTIONS over 10^5 trajectories within 3 sigma of the unmodified reference —
+    tests/golden/stats_d0_1e5.npz holds 10^5 unmodified runs of OLED.py's own device (OLED.py:6-11: 10x10x5,
+    charges = 4, operations(100)) with the species every exciton decayed on and whether it emitted
+    (make_golden.py --stats-d0-1e5).  Device: 10^5 trajectories, one lattice realisation each, like the reference."""
+    import os
+    from tests.conftest import GOLDEN_DIR
+    ref = np.load(os.path.join(GOLDEN_DIR, "stats_d0_1e5.npz"))
+    dims = tuple(int(v) for v in ref["dims"])
+    props = tuple(float(v) for v in ref["props"])
+    charges, steps = int(ref["charges"]), int(ref["steps"])
+    B = 100_000
+    sim = nat.Sim(dims, props, 0.1, charges, 1, n_trajectories=B, n_realisations=B, seed=20261020)
+    try:
+        sim.generate_lattice()
+        sim.inject()
+        sim.run(steps)
+        sim.sync()
+        infos = sim.infos(0, B)
+        t = sim.tallies()
+    finally:
+        sim.close()
+    em, rec, inj = (infos[k].astype(float) for k in ("emission", "recombination", "injection"))
+    n_ref = ref["emission"].size
+    assert n_ref >= 100_000
+    # per-run means: recombinations, emissions, IQE (a swallowed ZeroDivisionError leaves IQE at 0: reseau.py:585-595)
+    stopped = infos["status"] != 0
+    iqe = np.where(stopped, 0.0, 200.0 * em / inj)
+    for name, ours, theirs in (("recombination", rec, ref["recombination"].astype(float)),
+                               ("emission", em, ref["emission"].astype(float)),
+                               ("IQE", iqe, ref["iqe"].astype(float))):
+        sigma = np.sqrt(ours.var(ddof=1) / ours.size + theirs.var(ddof=1) / theirs.size)
+        assert abs(ours.mean() - theirs.mean()) < 3 * sigma, (name, ours.mean(), theirs.mean(), sigma)
+    # channel fractions: where excitons decay and where photons come from (binomial proportions, pooled sigma)
+    ref_rec = float(ref["recombination"].sum())
+    ref_em = float(ref["emission"].sum())
+    for name, k_ours, n_ours, k_ref, n_r in (
+            ("recomb_host", t["recomb_host"], t["recombination"], float(ref["recomb_host"].sum()), ref_rec),
+            ("recomb_tadf", t["recomb_tadf"], t["recombination"], float(ref["recomb_tadf"].sum()), ref_rec),
+            ("recomb_fluo", t["recomb_fluo"], t["recombination"], float(ref["recomb_fluo"].sum()), ref_rec),
+            ("emit_tadf", t["emit_tadf"], t["emission"], float(ref["emit_tadf"].sum()), ref_em),
+            ("emit_fluo", t["emit_fluo"], t["emission"], float(ref["emit_fluo"].sum()), ref_em),
+            ("photons_per_recombination", t["emission"], t["recombination"], ref_em, ref_rec)):
+        p1, p2 = k_ours / n_ours, k_ref / n_r
+        pool = (k_ours + k_ref) / (n_ours + n_r)
+        sigma = np.sqrt(pool * (1 - pool) * (1 / n_ours + 1 / n_r))
+        assert abs(p1 - p2) < 3 * sigma + 1e-12, (name, p1, p2, sigma)
+    assert float(ref["emit_host"].sum()) == 0 and t["recombination"] > 50_000
+
+
+REFERENCE_STYLE_DRIVER = """
+from time import time
+from reseau import Lattice
+from plot import plot
+from event import EVENTS, Point
+from molecule import Host, TADF, Fluorescent
+import constants
+
+started = time()
+device = Lattice((10, 10, 5), (0.84, 0.15, 0.01), charges = 4)
+device.operations(10**2)
+electrons, holes, excitons = device.get_particules_positions()
+assert len(electrons) + len(excitons) <= 4 and all(kind in (Host, TADF, Fluorescent) for _, kind in electrons + holes)
+assert callable(plot) and EVENTS["move"] == 1 and isinstance(electrons[0][0], Point)
+print(f"IQE : {device.get_IQE()}")
+print(f"emissions : {device._emission}")
+print(f"injections : {device._injection}")
+print(f"{time() - started} s")
+"""
+
+
+def test_dropin_shims_run_a_reference_style_script(nat, tmp_path):
+    """The zero-touch path of INTEGRATION.md section 1: a script written against the reference's flat modules
+    (`from reseau import Lattice; from plot import plot`, the statements of OLED.py:1-22) runs unmodified in a
+    fresh interpreter with only PYTHONPATH=hyperfluorescence_b200/dropin, and prints what the oracle computes for
+    the same seed (the shim has no seed argument: $HF_SEED)."""
+    import os
+    import subprocess
+    import sys
+    from oracle import frm_oracle as fo
+    from tests.conftest import ROOT
+    script = tmp_path / "driver.py"
+    script.write_text(REFERENCE_STYLE_DRIVER)
+    seed = 424242
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "hyperfluorescence_b200", "dropin"), HF_SEED=str(seed))
+    res = subprocess.run([sys.executable, str(script)], cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = dict(l.split(" : ") for l in res.stdout.splitlines() if " : " in l)
+    olat = fo.OracleLattice.generate((10, 10, 5), (0.84, 0.15, 0.01), seed)
+    otr = fo.OracleTrajectory(olat, 4, seed, 0, 0.1)
+    otr.run(100)
+    t = otr.tallies()
+    assert float(lines["IQE"]) == t["IQE"]
+    assert (int(lines["emissions"]), int(lines["injections"])) == (t["emission"], t["injection"])
+
+
 def test_zero_division_is_swallowed_like_the_reference(nat, capsys):
     """dense_s8 hits ZeroDivisionError at step 111 (two electrons on one site): operations() prints
     the cache and returns without refreshing IQE; a later call continues (reseau.py:585-589)."""

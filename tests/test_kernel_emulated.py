@@ -47,13 +47,13 @@ def test_emulated_kernel_matches_reference(golden, small_kernel):
     """small_kernel: the thread-per-trajectory kernel for 2 <= charges <= 12 (hf_frm_small.cuh): hf_step<1>
     and the screened candidate loop must reproduce the same golden trajectories."""
     g = golden
-    if small_kernel and not 2 <= g["charges"] <= 12:
+    if small_kernel and (not 2 <= g["charges"] <= 12 or g["distance"] != 1):
         pytest.skip("the thread-per-trajectory kernel of hf_frm_small.cuh covers 2 <= charges <= 12")
     total = len(g["trace_kind"])
     complete = total <= _step_cap(g) or bool(g["error_s"])
     stop = g["n_steps"] if complete else _step_cap(g)
     out = emu.run(g["dims"], g["field_f"], g["charges"], g["seed_int"], g["trajectory"], g["species"], g["homo"],
-                  g["lumo"], stop=stop, replay=g.get("replay_traj"), small_kernel=small_kernel)
+                  g["lumo"], stop=stop, replay=g.get("replay_traj"), small_kernel=small_kernel, distance=g["distance"])
     _check_prefix(g, out, total if complete else stop)
     if complete:
         # complete run: final lists, events, tallies and the stop reason must match too
