@@ -165,6 +165,7 @@ class Sim:
         cfg.props[:] = [float(p) for p in props]
         cfg.electric_field = float(electric_field)
         cfg.charges, cfg.distance = int(charges), int(distance)
+        self.exciton_mode = 0
         cfg.n_trajectories, cfg.n_realisations = int(n_trajectories), int(n_realisations)
         cfg.first_trajectory, cfg.first_realisation = int(first_trajectory), int(first_realisation)
         cfg.seed, cfg.flags, cfg.device = int(seed) & (2 ** 64 - 1), int(flags), int(device)

@@ -4,7 +4,7 @@
 // TADF.intersystem_crossing molecule.py:299-307).  Included by hf_frm.cuh (before hf_step).
 //
 // OWN MODEL, PARITY UNPINNED beyond mode 1: the specification is the "integrated excitons" block of
-// oracle/frm_oracle.c (x_new_event and the xsel branch of first_reaction_method); every statement below follows
+// the Path P restatement under oracle/ (its x_new_event and the xsel branch of first_reaction_method); every statement below follows
 // it operation for operation, so event sequences and taus are bit-identical to it (log() aside).  HfParams.xi.mode:
 //   0  off — the reference as it is: the decay event is the `special` slot with tau = 0
 //   1  "decay at once" THROUGH the exciton slots and lists: must reproduce every golden trajectory of the

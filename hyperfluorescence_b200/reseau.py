@@ -117,13 +117,20 @@ class Lattice:
       lattice         dict(species, homo, lumo[, s1, t1]) of flat z,y,x arrays to upload instead
                       of generating the lattice on the device (e.g. taken from a reference run)
       replay          uniforms replacing the trajectory stream (parity testing)
+      excitons        None (default): the reference as it is — an exciton decays at tau = 0 on the site it formed on
+                      (reseau.py:529-533).  True or a dict of exciton parameters (``_native.x_params_from_dict``:
+                      cutoff, forster_radius, dexter_prefactor, k_isc, k_risc, k_rad, k_nonrad ...): the exciton
+                      formed by a `bound` event hops, crosses and decays in the SAME First Reaction Method as the
+                      carriers — the slots the reference reserves (`_move_exciton_events`, `_isc_events`,
+                      `_decay_events`, reseau.py:233-235, 526-550).  Own model.
+                      "instant": the default behaviour routed through those slots (parity gate).
     """
 
     def __init__(self, dimension: tuple[int, int, int], proportions: tuple[float, float, float],
                  electric_field: float = 10.**(-1), charges: int = 10, charge_tranfer_distance: int = 1,
                  architecture: str = NotImplemented, *, seed: int | None = None, trajectories: int = 1,
                  realisations: int = 1, first_trajectory: int = 0, first_realisation: int = 0, device: int = 0,
-                 lattice: dict | None = None, replay=None) -> None:
+                 lattice: dict | None = None, replay=None, excitons=None) -> None:
         self._init_raises(dimension, proportions)
         self._lattice_parameters_creation(dimension, proportions, electric_field, charges)
         molecules = self._dimension.x * self._dimension.y
@@ -146,6 +153,13 @@ class Lattice:
                 self._sim.upload_lattice(r, src["species"], src["homo"], src["lumo"], src.get("s1"), src.get("t1"))
         if replay is not None:
             self._sim.set_replay(replay)
+        self._exciton_params = None
+        if isinstance(excitons, str) and excitons == "instant":
+            self._sim.p_excitons(1)
+        elif excitons:
+            self._exciton_params = nat.x_params_from_dict({} if excitons is True else dict(excitons))
+            self._sim.x_configure(self._exciton_params)
+            self._sim.p_excitons(2)
         self._sim.inject()                                                         # reseau.py:116-117
         self._IQE: float = 0.
         self._time: float = 0.                                                     # never advanced (Q9)
@@ -273,11 +287,32 @@ class Lattice:
         p = self._point(info.special_site)
         return [Event(p, p, 0., kind, info.special_particule)]
 
+    def _exciton_events(self, kinds):
+        """Pending events of the exciton slots whose kind is in ``kinds`` (integrated excitons), in slot order."""
+        x = self._sim.excitons(0)
+        return [Event(self._point(s), self._point(f), float(t), int(k), PARTICULES["exciton"])
+                for s, f, t, k in zip(x["site"], x["final"], x["tau"], x["kind"]) if int(k) in kinds]
+
+    def _decay_event_list(self):
+        if getattr(self._sim, "exciton_mode", 0):
+            return self._exciton_events((EVENTS["decay"],))
+        return self._special_events(EVENTS["decay"])
+
     _binding_events = property(lambda self: self._special_events(EVENTS["bound"]))
-    _decay_events = property(lambda self: self._special_events(EVENTS["decay"]))
+    _decay_events = property(_decay_event_list)
     _capture_events = property(lambda self: self._special_events(EVENTS["capture"]))
-    _move_exciton_events = property(lambda self: [])
-    _isc_events = property(lambda self: [])
+    # reseau.py:233-235: empty in the reference; filled when the excitons live in the device loop (excitons=...)
+    _move_exciton_events = property(lambda self: self._exciton_events((EVENTS["move"], EVENTS["Forster"]))
+                                    if getattr(self._sim, "exciton_mode", 0) else [])
+    _isc_events = property(lambda self: self._exciton_events((EVENTS["ISC"],))
+                           if getattr(self._sim, "exciton_mode", 0) else [])
+
+    def get_EQE(self, outcoupling: float | None = None) -> float:
+        """External quantum efficiency in percent: IQE (reseau.py:595) times the outcoupling efficiency (the
+        exciton parameters' ``outcoupling``, 0.2 by default).  Not in the reference, which stops at the IQE."""
+        if outcoupling is None:
+            outcoupling = self._exciton_params.outcoupling if self._exciton_params is not None else 0.2
+        return float(outcoupling) * self._IQE
 
     def _get_all_events(self):
         return (self._move_electron_events + self._move_hole_events + self._move_exciton_events + self._isc_events
@@ -303,6 +338,10 @@ class Lattice:
         s = self._site(p)
         info = self._sim.info(0)
         exciton = info.exciton_state if (info.special_kind == EVENTS["decay"] and info.special_site == s) else 0
+        if getattr(self._sim, "exciton_mode", 0):
+            xs = self._sim.excitons(0)
+            here = [int(sp) for st, sp in zip(xs["site"], xs["spin"]) if int(st) == s]
+            exciton = here[0] if here else 0
         return molecule_from_device(int(a["species"][s]), p, self._neighbourhood(p, self._distance),
                                     float(a["homo"][s]), float(a["lumo"][s]), float(a["s1"][s]), float(a["t1"][s]),
                                     bool(s in self._sim.flags(0, 0)), bool(s in self._sim.flags(0, 1)), int(exciton))

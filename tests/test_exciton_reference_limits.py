@@ -120,7 +120,9 @@ def test_specification_isc_only_limit_flips_like_the_reference():
                 assert {int(prev), int(spin_after)} == {1, 3}
                 flips += 1
     assert flips > 200
-    t = o.run_batch(seed, 0, 200_000, 12, n_threads=os.cpu_count() or 1)
+    # long trajectories: an exciton still alive when its trajectory ends is not counted, which biases the yield of a
+    # short run towards short-lived excitons; 2000 events per trajectory push that bias far below the 3 sigma band
+    t = o.run_batch(seed, 0, 4000, 2000, n_threads=os.cpu_count() or 1)
     n = t["rad_tadf"] + t["nonrad_s_tadf"] + t["nonrad_t_tadf"]
     y, _, _ = isc_chain_yield(kappa, K, k_t)
     assert n > 50_000 and t["isc"] > 0 and t["risc"] > 0
@@ -172,18 +174,18 @@ def test_gpu_exciton_kernel_degenerate_limit_equals_the_reference_facts():
 @pytest.mark.gpu
 def test_gpu_exciton_kernel_isc_only_limit():
     from hyperfluorescence_b200 import _native as nat
-    dims, B, n, kappa, k_t = (16, 16, 8), 400_000, 10, 3e8, 5e7
+    dims, B, n, kappa, k_t = (16, 16, 8), 8192, 2000, 3e8, 5e7     # long trajectories: see the CPU twin of this test
     a = _lattice(dims, 42, flat_st=True)
     sim = nat.Sim(dims, PROPS, 0.1, 1, 1, n_trajectories=B, seed=42)
     try:
         sim.upload_lattice(0, a["species"], a["homo"], a["lumo"], a["s1"], a["t1"])
         sim.x_configure(_gpu_params(nat, k_isc=kappa, k_risc=kappa, k_t=k_t))
-        sim.set_trace(0, 64, n)
+        sim.set_trace(0, 64, 100)
         sim.x_spawn()
         sim.x_run(n)
         sim.sync()
         t = sim.x_tallies()
-        traces = [sim.x_trace(b, n) for b in range(64)]
+        traces = [sim.x_trace(b, 100) for b in range(64)]
     finally:
         sim.close()
     n_tadf = t["rad_tadf"] + t["nonrad_s_tadf"] + t["nonrad_t_tadf"]

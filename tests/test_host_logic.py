@@ -32,7 +32,8 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (hf_[a-z_0-9]+)\b", out))
     assert set(declared) <= exported
-    assert lib.hf_abi_version() == 1
+    m = re.search(r"#define HF_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "hfkmc.h")).read())
+    assert lib.hf_abi_version() == int(m.group(1)) == 2
 
 
 def test_struct_layouts_match_the_header():
