@@ -50,7 +50,7 @@ CHARGES = 1
 FIELD = 0.1
 SEED = 0x48464B4D43            # "HFKMC" 
 TRAJ_PER_GPU = 1_000_000
-EVENTS_PER_STEP = 200          # KMC events per trajectory per bench step
+EVENTS_PER_STEP = 1000         # KMC events per trajectory per bench step (one launch: 10^9 events, ~0.18 s)
 C1_DIMS, C1_TRAJ_PER_GPU, C1_EVENTS = (64, 64, 64), 100_000, 1000     # BASELINE configs[1], the leg `configs1`
 NEIGHBOURS = 26
 # compulsory bytes per event, no caching credit
@@ -154,7 +154,7 @@ class ClockSampler(threading.Thread):
 _ORACLE_LATTICES = {}
 
 
-def cpu_sample(cores, per_core_trajectories=2000, dims=DIMS, events=EVENTS_PER_STEP, total=TRAJ_PER_GPU):
+def cpu_sample(cores, per_core_trajectories=500, dims=DIMS, events=EVENTS_PER_STEP, total=TRAJ_PER_GPU):
     """The CPU baseline: oracle port (oracle/frm_oracle.c, pinned bit-exactly to the unmodified
     reference) on `cores` host threads, a bounded sample of the same workload."""
     from oracle import frm_oracle as fo
@@ -180,7 +180,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     cpu_sample(cores, 16)                                                           # builds the 128^3 lattice (untimed)
     for _ in range(args.warmup):
-        cpu_sample(cores, 200)
+        cpu_sample(cores, 50)
     t0 = time.perf_counter()
     events = 0
     sample = ""
@@ -359,8 +359,8 @@ def run_ours(args):
         line["high_density"] = dense_rate(rank, local_rank, world, cpu=not args.no_cpu)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        v, sample, _ = cpu_sample(cores, 4000)
-        v1, _, _ = cpu_sample(1, 4000)
+        v, sample, _ = cpu_sample(cores, 1500)
+        v1, _, _ = cpu_sample(1, 3000)
         line["cpu_baseline"] = {"value": v, "unit": "events/s", "cores": cores, "kind": "port", "sample": sample,
                                 "one_core_value": v1}
     if rank == 0:

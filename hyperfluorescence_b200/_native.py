@@ -19,6 +19,7 @@ TALLY_NAMES = ("emission", "recombination", "injection", "steps", "fired", "move
                "capture_e", "capture_h", "recomb_host", "recomb_tadf", "recomb_fluo", "emit_tadf", "emit_fluo", "stopped",
                "x_forster", "x_dexter", "x_isc", "x_risc")
 
+HF_FLAG_NONE, HF_FLAG_WARP_KERNEL = 0, 1     # hf_config.flags: force the warp-per-trajectory kernel (cross-checks)
 HF_OK, HF_ERR_BAD_ARG, HF_ERR_CUDA, HF_ERR_NO_DEVICE, HF_ERR_UNSUPPORTED, HF_ERR_STATE = range(6)
 TRAJ_OK, TRAJ_NO_EVENTS, TRAJ_ZERO_DIVISION, TRAJ_VALUE_ERROR, TRAJ_REPLAY_EXHAUSTED, TRAJ_CAPACITY = range(6)
 

@@ -28,7 +28,7 @@
 #define HFXD_T_N 24
 #define HFXD_MAX_EXCITONS 1024
 #ifndef HFXD_MIN_BLOCKS
-#define HFXD_MIN_BLOCKS 5
+#define HFXD_MIN_BLOCKS 7              // 7 CTAs x 4 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
 #endif
 #ifndef HFXD_CHUNK
 #define HFXD_CHUNK 3                   // slots whose gathers (weight + occupancy word) are in flight together
@@ -50,9 +50,10 @@ struct HfxdParams {
 };
 
 __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
-    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T, birth (f64) | rates (f64) | pos (u32) | counters (u32)
+    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T (f64) | rates (f64) | pos (u32) | counters (u32)
+    // (birth[] stays in global memory: it is touched once per LOST exciton, by one lane)
     return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 2 * (size_t)((M + 1) & ~1) +
-           (size_t)warps * (8 * (2 * (size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64));
+           (size_t)warps * (8 * ((size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64));
 }
 
 __device__ __forceinline__ int hfxd_occ_get(const uint32_t *occ, int64_t idx) {
@@ -67,7 +68,7 @@ struct HfxdWarp {                      // one warp's view of its device
     const HfxdParams *P;
     const double *s_g6, *s_gd, *s_k, *s_ann;
     const int32_t *s_lin, *s_off;
-    double *s_T, *s_birth, *s_rates;
+    double *s_T, *s_rates;
     uint32_t *s_pos, *s_cnt, *s_dirty;
     const double *ws1, *wt1;           // this device's realisation, site 0
     uint32_t *occ;                     // this device's mask (index = site + halo)
@@ -222,10 +223,10 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     int32_t *s_lin = reinterpret_cast<int32_t *>(s_ann + 4);
     int32_t *s_off = s_lin + ((M + 1) & ~1);
     unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 1) & ~1)) +
-                         (size_t)warp * (8 * (2 * (size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64));
+                         (size_t)warp * (8 * ((size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64));
     HfxdWarp W;
     W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_lin = s_lin; W.s_off = s_off;
-    W.s_T = reinterpret_cast<double *>(wsm); W.s_birth = W.s_T + n_pad; W.s_rates = W.s_birth + n_pad;
+    W.s_T = reinterpret_cast<double *>(wsm); W.s_rates = W.s_T + n_pad;
     W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
     W.lane = lane; W.K = K; W.M = M;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         if (P.fill) {
             // hf_xd_spawn: an empty mask (memset by the host), slots filled in order, then every total
             time = 0.0; life = 0.0; draws = 0;
-            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = 0; W.s_T[q] = 0.0; W.s_birth[q] = 0.0; }
+            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = 0; W.s_T[q] = 0.0; g_birth[q] = 0.0; }
             __syncwarp();
             for (int k = 0; k < P.n; ++k) {
                 const uint32_t ps = hfxd_replace(W, ident, draws);
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             }
         } else {
             time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
-            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; W.s_birth[q] = g_birth[q]; }
+            for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; }
         }
         __syncwarp();
         const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
@@ -346,10 +347,10 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             }
             if (lost) {
                 if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, 0);
-                life = __dadd_rn(life, __dsub_rn(time, W.s_birth[kx]));
+                life = __dadd_rn(life, __dsub_rn(time, g_birth[kx]));            // every lane reads the same word
                 __syncwarp();
                 ps_after = hfxd_replace(W, ident, draws);
-                if (lane == 0) { W.s_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
+                if (lane == 0) { g_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
             }
             if (lane == 0) {
                 W.s_pos[kx] = ps_after;
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             }
             __syncwarp();
         }
-        for (int q = lane; q < n_pad; q += 32) { g_pos[q] = W.s_pos[q]; g_T[q] = W.s_T[q]; g_birth[q] = W.s_birth[q]; }
+        for (int q = lane; q < n_pad; q += 32) { g_pos[q] = W.s_pos[q]; g_T[q] = W.s_T[q]; }
         if (lane == 0) {
             P.time[dev] = time; P.life[dev] = life; P.draws[dev] = draws;
             if (traced) X.trace_len[dev - X.trace_first] = trace_at;

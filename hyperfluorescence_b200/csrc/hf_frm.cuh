@@ -72,13 +72,22 @@ struct HfTraceRec {                // == hf_event in include/hfkmc.h
 #define HFI_RAD 8
 #define HFI_KIND(m) (((m) >> 4) & 15)
 
-struct HfIntegrated {
-    int32_t mode, M;
+// Tables of the integrated mode 2, in GLOBAL memory (written once by hf_p_excitons): the event generator is a
+// separate, non-inlined function that must not take the address of a kernel parameter (that would copy the whole
+// parameter block to the stack) nor share the step kernels' register allocation.
+struct HfiTables {
+    int32_t M, X, Y, Z;
+    uint32_t k0, k1;
     const int32_t *offsets;           // [M] packed (dx+128) | (dy+128) << 8 | (dz+128) << 16   (hf_x_configure)
     const double *g6, *gd;            // [M]
-    double kf[9], kd[9], k_isc[3], k_risc[3], k_rad[6], k_nonrad[6];
     const double *ws1, *wt1;          // [n_real][w_stride] tagged weights, zero halo of w_halo sites below and above
     int64_t w_stride, w_halo;
+    double k[36];                     // kf[9] kd[9] k_isc[3] k_risc[3] k_rad[6] k_nonrad[6]
+};
+
+struct HfIntegrated {
+    int32_t mode;
+    const HfiTables *tab;             // mode 2 only
     // state [B][cap_c] / [B]
     int32_t *x_site, *x_meta, *x_final, *x_n;
     double *x_tau, *x_clock;
@@ -873,9 +882,24 @@ __device__ __forceinline__ int hf_regen(const HfParams &P, HfWarp &w, int t, boo
 
 // ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
 // Returns HF_ST_OK when an event fired; ev_* describe it (packed coordinates).
+template <int L>
+__device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
+                                            int *ev_init, int *ev_final, double *ev_tau, int *queue, int *xnew);
+
+// xnew: the exciton slot (integrated modes) that needs a new pending event after this step; it is drawn in ONE
+// place so that the generator is instantiated once per kernel.
 template <int L = 32>
 __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                        int *ev_init, int *ev_final, double *ev_tau, int *queue = nullptr) {
+    int xnew = -1;
+    const int st = hf_step_core<L>(P, w, lane, ev_kind, ev_part, ev_init, ev_final, ev_tau, queue, &xnew);
+    if (st == HF_ST_OK && xnew >= 0) hfi_new_event<L>(P, w, xnew, lane);
+    return st;
+}
+
+template <int L>
+__device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
+                                            int *ev_init, int *ev_final, double *ev_tau, int *queue, int *xnew) {
     int kind, part, ini, fin;
     double tau;
     if (w.special) {
@@ -933,7 +957,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
             w.cache_head = w.cache_head + 1 == HF_CACHE ? 0 : w.cache_head + 1;
             if (w.cache_n < HF_CACHE) w.cache_n += 1;
             *ev_kind = kind; *ev_part = part; *ev_init = ini; *ev_final = fin; *ev_tau = tau;
-            return hfi_fire<L>(P, w, xsel, kind, fin, tau, lane, queue);
+            return hfi_fire<L>(P, w, xsel, kind, fin, tau, lane, queue, xnew);
         }
         const int t = bidx < ne ? 0 : 1, i = bidx - (t ? ne : 0);
         kind = HF_K_MOVE; part = t + 1; tau = btau;
@@ -998,7 +1022,7 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
             w.n_x = k + 1;
             w.xstate = 0;
             hf_sync<L>();
-            hfi_new_event<L>(P, w, k, lane);
+            *xnew = k;
             return HF_ST_OK;
         }
         w.special = HF_K_DECAY | (HF_PART_EXCITON << 8); w.special_site = site;
@@ -1033,8 +1057,10 @@ __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, i
 // ---- kernels -------------------------------------------------------------------------------------
 // Lattice.operations(stop) (reseau.py:580-595) for every trajectory: one warp per trajectory,
 // grid-stride over trajectories.
+// min blocks: 512 threads per SM, i.e. at most 128 registers (what the kernel needed before the exciton generator
+// became one of its callees; the generator's own needs must not halve the occupancy of the carrier path)
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32) hf_run_kernel(const HfParams P) {
+__global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) hf_run_kernel(const HfParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HfWarp w;

@@ -404,3 +404,32 @@ __global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_ker
     }
     hf_c1_store(P, s, c, local);
 }
+
+// Lattice._charges_injection + _events_creation (reseau.py:207-276) for charges == 1, one thread per trajectory.
+// random.sample(positions, k = 1) is one randbelow(X * Y) in both of its variants (random.py:421-448: the pool
+// variant returns pool[j] = j, the set variant j), i.e. hf_c1_reinject; the initial events are hf_c1_gen with the
+// membership test of reseau.py:249 / 268, which for a single charge of each type blocks nothing.  Draw order:
+// electron site, hole site, the electron's candidates, the hole's candidates — as in hf_inject_kernel, whose
+// results this kernel reproduces bit for bit (the golden vectors' init_* arrays check both).
+__global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_inject_c1_kernel(const HfParams P) {
+    __shared__ float approx_all[HF_C1_MAXCAND * HF_C1_THREADS];
+    float *approx = approx_all + threadIdx.x;
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= P.B) return;
+    HfC1 s;
+    HfC1Counters c = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    s.e_pos = s.h_pos = s.e_fin = s.h_fin = -1;
+    s.e_tau = s.h_tau = 0.0;
+    s.special = s.special_site = s.xstate = s.status = s.cache_head = s.cache_n = 0;
+    s.draws = s.spins = s.emission = s.recombination = s.injection = s.steps = s.fired = 0;
+    const uint32_t ident = P.first_traj + (uint32_t)local;
+    const int64_t r = local / P.traj_per_real;
+    const double *lumo = P.lumo + r * P.N, *homo = P.homo + r * P.N;
+    int st = hf_c1_reinject(P, s, 0, local, ident);                              // 219
+    if (st == HF_ST_OK) st = hf_c1_reinject(P, s, 1, local, ident);              // 225
+    if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, 0, s, local, ident, approx);   // 240-257
+    if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, 1, s, local, ident, approx);   // 259-276
+    s.injection = 2;                                                             // 118
+    s.status = st;
+    hf_c1_store(P, s, c, local);
+}

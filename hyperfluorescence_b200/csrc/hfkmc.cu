@@ -99,6 +99,7 @@ struct hf_sim {
     int32_t *d_pi_site = nullptr, *d_pi_meta = nullptr, *d_pi_final = nullptr, *d_pi_n = nullptr;
     double *d_pi_tau = nullptr, *d_pi_clock = nullptr;
     uint64_t *d_pi_draws = nullptr;
+    HfiTables *d_pi_tab = nullptr;
     // timing of hf_run launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -330,15 +331,23 @@ int x_configure_launch(hf_sim *s) {
     return HF_OK;
 }
 
-// HfParams.xi <- the tables, rate constants and weights of hf_x_configure (integrated mode 2)
-static void sync_integrated(hf_sim *s) {
-    HfIntegrated &I = s->P.xi;
+// HfParams.xi.tab <- the tables, rate constants and weights of hf_x_configure (integrated mode 2)
+static int sync_integrated(hf_sim *s) {
+    HfiTables T;
+    memset(&T, 0, sizeof(T));
     const HfxParams &X = s->X;
-    I.M = X.M; I.offsets = X.offsets; I.g6 = X.g6; I.gd = X.gd;
-    memcpy(I.kf, X.kf, sizeof(I.kf)); memcpy(I.kd, X.kd, sizeof(I.kd));
-    memcpy(I.k_isc, X.k_isc, sizeof(I.k_isc)); memcpy(I.k_risc, X.k_risc, sizeof(I.k_risc));
-    memcpy(I.k_rad, X.k_rad, sizeof(I.k_rad)); memcpy(I.k_nonrad, X.k_nonrad, sizeof(I.k_nonrad));
-    I.ws1 = X.ws1; I.wt1 = X.wt1; I.w_stride = X.w_stride; I.w_halo = X.w_halo;
+    T.M = X.M; T.X = s->P.X; T.Y = s->P.Y; T.Z = s->P.Z; T.k0 = s->P.k0; T.k1 = s->P.k1;
+    T.offsets = X.offsets; T.g6 = X.g6; T.gd = X.gd;
+    memcpy(T.k, X.kf, sizeof(X.kf)); memcpy(T.k + 9, X.kd, sizeof(X.kd));
+    memcpy(T.k + 18, X.k_isc, sizeof(X.k_isc)); memcpy(T.k + 21, X.k_risc, sizeof(X.k_risc));
+    memcpy(T.k + 24, X.k_rad, sizeof(X.k_rad)); memcpy(T.k + 30, X.k_nonrad, sizeof(X.k_nonrad));
+    T.ws1 = X.ws1; T.wt1 = X.wt1; T.w_stride = X.w_stride; T.w_halo = X.w_halo;
+    int rc;
+    if (!s->d_pi_tab && (rc = dev_alloc(&s->d_pi_tab, 1))) return rc;
+    HF_CUDA(cudaMemcpyAsync(s->d_pi_tab, &T, sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    HF_CUDA(cudaStreamSynchronize(s->stream));
+    s->P.xi.tab = s->d_pi_tab;
+    return HF_OK;
 }
 
 extern "C" {
@@ -470,7 +479,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
     cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
-    cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws);
+    cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HF_OK;
@@ -665,6 +674,14 @@ int hf_inject(hf_sim *s) {
         HF_CUDA(cudaMemsetAsync(s->d_trace_base, 0, sizeof(uint64_t) * s->trace_base.size(), s->stream));
         std::fill(s->trace_base.begin(), s->trace_base.end(), 0);
     }
+    if (P.C == 1 && P.dist == 1 && P.xi.mode == 0 && P.cap_f == 2 && !(s->cfg.flags & HF_FLAG_WARP_KERNEL)) {
+        // one thread per trajectory, like the step kernel (hf_frm_c1.cuh)
+        const int64_t blocks = (P.B + HF_C1_THREADS - 1) / HF_C1_THREADS;
+        hf_inject_c1_kernel<<<(unsigned)blocks, HF_C1_THREADS, 0, s->stream>>>(P);
+        HF_CUDA(cudaGetLastError());
+        s->injected = true;
+        return HF_OK;
+    }
     int32_t *pool = nullptr;
     const int64_t molecules = (int64_t)P.X * P.Y;
     if (molecules <= P.setsize)
@@ -830,7 +847,7 @@ int hf_p_excitons(hf_sim *s, int32_t mode) {
     I.mode = mode;
     I.x_site = s->d_pi_site; I.x_meta = s->d_pi_meta; I.x_final = s->d_pi_final; I.x_tau = s->d_pi_tau;
     I.x_n = s->d_pi_n; I.x_draws = s->d_pi_draws; I.x_clock = s->d_pi_clock;
-    if (mode == 2) sync_integrated(s);
+    if (mode == 2 && (rc = sync_integrated(s))) return rc;
     s->injected = false;                               // the event lists change shape: hf_inject starts the trajectories
     return pick_launch(s);
 }
@@ -1145,7 +1162,7 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
     if ((rc = x_configure_launch(s))) return rc;
     s->x_configured = true;
     s->x_spawned = false;
-    if (s->P.xi.mode == 2) sync_integrated(s);             // the integrated mode reads these tables and weights
+    if (s->P.xi.mode == 2 && (rc = sync_integrated(s))) return rc;   // the integrated mode reads these tables and weights
     s->xd_configured = false; s->xd_spawned = false;      // the dense devices share these tables and weights
     return HF_OK;
 }

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 WHAT="${*:-tests bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.csv 2>&1
 if [[ " $WHAT " == *" tests "* ]]; then
-    timeout 2400 python -m pytest tests -m gpu -q --timeout 1200 -x > gpurun_out/pytest_gpu.log 2>&1
+    timeout 2400 python -m pytest tests -m gpu -q --timeout 1200 > gpurun_out/pytest_gpu.log 2>&1
     echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
     tail -25 gpurun_out/pytest_gpu.log
     timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1

@@ -61,22 +61,27 @@ struct EmuXModel {
     const int32_t *offsets; const double *g6, *gd, *kf, *kd, *k_isc, *k_risc, *k_rad, *k_nonrad, *ws1, *wt1;
     int64_t w_stride, w_halo;
 };
+HfiTables g_emu_tab;
 void apply_xmodel(HfParams &P, const EmuXModel *m) {
     memset(&P.xi, 0, sizeof(P.xi));
     if (!m) return;
     P.xi.mode = m->mode;
     if (m->mode != 2) return;
-    P.xi.M = m->M; P.xi.offsets = m->offsets; P.xi.g6 = m->g6; P.xi.gd = m->gd;
-    memcpy(P.xi.kf, m->kf, sizeof(P.xi.kf)); memcpy(P.xi.kd, m->kd, sizeof(P.xi.kd));
-    memcpy(P.xi.k_isc, m->k_isc, sizeof(P.xi.k_isc)); memcpy(P.xi.k_risc, m->k_risc, sizeof(P.xi.k_risc));
-    memcpy(P.xi.k_rad, m->k_rad, sizeof(P.xi.k_rad)); memcpy(P.xi.k_nonrad, m->k_nonrad, sizeof(P.xi.k_nonrad));
-    P.xi.ws1 = m->ws1; P.xi.wt1 = m->wt1; P.xi.w_stride = m->w_stride; P.xi.w_halo = m->w_halo;
+    HfiTables &T = g_emu_tab;
+    memset(&T, 0, sizeof(T));
+    T.M = m->M; T.X = P.X; T.Y = P.Y; T.Z = P.Z; T.k0 = P.k0; T.k1 = P.k1;
+    T.offsets = m->offsets; T.g6 = m->g6; T.gd = m->gd;
+    memcpy(T.k, m->kf, 72); memcpy(T.k + 9, m->kd, 72); memcpy(T.k + 18, m->k_isc, 24); memcpy(T.k + 21, m->k_risc, 24);
+    memcpy(T.k + 24, m->k_rad, 48); memcpy(T.k + 30, m->k_nonrad, 48);
+    T.ws1 = m->ws1; T.wt1 = m->wt1; T.w_stride = m->w_stride; T.w_halo = m->w_halo;
+    P.xi.tab = &T;
 }
 
 struct InjectArgs { const HfParams *P; int32_t *pool; };
 void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P, x->pool); }
 void run_body(void *a) { hf_run_kernel<1>(*(const HfParams *)a); }
 void run_c1_body(void *a) { hf_run_c1_kernel(*(const HfParams *)a); }
+void inject_c1_body(void *a) { hf_inject_c1_kernel(*(const HfParams *)a); }
 void run_small_body(void *a) { hf_run_small_kernel(*(const HfParams *)a); }
 
 struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
@@ -137,7 +142,6 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
             double *x_scalars_out /* n_x, draws, clock */) {
     HfParams P;
     memset(&P, 0, sizeof(P));
-    apply_xmodel(P, xmodel);
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
     P.field = field; P.C = charges; P.cap_c = charges; P.cap_f = (charges == 1 && distance == 1) ? 2 : 2 * charges + 8;
     P.dist = distance;
@@ -146,6 +150,7 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
     P.setsize = sample_setsize(charges);
     P.species = species; P.homo = homo; P.lumo = lumo;
     P.replay = replay; P.n_replay = n_replay;
+    apply_xmodel(P, xmodel);
     Buffers b;
     wire(P, b, trace_cap);
     if (hf_warp_smem_bytes(P.cap_c, P.cap_f, hf_xcap(P)) > sizeof(hf_smem)) return 2;
@@ -224,7 +229,8 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     b.pool.assign((size_t)((int64_t)P.X * P.Y), 0);
     InjectArgs ia{&P, b.pool.data()};
-    emu_run_warp(inject_body, &ia);
+    if (use_c1) emu_run_warp(inject_c1_body, &P);                  // thread-per-trajectory injection, like the product path
+    else emu_run_warp(inject_body, &ia);
     for (int c = 0; c < n_calls; ++c) {
         P.n_steps = stop;
         emu_run_warp(use_c1 ? run_c1_body : run_body, &P);
