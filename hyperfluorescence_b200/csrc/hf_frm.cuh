@@ -862,22 +862,15 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
 
 #include "hf_frm_x.cuh"
 
-// Re-inject (optionally) and regenerate the move event of the LAST charge of type t.  The warp kernel does it
-// on the spot; the thread-per-trajectory kernel queues it (4 bits per request: 8 | 4 * reinject | t, at most two
-// per event) and runs the queue in ONE place after hf_step, so that the lanes of a warp — each with its own
-// trajectory, most of them regenerating one event per step — execute the candidate loop together.
+// Re-inject (optionally) and regenerate the move event of the LAST charge of type t: queued (4 bits per request:
+// 8 | 4 * reinject | t, at most two per event) and run in ONE place after the bookkeeping — by hf_step itself in the
+// warp kernel, by the kernel's common tail in the thread-per-trajectory kernel (so that the lanes of a warp, each
+// with its own trajectory, execute the candidate loop together).  One instance of the candidate loop per kernel
+// instead of one per branch of the dispatcher.
 template <int L>
 __device__ __forceinline__ int hf_regen(const HfParams &P, HfWarp &w, int t, bool reinject, int lane, int *queue) {
-    if constexpr (L == 1) {
-        *queue |= (8 | (reinject ? 4 : 0) | t) << (*queue ? 4 : 0);
-        return HF_ST_OK;
-    } else {
-        if (reinject) {
-            const int st = hf_reinject<L>(P, w, t, lane);
-            if (st != HF_ST_OK) return st;
-        }
-        return hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
-    }
+    *queue |= (8 | (reinject ? 4 : 0) | t) << (*queue ? 4 : 0);
+    return HF_ST_OK;
 }
 
 // ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
@@ -891,8 +884,13 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
 template <int L = 32>
 __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                        int *ev_init, int *ev_final, double *ev_tau, int *queue = nullptr) {
-    int xnew = -1;
-    const int st = hf_step_core<L>(P, w, lane, ev_kind, ev_part, ev_init, ev_final, ev_tau, queue, &xnew);
+    int xnew = -1, own_queue = 0;
+    int st = hf_step_core<L>(P, w, lane, ev_kind, ev_part, ev_init, ev_final, ev_tau, queue ? queue : &own_queue, &xnew);
+    for (; st == HF_ST_OK && own_queue; own_queue >>= 4) {                       // the regenerations the step asked for
+        const int t = own_queue & 1;
+        if (own_queue & 4) st = hf_reinject<L>(P, w, t, lane);
+        if (st == HF_ST_OK) st = hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
+    }
     if (st == HF_ST_OK && xnew >= 0) hfi_new_event<L>(P, w, xnew, lane);
     return st;
 }

@@ -14,3 +14,4 @@ python scripts/bench_dense.py --B 16384 --n 64
 python scripts/bench_dense.py --B 4096 --n 1024 --events 100
 } > gpurun_out/perf_suite.jsonl 2> gpurun_out/perf_suite.err
 cat gpurun_out/perf_suite.jsonl; tail -5 gpurun_out/perf_suite.err
+if [ -x scripts/micro/tma_box ]; then scripts/micro/tma_box > gpurun_out/tma_box.txt 2>&1; cat gpurun_out/tma_box.txt; fi
