@@ -338,13 +338,13 @@ __device__ __forceinline__ void hf_remove_events(HfWarp &w, int t, int a, int b,
 }
 
 // _update_events (reseau.py:564-578): tau -= time on every pending move event
-template <int L = 32>
+template <int L = 32, bool kX = false>
 __device__ __forceinline__ void hf_update_events(HfWarp &w, double time, int lane) {
 #pragma unroll
     for (int t = 0; t < 2; ++t)
 #pragma unroll 1
         for (int i = lane; i < w.n_ev(t); i += L) w.ev_tau(t)[i] = __dsub_rn(w.ev_tau(t)[i], time);
-    if (w.x_tau) {                                 // _move_exciton_events, _isc_events, _decay_events (reseau.py:569-576)
+    if constexpr (kX) {                            // _move_exciton_events, _isc_events, _decay_events (reseau.py:569-576)
         w.clock = __dadd_rn(w.clock, time);
 #pragma unroll 1
         for (int i = lane; i < w.n_x; i += L) w.x_tau[i] = __dsub_rn(w.x_tau[i], time);
@@ -752,7 +752,8 @@ __device__ __forceinline__ int hf_reinject(const HfParams &P, HfWarp &w, int t, 
 }
 
 // ---- state load / store ------------------------------------------------------------------------
-template <int L = 32>
+// kX: the integrated exciton modes are compiled in (P.xi.mode != 0); the kernels of the reference mode carry none of it
+template <int L = 32, bool kX = false>
 __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int64_t local, int lane) {
     const HfScalars sc = P.sc[local];
     w.local = local;
@@ -795,7 +796,7 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
     w.c_recomb_host = w.c_recomb_tadf = w.c_recomb_fluo = w.c_emit_tadf = w.c_emit_fluo = 0;
     w.c_x_forster = w.c_x_dexter = w.c_x_isc = w.c_x_risc = 0;
     w.n_x = 0; w.xdraws = 0; w.clock = 0.0;
-    if (P.xi.mode) {
+    if constexpr (kX) {
         w.n_x = P.xi.x_n[local]; w.xdraws = P.xi.x_draws[local]; w.clock = P.xi.x_clock[local];
 #pragma unroll 1
         for (int i = lane; i < w.n_x; i += L) {
@@ -806,7 +807,7 @@ __device__ __forceinline__ void hf_load_state(const HfParams &P, HfWarp &w, int6
     hf_sync<L>();
 }
 
-template <int L = 32>
+template <int L = 32, bool kX = false>
 __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int lane) {
     const int64_t local = w.local;
     hf_sync<L>();
@@ -830,7 +831,7 @@ __device__ __forceinline__ void hf_store_state(const HfParams &P, HfWarp &w, int
         P.cache_kp[c * P.B + local] = w.cache_kp[c];
         P.cache_tau[c * P.B + local] = w.cache_tau[c];
     }
-    if (P.xi.mode) {
+    if constexpr (kX) {
 #pragma unroll 1
         for (int i = lane; i < w.n_x; i += L) {
             P.xi.x_site[local * P.cap_c + i] = w.x_site[i]; P.xi.x_meta[local * P.cap_c + i] = w.x_meta[i];
@@ -875,27 +876,27 @@ __device__ __forceinline__ int hf_regen(const HfParams &P, HfWarp &w, int t, boo
 
 // ---- one KMC step: _first_reaction_method (reseau.py:483-562) ---------------------------------
 // Returns HF_ST_OK when an event fired; ev_* describe it (packed coordinates).
-template <int L>
+template <int L, bool kX>
 __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                             int *ev_init, int *ev_final, double *ev_tau, int *queue, int *xnew);
 
 // xnew: the exciton slot (integrated modes) that needs a new pending event after this step; it is drawn in ONE
 // place so that the generator is instantiated once per kernel.
-template <int L = 32>
+template <int L = 32, bool kX = false>
 __device__ __forceinline__ int hf_step(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                        int *ev_init, int *ev_final, double *ev_tau, int *queue = nullptr) {
     int xnew = -1, own_queue = 0;
-    int st = hf_step_core<L>(P, w, lane, ev_kind, ev_part, ev_init, ev_final, ev_tau, queue ? queue : &own_queue, &xnew);
+    int st = hf_step_core<L, kX>(P, w, lane, ev_kind, ev_part, ev_init, ev_final, ev_tau, queue ? queue : &own_queue, &xnew);
     for (; st == HF_ST_OK && own_queue; own_queue >>= 4) {                       // the regenerations the step asked for
         const int t = own_queue & 1;
         if (own_queue & 4) st = hf_reinject<L>(P, w, t, lane);
         if (st == HF_ST_OK) st = hf_gen_move_event<L>(P, w, t, w.pos(t)[w.n_pos(t) - 1], true, lane);
     }
-    if (st == HF_ST_OK && xnew >= 0) hfi_new_event<L>(P, w, xnew, lane);
+    if constexpr (kX) { if (st == HF_ST_OK && xnew >= 0) hfi_new_event<L>(P, w, xnew, lane); }
     return st;
 }
 
-template <int L>
+template <int L, bool kX>
 __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int lane, int *ev_kind, int *ev_part,
                                             int *ev_init, int *ev_final, double *ev_tau, int *queue, int *xnew) {
     int kind, part, ini, fin;
@@ -907,7 +908,7 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
     } else {
         // min tau over move_e + move_h, LAST one in concatenation order on ties (Q6)
         const int ne = w.n_ev(0), total = ne + w.n_ev(1);
-        if (total == 0 && w.n_x == 0) return HF_ST_NO_EVENTS;                    // 487-488
+        if (total == 0 && (!kX || w.n_x == 0)) return HF_ST_NO_EVENTS;           // 487-488
         double btau = INFINITY;
         int bidx = -1;
         for (int base = 0; base < total; base += L) {
@@ -926,7 +927,7 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
         // the excitons' events follow the carriers' in _get_all_events (reseau.py:608-612): move_x, isc, decay lists,
         // slots in creation order inside each; equal taus -> the later one wins
         int xsel = -1;
-        if (w.n_x > 0) {
+        if (kX && w.n_x > 0) {
             double xt = INFINITY;
             int xkey = -1;
 #pragma unroll 1
@@ -943,7 +944,7 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
             }
             if (bidx < 0 || xt <= btau) { xsel = xkey & 0xffff; btau = xt; }
         }
-        if (xsel >= 0) {
+        if (kX && xsel >= 0) {
             kind = HFI_KIND(w.x_meta[xsel]); part = HF_PART_EXCITON; tau = btau;
             ini = w.x_site[xsel]; fin = w.x_final[xsel];
             hf_sync<L>();
@@ -955,7 +956,7 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
             w.cache_head = w.cache_head + 1 == HF_CACHE ? 0 : w.cache_head + 1;
             if (w.cache_n < HF_CACHE) w.cache_n += 1;
             *ev_kind = kind; *ev_part = part; *ev_init = ini; *ev_final = fin; *ev_tau = tau;
-            return hfi_fire<L>(P, w, xsel, kind, fin, tau, lane, queue, xnew);
+            if constexpr (kX) return hfi_fire<L>(P, w, xsel, kind, fin, tau, lane, queue, xnew);
         }
         const int t = bidx < ne ? 0 : 1, i = bidx - (t ? ne : 0);
         kind = HF_K_MOVE; part = t + 1; tau = btau;
@@ -984,14 +985,14 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
         const bool opposite_here = hf_contains<L>(w.flag(o), w.n_flag(o), fin, lane);
         const int capture_z = t == 0 ? 0 : P.Z - 1;
         if (!opposite_here && hf_pz(fin) != capture_z) {                         // 498-500 / 514-516
-            hf_update_events<L>(w, tau, lane);
+            hf_update_events<L, kX>(w, tau, lane);
             return hf_regen<L>(P, w, t, false, lane, queue);                    // the moved charge is the last of its list
         } else if (opposite_here) {                                              // 501-505 / 517-521
             hf_remove_events<L>(w, o, fin, fin, lane);
             // _update_events(0.) leaves every tau unchanged (Q5)
             w.special = HF_K_BOUND | (HF_PART_EXCITON << 8); w.special_site = fin;
         } else {                                                                 // 506-508 / 522-524
-            hf_update_events<L>(w, tau, lane);
+            hf_update_events<L, kX>(w, tau, lane);
             w.special = HF_K_CAPTURE | (part << 8); w.special_site = fin;
         }
         return HF_ST_OK;
@@ -1012,7 +1013,7 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
             hf_remove_at<L>(w.pos(t), w.n_pos(t), idx, lane);
             w.set_n_pos(t, w.n_pos(t) - 1);
         }
-        if (P.xi.mode) {                       // integrated: the exciton gets a slot and its first event (hf_frm_x.cuh)
+        if constexpr (kX) {                    // integrated: the exciton gets a slot and its first event (hf_frm_x.cuh)
             if (w.n_x >= P.cap_c) return HF_ST_CAPACITY;
             const int k = w.n_x;
             hf_sync<L>();
@@ -1057,14 +1058,14 @@ __device__ __forceinline__ int hf_step_core(const HfParams &P, HfWarp &w, int la
 // grid-stride over trajectories.
 // min blocks: 512 threads per SM, i.e. at most 128 registers (what the kernel needed before the exciton generator
 // became one of its callees; the generator's own needs must not halve the occupancy of the carrier path)
-template <int kWarps>
+template <int kWarps, bool kX = false>
 __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) hf_run_kernel(const HfParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     HfWarp w;
     hf_carve(w, hf_smem + (size_t)warp * hf_warp_smem_bytes(P.cap_c, P.cap_f, hf_xcap(P)), P.cap_c, P.cap_f, hf_xcap(P));
     for (int64_t local = (int64_t)blockIdx.x * kWarps + warp; local < P.B; local += (int64_t)gridDim.x * kWarps) {
-        hf_load_state(P, w, local, lane);
+        hf_load_state<32, kX>(P, w, local, lane);
         // a ZeroDivisionError only ends the operations() call it happened in (reseau.py:587-589)
         if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;
         const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
@@ -1075,7 +1076,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) hf_run_kernel(const 
                 w.steps += 1;                                                    // 582
                 int kind, part, ini, fin;
                 double tau;
-                const int st = hf_step(P, w, lane, &kind, &part, &ini, &fin, &tau);
+                const int st = hf_step<32, kX>(P, w, lane, &kind, &part, &ini, &fin, &tau);
                 if (st != HF_ST_OK) { w.status = st; break; }                    // 587-591
                 if (kind == HF_K_BOUND) w.c_bound += 1;
                 else if (kind == HF_K_DECAY) w.c_decay += 1;
@@ -1093,7 +1094,7 @@ __global__ void __launch_bounds__(kWarps * 32, 16 / kWarps) hf_run_kernel(const 
                 w.fired += 1;
             }
         }
-        hf_store_state(P, w, lane);
+        hf_store_state<32, kX>(P, w, lane);
     }
 }
 

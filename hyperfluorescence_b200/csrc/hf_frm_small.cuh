@@ -192,6 +192,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
 }
 
 // Lattice.operations(stop) for 2 <= charges <= HF_SMALL_MAX_CHARGES: one thread per trajectory.
+template <bool kX = false>
 __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_small_kernel(const HfParams P) {
     extern __shared__ __align__(16) unsigned char hf_smem[];
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
     const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P));
     HfWarp w;
     hf_small_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f, hf_xcap(P));
-    hf_load_state<1>(P, w, local, 0);
+    hf_load_state<1, kX>(P, w, local, 0);
     if (w.status == HF_ST_ZERO_DIVISION || w.status == HF_ST_NO_EVENTS) w.status = HF_ST_OK;   // reseau.py:587-589
     const bool traced = P.trace && local >= P.trace_first && local < P.trace_first + P.trace_n;
     HfTraceRec *trace = traced ? P.trace + (local - P.trace_first) * P.trace_cap : nullptr;
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
             int kind, part, ini, fin;
             double tau;
             int queue = 0;
-            int st = hf_step<1>(P, w, 0, &kind, &part, &ini, &fin, &tau, &queue);
+            int st = hf_step<1, kX>(P, w, 0, &kind, &part, &ini, &fin, &tau, &queue);
             // common tail: the regenerations the step asked for (one after a move or a capture, two after a decay)
             for (; st == HF_ST_OK && queue; queue >>= 4) {
                 const int t = queue & 1;
@@ -234,5 +235,5 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
             w.fired += 1;
         }
     }
-    hf_store_state<1>(P, w, 0);
+    hf_store_state<1, kX>(P, w, 0);
 }

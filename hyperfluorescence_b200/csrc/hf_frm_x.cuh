@@ -195,7 +195,7 @@ __device__ __forceinline__ int hfi_fire(const HfParams &P, HfWarp &w, int k, int
         if (spin == HF_XS_SINGLET) w.c_x_forster += 1; else w.c_x_dexter += 1;
         if (lane == 0) { w.x_site[k] = fin; w.x_meta[k] = meta & 3; }
         hf_sync<L>();
-        hf_update_events<L>(w, tau, lane);
+        hf_update_events<L, true>(w, tau, lane);
         *xnew = k;
         return HF_ST_OK;
     }
@@ -203,7 +203,7 @@ __device__ __forceinline__ int hfi_fire(const HfParams &P, HfWarp &w, int k, int
         if (spin == HF_XS_SINGLET) w.c_x_isc += 1; else w.c_x_risc += 1;
         if (lane == 0) w.x_meta[k] = (meta & HFI_ONSITE) | (spin == HF_XS_SINGLET ? HF_XS_TRIPLET : HF_XS_SINGLET);
         hf_sync<L>();
-        hf_update_events<L>(w, tau, lane);
+        hf_update_events<L, true>(w, tau, lane);
         *xnew = k;
         return HF_ST_OK;
     }
@@ -228,7 +228,7 @@ __device__ __forceinline__ int hfi_fire(const HfParams &P, HfWarp &w, int k, int
     w.recombination += 1;                                                        // 472-476
     w.c_recomb_host += sp == 0; w.c_recomb_tadf += sp == 1; w.c_recomb_fluo += sp == 2;
     if (photon) { w.emission += 1; w.c_emit_tadf += sp == 1; w.c_emit_fluo += sp == 2; }
-    hf_update_events<L>(w, tau, lane);
+    hf_update_events<L, true>(w, tau, lane);
     const int st = hf_regen<L>(P, w, 0, true, lane, queue);
     if (st != HF_ST_OK) return st;
     return hf_regen<L>(P, w, 1, true, lane, queue);

@@ -114,11 +114,13 @@ int configure_launch(hf_sim *s) {
     const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P));
     const size_t smem = per_warp * W;
     if (smem > 48 * 1024) {
-        HF_CUDA(cudaFuncSetAttribute(hf_run_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(cudaFuncSetAttribute(hf_run_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HF_CUDA(cudaFuncSetAttribute(hf_run_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HF_CUDA(cudaFuncSetAttribute(hf_inject_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     int per_sm = 0;
-    HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hf_run_kernel<W>, W * 32, smem));
+    if (s->P.xi.mode) HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hf_run_kernel<W, true>, W * 32, smem));
+    else HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hf_run_kernel<W, false>, W * 32, smem));
     if (per_sm < 1) return fail(HF_ERR_UNSUPPORTED, "step kernel does not fit an SM (charges=%d)", s->P.C);
     const int64_t need = (s->P.B + W - 1) / W;
     const int64_t cap = (int64_t)s->sm_count * per_sm;
@@ -201,7 +203,8 @@ void fold_timing(hf_sim *s) {
 
 template <int W>
 void launch_run(hf_sim *s) {
-    hf_run_kernel<W><<<s->grid, W * 32, s->smem, s->stream>>>(s->P);
+    if (s->P.xi.mode) hf_run_kernel<W, true><<<s->grid, W * 32, s->smem, s->stream>>>(s->P);
+    else hf_run_kernel<W, false><<<s->grid, W * 32, s->smem, s->stream>>>(s->P);
 }
 template <int W>
 void launch_inject(hf_sim *s, int32_t *pool) {
@@ -718,9 +721,14 @@ int hf_run(hf_sim *s, int64_t stop) {
     } else if (s->P.C <= HF_SMALL_MAX_CHARGES && thread_kernels) {
         // one thread per trajectory, lists in per-thread shared memory (hf_frm_small.cuh)
         const size_t smem = hf_small_thread_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P)) * HF_SMALL_THREADS;
-        if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_run_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t blocks = (s->P.B + HF_SMALL_THREADS - 1) / HF_SMALL_THREADS;
-        hf_run_small_kernel<<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(s->P);
+        if (s->P.xi.mode) {
+            if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_run_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hf_run_small_kernel<true><<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(s->P);
+        } else {
+            if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_run_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            hf_run_small_kernel<false><<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(s->P);
+        }
     } else {
         switch (s->warps) {
             case 8: launch_run<8>(s); break;
