@@ -171,3 +171,6 @@ static inline double __longlong_as_double(long long a) { double b; memcpy(&b, &a
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     unsigned long long old = *p; *p += v; return old;
 }
+// lanes are coroutines of one host thread that only switch at collectives: plain read-modify-write is atomic enough
+static inline unsigned atomicOr(unsigned *p, unsigned v) { const unsigned o = *p; *p = o | v; return o; }
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned v) { const unsigned o = *p; if (o == cmp) *p = v; return o; }
