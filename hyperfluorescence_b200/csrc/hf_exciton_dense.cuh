@@ -125,8 +125,9 @@ __device__ __forceinline__ void hfxd_hset_spin(const HfxdWarp &W, uint32_t site,
 // rr[] (registers, K <= HFXD_KREG) or in s_rates.  kMark: the excitons met on occupied acceptor sites are marked
 // dirty (they see the site that is about to change / has just changed).  HFXD_CHUNK slots are gathered before any
 // of them is consumed.
-template <bool kKeep, bool kMark>
-__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, double (&rr)[HFXD_KREG]) {
+// ONE inlined instance per kernel (kKeep / kMark are run-time flags): with five inlined copies the kernel was 16 800
+// instructions and bound by instruction fetch.
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, double (&rr)[HFXD_KREG], const bool kKeep, const bool kMark) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
     const bool singlet = spin == HFX_SINGLET;
@@ -215,7 +216,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
         if (kKeep) W.s_rates[c] = rate;
         S = __dadd_rn(S, rate);
     }
-    if (kMark) __syncwarp();
+    __syncwarp();
     return S;
 }
 
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         for (int h = lane; h < H; h += 32) W.s_keys[h] = 0;
         __syncwarp();
         if (P.fill) {
-            // hf_xd_spawn: an empty device, slots filled in order, then every total
+            // hf_xd_spawn: an empty device, slots filled in order; their totals are computed by the refresh pass below
             time = 0.0; life = 0.0; draws = 0;
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = 0; W.s_T[q] = 0.0; g_birth[q] = 0.0; }
             __syncwarp();
@@ -334,11 +335,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 if (lane == 0) { W.s_pos[k] = ps; W.s_cnt[HFX_T_GENERATED] += 1; }
             }
             __syncwarp();
-            for (int k = 0; k < P.n; ++k) {
-                const double S = hfxd_lane_sum<false, false>(W, W.s_pos[k], rr);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(S, lane), 31);
-                if (lane == 0) W.s_T[k] = tot;
-            }
+            if (lane < n_slots) W.s_dirty[lane] = (lane << 5) + 32 <= P.n ? 0xffffffffu : ((lane << 5) < P.n ? (1u << (P.n & 31)) - 1u : 0u);
         } else {
             time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; }
@@ -354,137 +351,141 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
         uint64_t trace_at = traced ? X.trace_len[dev - X.trace_first] : 0;
 
-        for (int64_t ev = 0; ev < X.n_events; ++ev) {
-            // (1) the exciton: canonical scan over the cached totals
-            double A = 0.0;
-            for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
-            const double G = hfx_scan(A, lane);
-            const double R = __shfl_sync(HF_FULL, G, 31);
-            const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
-            draws += 2;
-            const double u_sel = hf_block_uniform(rnd, 0), u_time = hf_block_uniform(rnd, 1);
-            const double target = __dmul_rn(u_sel, R);
-            double base;
-            const int kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
-            // (2) its channel; the excitons it meets see the site that is about to change
-            const uint32_t ps = W.s_pos[kx];
-            const double S = hfxd_lane_sum<true, true>(W, ps, rr);
-            const double L = hfx_scan(S, lane);
-            int chosen;
-            if (in_regs) {
-                chosen = hfxd_pick_regs(rr, K, S, L, __dsub_rn(target, base), lane);
-            } else {
-                double base2;
-                __syncwarp();
-                chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
+        // ev = -1: the refresh pass that computes the totals of a freshly filled device (every slot marked dirty)
+        for (int64_t ev = P.fill ? -1 : 0; ev < X.n_events; ++ev) {
+            // stage 0: evaluate the chosen exciton, pick its channel, apply the event
+            //       1: refresh a slot whose own site / spin changed (its evaluation marks the excitons it meets)
+            //       2: refresh the slots marked dirty
+            int stage = 2, tgt = -1, kx = -1, promoted = -1;
+            uint32_t job = 0;
+            double target = 0.0, base = 0.0, R = 0.0, u_time = 0.0;
+            if (ev >= 0) {
+                // (1) the exciton: canonical scan over the cached totals
+                double A = 0.0;
+                for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
+                const double G = hfx_scan(A, lane);
+                R = __shfl_sync(HF_FULL, G, 31);
+                const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+                draws += 2;
+                const double u_sel = hf_block_uniform(rnd, 0);
+                u_time = hf_block_uniform(rnd, 1);
+                target = __dmul_rn(u_sel, R);
+                kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
+                stage = 0; tgt = kx; job = W.s_pos[kx];
             }
-            const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
-            time = __dadd_rn(time, dt);
-            // (3) apply
-            const uint32_t site = ps & 0x3fffffffu;
-            const int spin = (int)(ps >> 30);
-            const bool singlet = spin == HFX_SINGLET;
-            const int sidx = singlet ? 0 : 1;
-            const int px = hf_px((int)site), py = hf_py((int)site), pz = hf_pz((int)site);
-            const int64_t i = hf_site(X.X, X.Y, (int)site);
-            const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
-            int kind, tally, fin = (int)site, promoted = -1;
-            bool lost = false;
-            uint32_t ps_after = ps;
-            if (chosen < M) {
-                const int o = W.s_off[chosen];
-                int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
-                if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
-                fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
-                const int hj = hfxd_hfind(W, (uint32_t)fin);
-                const int occ_j = hj < 0 ? 0 : (int)(W.s_keys[hj] >> 30);
-                __syncwarp();
-                if (occ_j == 0) {
-                    ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
-                    if (lane == 0) { hfxd_herase(W, site); hfxd_hinsert(W, ps_after, kx); }
-                    kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
-                    tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+            for (;;) {
+                if (stage == 2) {                                                // next slot marked dirty, ascending
+                    int q = -1;
+                    for (int wq = 0; wq < n_slots && q < 0; ++wq) {
+                        const unsigned todo = W.s_dirty[wq];
+                        if (todo) q = (wq << 5) + __ffs(todo) - 1;
+                    }
+                    if (q < 0) break;
+                    tgt = q; job = W.s_pos[q];
+                }
+                const double S = hfxd_lane_sum(W, job, rr, stage == 0, stage < 2);
+                const double L = hfx_scan(S, lane);
+                if (stage != 0) {
+                    const double tot = __shfl_sync(HF_FULL, L, 31);
+                    if (lane == 0) { W.s_T[tgt] = tot; W.s_dirty[tgt >> 5] &= ~(1u << (tgt & 31)); }
+                    __syncwarp();
+                    if (stage == 1 && promoted >= 0 && tgt != promoted) { tgt = promoted; job = W.s_pos[promoted]; continue; }
+                    stage = 2;
+                    continue;
+                }
+                // (2) the channel of the chosen exciton; the excitons its evaluation met see the site that is about to change
+                const uint32_t ps = job;
+                int chosen;
+                if (in_regs) {
+                    chosen = hfxd_pick_regs(rr, K, S, L, __dsub_rn(target, base), lane);
                 } else {
-                    const int oidx = occ_j == HFX_SINGLET ? 0 : 1;
-                    kind = HFXD_K_ANNIHILATION;
-                    tally = HFXD_T_ANN + 2 * sidx + oidx;
-                    if (sidx == 1 && oidx == 1) {                               // triplet on triplet: the survivor may be promoted
-                        const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
-                        draws += 2;
-                        if (hf_block_uniform(b2, 0) < P.p_tta) {
-                            promoted = (int)W.s_vals[hj];
-                            __syncwarp();
-                            if (lane == 0) {
-                                W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
-                                W.s_keys[hj] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
-                                W.s_cnt[HFXD_T_TTA_UP] += 1;
+                    double base2;
+                    chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
+                }
+                const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
+                time = __dadd_rn(time, dt);
+                // (3) apply
+                const uint32_t site = ps & 0x3fffffffu;
+                const int spin = (int)(ps >> 30);
+                const bool singlet = spin == HFX_SINGLET;
+                const int sidx = singlet ? 0 : 1;
+                const int px = hf_px((int)site), py = hf_py((int)site), pz = hf_pz((int)site);
+                const int64_t i = hf_site(X.X, X.Y, (int)site);
+                const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
+                int kind, tally, fin = (int)site;
+                bool lost = false;
+                uint32_t ps_after = ps;
+                if (chosen < M) {
+                    const int o = W.s_off[chosen];
+                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                    if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+                    if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+                    fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
+                    const int hj = hfxd_hfind(W, (uint32_t)fin);
+                    const int occ_j = hj < 0 ? 0 : (int)(W.s_keys[hj] >> 30);
+                    __syncwarp();
+                    if (occ_j == 0) {
+                        ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
+                        if (lane == 0) { hfxd_herase(W, site); hfxd_hinsert(W, ps_after, kx); }
+                        kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
+                        tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+                    } else {
+                        const int oidx = occ_j == HFX_SINGLET ? 0 : 1;
+                        kind = HFXD_K_ANNIHILATION;
+                        tally = HFXD_T_ANN + 2 * sidx + oidx;
+                        if (sidx == 1 && oidx == 1) {                           // triplet on triplet: the survivor may be promoted
+                            const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+                            draws += 2;
+                            if (hf_block_uniform(b2, 0) < P.p_tta) {
+                                promoted = (int)W.s_vals[hj];
+                                __syncwarp();
+                                if (lane == 0) {
+                                    W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
+                                    W.s_keys[hj] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
+                                    W.s_cnt[HFXD_T_TTA_UP] += 1;
+                                }
                             }
                         }
+                        lost = true;
                     }
+                } else if (chosen == M) {
+                    kind = HFX_K_ISC;                                           // molecule.py:299-307
+                    tally = singlet ? HFX_T_ISC : HFX_T_RISC;
+                    const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
+                    ps_after = site | ((uint32_t)flipped << 30);
+                    __syncwarp();
+                    if (lane == 0) hfxd_hset_spin(W, site, flipped);
+                } else {
+                    kind = HFX_K_DECAY;
+                    tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
                     lost = true;
                 }
-            } else if (chosen == M) {
-                kind = HFX_K_ISC;                                               // molecule.py:299-307
-                tally = singlet ? HFX_T_ISC : HFX_T_RISC;
-                const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
-                ps_after = site | ((uint32_t)flipped << 30);
-                __syncwarp();
-                if (lane == 0) hfxd_hset_spin(W, site, flipped);
-            } else {
-                kind = HFX_K_DECAY;
-                tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
-                lost = true;
-            }
-            if (lost) {
-                __syncwarp();
-                if (lane == 0) hfxd_herase(W, site);
-                life = __dadd_rn(life, __dsub_rn(time, g_birth[kx]));            // every lane reads the same word
-                __syncwarp();
-                ps_after = hfxd_replace(W, ident, draws, kx);
-                if (lane == 0) { g_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
-            }
-            if (lane == 0) {
-                W.s_pos[kx] = ps_after;
-                W.s_cnt[HFX_T_EVENTS] += 1;
-                W.s_cnt[tally] += 1;
-                if (traced && trace_at < (uint64_t)X.trace_cap) {
-                    HfTraceRec rec;
-                    rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(X.X, X.Y, fin);
-                    rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
-                    rec.pad[0] = (uint8_t)(ps_after >> 30); rec.pad[1] = 0;
-                    rec.spins = (uint32_t)chosen | ((uint32_t)kx << 16); rec.draws = draws;
-                    X.trace[(dev - X.trace_first) * X.trace_cap + trace_at] = rec;
+                if (lost) {
+                    __syncwarp();
+                    if (lane == 0) hfxd_herase(W, site);
+                    life = __dadd_rn(life, __dsub_rn(time, g_birth[kx]));        // every lane reads the same word
+                    __syncwarp();
+                    ps_after = hfxd_replace(W, ident, draws, kx);
+                    if (lane == 0) { g_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
                 }
-            }
-            trace_at += 1;
-            __syncwarp();
-            // (4) refresh the cached totals: the slot itself in its new state (its evaluation marks the neighbours of
-            //     the site it now occupies), a promoted acceptor (whose neighbours see a different spin), then everybody marked
-            {
-                const double Sk = hfxd_lane_sum<false, true>(W, ps_after, rr);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sk, lane), 31);
-                if (lane == 0) W.s_T[kx] = tot;
-            }
-            if (promoted >= 0) {
-                const double Sa = hfxd_lane_sum<false, true>(W, W.s_pos[promoted], rr);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sa, lane), 31);
-                __syncwarp();
-                if (lane == 0) { W.s_T[promoted] = tot; W.s_dirty[promoted >> 5] &= ~(1u << (promoted & 31)); }
-            }
-            __syncwarp();
-            for (int wq = 0; wq < n_slots; ++wq) {
-                unsigned todo = W.s_dirty[wq];
-                if (wq == (kx >> 5)) todo &= ~(1u << (kx & 31));                 // done above
-                __syncwarp();
-                if (lane == 0) W.s_dirty[wq] = 0;
-                while (todo) {
-                    const int q = (wq << 5) + __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const double Sq = hfxd_lane_sum<false, false>(W, W.s_pos[q], rr);
-                    const double tot = __shfl_sync(HF_FULL, hfx_scan(Sq, lane), 31);
-                    if (lane == 0) W.s_T[q] = tot;
+                if (lane == 0) {
+                    W.s_pos[kx] = ps_after;
+                    W.s_cnt[HFX_T_EVENTS] += 1;
+                    W.s_cnt[tally] += 1;
+                    if (traced && trace_at < (uint64_t)X.trace_cap) {
+                        HfTraceRec rec;
+                        rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(X.X, X.Y, fin);
+                        rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
+                        rec.pad[0] = (uint8_t)(ps_after >> 30); rec.pad[1] = 0;
+                        rec.spins = (uint32_t)chosen | ((uint32_t)kx << 16); rec.draws = draws;
+                        X.trace[(dev - X.trace_first) * X.trace_cap + trace_at] = rec;
+                    }
                 }
+                trace_at += 1;
+                __syncwarp();
+                // (4) refresh the cached totals: the slot itself in its new state, a promoted acceptor (whose neighbours
+                //     see a different spin), then everybody marked
+                stage = 1; tgt = kx; job = ps_after;
             }
             __syncwarp();
         }
