@@ -55,22 +55,22 @@ struct HfxdParams {
 __host__ __device__ inline int hfxd_hash_size(int n_pad) { int h = 64; while (h < 2 * n_pad) h <<= 1; return h; }
 __host__ __device__ inline bool hfxd_rates_in_registers(int M) { return (M + 3 + 31) / 32 <= HFXD_KREG; }
 __host__ __device__ inline size_t hfxd_warp_bytes(int M, int n_pad) {
-    // T (f64) | rates (f64, only when they do not fit the registers) | pos, keys (u32) | counters, dirty (u32) | vals (u16)
+    // T (f64) | rates (f64, only when they do not fit the registers) | pos, keys (u32) | counters, dirty (u32) | bitmap (u32) | vals (u16)
     const size_t h = (size_t)hfxd_hash_size(n_pad);
-    size_t b = 8 * ((size_t)n_pad + (hfxd_rates_in_registers(M) ? 0 : hfx_padded_channels(M))) + 4 * ((size_t)n_pad + h + 64) + 2 * h;
+    size_t b = 8 * ((size_t)n_pad + (hfxd_rates_in_registers(M) ? 0 : hfx_padded_channels(M))) + 4 * ((size_t)n_pad + h + 64 + h / 4) + 2 * h;
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
-    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | off (i32)   + per warp
-    return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * (size_t)((M + 3) & ~3) + (size_t)warps * hfxd_warp_bytes(M, n_pad);
+    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | off, lin, pk (i32)   + per warp
+    return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 3 * (size_t)((M + 3) & ~3) + (size_t)warps * hfxd_warp_bytes(M, n_pad);
 }
 
 struct HfxdWarp {                      // one warp's view of its device
     const HfxdParams *P;
     const double *s_g6, *s_gd, *s_k, *s_ann;
-    const int32_t *s_off;
+    const int32_t *s_off, *s_lin, *s_pk;   // packed offsets; linear and packed site deltas (valid away from the x / y seams)
     double *s_T, *s_rates;
-    uint32_t *s_pos, *s_cnt, *s_dirty, *s_keys;
+    uint32_t *s_pos, *s_cnt, *s_dirty, *s_keys, *s_bits;
     uint16_t *s_vals;
     const double *ws1, *wt1;           // this device's realisation, site 0
     uint32_t hmask;
@@ -79,7 +79,18 @@ struct HfxdWarp {                      // one warp's view of its device
 };
 
 // ---- the occupancy hash set -------------------------------------------------------------------------------------
+// keys[H] / vals[H]: open addressing, linear probing, bucket = top bits of site * golden ratio.  bits[8 H]: one bit per
+// finer bucket (the same product, three more bits), set on insert and never cleared before the next rebuild: a clear
+// bit proves the site empty — 15 of 16 lookups of a rate evaluation end there, with no divergent probe loop.
 __device__ __forceinline__ uint32_t hfxd_hslot(const HfxdWarp &W, uint32_t site) { return (site * 0x9E3779B1u) >> W.hshift; }
+__device__ __forceinline__ bool hfxd_maybe(const HfxdWarp &W, uint32_t site) {
+    const uint32_t f = (site * 0x9E3779B1u) >> (W.hshift - 3);
+    return (W.s_bits[f >> 5] >> (f & 31)) & 1u;
+}
+__device__ __forceinline__ void hfxd_bit_set(const HfxdWarp &W, uint32_t site) {
+    const uint32_t f = (site * 0x9E3779B1u) >> (W.hshift - 3);
+    W.s_bits[f >> 5] |= 1u << (f & 31);
+}
 // entry of the exciton on packed `site`, -1 if the site is empty (any lane, any site)
 __device__ __forceinline__ int hfxd_hfind(const HfxdWarp &W, uint32_t site) {
     uint32_t h = hfxd_hslot(W, site);
@@ -99,6 +110,18 @@ __device__ __forceinline__ void hfxd_hinsert(const HfxdWarp &W, uint32_t ps, int
     uint32_t h = hfxd_hslot(W, ps & 0x3fffffffu);
     while (W.s_keys[h]) h = (h + 1) & W.hmask;
     W.s_keys[h] = ps; W.s_vals[h] = (uint16_t)slot;
+    hfxd_bit_set(W, ps & 0x3fffffffu);
+}
+// all lanes: the bitmap from the slots (start of a launch, and every so often to shed the stale bits of erased entries)
+__device__ __forceinline__ void hfxd_bits_rebuild(const HfxdWarp &W, int n, int H) {
+    __syncwarp();
+    for (int q = W.lane; q < H / 4; q += 32) W.s_bits[q] = 0;
+    __syncwarp();
+    for (int q = W.lane; q < n; q += 32) {
+        const uint32_t ps = W.s_pos[q];
+        if (ps) { const uint32_t f = ((ps & 0x3fffffffu) * 0x9E3779B1u) >> (W.hshift - 3); atomicOr(&W.s_bits[f >> 5], 1u << (f & 31)); }
+    }
+    __syncwarp();
 }
 __device__ __forceinline__ void hfxd_herase(const HfxdWarp &W, uint32_t site) {
     int i = hfxd_hfind(W, site);
@@ -142,6 +165,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     const double *g = singlet ? W.s_g6 : W.s_gd;
     const double *ann = W.s_ann + (singlet ? 0 : 2);
     const bool in_regs = hfxd_rates_in_registers(W.M);
+    const bool nowrap = px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
     double S = 0.0;
 #pragma unroll
     for (int k0 = 0; k0 < HFXD_KREG; k0 += HFXD_CHUNK) {
@@ -153,14 +177,18 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 const int c = ((k0 + u) << 5) + W.lane;
                 wj[u] = 0.0; nb[u] = -1;
                 if (c < W.M) {
-                    const int o = W.s_off[c];
-                    const int dz = ((o >> 16) & 255) - 128;
-                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                    if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
-                    if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
-                    wj[u] = __ldg(w + (dz * plane + (yy - py) * X.X + (xx - px)));
-                    const int zz = pz + dz;
-                    if (zz >= 0 && zz < X.Z) nb[u] = hf_pack(xx, yy, zz);        // outside: the halo's weight 0 gives rate 0
+                    const int zz = pz + ((W.s_off[c] >> 16) & 255) - 128;
+                    if (nowrap) {
+                        wj[u] = __ldg(w + W.s_lin[c]);
+                        if (zz >= 0 && zz < X.Z) nb[u] = site + W.s_pk[c];        // no borrow: every coordinate stays in range
+                    } else {
+                        const int o = W.s_off[c];
+                        int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                        if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+                        if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+                        wj[u] = __ldg(w + ((zz - pz) * plane + (yy - py) * X.X + (xx - px)));
+                        if (zz >= 0 && zz < X.Z) nb[u] = hf_pack(xx, yy, zz);    // outside: the halo's weight 0 gives rate 0
+                    }
                 }
             }
 #pragma unroll
@@ -170,10 +198,12 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 if (k < W.K) {
                     if (c < W.M) {
                         rate = hfx_rate(pref, g[c], wj[u], inv_wi);
-                        const int h = nb[u] >= 0 ? hfxd_hfind(W, (uint32_t)nb[u]) : -1;
-                        if (h >= 0) {
-                            rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
-                            if (kMark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
+                        if (nb[u] >= 0 && hfxd_maybe(W, (uint32_t)nb[u])) {
+                            const int h = hfxd_hfind(W, (uint32_t)nb[u]);
+                            if (h >= 0) {
+                                rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
+                                if (kMark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
+                            }
                         }
                     } else if (c == W.M) {
                         rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
@@ -201,7 +231,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
             if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
             rate = hfx_rate(pref, g[c], __ldg(w + (dz * plane + (yy - py) * X.X + (xx - px))), inv_wi);
             const int zz = pz + dz;
-            const int h = (zz >= 0 && zz < X.Z) ? hfxd_hfind(W, (uint32_t)hf_pack(xx, yy, zz)) : -1;
+            const int h = (zz >= 0 && zz < X.Z && hfxd_maybe(W, (uint32_t)hf_pack(xx, yy, zz))) ? hfxd_hfind(W, (uint32_t)hf_pack(xx, yy, zz)) : -1;
             if (h >= 0) {
                 rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
                 if (kMark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
@@ -296,17 +326,23 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     double *s_k = s_gd + M;
     double *s_ann = s_k + HFX_N_K;
     int32_t *s_off = reinterpret_cast<int32_t *>(s_ann + 4);
-    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 3) & ~3)) + (size_t)warp * hfxd_warp_bytes(M, n_pad);
+    int32_t *s_lin = s_off + ((M + 3) & ~3), *s_pk = s_lin + ((M + 3) & ~3);
+    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_pk + ((M + 3) & ~3)) + (size_t)warp * hfxd_warp_bytes(M, n_pad);
     HfxdWarp W;
-    W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_off = s_off;
+    W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_off = s_off; W.s_lin = s_lin; W.s_pk = s_pk;
     W.s_T = reinterpret_cast<double *>(wsm);
     W.s_rates = W.s_T + n_pad;
     W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + (in_regs ? 0 : padded));
-    W.s_keys = W.s_pos + n_pad; W.s_cnt = W.s_keys + H; W.s_dirty = W.s_cnt + 32;
-    W.s_vals = reinterpret_cast<uint16_t *>(W.s_dirty + 32);
+    W.s_keys = W.s_pos + n_pad; W.s_cnt = W.s_keys + H; W.s_dirty = W.s_cnt + 32; W.s_bits = W.s_dirty + 32;
+    W.s_vals = reinterpret_cast<uint16_t *>(W.s_bits + H / 4);
     W.hmask = (uint32_t)H - 1u; W.hshift = 32 - (31 - __clz(H));
     W.lane = lane; W.K = K; W.M = M;
-    for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_off[m] = X.offsets[m]; }
+    for (int m = threadIdx.x; m < M; m += kWarps * 32) {
+        const int o = X.offsets[m];
+        const int dx = (o & 255) - 128, dy = ((o >> 8) & 255) - 128, dz = ((o >> 16) & 255) - 128;
+        s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_off[m] = o; s_lin[m] = X.lin[m];
+        s_pk[m] = dx + (dy << 10) + (dz << 20);
+    }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = X.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = X.k_risc[threadIdx.x]; }
     if (threadIdx.x < 6) { s_k[24 + threadIdx.x] = X.k_rad[threadIdx.x]; s_k[30 + threadIdx.x] = X.k_nonrad[threadIdx.x]; }
@@ -324,6 +360,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
         for (int h = lane; h < H; h += 32) W.s_keys[h] = 0;
+        for (int h = lane; h < H / 4; h += 32) W.s_bits[h] = 0;
         __syncwarp();
         if (P.fill) {
             // hf_xd_spawn: an empty device, slots filled in order; their totals are computed by the refresh pass below
@@ -346,6 +383,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 while (atomicCAS(&W.s_keys[h], 0u, ps) != 0u) h = (h + 1) & W.hmask;
                 W.s_vals[h] = (uint16_t)q;
             }
+            hfxd_bits_rebuild(W, P.n, H);
         }
         __syncwarp();
         const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
@@ -356,6 +394,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             // stage 0: evaluate the chosen exciton, pick its channel, apply the event
             //       1: refresh a slot whose own site / spin changed (its evaluation marks the excitons it meets)
             //       2: refresh the slots marked dirty
+            if ((ev & 127) == 127) hfxd_bits_rebuild(W, P.n, H);                 // shed the stale bits of erased entries
             int stage = 2, tgt = -1, kx = -1, promoted = -1;
             uint32_t job = 0;
             double target = 0.0, base = 0.0, R = 0.0, u_time = 0.0;
