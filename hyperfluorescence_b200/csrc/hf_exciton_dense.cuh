@@ -31,7 +31,7 @@
 #define HFXD_T_N 24
 #define HFXD_MAX_EXCITONS 1024
 #ifndef HFXD_MIN_BLOCKS
-#define HFXD_MIN_BLOCKS 4              // 4 CTAs x 7 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
+#define HFXD_MIN_BLOCKS 2              // 2 CTAs x 14 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
 #endif
 #define HFXD_KREG 9                    // slots of 32 channels whose rates stay in registers between evaluation and pick (cutoff <= 4)
 #ifndef HFXD_CHUNK
@@ -57,18 +57,18 @@ __host__ __device__ inline bool hfxd_rates_in_registers(int M) { return (M + 3 +
 __host__ __device__ inline size_t hfxd_warp_bytes(int M, int n_pad) {
     // T (f64) | rates (f64, only when they do not fit the registers) | pos, keys (u32) | counters, dirty (u32) | bitmap (u32) | vals (u16)
     const size_t h = (size_t)hfxd_hash_size(n_pad);
-    size_t b = 8 * ((size_t)n_pad + (hfxd_rates_in_registers(M) ? 0 : hfx_padded_channels(M))) + 4 * ((size_t)n_pad + h + 64 + h / 4) + 2 * h;
+    size_t b = 8 * ((size_t)n_pad + (hfxd_rates_in_registers(M) ? 0 : hfx_padded_channels(M))) + 4 * ((size_t)n_pad + h + 64 + h / 2) + 2 * h;
     return (b + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
-    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | off, lin, pk (i32)   + per warp
-    return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 3 * (size_t)((M + 3) & ~3) + (size_t)warps * hfxd_warp_bytes(M, n_pad);
+    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | off, lin, pk, pkc, pkc2 (i32)   + per warp
+    return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 5 * (size_t)((M + 3) & ~3) + (size_t)warps * hfxd_warp_bytes(M, n_pad);
 }
 
 struct HfxdWarp {                      // one warp's view of its device
     const HfxdParams *P;
     const double *s_g6, *s_gd, *s_k, *s_ann;
-    const int32_t *s_off, *s_lin, *s_pk;   // packed offsets; linear and packed site deltas (valid away from the x / y seams)
+    const int32_t *s_off, *s_lin, *s_pk, *s_pkc, *s_pkc2;   // packed offsets; linear, packed and hashed-packed site deltas (valid away from the x / y seams)
     double *s_T, *s_rates;
     uint32_t *s_pos, *s_cnt, *s_dirty, *s_keys, *s_bits;
     uint16_t *s_vals;
@@ -79,17 +79,23 @@ struct HfxdWarp {                      // one warp's view of its device
 };
 
 // ---- the occupancy hash set -------------------------------------------------------------------------------------
-// keys[H] / vals[H]: open addressing, linear probing, bucket = top bits of site * golden ratio.  bits[8 H]: one bit per
-// finer bucket (the same product, three more bits), set on insert and never cleared before the next rebuild: a clear
-// bit proves the site empty — 15 of 16 lookups of a rate evaluation end there, with no divergent probe loop.
-__device__ __forceinline__ uint32_t hfxd_hslot(const HfxdWarp &W, uint32_t site) { return (site * 0x9E3779B1u) >> W.hshift; }
-__device__ __forceinline__ bool hfxd_maybe(const HfxdWarp &W, uint32_t site) {
-    const uint32_t f = (site * 0x9E3779B1u) >> (W.hshift - 3);
-    return (W.s_bits[f >> 5] >> (f & 31)) & 1u;
+// keys[H] / vals[H]: open addressing, linear probing, bucket = top bits of site * C1.  bits[16 H]: a Bloom filter with
+// two hash functions (top bits of site * C1 and of site * C2), set on insert and never cleared before the next rebuild
+// (stale bits only cost a wasted exact lookup): a clear bit proves the site empty.  With n = H / 2 entries a lane's
+// lookup passes the filter with probability (1 - exp(-1/16))^2 = 0.4 %, a warp's with 11 %: the divergent exact probe
+// is the exception, not the rule.
+#define HFXD_C1 0x9E3779B1u
+#define HFXD_C2 0x85EBCA6Bu
+__device__ __forceinline__ uint32_t hfxd_hslot(const HfxdWarp &W, uint32_t site) { return (site * HFXD_C1) >> W.hshift; }
+__device__ __forceinline__ bool hfxd_bloom(const HfxdWarp &W, uint32_t p1, uint32_t p2) {    // p1 = site * C1, p2 = site * C2
+    const uint32_t f1 = p1 >> (W.hshift - 4), f2 = p2 >> (W.hshift - 4);
+    return ((W.s_bits[f1 >> 5] >> (f1 & 31)) & (W.s_bits[f2 >> 5] >> (f2 & 31)) & 1u) != 0;
 }
+__device__ __forceinline__ bool hfxd_maybe(const HfxdWarp &W, uint32_t site) { return hfxd_bloom(W, site * HFXD_C1, site * HFXD_C2); }
 __device__ __forceinline__ void hfxd_bit_set(const HfxdWarp &W, uint32_t site) {
-    const uint32_t f = (site * 0x9E3779B1u) >> (W.hshift - 3);
-    W.s_bits[f >> 5] |= 1u << (f & 31);
+    const uint32_t f1 = (site * HFXD_C1) >> (W.hshift - 4), f2 = (site * HFXD_C2) >> (W.hshift - 4);
+    W.s_bits[f1 >> 5] |= 1u << (f1 & 31);
+    W.s_bits[f2 >> 5] |= 1u << (f2 & 31);
 }
 // entry of the exciton on packed `site`, -1 if the site is empty (any lane, any site)
 __device__ __forceinline__ int hfxd_hfind(const HfxdWarp &W, uint32_t site) {
@@ -115,11 +121,15 @@ __device__ __forceinline__ void hfxd_hinsert(const HfxdWarp &W, uint32_t ps, int
 // all lanes: the bitmap from the slots (start of a launch, and every so often to shed the stale bits of erased entries)
 __device__ __forceinline__ void hfxd_bits_rebuild(const HfxdWarp &W, int n, int H) {
     __syncwarp();
-    for (int q = W.lane; q < H / 4; q += 32) W.s_bits[q] = 0;
+    for (int q = W.lane; q < H / 2; q += 32) W.s_bits[q] = 0;
     __syncwarp();
     for (int q = W.lane; q < n; q += 32) {
-        const uint32_t ps = W.s_pos[q];
-        if (ps) { const uint32_t f = ((ps & 0x3fffffffu) * 0x9E3779B1u) >> (W.hshift - 3); atomicOr(&W.s_bits[f >> 5], 1u << (f & 31)); }
+        const uint32_t site = W.s_pos[q] & 0x3fffffffu;
+        if (site) {
+            const uint32_t f1 = (site * HFXD_C1) >> (W.hshift - 4), f2 = (site * HFXD_C2) >> (W.hshift - 4);
+            atomicOr(&W.s_bits[f1 >> 5], 1u << (f1 & 31));
+            atomicOr(&W.s_bits[f2 >> 5], 1u << (f2 & 31));
+        }
     }
     __syncwarp();
 }
@@ -144,19 +154,42 @@ __device__ __forceinline__ void hfxd_hset_spin(const HfxdWarp &W, uint32_t site,
     if (h >= 0) W.s_keys[h] = site | ((uint32_t)spin << 30);
 }
 
-// Lane sums of the channel rates of an exciton (packed site + spin).  kKeep: leave the rates for the pick — in
-// rr[] (registers, K <= HFXD_KREG) or in s_rates.  kMark: the excitons met on occupied acceptor sites are marked
-// dirty (they see the site that is about to change / has just changed).  HFXD_CHUNK slots are gathered before any
-// of them is consumed.
-// ONE inlined instance per kernel (kKeep / kMark are run-time flags): with five inlined copies the kernel was 16 800
-// instructions and bound by instruction fetch.
-__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, double (&rr)[HFXD_KREG], const bool kKeep, const bool kMark) {
+// One transfer channel the slow way: periodic wrap in x and y, exact occupancy lookup, marking.  Returns the rate.
+__device__ __forceinline__ double hfxd_channel(const HfxdWarp &W, const double *w, const double *pref, const double *g, const double *ann,
+                                               double inv_wi, int px, int py, int pz, int c, bool mark) {
+    const HfxParams &X = W.P->X;
+    const int o = W.s_off[c];
+    const int zz = pz + ((o >> 16) & 255) - 128;
+    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+    if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+    if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+    double rate = hfx_rate(pref, g[c], __ldg(w + ((zz - pz) * X.X * X.Y + (yy - py) * X.X + (xx - px))), inv_wi);
+    if (zz >= 0 && zz < X.Z) {                                                   // outside: the halo's weight 0 gave rate 0
+        const uint32_t nb = (uint32_t)hf_pack(xx, yy, zz);
+        if (hfxd_maybe(W, nb)) {
+            const int h = hfxd_hfind(W, nb);
+            if (h >= 0) {
+                rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
+                if (mark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
+            }
+        }
+    }
+    return rate;
+}
+
+// Lane sums of the channel rates of an exciton (packed site + spin): S = the lane's rates added in slot order.
+// keep: leave the rates for the pick — in rr[] (registers, K <= HFXD_KREG) or in s_rates.  mark: the excitons met on
+// occupied acceptor sites are marked dirty (they see the site that is about to change / has just changed).
+// ONE inlined instance per kernel (keep / mark are run-time flags).
+// Fast path (site away from the x / y seams, K <= HFXD_KREG — the usual case): linear offsets and hashed packed
+// offsets from shared-memory tables, HFXD_CHUNK gathers in flight, occupancy through the bitmap only; the rare lanes
+// whose bitmap test passes resolve it exactly afterwards and re-add their nine rates in slot order.
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, double (&rr)[HFXD_KREG], const bool keep, const bool mark) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
     const bool singlet = spin == HFX_SINGLET;
     const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-    const int plane = X.X * X.Y;
-    const int64_t i = (int64_t)pz * plane + py * X.X + px;
+    const int64_t i = ((int64_t)pz * X.Y + py) * X.X + px;
     const double *w = (singlet ? W.ws1 : W.wt1) + i;
     const double wi = __ldg(w);
     const int a = hfx_tag_of(wi);
@@ -164,87 +197,77 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     const double *pref = W.s_k + (singlet ? 0 : 9) + 3 * a;
     const double *g = singlet ? W.s_g6 : W.s_gd;
     const double *ann = W.s_ann + (singlet ? 0 : 2);
-    const bool in_regs = hfxd_rates_in_registers(W.M);
-    const bool nowrap = px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
+    const double on0 = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
+    const double on1 = W.s_k[24 + 2 * a + (singlet ? 0 : 1)], on2 = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+    const bool fast = hfxd_rates_in_registers(W.M) && px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
     double S = 0.0;
+    if (fast) {
+        const uint32_t site_c1 = (uint32_t)site * HFXD_C1, site_c2 = (uint32_t)site * HFXD_C2;
+        unsigned hits = 0;
 #pragma unroll
-    for (int k0 = 0; k0 < HFXD_KREG; k0 += HFXD_CHUNK) {
-        if (k0 < W.K) {
+        for (int k0 = 0; k0 < HFXD_KREG; k0 += HFXD_CHUNK) {
             double wj[HFXD_CHUNK];
-            int nb[HFXD_CHUNK];
 #pragma unroll
             for (int u = 0; u < HFXD_CHUNK; ++u) {
                 const int c = ((k0 + u) << 5) + W.lane;
-                wj[u] = 0.0; nb[u] = -1;
-                if (c < W.M) {
-                    const int zz = pz + ((W.s_off[c] >> 16) & 255) - 128;
-                    if (nowrap) {
-                        wj[u] = __ldg(w + W.s_lin[c]);
-                        if (zz >= 0 && zz < X.Z) nb[u] = site + W.s_pk[c];        // no borrow: every coordinate stays in range
-                    } else {
-                        const int o = W.s_off[c];
-                        int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                        if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
-                        if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
-                        wj[u] = __ldg(w + ((zz - pz) * plane + (yy - py) * X.X + (xx - px)));
-                        if (zz >= 0 && zz < X.Z) nb[u] = hf_pack(xx, yy, zz);    // outside: the halo's weight 0 gives rate 0
-                    }
-                }
+                wj[u] = c < W.M ? __ldg(w + W.s_lin[c]) : 0.0;
             }
 #pragma unroll
             for (int u = 0; u < HFXD_CHUNK; ++u) {
                 const int k = k0 + u, c = (k << 5) + W.lane;
-                double rate = 0.0;
-                if (k < W.K) {
-                    if (c < W.M) {
-                        rate = hfx_rate(pref, g[c], wj[u], inv_wi);
-                        if (nb[u] >= 0 && hfxd_maybe(W, (uint32_t)nb[u])) {
-                            const int h = hfxd_hfind(W, (uint32_t)nb[u]);
-                            if (h >= 0) {
-                                rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
-                                if (kMark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
-                            }
-                        }
-                    } else if (c == W.M) {
-                        rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
-                    } else if (c == W.M + 1) {
-                        rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
-                    } else if (c == W.M + 2) {
-                        rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
-                    }
-                    if (kKeep && !in_regs) W.s_rates[c] = rate;
-                    S = __dadd_rn(S, rate);
+                double rate;
+                if (c < W.M) {
+                    rate = hfx_rate(pref, g[c], wj[u], inv_wi);
+                    // (site + pk) * C == site * C + pk * C (mod 2^32): the neighbour's two hashes without a multiply
+                    hits |= (hfxd_bloom(W, site_c1 + (uint32_t)W.s_pkc[c], site_c2 + (uint32_t)W.s_pkc2[c]) ? 1u : 0u) << k;
+                } else {
+                    rate = c == W.M ? on0 : (c == W.M + 1 ? on1 : (c == W.M + 2 ? on2 : 0.0));
                 }
-                if (kKeep) rr[k] = rate;
+                rr[k] = rate;
+                S = __dadd_rn(S, rate);
             }
         }
-    }
-    // cutoffs above 4: the slots beyond HFXD_KREG, one at a time (rates kept in shared memory)
-    for (int k = HFXD_KREG; k < W.K; ++k) {
-        const int c = (k << 5) + W.lane;
-        double rate = 0.0;
-        if (c < W.M) {
-            const int o = W.s_off[c];
-            const int dz = ((o >> 16) & 255) - 128;
-            int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-            if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
-            if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
-            rate = hfx_rate(pref, g[c], __ldg(w + (dz * plane + (yy - py) * X.X + (xx - px))), inv_wi);
-            const int zz = pz + dz;
-            const int h = (zz >= 0 && zz < X.Z && hfxd_maybe(W, (uint32_t)hf_pack(xx, yy, zz))) ? hfxd_hfind(W, (uint32_t)hf_pack(xx, yy, zz)) : -1;
-            if (h >= 0) {
-                rate = __dmul_rn(rate, ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
-                if (kMark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
+        if (__any_sync(HF_FULL, hits != 0)) {                                    // somebody may have a neighbour: exact lookups
+            if (hits) {
+                bool changed = false;
+#pragma unroll
+                for (int k = 0; k < HFXD_KREG; ++k) {
+                    if (hits >> k & 1u) {
+                        const int c = (k << 5) + W.lane;
+                        const int zz = pz + ((W.s_off[c] >> 16) & 255) - 128;
+                        const int h = (zz >= 0 && zz < X.Z) ? hfxd_hfind(W, (uint32_t)(site + W.s_pk[c])) : -1;
+                        if (h >= 0) {
+                            rr[k] = __dmul_rn(rr[k], ann[(W.s_keys[h] >> 30) == HFX_SINGLET ? 0 : 1]);
+                            changed = true;
+                            if (mark) { const int q = W.s_vals[h]; atomicOr(&W.s_dirty[q >> 5], 1u << (q & 31)); }
+                        }
+                    }
+                }
+                if (changed) {
+                    S = 0.0;
+#pragma unroll
+                    for (int k = 0; k < HFXD_KREG; ++k) S = __dadd_rn(S, rr[k]);  // slots >= K hold +0.0: S + 0.0 == S
+                }
             }
-        } else if (c == W.M) {
-            rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
-        } else if (c == W.M + 1) {
-            rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
-        } else if (c == W.M + 2) {
-            rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
         }
-        if (kKeep) W.s_rates[c] = rate;
-        S = __dadd_rn(S, rate);
+    } else {
+        const bool in_regs = hfxd_rates_in_registers(W.M);
+#pragma unroll 1
+        for (int k = 0; k < W.K; ++k) {
+            const int c = (k << 5) + W.lane;
+            double rate;
+            if (c < W.M) rate = hfxd_channel(W, w, pref, g, ann, inv_wi, px, py, pz, c, mark);
+            else rate = c == W.M ? on0 : (c == W.M + 1 ? on1 : (c == W.M + 2 ? on2 : 0.0));
+            if (keep) {
+                if (in_regs) {
+#pragma unroll
+                    for (int q = 0; q < HFXD_KREG; ++q) if (q == k) rr[q] = rate;
+                } else {
+                    W.s_rates[c] = rate;
+                }
+            }
+            S = __dadd_rn(S, rate);
+        }
     }
     __syncwarp();
     return S;
@@ -326,15 +349,15 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     double *s_k = s_gd + M;
     double *s_ann = s_k + HFX_N_K;
     int32_t *s_off = reinterpret_cast<int32_t *>(s_ann + 4);
-    int32_t *s_lin = s_off + ((M + 3) & ~3), *s_pk = s_lin + ((M + 3) & ~3);
-    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_pk + ((M + 3) & ~3)) + (size_t)warp * hfxd_warp_bytes(M, n_pad);
+    int32_t *s_lin = s_off + ((M + 3) & ~3), *s_pk = s_lin + ((M + 3) & ~3), *s_pkc = s_pk + ((M + 3) & ~3), *s_pkc2 = s_pkc + ((M + 3) & ~3);
+    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_pkc2 + ((M + 3) & ~3)) + (size_t)warp * hfxd_warp_bytes(M, n_pad);
     HfxdWarp W;
-    W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_off = s_off; W.s_lin = s_lin; W.s_pk = s_pk;
+    W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_off = s_off; W.s_lin = s_lin; W.s_pk = s_pk; W.s_pkc = s_pkc; W.s_pkc2 = s_pkc2;
     W.s_T = reinterpret_cast<double *>(wsm);
     W.s_rates = W.s_T + n_pad;
     W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + (in_regs ? 0 : padded));
     W.s_keys = W.s_pos + n_pad; W.s_cnt = W.s_keys + H; W.s_dirty = W.s_cnt + 32; W.s_bits = W.s_dirty + 32;
-    W.s_vals = reinterpret_cast<uint16_t *>(W.s_bits + H / 4);
+    W.s_vals = reinterpret_cast<uint16_t *>(W.s_bits + H / 2);
     W.hmask = (uint32_t)H - 1u; W.hshift = 32 - (31 - __clz(H));
     W.lane = lane; W.K = K; W.M = M;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) {
@@ -342,6 +365,8 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         const int dx = (o & 255) - 128, dy = ((o >> 8) & 255) - 128, dz = ((o >> 16) & 255) - 128;
         s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_off[m] = o; s_lin[m] = X.lin[m];
         s_pk[m] = dx + (dy << 10) + (dz << 20);
+        s_pkc[m] = (int32_t)((uint32_t)s_pk[m] * HFXD_C1);                       // (site + pk) * C == site * C + pk * C  (mod 2^32)
+        s_pkc2[m] = (int32_t)((uint32_t)s_pk[m] * HFXD_C2);
     }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = X.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = X.k_risc[threadIdx.x]; }
@@ -360,7 +385,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
         for (int h = lane; h < H; h += 32) W.s_keys[h] = 0;
-        for (int h = lane; h < H / 4; h += 32) W.s_bits[h] = 0;
+        for (int h = lane; h < H / 2; h += 32) W.s_bits[h] = 0;
         __syncwarp();
         if (P.fill) {
             // hf_xd_spawn: an empty device, slots filled in order; their totals are computed by the refresh pass below
