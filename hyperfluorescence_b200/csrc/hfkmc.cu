@@ -89,7 +89,7 @@ struct hf_sim {
     // high-density exciton devices (hf_xd_*)
     bool xd_configured = false, xd_spawned = false;
     HfxdParams XD;
-    uint32_t *d_xd_pos = nullptr;
+    uint32_t *d_xd_pos = nullptr, *d_xd_occ = nullptr;
     double *d_xd_T = nullptr, *d_xd_birth = nullptr, *d_xd_time = nullptr, *d_xd_life = nullptr;
     uint64_t *d_xd_draws = nullptr;
     unsigned long long *d_xd_totals = nullptr;
@@ -479,7 +479,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
-    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
     cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
     cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab);
@@ -1280,14 +1280,14 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
 // ---- high-density exciton devices (Path XD; model specified by oracle/exciton_dense_oracle.c) ------------
 
 #ifndef HF_XD_WARPS
-#define HF_XD_WARPS 14                 // x HFXD_MIN_BLOCKS = 2 CTAs per SM: 28 devices per SM, 4144 per B200
+#define HF_XD_WARPS 7                  // x HFXD_MIN_BLOCKS = 4 CTAs per SM: 28 devices per SM, 4144 per B200
 #endif
 constexpr int kXdWarps = HF_XD_WARPS;
 
 static void xd_free(hf_sim *s) {
-    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
-    s->d_xd_pos = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_time = nullptr;
+    s->d_xd_pos = nullptr; s->d_xd_occ = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_time = nullptr;
     s->d_xd_life = nullptr; s->d_xd_draws = nullptr; s->d_xd_totals = nullptr;
 }
 
@@ -1311,19 +1311,20 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
     for (int k = 0; k < 4; ++k) D.ann[k] = annihilation[k];
     D.p_tta = p_tta;
-    D.hash_size = hfxd_hash_size(D.n_pad);
+    D.occ_words = (s->X.w_stride + 15) / 16;
     const size_t B = (size_t)s->P.B, np = (size_t)D.n_pad;
     if ((rc = dev_alloc(&s->d_xd_pos, B * np))) return rc;
     if ((rc = dev_alloc(&s->d_xd_T, B * np))) return rc;
     if ((rc = dev_alloc(&s->d_xd_birth, B * np))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_occ, B * (size_t)D.occ_words))) return rc;
     if ((rc = dev_alloc(&s->d_xd_time, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_life, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_draws, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_totals, (size_t)s->n_real * HFXD_T_N))) return rc;
-    D.pos = s->d_xd_pos; D.T = s->d_xd_T; D.birth = s->d_xd_birth;
+    D.pos = s->d_xd_pos; D.T = s->d_xd_T; D.birth = s->d_xd_birth; D.occ = s->d_xd_occ;
     D.time = s->d_xd_time; D.life = s->d_xd_life; D.draws = s->d_xd_draws; D.totals = s->d_xd_totals;
     const size_t smem = hfxd_smem_bytes(s->X.M, D.n_pad, kXdWarps);
-    if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "%d excitons per device need %zu B of shared memory", n_excitons, smem);
+    if (smem > 227 * 1024) return fail(HF_ERR_UNSUPPORTED, "%d excitons per device need %zu B of shared memory", n_excitons, smem);
     if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hfxd_run_kernel<kXdWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfxd_run_kernel<kXdWarps>, kXdWarps * 32, smem));
@@ -1357,6 +1358,7 @@ int hf_xd_spawn(hf_sim *s) {
     if (!s->xd_configured) return fail(HF_ERR_STATE, "hf_xd_spawn before hf_xd_configure");
     int rc = use_device(s);
     if (rc) return rc;
+    HF_CUDA(cudaMemsetAsync(s->d_xd_occ, 0, 4 * (size_t)s->P.B * (size_t)s->XD.occ_words, s->stream));
     HF_CUDA(cudaMemsetAsync(s->d_xd_totals, 0, sizeof(unsigned long long) * (size_t)s->n_real * HFXD_T_N, s->stream));
     if (s->d_x_trace_len) HF_CUDA(cudaMemsetAsync(s->d_x_trace_len, 0, sizeof(uint64_t) * (size_t)s->P.trace_n, s->stream));
     if ((rc = xd_launch(s, 0, 1))) return rc;
@@ -1424,13 +1426,13 @@ int hf_xd_read_occupancy(hf_sim *s, int64_t device, uint8_t *codes) {
     if (!codes) return fail(HF_ERR_BAD_ARG, "null argument");
     if (!s->xd_spawned) return fail(HF_ERR_STATE, "no dense exciton devices yet");
     if ((rc = use_device(s))) return rc;
-    // the occupancy code of a site is the spin of the exciton sitting on it (the device keeps a hash set, not a mask)
-    const size_t n = (size_t)s->XD.n;
-    std::vector<uint32_t> pos(n);
-    HF_CUDA(cudaMemcpyAsync(pos.data(), s->d_xd_pos + (size_t)device * (size_t)s->XD.n_pad, 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    std::vector<uint32_t> words((size_t)s->XD.occ_words);
+    HF_CUDA(cudaMemcpyAsync(words.data(), s->d_xd_occ + (size_t)device * (size_t)s->XD.occ_words, 4 * words.size(), cudaMemcpyDeviceToHost, s->stream));
     HF_CUDA(cudaStreamSynchronize(s->stream));
-    memset(codes, 0, (size_t)s->P.N);
-    for (size_t k = 0; k < n; ++k) codes[unpack_site(s, (int32_t)(pos[k] & 0x3fffffffu))] = (uint8_t)(pos[k] >> 30);
+    for (int64_t i = 0; i < s->P.N; ++i) {
+        const int64_t idx = i + s->X.w_halo;
+        codes[i] = (uint8_t)((words[(size_t)(idx >> 4)] >> (2 * (int)(idx & 15))) & 3u);
+    }
     return HF_OK;
 }
 

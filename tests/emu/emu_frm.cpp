@@ -353,14 +353,14 @@ int emu_xd_run(const int32_t dims[3], const double *ws1, const double *wt1, int3
     D.n = n_excitons; D.n_pad = (n_excitons + 31) & ~31;
     memcpy(D.ann, ann, sizeof(D.ann));
     D.p_tta = p_tta; (void)cutoff;
-    D.hash_size = hfxd_hash_size(D.n_pad);
-    std::vector<uint32_t> pos((size_t)D.n_pad, 0);
+    D.occ_words = (P.w_stride + 15) / 16;
+    std::vector<uint32_t> pos((size_t)D.n_pad, 0), occ((size_t)D.occ_words, 0);
     std::vector<double> T((size_t)D.n_pad, 0.0), birth((size_t)D.n_pad, 0.0);
     double time = 0.0, life = 0.0;
     uint64_t draws = 0, tlen = 0;
     std::vector<unsigned long long> totals(HFXD_T_N, 0);
     std::vector<HfTraceRec> trace((size_t)(trace_cap + 1));
-    D.pos = pos.data(); D.T = T.data(); D.birth = birth.data();
+    D.pos = pos.data(); D.T = T.data(); D.birth = birth.data(); D.occ = occ.data();
     D.time = &time; D.life = &life; D.draws = &draws; D.totals = totals.data();
     P.trace = trace.data(); P.trace_first = 0; P.trace_n = 1; P.trace_cap = trace_cap; P.trace_len = &tlen;
     if (hfxd_smem_bytes(M, D.n_pad, 1) > sizeof(hf_smem)) return 2;
@@ -378,8 +378,10 @@ int emu_xd_run(const int32_t dims[3], const double *ws1, const double *wt1, int3
     }
     scalars_out[0] = time; scalars_out[1] = life; scalars_out[2] = (double)draws;
     memcpy(totals_out, totals.data(), sizeof(unsigned long long) * HFXD_T_N);
-    memset(occ_out, 0, (size_t)P.N);                          // occupancy code of a site = spin of the exciton on it
-    for (int k = 0; k < n_excitons; ++k) occ_out[site_out[k]] = (uint8_t)spin_out[k];
+    for (int64_t i = 0; i < P.N; ++i) {
+        const int64_t idx = i + P.w_halo;
+        occ_out[i] = (uint8_t)((occ[(size_t)(idx >> 4)] >> (2 * (int)(idx & 15))) & 3u);
+    }
     return 0;
 }
 
