@@ -85,7 +85,15 @@ struct HfxdWarp {                      // one warp's view of its device
 // ---- Bloom filter of the occupied sites (keys: index into the mask = site + halo) -------------------------------
 #define HFXD_C1 0x9E3779B1u
 #define HFXD_C2 0x85EBCA6Bu
+#ifdef HFXD_DEBUG_BLOOM
+static unsigned long long hfxd_dbg_total = 0, hfxd_dbg_pass = 0;
+#endif
 __device__ __forceinline__ bool hfxd_bloom(const HfxdWarp &W, uint32_t idx) {
+#ifdef HFXD_DEBUG_BLOOM
+    hfxd_dbg_total += 1;
+    { const uint32_t g1 = (idx * HFXD_C1) >> W.bshift, g2 = (idx * HFXD_C2) >> W.bshift;
+      if (((W.s_bits[g1 >> 5] >> (g1 & 31)) & (W.s_bits[g2 >> 5] >> (g2 & 31)) & 1u) != 0) hfxd_dbg_pass += 1; }
+#endif
     const uint32_t f1 = (idx * HFXD_C1) >> W.bshift, f2 = (idx * HFXD_C2) >> W.bshift;
     return ((W.s_bits[f1 >> 5] >> (f1 & 31)) & (W.s_bits[f2 >> 5] >> (f2 & 31)) & 1u) != 0;
 }
@@ -147,8 +155,10 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 const int delta = nowrap ? W.s_lin[c] : hfx_delta(W.s_off[c], px, py, X.X, X.Y, plane);
                 wj[u] = __ldg(w + delta);
                 const int64_t oj = oi + delta;
-                ow[u] = W.occ[oj >> 4];
-                sh[u] = 2 * (int)(oj & 15);
+                if (hfxd_bloom(W, (uint32_t)oj)) {                                // else: certainly empty, ow stays 0
+                    ow[u] = W.occ[oj >> 4];
+                    sh[u] = 2 * (int)(oj & 15);
+                }
             }
         }
 #pragma unroll
