@@ -121,6 +121,10 @@ struct HfParams {
     unsigned long long *totals;    // channel counters, HF_N_TALLIES
     int64_t n_steps;
     HfIntegrated xi;               // xi.mode == 0: the reference as it is
+    // 1 / sqrt(d2) for every squared distance of the lattice (IEEE division and square root on the host: the same
+    // bits as __ddiv_rn(1.0, __dsqrt_rn(d2))), or null.  The warp kernel's Coulomb sums take 2 (2C - 1) of them per
+    // verified candidate (reseau.py:299-312): one L2-resident load instead of ~60 instructions each.
+    const double *inv_dist;
 };
 
 struct HfWarp {
@@ -392,6 +396,10 @@ __device__ __noinline__ double hf_wait_call(double rng, double k) { return __ddi
 template <bool kCompact> __device__ __forceinline__ double hf_inv_dist(int d2) {
     if constexpr (kCompact) return hf_inv_dist_call(d2); else return __ddiv_rn(1.0, __dsqrt_rn((double)d2));
 }
+// the same value from the table when there is one (warp kernel)
+__device__ __forceinline__ double hf_inv_dist_tab(const HfParams &P, int d2) {
+    return P.inv_dist ? __ldg(P.inv_dist + d2) : __ddiv_rn(1.0, __dsqrt_rn((double)d2));
+}
 
 // One candidate hop of a charge of type t from `initial` to `cand` given its uniform u:
 // _time_move_electron / _time_move_hole (reseau.py:283-292, 315-324) with the Coulomb term of
@@ -435,14 +443,15 @@ __device__ __forceinline__ double hf_hop_time(const HfParams &P, const HfWarp &w
 // 1/|loc_j - initial| for both lists, computed once per regenerated event instead of once per
 // candidate (the reference recomputes it 26 times: SURVEY.md §8a2); same bits.
 template <int L = 32>
-__device__ __forceinline__ void hf_fill_inv_old(HfWarp &w, int t, int initial, int lane) {
+__device__ __forceinline__ void hf_fill_inv_old(const HfParams &P, HfWarp &w, int t, int initial, int lane) {
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
         const int32_t *list = s == 0 ? w.pos(t) : w.pos(1 - t);
         const int n = s == 0 ? w.n_pos(t) : w.n_pos(1 - t);
         for (int j = lane; j < n; j += L) {
             const int d2 = hf_dist2(list[j], initial);
-            w.inv_old(s)[j] = d2 == 0 ? 0.0 : hf_inv_dist<L == 1>(d2);
+            if constexpr (L == 1) w.inv_old(s)[j] = d2 == 0 ? 0.0 : hf_inv_dist<true>(d2);
+            else w.inv_old(s)[j] = d2 == 0 ? 0.0 : hf_inv_dist_tab(P, d2);
         }
     }
     hf_sync<L>();
@@ -493,11 +502,11 @@ __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWa
     const int ns = w.n_pos(t), no = w.n_pos(1 - t);
     for (int j = lane; j < ns; j += L) {
         const int loc = w.pos(t)[j];
-        w.term(0)[j] = loc == initial ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist<false>(hf_dist2(loc, cand)), w.inv_old(0)[j]));
+        w.term(0)[j] = loc == initial ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist_tab(P, hf_dist2(loc, cand)), w.inv_old(0)[j]));
     }
     for (int j = lane; j < no; j += L) {
         const int loc = w.pos(1 - t)[j];
-        w.term(1)[j] = loc == cand ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist<false>(hf_dist2(loc, cand)), w.inv_old(1)[j]));
+        w.term(1)[j] = loc == cand ? 0.0 : __dmul_rn(HF_ELECTROSTATIC, __dsub_rn(hf_inv_dist_tab(P, hf_dist2(loc, cand)), w.inv_old(1)[j]));
     }
     hf_sync<L>();
     // the sum itself, in list order.  A skipped entry (the moving charge itself, reseau.py:300 / 332) holds +0.0,
@@ -532,7 +541,7 @@ __device__ __forceinline__ int hf_gen_move_event_far(const HfParams &P, HfWarp &
     const int total = nx * ny * nz;
     const int32_t *blk = use_flags ? w.flag(t) : w.pos(t);
     const int nb = use_flags ? w.n_flag(t) : w.n_pos(t);
-    hf_fill_inv_old<L>(w, t, pos, lane);
+    hf_fill_inv_old<L>(P, w, t, pos, lane);
     double btau = INFINITY;
     int bfin = -1;
     uint64_t drawn = 0;
@@ -619,7 +628,7 @@ __device__ __forceinline__ int hf_gen_move_event(const HfParams &P, HfWarp &w, i
     const bool active = lane < total && cand != pos && !(blocked_m >> lane & 1u);
     const unsigned mask = hf_ballot<L>(active);
     if (mask == 0) return HF_ST_VALUE_ERROR;                                     // min() of an empty sequence
-    hf_fill_inv_old<L>(w, t, pos, lane);
+    hf_fill_inv_old<L>(P, w, t, pos, lane);
     bool exhausted = false;
     const int rank = __popc(mask & ((1u << lane) - 1u));
     double u = 0.5;
@@ -1162,7 +1171,7 @@ __global__ void hf_eval_hops_kernel(const HfParams P, int64_t local, int t, int 
     hf_load_state(P, w, local, lane);
     for (int i = 0; i < n; ++i) {
         const int ini = hf_pack_site(P, initial[i]), fin = hf_pack_site(P, final_[i]);
-        hf_fill_inv_old(w, t, ini, lane);
+        hf_fill_inv_old(P, w, t, ini, lane);
         if (lane == 0) {
             bool zd = false;
             double k = 0.0;

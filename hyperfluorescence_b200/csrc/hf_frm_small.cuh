@@ -119,7 +119,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
     slow |= (onto_same & amask) != 0;
     const int n = __popc(amask);
     if (n == 0) return HF_ST_VALUE_ERROR;                                        // min() of an empty sequence
-    hf_fill_inv_old<1>(w, t, pos, 0);
+    hf_fill_inv_old<1>(P, w, t, pos, 0);
     const uint64_t d0 = w.draws;
     bool exhausted = false;
     double best = 0.0;

@@ -71,7 +71,7 @@ struct hf_sim {
     uint64_t *d_trace_base = nullptr;
     std::vector<uint64_t> trace_base;  // host copy of d_trace_base
     // launch shape of the step kernel
-    int warps = 4, grid = 1;
+    int warps = 4, grid = 1, resident_warps = 0;
     size_t smem = 0;
     // exciton path (hf_x_*)
     bool x_configured = false, x_spawned = false;
@@ -100,6 +100,7 @@ struct hf_sim {
     double *d_pi_tau = nullptr, *d_pi_clock = nullptr;
     uint64_t *d_pi_draws = nullptr;
     HfiTables *d_pi_tab = nullptr;
+    double *d_inv_dist = nullptr;      // 1 / sqrt(d2) table of the warp kernel
     // timing of hf_run launches
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
     std::vector<cudaEvent_t> event_pool;
@@ -126,19 +127,30 @@ int configure_launch(hf_sim *s) {
     const int64_t cap = (int64_t)s->sm_count * per_sm;
     s->warps = W;
     s->smem = smem;
+    s->resident_warps = (int)(((int64_t)per_sm * W * s->sm_count < s->P.B ? (int64_t)per_sm * W * s->sm_count : s->P.B));
     s->grid = (int)(need < cap ? need : cap);
     if (s->grid < 1) s->grid = 1;
     return HF_OK;
 }
 
+// Warps per CTA: the choice that keeps the most trajectories resident (a trajectory is one warp), so that a batch is
+// one wave whenever it can be; ties go to the larger CTA.  With many charges the lists of one trajectory are ~15 KB of
+// shared memory and the choice is worth up to 1.7x (2048 devices of 164 + 164 charges: 12 resident warps per SM with
+// 4-warp CTAs = two rounds, 15 with 1-warp CTAs = one).
 int pick_launch(hf_sim *s) {
     const size_t per_warp = hf_warp_smem_bytes(s->P.cap_c, s->P.cap_f, hf_xcap(s->P));
-    const size_t limit = 200 * 1024;
-    if (per_warp * 8 <= limit / 4) return configure_launch<8>(s);   // >= 4 CTAs of 8 warps per SM
-    if (per_warp * 4 <= limit) return configure_launch<4>(s);
-    if (per_warp <= limit) return configure_launch<1>(s);
-    return fail(HF_ERR_UNSUPPORTED, "charges=%d needs %zu B of shared memory per trajectory (limit %zu)",
-                s->P.C, per_warp, limit);
+    const size_t limit = 227 * 1024;
+    if (per_warp > limit)
+        return fail(HF_ERR_UNSUPPORTED, "charges=%d needs %zu B of shared memory per trajectory (limit %zu)", s->P.C, per_warp, limit);
+    int best_w = 0;
+    int64_t best_resident = -1;
+    int rc;
+    if (per_warp * 8 <= limit) { if ((rc = configure_launch<8>(s))) return rc; best_w = 8; best_resident = (int64_t)s->resident_warps; }
+    if (per_warp * 4 <= limit) { if ((rc = configure_launch<4>(s))) return rc; if ((int64_t)s->resident_warps > best_resident) { best_w = 4; best_resident = s->resident_warps; } }
+    { if ((rc = configure_launch<1>(s))) return rc; if ((int64_t)s->resident_warps > best_resident) { best_w = 1; best_resident = s->resident_warps; } }
+    if (best_w == 8) return configure_launch<8>(s);
+    if (best_w == 4) return configure_launch<4>(s);
+    return configure_launch<1>(s);
 }
 
 template <typename T>
@@ -460,6 +472,19 @@ int hf_create(const hf_config *c, hf_sim **out) {
     cudaMemsetAsync(s->d_species, 0, (size_t)(R * N), s->stream);
     for (double *p : {s->d_homo, s->d_lumo, s->d_s1, s->d_t1}) cudaMemsetAsync(p, 0, 8 * (size_t)(R * N), s->stream);
     s->have_st.assign((size_t)R, 0);
+    if (c->charges > HF_SMALL_MAX_CHARGES || (c->flags & HF_FLAG_WARP_KERNEL) || c->distance != 1) {
+        const int m = (X > Y ? (X > Z ? X : Z) : (Y > Z ? Y : Z)) - 1;
+        const size_t n = 3 * (size_t)m * (size_t)m + 1;
+        if (n * 8 <= ((size_t)64 << 20)) {                                        // <= 64 MB; larger lattices compute on the fly
+            std::vector<double> tab(n);
+            tab[0] = 0.0;
+            for (size_t d2 = 1; d2 < n; ++d2) tab[d2] = 1.0 / std::sqrt((double)d2);   // IEEE: the bits of __ddiv_rn(1, __dsqrt_rn(d2))
+            if ((rc = dev_alloc(&s->d_inv_dist, n))) return bail(rc);
+            if (cudaMemcpyAsync(s->d_inv_dist, tab.data(), n * 8, cudaMemcpyHostToDevice, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess) return bail(fail(HF_ERR_CUDA, "inverse-distance table upload failed"));
+            P.inv_dist = s->d_inv_dist;
+        }
+    }
     fill_params(s);
     if ((rc = pick_launch(s))) return bail(rc);
     *out = s;
@@ -482,7 +507,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
     cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
-    cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab);
+    cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab); cudaFree(s->d_inv_dist);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HF_OK;
