@@ -354,6 +354,7 @@ def run_ours(args):
                             "e2e": {"value": mc["e2e_value"], "unit": "events/s", "h2d_bytes_per_step": mc["h2d"],
                                     "d2h_bytes_per_step": mc["d2h"], "steps": mc["e2e_steps"]}}
         line["ga"] = ga_fitness_rate(rank, local_rank, world)
+        line["device_eqe"] = device_eqe_rate(rank, local_rank, world)
         line["exciton_path"] = exciton_rate(rank, local_rank, world, cpu=not args.no_cpu)
         line["disorder_sweep"] = exciton_rate(rank, local_rank, world, lattice=256, realisations_total=64, label="disorder_sweep")
         line["high_density"] = dense_rate(rank, local_rank, world, cpu=not args.no_cpu)
@@ -423,6 +424,47 @@ def ga_fitness_rate(rank, local_rank, world):
                        "trajectories_per_candidate": GA_TRAJECTORIES, "events_per_trajectory": GA_STEPS,
                        "sharding": f"{GA_POPULATION // world} candidates per GPU"},
             "best_iqe_percent": float(f.max()), "mean_iqe_percent": float(f.mean())}
+
+
+DE_TRAJ_PER_GPU, DE_STEPS, DE_CUTOFF = 200_000, 2000, 3.0
+
+
+def device_eqe_rate(rank, local_rank, world):
+    """The integrated device: the reference driver's own device (OLED.py:6-10: 10x10x5,
+    charges = 4) with the excitons living in the SAME First Reaction Method as the carriers — formed where the
+    carriers meet (reseau.py:529-533), then hopping (Forster / Dexter), crossing (ISC / RISC) and decaying with the
+    exciton path's rate laws instead of decaying at tau = 0.  Reports events/s and the device EQE = outcoupling x IQE.
+    The exciton part is this repository's own model (parity unpinned); with the excitons set to decay at once the
+    same code path reproduces every golden trajectory of the reference bit for bit."""
+    from hyperfluorescence_b200 import _native as nat
+    from hyperfluorescence_b200 import distributed as hd
+    B = DE_TRAJ_PER_GPU
+    sim = nat.Sim(GA_DIMS, PROPS, FIELD, GA_CHARGES, 1, n_trajectories=B, n_realisations=1, seed=SEED,
+                  first_trajectory=rank * B, device=local_rank)
+    sim.generate_lattice()
+    params = nat.x_params_from_dict(dict(cutoff=DE_CUTOFF))
+    sim.x_configure(params)
+    sim.p_excitons(2)
+    sim.inject()
+    sim.run(DE_STEPS // 4)                                     # warm-up: the first excitons form
+    sim.sync()
+    sim.run_timing()
+    for _ in range(3):
+        sim.run(DE_STEPS)
+    ms, n = sim.run_timing()
+    t = hd.all_reduce_tallies(sim)
+    sim.close()
+    ms = max_over_ranks(ms, world)
+    fired_timed = world * B * DE_STEPS * n
+    iqe = 200.0 * t["emission"] / max(t["injection"], 1)
+    return {"metric": "KMC events/sec (box), integrated device (carriers + excitons in one event loop)",
+            "value": fired_timed / (ms * 1e-3), "unit": "events/s",
+            "config": {"lattice": list(GA_DIMS), "charges": GA_CHARGES, "trajectories_per_gpu": B, "events_per_trajectory_per_launch": DE_STEPS,
+                       "cutoff": DE_CUTOFF, "kernel": "hf_run_small_kernel<true>",
+                       "model": "own (parity unpinned) beyond the decay-at-once gate: DESIGN.md section 11"},
+            "device_iqe_percent": iqe, "device_eqe_percent": params.outcoupling * iqe,
+            "events": {k: t[k] for k in ("fired", "stopped", "move_e", "move_h", "bound", "decay", "x_forster", "x_dexter", "x_isc", "x_risc",
+                                         "recombination", "emission", "injection")}}
 
 
 X_L, X_TRAJ_PER_GPU, X_EVENTS, X_CUTOFF = 128, 1_000_000, 100, 4.0

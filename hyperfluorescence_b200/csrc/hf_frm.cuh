@@ -517,10 +517,25 @@ __device__ __forceinline__ double hf_hop_time_coop(const HfParams &P, const HfWa
     if (onto_opposite) {
         out = -INFINITY;
     } else {
+        // two terms per 16-byte load where the lists allow it (even capacity: both term arrays 16-byte aligned); the
+        // additions stay one after the other, in list order
+        const bool wide = (w.cap_c & 1) == 0;
+        int j = 0;
+        if (wide) {
+            const double2 *t0 = reinterpret_cast<const double2 *>(w.term(0));
 #pragma unroll 4
-        for (int j = 0; j < ns; ++j) out = __dadd_rn(out, w.term(0)[j]);         // 299-304 / 331-336
+            for (; j + 1 < ns; j += 2) { const double2 v = t0[j >> 1]; out = __dadd_rn(__dadd_rn(out, v.x), v.y); }
+        }
 #pragma unroll 4
-        for (int j = 0; j < no; ++j) out = __dsub_rn(out, w.term(1)[j]);         // 309-312 / 341-344
+        for (; j < ns; ++j) out = __dadd_rn(out, w.term(0)[j]);                  // 299-304 / 331-336
+        j = 0;
+        if (wide) {
+            const double2 *t1 = reinterpret_cast<const double2 *>(w.term(1));
+#pragma unroll 4
+            for (; j + 1 < no; j += 2) { const double2 v = t1[j >> 1]; out = __dsub_rn(__dsub_rn(out, v.x), v.y); }
+        }
+#pragma unroll 4
+        for (; j < no; ++j) out = __dsub_rn(out, w.term(1)[j]);                  // 309-312 / 341-344
     }
     hf_sync<L>();
     dE = __dadd_rn(dE, out);                                                     // 288 / 320

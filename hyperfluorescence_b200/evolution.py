@@ -173,6 +173,38 @@ class ExcitonFitness(DeviceFitness):
         return all_gather_fitness(local, self.world)
 
 
+class DeviceEQEFitness(DeviceFitness):
+    """EQE (percent) of a population of compositions from the INTEGRATED device: carriers are injected, drift, meet
+    and bind (the reference's First Reaction Method), and the exciton they form hops, crosses and decays in the same
+    event loop (``Lattice(..., excitons=...)``), so the fitness sees WHERE recombination
+    happens.  EQE = outcoupling x IQE with the reference's IQE = 100 * 2 * emission / injection (reseau.py:595).
+    The exciton part is this package's own model (parity unpinned)."""
+
+    def __init__(self, dims, charges=4, parameters=None, electric_field=0.1, cfg: GAConfig | None = None, seed=0,
+                 device=0, rank=0, world=1):
+        super().__init__(dims, charges, electric_field, cfg, seed, device, rank, world)
+        self.parameters = parameters or {}
+
+    def __call__(self, counts):
+        from . import _native as nat
+        counts = np.asarray(counts, dtype=np.int64)
+        if len(counts) != self.cfg.population:
+            raise ValueError("population size mismatch")
+        sim = self._handle()
+        mine = counts[self.rank * self.local:(self.rank + 1) * self.local]
+        sim.generate_lattice_mixed(self.comps.proportions(mine))
+        params = nat.x_params_from_dict(self.parameters)
+        sim.x_configure(params)                                # tables and Boltzmann weights of the new lattices
+        sim.p_excitons(2)
+        sim.inject()
+        sim.run(self.cfg.steps)
+        t = sim.realisation_tallies()
+        self.last_tallies = t
+        local = params.outcoupling * 100.0 * 2.0 * t["emission"].astype(np.float64) / t["injection"].astype(np.float64)
+        self.generation += 1
+        return all_gather_fitness(local, self.world)
+
+
 def all_gather_fitness(local, world):
     """Concatenate the per-rank fitness blocks (identity for one rank)."""
     local = np.ascontiguousarray(local, dtype=np.float64)

@@ -168,6 +168,7 @@ static inline double __longlong_as_double(long long a) { double b; memcpy(&b, &a
 // fast-math intrinsics used by the screening pass (glibc's math.h reserves the __logf/__expf names)
 #define __logf(x) logf(x)
 #define __expf(x) expf(x)
+struct double2 { double x, y; };
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
     unsigned long long old = *p; *p += v; return old;
 }

@@ -100,3 +100,32 @@ def test_exciton_fitness_ranks_compositions_and_equals_specification():
         lost = rad + sum(v for k, v in ref.items() if k.startswith("nonrad_"))
         assert abs(f[r] - 100.0 * 0.2 * rad / lost) < 1e-12
     fit.close()
+
+
+@pytest.mark.gpu
+def test_device_eqe_fitness_equals_specification_per_candidate():
+    """EQE fitness from the INTEGRATED device (carriers and excitons in one event loop): the per-candidate tallies equal
+    the specification (the integrated block of the Path P restatement) run on each candidate's own lattice."""
+    from hyperfluorescence_b200 import _native as nat
+    from hyperfluorescence_b200.evolution import DeviceEQEFitness, GAConfig
+    from oracle import frm_oracle as fo
+    from tests.test_integrated_excitons import fast_params
+    dims, charges, T, steps = (8, 8, 5), 3, 64, 1500
+    params = fast_params(2.0)
+    cfg = GAConfig(population=4, trajectories_per_candidate=T, steps=steps)
+    fit = DeviceEQEFitness(dims, charges=charges, parameters=params, cfg=cfg, seed=33)
+    counts = fit.comps.clip(np.array([[4, 4], [60, 10], [100, 30], [30, 60]]))
+    f = fit(counts)
+    assert f.shape == (4,) and np.all(f >= 0) and np.all(f <= 20.0) and f.max() > 0
+    sim = fit._handle()
+    per = fit.last_tallies
+    tab = sim.x_tables()
+    for r in (1, 3):
+        lat = sim.download_lattice(r)
+        ws1, wt1 = sim.x_weights(r)
+        olat = fo.OracleLattice.from_arrays(dims, lat["species"], lat["homo"], lat["lumo"], lat["s1"], lat["t1"])
+        ref = olat.run_batch_x(charges, 0.1, 33, r * T, T, steps, fo.ExcitonModel(2, params, tab, ws1, wt1), n_threads=4)
+        assert (int(per["emission"][r]), int(per["recombination"][r]), int(per["injection"][r])) == \
+            (ref["emission"], ref["recombination"], ref["injection"]), r
+        assert abs(f[r] - 0.2 * 200.0 * ref["emission"] / ref["injection"]) < 1e-12
+    fit.close()
