@@ -131,8 +131,9 @@ __device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, 
 // tests/test_gpu_parity.py::test_adjacent_charges_screening_is_exact keeps the two carriers on neighbouring sites
 // for > 10^6 regenerated events and compares every one with the all-exact C restatement.
 // Result: bit-identical events and taus at ~1.06 exact evaluations per event instead of 26.
+template <int kStride = HF_C1_THREADS>
 __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, const double *homo, int t, HfC1 &s,
-                                         int64_t local, uint32_t ident, float *approx /* [l * HF_C1_THREADS] */) {
+                                         int64_t local, uint32_t ident, float *approx /* [l * kStride]: this thread's column */) {
     const int pos = s.pos(t), other = s.pos(1 - t);
     const double *__restrict__ E = t ? homo : lumo;
     const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
@@ -162,7 +163,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
                         const int cand = hf_pack(cx, cy, cz);
                         if (cand == pos) self_l = l;
                         const double dE = (__ldg(row + cz * plane) - e_init) + fz * (double)(cz - pz);
-                        approx[l * HF_C1_THREADS] = cand == other ? -INFINITY : (float)dE;   // onto the opposite charge: k = 1e13
+                        approx[l * kStride] = cand == other ? -INFINITY : (float)dE;   // onto the opposite charge: k = 1e13
                         ++l;
                     }
                 }
@@ -197,11 +198,11 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
                 t0 = -__logf((float)(1.0 - u));
             }
             float a = t0;
-            const float x = approx[l * HF_C1_THREADS] * inv_kt;
+            const float x = approx[l * kStride] * inv_kt;
             if (x > 0.0f) a = t0 * __expf(x);
             if (x > 700.0f) forced |= 1u << l;
             if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
-            approx[l * HF_C1_THREADS] = a;
+            approx[l * kStride] = a;
             if (a < amin) { amin2 = amin; amin = a; lmin = l; }
             else if (!(a >= amin2)) amin2 = a;                                   // also catches NaN
         }
@@ -212,7 +213,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     unsigned mask = forced | (1u << lmin);
     if (!(amin2 > thr)) {                                                        // a runner-up inside the window: scan
         for (int i = 0; i < total; ++i)
-            if (i != self_l && !(approx[i * HF_C1_THREADS] > thr)) mask |= 1u << i;
+            if (i != self_l && !(approx[i * kStride] > thr)) mask |= 1u << i;
     }
     // ---- pass 2: exact evaluation in candidate order, first minimum ----
     const bool other_has = other >= 0;
@@ -358,8 +359,15 @@ __device__ __forceinline__ void hf_c1_store(const HfParams &P, const HfC1 &s, co
 }
 
 // Lattice.operations(stop) for charges == 1: one thread per trajectory.
-__global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_kernel(const HfParams P) {
-    __shared__ float approx_all[HF_C1_MAXCAND * HF_C1_THREADS];
+// Two shapes: 384 threads x 2 CTAs per SM (80 registers: 113 664 trajectories per wave on 148 SMs, the fastest per
+// event) and 288 x 3 (72 registers: 127 872 per wave, ~14 % slower per event).  The host picks the one that finishes
+// the batch sooner: a batch just above a multiple of the first wave size (10^6 trajectories over 8 GPUs = 125 000
+// each) would otherwise pay a whole extra wave for its last 10 %.
+#define HF_C1_THREADS_B 288
+#define HF_C1_MIN_BLOCKS_B 3
+template <int kThreads = HF_C1_THREADS, int kMinBlocks = HF_C1_MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) hf_run_c1_kernel(const HfParams P) {
+    __shared__ float approx_all[HF_C1_MAXCAND * kThreads];
     float *approx = approx_all + threadIdx.x;
     const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= P.B) return;
@@ -384,7 +392,7 @@ __global__ void __launch_bounds__(HF_C1_THREADS, HF_C1_MIN_BLOCKS) hf_run_c1_ker
             for (; st == HF_ST_OK && gen; gen >>= 4) {
                 const int t = gen & 1;
                 if (gen & 4) st = hf_c1_reinject(P, s, t, local, ident);
-                if (st == HF_ST_OK) st = hf_c1_gen(P, lumo, homo, t, s, local, ident, approx);
+                if (st == HF_ST_OK) st = hf_c1_gen<kThreads>(P, lumo, homo, t, s, local, ident, approx);
             }
             if (st != HF_ST_OK) { s.status = st; break; }                        // 587-591
             if (kind == HF_K_MOVE) { if (part == 1) c.move_e += 1; else c.move_h += 1; }

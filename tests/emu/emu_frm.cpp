@@ -80,7 +80,7 @@ void apply_xmodel(HfParams &P, const EmuXModel *m) {
 struct InjectArgs { const HfParams *P; int32_t *pool; };
 void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P, x->pool); }
 void run_body(void *a) { const HfParams &P = *(const HfParams *)a; if (P.xi.mode) hf_run_kernel<1, true>(P); else hf_run_kernel<1, false>(P); }
-void run_c1_body(void *a) { hf_run_c1_kernel(*(const HfParams *)a); }
+void run_c1_body(void *a) { hf_run_c1_kernel<HF_C1_THREADS, HF_C1_MIN_BLOCKS>(*(const HfParams *)a); }
 void inject_c1_body(void *a) { hf_inject_c1_kernel(*(const HfParams *)a); }
 void run_small_body(void *a) { const HfParams &P = *(const HfParams *)a; if (P.xi.mode) hf_run_small_kernel<true>(P); else hf_run_small_kernel<false>(P); }
 
