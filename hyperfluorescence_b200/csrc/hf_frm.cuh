@@ -102,6 +102,7 @@ struct HfParams {
     int32_t dist;                  // charge_tranfer_distance (reseau.py:110): 1 = the 3x3x3 table, > 1 = hf_gen_move_event_far
     int64_t B, traj_per_real;
     uint32_t k0, k1, first_traj, first_real;
+    uint32_t rk[20];               // the ten Philox round keys of (k0, k1): hf_philox_round_keys
     int64_t setsize;               // random.sample's pool/set switch for k = C (random.py:421-424)
     // lattice [n_real][N]
     const uint8_t *species;
@@ -225,7 +226,7 @@ __device__ __forceinline__ double hf_traj_uniform(const HfParams &P, const HfWar
         if (d >= (uint64_t)P.n_replay) { *exhausted = true; return 0.5; }
         return P.replay[w.local * P.n_replay + (int64_t)d];
     }
-    return hf_philox_uniform(P.k0, P.k1, HF_STREAM_TRAJ, w.ident, d);
+    return hf_block_uniform(hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, w.ident, d >> 1), d);
 }
 
 // random.py:264-269 _randbelow_without_getrandbits (warp-uniform; every lane computes the same)

@@ -48,7 +48,7 @@ __device__ __forceinline__ double hf_c1_uniform(const HfParams &P, int64_t local
         if (d >= (uint64_t)P.n_replay) { *exhausted = true; return 0.5; }
         return P.replay[local * P.n_replay + (int64_t)d];
     }
-    return hf_philox_uniform(P.k0, P.k1, HF_STREAM_TRAJ, ident, d);
+    return hf_block_uniform(hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, d >> 1), d);
 }
 
 // _electron_reinjection / _hole_reinjection with an empty own list (reseau.py:448-470)
@@ -113,15 +113,16 @@ __device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, 
 // Screen-then-verify.  Evaluating exp(), log(), a square root and three divisions in fp64 for all
 // 26 candidates costs ~420 instructions per candidate (ncu, profiles/r01b_*), yet only the
 // minimum is kept.  Pass 1 computes a cheap fp32 estimate a_i of 1e13 * tau_i for every candidate
-// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by eps = 6e-5:
+// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by eps = 7e-5:
 //   -log(rng): rng >= 2^-6 away from 1: __logf abs error 2^-21.41 on |log| >= 0.0157  -> 2.7e-5
-//              otherwise the series u + u^2/2 + u^3/3 (truncation u^3/4 <= 9.5e-7)      -> 1.3e-6
+//              plus its fp32 argument (rounded, or built from the high word of the draw)  -> 3.8e-6
+//              otherwise the series u + u^2/2 + u^3/3 (truncation u^3/4 <= 9.5e-7)      -> 2e-6
 //   exp(dE/kT): float rounding of x (6e-8 x) + __expf (2 + 1.173 x ulp), x <= 88        -> 1.2e-5
 //              neglected Coulomb term of the one opposite charge: C_e |1/r' - 1/r| with r, r' >= 1 is below
 //              C_e = 4.8e-7 eV whatever the geometry (adjacent charges: C_e (1 - 1/2) = 2.4e-7 eV), i.e.
 //              below C_e / kT = 1.86e-5 in x                                            -> 1.9e-5
-//   sum 5.8e-5 < eps.
-// Every candidate whose estimate lies within a factor 1 + W, W = 2^-9 (16x the 2 eps / (1 - eps) = 1.2e-4 the
+//   sum 6.2e-5 < eps.
+// Every candidate whose estimate lies within a factor 1 + W, W = 2^-9 (14x the 2 eps / (1 - eps) = 1.4e-4 the
 // argument needs) of the smallest estimate is then evaluated EXACTLY, in candidate order, by hf_c1_exact_tau;
 // the first minimum among those is the reference's min().  A candidate outside the window has
 // tau_i >= a_i (1 - eps) > a_min (1 + W)(1 - eps) > a_min (1 + eps) >= tau of the best
@@ -182,20 +183,33 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     bool exhausted = false;
     for (int j = 0; 2 * j < n + p; ++j) {
         HfPhiloxBlock blk = {0, 0, 0, 0};
-        if (!P.replay) blk = hf_philox_block(P.k0, P.k1, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
+        if (!P.replay) blk = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = 2 * j + h - p;
             if (r < 0 || r >= n) continue;
             const int l = r + (r >= self_l ? 1 : 0);
-            const double u = P.replay ? hf_c1_uniform(P, local, ident, d0 + (uint64_t)r, &exhausted)
-                                      : hf_block_uniform(blk, (uint64_t)h);
             float t0;
-            if (u < 0x1p-6) {
-                const float uf = (float)u;
-                t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+            const uint32_t hi = h ? blk.w3 : blk.w1;                             // u = hi * 2^-32 + (lower bits) * 2^-53
+            if (!P.replay && hi - 0x00100000u < 0xffe00000u) {
+                // 2^-12 <= u < 1 - 2^-12 (all but 5e-4 of the draws): the estimate straight from the high word, no fp64.
+                // u_f = hi 2^-32 and v = (~hi) 2^-32 ~ 1 - u are off by < 2^-32 absolute and 2^-24 relative:
+                // relative error of the series <= 1e-6, of -log(v) <= (2^-32 / v + 2^-24) / |log v| <= 3.8e-6.
+                if (hi < 0x04000000u) {                                          // u < 2^-6
+                    const float uf = (float)hi * 0x1p-32f;
+                    t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                } else {
+                    t0 = -__logf((float)(~hi) * 0x1p-32f);
+                }
             } else {
-                t0 = -__logf((float)(1.0 - u));
+                const double u = P.replay ? hf_c1_uniform(P, local, ident, d0 + (uint64_t)r, &exhausted)
+                                          : hf_block_uniform(blk, (uint64_t)h);
+                if (u < 0x1p-6) {
+                    const float uf = (float)u;
+                    t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                } else {
+                    t0 = -__logf((float)(1.0 - u));
+                }
             }
             float a = t0;
             const float x = approx[l * kStride] * inv_kt;

@@ -134,7 +134,7 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
         unsigned forced = 0, rem = amask;
         for (int j = 0; 2 * j < n + p; ++j) {
             HfPhiloxBlock rnd = {0, 0, 0, 0};
-            if (!P.replay) rnd = hf_philox_block(P.k0, P.k1, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
+            if (!P.replay) rnd = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = 2 * j + h - p;

@@ -42,6 +42,26 @@ __device__ __forceinline__ HfPhiloxBlock hf_philox_block(uint32_t k0, uint32_t k
     return out;
 }
 
+// The same block with the ten round keys precomputed (rk[2r] = k0 + r * 0x9E3779B9, rk[2r+1] = k1 + r * 0xBB67AE85):
+// when rk lives in the kernel's parameter block the xor takes it straight from the constant bank and the twenty key
+// bumps per block disappear (16 of the 113 instructions of a block in hf_run_c1_kernel, ncu r02a).
+__device__ __forceinline__ HfPhiloxBlock hf_philox_block_rk(const uint32_t (&rk)[20], uint32_t stream, uint32_t ident, uint64_t b) {
+    uint32_t c0 = (uint32_t)b, c1 = (uint32_t)(b >> 32), c2 = ident, c3 = stream;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        const uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    }
+    HfPhiloxBlock out = {c0, c1, c2, c3};
+    return out;
+}
+__host__ __device__ inline void hf_philox_round_keys(uint32_t k0, uint32_t k1, uint32_t (&rk)[20]) {
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+}
+
 __device__ __forceinline__ double hf_block_uniform(const HfPhiloxBlock &blk, uint64_t d) {
     const uint64_t w = (d & 1) ? (((uint64_t)blk.w3 << 32) | blk.w2) : (((uint64_t)blk.w1 << 32) | blk.w0);
     return (double)(w >> 11) * 0x1p-53;

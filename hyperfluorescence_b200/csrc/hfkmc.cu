@@ -435,6 +435,7 @@ int hf_create(const hf_config *c, hf_sim **out) {
     P.B = c->n_trajectories;
     P.traj_per_real = c->n_trajectories / c->n_realisations;
     P.k0 = (uint32_t)c->seed; P.k1 = (uint32_t)(c->seed >> 32);
+    hf_philox_round_keys(P.k0, P.k1, P.rk);
     P.first_traj = c->first_trajectory; P.first_real = c->first_realisation;
     {   // random.sample's setsize for k = charges (random.py:421-424)
         int64_t setsize = 21;

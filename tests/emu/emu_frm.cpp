@@ -110,7 +110,7 @@ int emu_generate(const int32_t dims[3], const double props[3], uint64_t seed, ui
     HfParams P;
     memset(&P, 0, sizeof(P));
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
-    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_real = realisation;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); hf_philox_round_keys(P.k0, P.k1, P.rk); P.first_real = realisation;
     const int64_t xy = (int64_t)P.X * P.Y;
     const int64_t n_fluo = (int64_t)((double)P.N * props[2]), n_tadf = (int64_t)((double)P.N * props[1]);
     const int64_t n_host = P.N - 2 * xy - n_fluo - n_tadf, total = n_host + n_tadf + n_fluo;
@@ -146,7 +146,7 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
     P.field = field; P.C = charges; P.cap_c = charges; P.cap_f = (charges == 1 && distance == 1) ? 2 : 2 * charges + 8;
     P.dist = distance;
     P.B = 1; P.traj_per_real = 1;
-    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = trajectory; P.first_real = 0;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); hf_philox_round_keys(P.k0, P.k1, P.rk); P.first_traj = trajectory; P.first_real = 0;
     P.setsize = sample_setsize(charges);
     P.species = species; P.homo = homo; P.lumo = lumo;
     P.replay = replay; P.n_replay = n_replay;
@@ -221,7 +221,7 @@ int emu_run_batch_c1(const int32_t dims[3], double field, uint64_t seed, uint32_
     P.X = dims[0]; P.Y = dims[1]; P.Z = dims[2]; P.N = (int64_t)P.X * P.Y * P.Z;
     P.field = field; P.C = 1; P.cap_c = 1; P.cap_f = 2; P.dist = 1;
     P.B = B; P.traj_per_real = B;
-    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); P.first_traj = first_traj; P.first_real = 0;
+    P.k0 = (uint32_t)seed; P.k1 = (uint32_t)(seed >> 32); hf_philox_round_keys(P.k0, P.k1, P.rk); P.first_traj = first_traj; P.first_real = 0;
     P.setsize = sample_setsize(1);
     P.species = species; P.homo = homo; P.lumo = lumo;
     Buffers b;
