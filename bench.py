@@ -353,11 +353,12 @@ def run_ours(args):
                                        "events_per_trajectory_per_step": C1_EVENTS, "charges": CHARGES},
                             "e2e": {"value": mc["e2e_value"], "unit": "events/s", "h2d_bytes_per_step": mc["h2d"],
                                     "d2h_bytes_per_step": mc["d2h"], "steps": mc["e2e_steps"]}}
-        line["ga"] = ga_fitness_rate(rank, local_rank, world)
-        line["device_eqe"] = device_eqe_rate(rank, local_rank, world)
-        line["exciton_path"] = exciton_rate(rank, local_rank, world, cpu=not args.no_cpu)
-        line["disorder_sweep"] = exciton_rate(rank, local_rank, world, lattice=256, realisations_total=64, label="disorder_sweep")
-        line["high_density"] = dense_rate(rank, local_rank, world, cpu=not args.no_cpu)
+        line["ga"] = with_clocks(ga_fitness_rate, local_rank, rank, local_rank, world)
+        line["device_eqe"] = with_clocks(device_eqe_rate, local_rank, rank, local_rank, world)
+        line["exciton_path"] = with_clocks(exciton_rate, local_rank, rank, local_rank, world, cpu=not args.no_cpu)
+        line["disorder_sweep"] = with_clocks(exciton_rate, local_rank, rank, local_rank, world, lattice=256, realisations_total=64,
+                                             label="disorder_sweep")
+        line["high_density"] = with_clocks(dense_rate, local_rank, rank, local_rank, world, cpu=not args.no_cpu)
     if world == 1 and rank == 0 and not args.no_cpu:
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_sample(cores, 1500)
@@ -371,6 +372,19 @@ def run_ours(args):
 
 
 GA_DIMS, GA_CHARGES, GA_POPULATION, GA_TRAJECTORIES, GA_STEPS = (10, 10, 5), 4, 256, 10_000, 500
+
+
+def with_clocks(fn, local_rank, *a, **kw):
+    """Run one bench leg with the SM clock / throttle sampler around it; the leg's dict gets `clocks`."""
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    try:
+        out = fn(*a, **kw)
+    finally:
+        clocks = sampler.stop()
+    if isinstance(out, dict):
+        out["clocks"] = clocks
+    return out
 
 
 def ga_fitness_rate(rank, local_rank, world):
@@ -423,7 +437,11 @@ def ga_fitness_rate(rank, local_rank, world):
             "config": {"lattice": list(GA_DIMS), "charges": GA_CHARGES, "population": GA_POPULATION,
                        "trajectories_per_candidate": GA_TRAJECTORIES, "events_per_trajectory": GA_STEPS,
                        "sharding": f"{GA_POPULATION // world} candidates per GPU"},
-            "best_iqe_percent": float(f.max()), "mean_iqe_percent": float(f.mean())}
+            "best_iqe_percent": float(f.max()), "mean_iqe_percent": float(f.mean()),
+            "timing": "wall clock around the public call DeviceFitness(population), end to end: compositions host -> device "
+                      "(256 x 3 doubles), lattice generation, injection, stepping, per-candidate tallies device -> host, all-gather",
+            "e2e": {"value": GA_POPULATION / dt, "unit": "evals/s", "h2d_bytes_per_step": GA_POPULATION // world * 24,
+                    "d2h_bytes_per_step": GA_POPULATION // world * 40}}
 
 
 DE_TRAJ_PER_GPU, DE_STEPS, DE_CUTOFF = 200_000, 2000, 3.0
@@ -630,6 +648,28 @@ def dense_rate(rank, local_rank, world, cpu=False):
     from hyperfluorescence_b200 import distributed as hd
     t = hd.all_reduce_named(sim.xd_tallies())                                   # the one collective of the path
     cpu_line = dense_cpu_sample(sim, sim.x_tables()) if (cpu and world == 1 and rank == 0) else None
+    # end to end through the C-ABI with HOST buffers every step: lattice from pinned host memory -> hf_upload_lattice,
+    # hf_x_configure (tables + Boltzmann weights), hf_xd_configure, hf_xd_spawn (fill), hf_xd_run, tallies + all-reduce
+    host = sim.download_lattice(0)
+    pinned = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in host.items()}
+    xp = nat.x_params_from_dict(dict(cutoff=X_CUTOFF))
+    def e2e_step():
+        sim.upload_lattice(0, pinned["species"], pinned["homo"], pinned["lumo"], pinned["s1"], pinned["t1"])
+        sim.x_configure(xp)
+        sim.xd_configure(XD_EXCITONS)
+        sim.xd_spawn()
+        sim.xd_run(XD_EVENTS)
+        return hd.all_reduce_named(sim.xd_tallies())
+    e2e_step()
+    sim.sync()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        e2e_step()
+    sim.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e = {"value": world * XD_DEVICES_PER_GPU * XD_EVENTS * 2 / e2e_s, "unit": "events/s",
+           "h2d_bytes_per_step": int(sum(v.nbytes for v in pinned.values())), "d2h_bytes_per_step": 24 * 8, "steps": 2,
+           "path": "hf_upload_lattice(pinned host) + hf_x_configure + hf_xd_configure + hf_xd_spawn (fill) + hf_xd_run + tallies"}
     sim.close()
     if world > 1:
         import torch.distributed as dist
@@ -642,7 +682,7 @@ def dense_rate(rank, local_rank, world, cpu=False):
             "config": {"lattice": [XD_L] * 3, "devices_per_gpu": XD_DEVICES_PER_GPU, "excitons_per_device": XD_EXCITONS,
                        "cutoff": X_CUTOFF, "events_per_device_per_launch": XD_EVENTS, "kernel": "hfxd_run_kernel",
                        "model": "own (parity unpinned): DESIGN.md section 10, oracle/exciton_dense_oracle.c"},
-            "annihilation_fraction": (t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]) / lost,
+            "annihilation_fraction": (t["ann_ss"] + t["ann_st"] + t["ann_ts"] + t["ann_tt"]) / lost, "e2e": e2e,
             **({"cpu_baseline": cpu_line} if cpu_line else {})}
 
 

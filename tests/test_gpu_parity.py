@@ -472,6 +472,49 @@ def test_channel_fractions_over_1e5_trajectories(nat):
     assert float(ref["emit_host"].sum()) == 0 and t["recombination"] > 50_000
 
 
+@pytest.mark.parametrize("charges", [1, 4, 16])
+def test_trace_armed_after_earlier_runs(nat, charges):
+    """hf_set_trace after hf_run: the records start at the first event fired AFTER arming (all three step kernels),
+    and equal the tail of a trace armed from the start."""
+    dims, props, seed = (10, 10, 5), (0.84, 0.15, 0.01), 77
+    def run(arm_late):
+        sim = nat.Sim(dims, props, 0.1, charges, 1, n_trajectories=3, seed=seed)
+        try:
+            sim.generate_lattice(); sim.inject()
+            if not arm_late:
+                sim.set_trace(0, 3, 500)
+            sim.run(200)
+            if arm_late:
+                sim.set_trace(0, 3, 300)
+            sim.run(300)
+            sim.sync()
+            return [sim.trace(t, 500) for t in range(3)]
+        finally:
+            sim.close()
+    full, late = run(False), run(True)
+    for t in range(3):
+        assert len(full[t]) == 500 and len(late[t]) == 300
+        for k in ("kind", "particule", "initial", "final", "tau", "draws"):
+            assert np.array_equal(late[t][k], full[t][k][200:]), (t, k)
+
+
+def test_exciton_rates_need_s1_t1(nat):
+    """A lattice uploaded without S1 / T1 energies reads zeros through the facade and cannot feed the exciton rates."""
+    from hyperfluorescence_b200._native import HfError
+    g = load_golden("d0_s1")
+    sim = nat.Sim(g["dims"], tuple(float(p) for p in g["props"]), 0.1, 4, 1, n_trajectories=1, seed=1)
+    try:
+        sim.upload_lattice(0, g["species"], g["homo"], g["lumo"])
+        a = sim.download_lattice(0)
+        assert not a["s1"].any() and not a["t1"].any() and np.array_equal(a["homo"], g["homo"])
+        with pytest.raises(HfError):
+            sim.x_configure()
+        sim.upload_lattice(0, g["species"], g["homo"], g["lumo"], g["s1"], g["t1"])
+        sim.x_configure(nat.x_params_from_dict(dict(cutoff=2.0)))
+    finally:
+        sim.close()
+
+
 REFERENCE_STYLE_DRIVER = """
 from time import time
 from reseau import Lattice
