@@ -73,13 +73,20 @@ struct HfxdWarp {                      // one warp's view of its device
     const double *ws1, *wt1;           // this device's realisation, site 0
     uint32_t *occ;                     // this device's mask (index = site + halo)
     int lane, K, M;
+    bool aligned;                      // M == 32 * HFXD_KF and every mask index fits 31 bits: the static fast path
 };
 
-// Lane sums of the channel rates of an exciton (packed site + spin); kStore: also leave the rates in s_rates.
+// Lane sums of the channel rates of an exciton (packed site + spin); store: also leave the rates in s_rates.
 // `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  HFXD_CHUNK slots are
-// gathered (weight + occupancy word) before any of them is consumed.
-template <bool kStore>
-__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen) {
+// gathered (weight + occupancy word) before any of them is consumed.  ONE inlined instance per kernel (the event
+// loop is a small state machine around a single call): with five copies the kernel was 7 100 instructions and a
+// third of its issue stalls were instruction fetches.
+//
+// Fast path (KF = M / 32 full slots of transfer channels followed by the three on-site channels on lanes 0-2 of slot
+// KF — cutoff 4 gives M = 256 = 8 x 32 — and a site away from the x / y seams): no per-slot channel-range tests, no
+// wrap arithmetic, 32-bit offsets.  Everything else takes the generic loop.
+#define HFXD_KF 8
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen, const bool store) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
     const bool singlet = spin == HFX_SINGLET;
@@ -97,6 +104,44 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     const int64_t oi = i + X.w_halo;
     double S = 0.0;
     seen = 0;
+    if (W.aligned && nowrap) {
+        const uint32_t *occ = W.occ;
+        const int oi32 = (int)oi;                                                // the host checked that the mask index fits
+        const int32_t *lin = W.s_lin + W.lane;
+        const double *gl = g + W.lane;
+        double *rates = W.s_rates + W.lane;
+#pragma unroll
+        for (int k0 = 0; k0 < HFXD_KF; k0 += HFXD_CHUNK) {
+            double wj[HFXD_CHUNK];
+            uint32_t ow[HFXD_CHUNK];
+            int sh[HFXD_CHUNK];
+#pragma unroll
+            for (int u = 0; u < HFXD_CHUNK; ++u)
+                if (k0 + u < HFXD_KF) {
+                    const int d = lin[32 * (k0 + u)];
+                    wj[u] = __ldg(w + d);
+                    const int oj = oi32 + d;
+                    ow[u] = occ[oj >> 4];
+                    sh[u] = 2 * (oj & 15);
+                }
+#pragma unroll
+            for (int u = 0; u < HFXD_CHUNK; ++u)
+                if (k0 + u < HFXD_KF) {
+                    double rate = hfx_rate(pref, gl[32 * (k0 + u)], wj[u], inv_wi);
+                    const int o = (int)((ow[u] >> sh[u]) & 3u);
+                    if (o) { rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]); seen |= 1u << (k0 + u); }
+                    if (store) rates[32 * (k0 + u)] = rate;
+                    S = __dadd_rn(S, rate);
+                }
+        }
+        double rate = 0.0;                                                       // slot KF: ISC / RISC, radiative, non-radiative on lanes 0, 1, 2
+        if (W.lane == 0) rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
+        else if (W.lane == 1) rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
+        else if (W.lane == 2) rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+        if (store) rates[32 * HFXD_KF] = rate;
+        return __dadd_rn(S, rate);
+    }
+#pragma unroll 1
     for (int k0 = 0; k0 < W.K; k0 += HFXD_CHUNK) {
         double wj[HFXD_CHUNK];
         uint32_t ow[HFXD_CHUNK];
@@ -129,7 +174,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 } else if (c == W.M + 2) {
                     rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
                 }
-                if (kStore) W.s_rates[c] = rate;
+                if (store) W.s_rates[c] = rate;
                 S = __dadd_rn(S, rate);
             }
         }
@@ -229,6 +274,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     W.s_T = reinterpret_cast<double *>(wsm); W.s_rates = W.s_T + n_pad;
     W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
     W.lane = lane; W.K = K; W.M = M;
+    W.aligned = M == 32 * HFXD_KF && X.w_stride < 0x7fffffff;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = X.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = X.k_risc[threadIdx.x]; }
@@ -246,9 +292,11 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         double time, life;
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
+        __syncwarp();
         unsigned seen;
         if (P.fill) {
-            // hf_xd_spawn: an empty mask (memset by the host), slots filled in order, then every total
+            // hf_xd_spawn: an empty mask (memset by the host), slots filled in order; their totals are computed by the
+            // refresh pass below (ev = -1: every slot marked dirty)
             time = 0.0; life = 0.0; draws = 0;
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = 0; W.s_T[q] = 0.0; g_birth[q] = 0.0; }
             __syncwarp();
@@ -257,11 +305,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 if (lane == 0) { W.s_pos[k] = ps; W.s_cnt[HFX_T_GENERATED] += 1; }
             }
             __syncwarp();
-            for (int k = 0; k < P.n; ++k) {
-                const double S = hfxd_lane_sum<false>(W, W.s_pos[k], seen);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(S, lane), 31);
-                if (lane == 0) W.s_T[k] = tot;
-            }
+            if (lane < n_slots) W.s_dirty[lane] = (lane << 5) + 32 <= P.n ? 0xffffffffu : ((lane << 5) < P.n ? (1u << (P.n & 31)) - 1u : 0u);
         } else {
             time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; }
@@ -270,130 +314,133 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
         uint64_t trace_at = traced ? X.trace_len[dev - X.trace_first] : 0;
 
-        for (int64_t ev = 0; ev < X.n_events; ++ev) {
-            // (1) the exciton: canonical scan over the cached totals
-            double A = 0.0;
-            for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
-            const double G = hfx_scan(A, lane);
-            const double R = __shfl_sync(HF_FULL, G, 31);
-            const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
-            draws += 2;
-            const double u_sel = hf_block_uniform(rnd, 0), u_time = hf_block_uniform(rnd, 1);
-            const double target = __dmul_rn(u_sel, R);
-            double base;
-            const int kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
-            // (2) its channel
-            const uint32_t ps = W.s_pos[kx];
-            const double S = hfxd_lane_sum<true>(W, ps, seen);
-            const double L = hfx_scan(S, lane);
-            __syncwarp();
-            hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), seen);                   // the neighbours of the site that is about to change
-            double base2;
-            const int chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
-            const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
-            time = __dadd_rn(time, dt);
-            // (3) apply
-            const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
-            const bool singlet = spin == HFX_SINGLET;
-            const int sidx = singlet ? 0 : 1;
-            const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-            const int64_t i = hf_site(X.X, X.Y, site);
-            const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
-            int kind, tally, fin = site, promoted = -1;
-            bool lost = false;
-            uint32_t ps_after = ps;
-            if (chosen < M) {
-                const int o = W.s_off[chosen];
-                int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
-                if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
-                fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
-                const int64_t oj = hf_site(X.X, X.Y, fin) + X.w_halo;
-                const int occ_j = hfxd_occ_get(W.occ, oj);
+        for (int64_t ev = P.fill ? -1 : 0; ev < X.n_events; ++ev) {
+            // stage 0: evaluate the chosen exciton, pick its channel, apply the event
+            //       1: refresh a slot whose own site / spin changed (its evaluation names the excitons it meets)
+            //       2: refresh the slots marked dirty
+            int stage = 2, tgt = -1, kx = -1, promoted = -1;
+            uint32_t job = 0;
+            double target = 0.0, base = 0.0, R = 0.0, u_time = 0.0;
+            if (ev >= 0) {
+                // (1) the exciton: canonical scan over the cached totals
+                double A = 0.0;
+                for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
+                const double G = hfx_scan(A, lane);
+                R = __shfl_sync(HF_FULL, G, 31);
+                const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+                draws += 2;
+                const double u_sel = hf_block_uniform(rnd, 0);
+                u_time = hf_block_uniform(rnd, 1);
+                target = __dmul_rn(u_sel, R);
+                kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
+                stage = 0; tgt = kx; job = W.s_pos[kx];
+            }
+            for (;;) {
+                if (stage == 2) {                                                // next slot marked dirty, ascending
+                    int q = -1;
+                    for (int wq = 0; wq < n_slots && q < 0; ++wq) {
+                        const unsigned todo = W.s_dirty[wq];
+                        if (todo) q = (wq << 5) + __ffs(todo) - 1;
+                    }
+                    if (q < 0) break;
+                    tgt = q; job = W.s_pos[q];
+                }
+                const double S = hfxd_lane_sum(W, job, seen, stage == 0);
+                const double L = hfx_scan(S, lane);
                 __syncwarp();
-                if (occ_j == 0) {
-                    if (lane == 0) { hfxd_occ_set(W.occ, i + X.w_halo, 0); hfxd_occ_set(W.occ, oj, spin); }
-                    ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
-                    kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
-                    tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
-                } else {
-                    const int oidx = occ_j == HFX_SINGLET ? 0 : 1;
-                    kind = HFXD_K_ANNIHILATION;
-                    tally = HFXD_T_ANN + 2 * sidx + oidx;
-                    if (sidx == 1 && oidx == 1) {                               // triplet on triplet: the survivor may be promoted
-                        const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
-                        draws += 2;
-                        if (hf_block_uniform(b2, 0) < P.p_tta) {
-                            promoted = hfxd_find(W, fin);
-                            if (lane == 0) {
-                                if (promoted >= 0) W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
-                                hfxd_occ_set(W.occ, oj, HFX_SINGLET);
-                                W.s_cnt[HFXD_T_TTA_UP] += 1;
+                if (stage < 2) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen);   // the neighbours of a site that changes / changed
+                if (stage != 0) {
+                    const double tot = __shfl_sync(HF_FULL, L, 31);
+                    if (lane == 0) { W.s_T[tgt] = tot; W.s_dirty[tgt >> 5] &= ~(1u << (tgt & 31)); }
+                    __syncwarp();
+                    if (stage == 1 && promoted >= 0 && tgt != promoted) { tgt = promoted; job = W.s_pos[promoted]; continue; }
+                    stage = 2;
+                    continue;
+                }
+                // (2) the channel of the chosen exciton
+                const uint32_t ps = job;
+                double base2;
+                const int chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
+                const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
+                time = __dadd_rn(time, dt);
+                // (3) apply
+                const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
+                const bool singlet = spin == HFX_SINGLET;
+                const int sidx = singlet ? 0 : 1;
+                const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+                const int64_t i = hf_site(X.X, X.Y, site);
+                const int a = hfx_tag_of(__ldg((singlet ? W.ws1 : W.wt1) + i));
+                int kind, tally, fin = site;
+                bool lost = false;
+                uint32_t ps_after = ps;
+                if (chosen < M) {
+                    const int o = W.s_off[chosen];
+                    int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
+                    if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
+                    if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
+                    fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
+                    const int64_t oj = hf_site(X.X, X.Y, fin) + X.w_halo;
+                    const int occ_j = hfxd_occ_get(W.occ, oj);
+                    __syncwarp();
+                    if (occ_j == 0) {
+                        if (lane == 0) { hfxd_occ_set(W.occ, i + X.w_halo, 0); hfxd_occ_set(W.occ, oj, spin); }
+                        ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
+                        kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
+                        tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
+                    } else {
+                        const int oidx = occ_j == HFX_SINGLET ? 0 : 1;
+                        kind = HFXD_K_ANNIHILATION;
+                        tally = HFXD_T_ANN + 2 * sidx + oidx;
+                        if (sidx == 1 && oidx == 1) {                           // triplet on triplet: the survivor may be promoted
+                            const HfPhiloxBlock b2 = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
+                            draws += 2;
+                            if (hf_block_uniform(b2, 0) < P.p_tta) {
+                                promoted = hfxd_find(W, fin);
+                                if (lane == 0) {
+                                    if (promoted >= 0) W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
+                                    hfxd_occ_set(W.occ, oj, HFX_SINGLET);
+                                    W.s_cnt[HFXD_T_TTA_UP] += 1;
+                                }
                             }
                         }
+                        lost = true;
                     }
+                } else if (chosen == M) {
+                    kind = HFX_K_ISC;                                           // molecule.py:299-307
+                    tally = singlet ? HFX_T_ISC : HFX_T_RISC;
+                    const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
+                    ps_after = (uint32_t)site | ((uint32_t)flipped << 30);
+                    if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, flipped);
+                } else {
+                    kind = HFX_K_DECAY;
+                    tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
                     lost = true;
                 }
-            } else if (chosen == M) {
-                kind = HFX_K_ISC;                                               // molecule.py:299-307
-                tally = singlet ? HFX_T_ISC : HFX_T_RISC;
-                const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
-                ps_after = (uint32_t)site | ((uint32_t)flipped << 30);
-                if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, flipped);
-            } else {
-                kind = HFX_K_DECAY;
-                tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;
-                lost = true;
-            }
-            if (lost) {
-                if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, 0);
-                life = __dadd_rn(life, __dsub_rn(time, g_birth[kx]));            // every lane reads the same word
-                __syncwarp();
-                ps_after = hfxd_replace(W, ident, draws);
-                if (lane == 0) { g_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
-            }
-            if (lane == 0) {
-                W.s_pos[kx] = ps_after;
-                W.s_cnt[HFX_T_EVENTS] += 1;
-                W.s_cnt[tally] += 1;
-                if (traced && trace_at < (uint64_t)X.trace_cap) {
-                    HfTraceRec rec;
-                    rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(X.X, X.Y, fin);
-                    rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
-                    rec.pad[0] = (uint8_t)(ps_after >> 30); rec.pad[1] = 0;
-                    rec.spins = (uint32_t)chosen | ((uint32_t)kx << 16); rec.draws = draws;
-                    X.trace[(dev - X.trace_first) * X.trace_cap + trace_at] = rec;
+                if (lost) {
+                    if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, 0);
+                    life = __dadd_rn(life, __dsub_rn(time, g_birth[kx]));        // every lane reads the same word
+                    __syncwarp();
+                    ps_after = hfxd_replace(W, ident, draws);
+                    if (lane == 0) { g_birth[kx] = time; W.s_cnt[HFX_T_GENERATED] += 1; }
                 }
-            }
-            trace_at += 1;
-            __syncwarp();
-            // (4) refresh the cached totals: the slot itself in its new state (its evaluation names the neighbours of
-            //     the site it now occupies), a promoted acceptor (whose neighbours see a different spin), then everybody marked
-            {
-                const double Sk = hfxd_lane_sum<false>(W, ps_after, seen);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sk, lane), 31);
-                if (lane == 0) W.s_T[kx] = tot;
-                hfxd_mark_seen(W, (int)(ps_after & 0x3fffffffu), seen);
-            }
-            if (promoted >= 0) {
-                const double Sa = hfxd_lane_sum<false>(W, W.s_pos[promoted], seen);
-                const double tot = __shfl_sync(HF_FULL, hfx_scan(Sa, lane), 31);
-                if (lane == 0) { W.s_T[promoted] = tot; W.s_dirty[promoted >> 5] &= ~(1u << (promoted & 31)); }
-                hfxd_mark_seen(W, fin, seen);
-            }
-            for (int wq = 0; wq < n_slots; ++wq) {
-                unsigned todo = W.s_dirty[wq];
-                if (wq == (kx >> 5)) todo &= ~(1u << (kx & 31));                 // done above
-                __syncwarp();
-                if (lane == 0) W.s_dirty[wq] = 0;
-                while (todo) {
-                    const int q = (wq << 5) + __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    unsigned unused;
-                    const double Sq = hfxd_lane_sum<false>(W, W.s_pos[q], unused);
-                    const double tot = __shfl_sync(HF_FULL, hfx_scan(Sq, lane), 31);
-                    if (lane == 0) W.s_T[q] = tot;
+                if (lane == 0) {
+                    W.s_pos[kx] = ps_after;
+                    W.s_cnt[HFX_T_EVENTS] += 1;
+                    W.s_cnt[tally] += 1;
+                    if (traced && trace_at < (uint64_t)X.trace_cap) {
+                        HfTraceRec rec;
+                        rec.initial = (int32_t)i; rec.final_ = (int32_t)hf_site(X.X, X.Y, fin);
+                        rec.tau = dt; rec.kind = (uint8_t)kind; rec.particule = HF_PART_EXCITON;
+                        rec.pad[0] = (uint8_t)(ps_after >> 30); rec.pad[1] = 0;
+                        rec.spins = (uint32_t)chosen | ((uint32_t)kx << 16); rec.draws = draws;
+                        X.trace[(dev - X.trace_first) * X.trace_cap + trace_at] = rec;
+                    }
                 }
+                trace_at += 1;
+                __syncwarp();
+                // (4) refresh the cached totals: the slot itself in its new state, a promoted acceptor (whose neighbours
+                //     see a different spin), then everybody marked
+                stage = 1; tgt = kx; job = ps_after;
             }
             __syncwarp();
         }

@@ -191,6 +191,7 @@ def test_gpu_dense_full_size_properties():
 @pytest.mark.parametrize("dims,cutoff,n,B,R", [((12, 12, 5), 2.0, 1, 5, 1),         # one exciton per device: never meets anybody
                                                  ((40, 40, 12), 3.0, 1024, 3, 1),     # the largest device (32 slots of excitons)
                                                  ((14, 13, 6), 4.0, 33, 9, 3),        # cutoff 4 with wrap everywhere, 3 devices per realisation
+                                                 ((26, 24, 7), 4.0, 200, 6, 2),       # cutoff 4 with wrap-free sites: the static fast path, crowded
                                                  ((16, 16, 8), 2.5, 100, 7, 7)])      # one device per realisation
 def test_gpu_dense_edge_shapes(dims, cutoff, n, B, R):
     """Extreme shapes of the high-density devices against the specification (with its cache verification)."""
