@@ -28,7 +28,7 @@
 #define HFXD_T_N 24
 #define HFXD_MAX_EXCITONS 1024
 #ifndef HFXD_MIN_BLOCKS
-#define HFXD_MIN_BLOCKS 4              // 4 CTAs x 7 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
+#define HFXD_MIN_BLOCKS 7              // 7 CTAs x 4 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
 #endif
 #ifndef HFXD_CHUNK
 #define HFXD_CHUNK 3                   // slots whose gathers (weight + occupancy word) are in flight together
@@ -53,8 +53,7 @@ __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
     // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T (f64) | rates (f64) | pos (u32) | counters (u32)
     // (birth[] stays in global memory: it is touched once per LOST exciton, by one lane)
     return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 2 * (size_t)((M + 1) & ~1) +
-           (size_t)warps * (8 * ((size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64 + (size_t)n_pad)) +
-           4 * 2 * (size_t)((M + 1) & ~1);                                      // + hashed linear offsets (CTA-wide)
+           (size_t)warps * (8 * ((size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64));
 }
 
 __device__ __forceinline__ int hfxd_occ_get(const uint32_t *occ, int64_t idx) {
@@ -64,56 +63,18 @@ __device__ __forceinline__ void hfxd_occ_set(uint32_t *occ, int64_t idx, int cod
     const int sh = 2 * (int)(idx & 15);
     occ[idx >> 4] = (occ[idx >> 4] & ~(3u << sh)) | ((uint32_t)code << sh);
 }
-// one lane: the mask and, for a site that becomes occupied, the warp's Bloom filter
-#define HFXD_OCC_SET(W, idx, code) do { hfxd_occ_set((W).occ, (idx), (code)); if (code) hfxd_bloom_set((W), (uint32_t)(idx)); } while (0)
 
 struct HfxdWarp {                      // one warp's view of its device
     const HfxdParams *P;
     const double *s_g6, *s_gd, *s_k, *s_ann;
     const int32_t *s_lin, *s_off;
     double *s_T, *s_rates;
-    uint32_t *s_pos, *s_cnt, *s_dirty, *s_bits;
-    const int32_t *s_linc1, *s_linc2;  // lin[c] * C1, lin[c] * C2: the hash of a neighbour's mask index without a multiply
-    int bshift;                        // 32 - log2(bits of the Bloom filter)
+    uint32_t *s_pos, *s_cnt, *s_dirty;
     const double *ws1, *wt1;           // this device's realisation, site 0
     uint32_t *occ;                     // this device's mask (index = site + halo)
     int lane, K, M;
     bool aligned;                      // M == 32 * HFXD_KF and every mask index fits 31 bits: the static fast path
 };
-
-// ---- Bloom filter of the device's occupied sites (keys: index into the mask = site + halo) ----------------------
-// 0.55 MB of mask per device (2.2 GB for BASELINE configs[3]) does not stay in the L2: a rate evaluation gathers 256
-// mask words and a third of them were DRAM misses.  Each warp keeps a Bloom filter of its device's occupied sites in
-// shared memory (32 bits per exciton slot, two hash functions, set when a site becomes occupied, rebuilt from pos[]
-// every 128 events): a clear bit proves the site empty, so the mask word is fetched for 0.4 % of the lookups only.
-#define HFXD_C1 0x9E3779B1u
-#define HFXD_C2 0x85EBCA6Bu
-__device__ __forceinline__ bool hfxd_bloom(const HfxdWarp &W, uint32_t p1, uint32_t p2) {     // p = mask index * C
-    const uint32_t f1 = p1 >> W.bshift, f2 = p2 >> W.bshift;
-    return ((W.s_bits[f1 >> 5] >> (f1 & 31)) & (W.s_bits[f2 >> 5] >> (f2 & 31)) & 1u) != 0;
-}
-__device__ __forceinline__ void hfxd_bloom_set(const HfxdWarp &W, uint32_t idx) {            // one lane
-    const uint32_t f1 = (idx * HFXD_C1) >> W.bshift, f2 = (idx * HFXD_C2) >> W.bshift;
-    W.s_bits[f1 >> 5] |= 1u << (f1 & 31);
-    W.s_bits[f2 >> 5] |= 1u << (f2 & 31);
-}
-// all lanes: the filter from the slots (start of a launch, and every so often to shed the bits of vacated sites)
-__device__ __forceinline__ void hfxd_bloom_rebuild(const HfxdWarp &W) {
-    const HfxParams &X = W.P->X;
-    __syncwarp();
-    for (int q = W.lane; q < W.P->n_pad; q += 32) W.s_bits[q] = 0;
-    __syncwarp();
-    for (int q = W.lane; q < W.P->n; q += 32) {
-        const uint32_t ps = W.s_pos[q];
-        if (ps) {
-            const uint32_t idx = (uint32_t)(hf_site(X.X, X.Y, (int)(ps & 0x3fffffffu)) + X.w_halo);
-            const uint32_t f1 = (idx * HFXD_C1) >> W.bshift, f2 = (idx * HFXD_C2) >> W.bshift;
-            atomicOr(&W.s_bits[f1 >> 5], 1u << (f1 & 31));
-            atomicOr(&W.s_bits[f2 >> 5], 1u << (f2 & 31));
-        }
-    }
-    __syncwarp();
-}
 
 // Lane sums of the channel rates of an exciton (packed site + spin); store: also leave the rates in s_rates.
 // `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  HFXD_CHUNK slots are
@@ -146,8 +107,7 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     if (W.aligned && nowrap) {
         const uint32_t *occ = W.occ;
         const int oi32 = (int)oi;                                                // the host checked that the mask index fits
-        const int32_t *lin = W.s_lin + W.lane, *linc1 = W.s_linc1 + W.lane, *linc2 = W.s_linc2 + W.lane;
-        const uint32_t oc1 = (uint32_t)oi32 * HFXD_C1, oc2 = (uint32_t)oi32 * HFXD_C2;
+        const int32_t *lin = W.s_lin + W.lane;
         const double *gl = g + W.lane;
         double *rates = W.s_rates + W.lane;
 #pragma unroll
@@ -160,13 +120,9 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 if (k0 + u < HFXD_KF) {
                     const int d = lin[32 * (k0 + u)];
                     wj[u] = __ldg(w + d);
-                    ow[u] = 0; sh[u] = 0;
-                    // (oi + d) * C == oi * C + d * C (mod 2^32): the neighbour's two hashes without a multiply
-                    if (hfxd_bloom(W, oc1 + (uint32_t)linc1[32 * (k0 + u)], oc2 + (uint32_t)linc2[32 * (k0 + u)])) {
-                        const int oj = oi32 + d;                                  // else: certainly empty
-                        ow[u] = occ[oj >> 4];
-                        sh[u] = 2 * (oj & 15);
-                    }
+                    const int oj = oi32 + d;
+                    ow[u] = occ[oj >> 4];
+                    sh[u] = 2 * (oj & 15);
                 }
 #pragma unroll
             for (int u = 0; u < HFXD_CHUNK; ++u)
@@ -293,7 +249,7 @@ __device__ __forceinline__ uint32_t hfxd_replace(const HfxdWarp &W, uint32_t ide
         if (hfxd_occ_get(W.occ, oi)) continue;                                   // same word for every lane: uniform
         const int spin = ub < X.singlet_fraction ? HFX_SINGLET : HFX_TRIPLET;
         __syncwarp();
-        if (W.lane == 0) HFXD_OCC_SET(W, oi, spin);
+        if (W.lane == 0) hfxd_occ_set(W.occ, oi, spin);
         __syncwarp();
         return (uint32_t)hf_pack(x, y, z) | ((uint32_t)spin << 30);
     }
@@ -311,21 +267,15 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     double *s_ann = s_k + HFX_N_K;
     int32_t *s_lin = reinterpret_cast<int32_t *>(s_ann + 4);
     int32_t *s_off = s_lin + ((M + 1) & ~1);
-    int32_t *s_linc1 = s_off + ((M + 1) & ~1), *s_linc2 = s_linc1 + ((M + 1) & ~1);
-    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_linc2 + ((M + 1) & ~1)) +
-                         (size_t)warp * (8 * ((size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64 + (size_t)n_pad));
+    unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 1) & ~1)) +
+                         (size_t)warp * (8 * ((size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64));
     HfxdWarp W;
     W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_lin = s_lin; W.s_off = s_off;
     W.s_T = reinterpret_cast<double *>(wsm); W.s_rates = W.s_T + n_pad;
-    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32; W.s_bits = W.s_dirty + 32;
-    W.s_linc1 = s_linc1; W.s_linc2 = s_linc2;
-    { int bits = 32; while (bits * 2 <= 32 * n_pad) bits *= 2; W.bshift = 32 - (31 - __clz(bits)); }   // largest power of two <= 32 n_pad bits
+    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
     W.lane = lane; W.K = K; W.M = M;
     W.aligned = M == 32 * HFXD_KF && X.w_stride < 0x7fffffff;
-    for (int m = threadIdx.x; m < M; m += kWarps * 32) {
-        s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m];
-        s_linc1[m] = (int32_t)((uint32_t)X.lin[m] * HFXD_C1); s_linc2[m] = (int32_t)((uint32_t)X.lin[m] * HFXD_C2);
-    }
+    for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
     if (threadIdx.x < 9) { s_k[threadIdx.x] = X.kf[threadIdx.x]; s_k[9 + threadIdx.x] = X.kd[threadIdx.x]; }
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = X.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = X.k_risc[threadIdx.x]; }
     if (threadIdx.x < 6) { s_k[24 + threadIdx.x] = X.k_rad[threadIdx.x]; s_k[30 + threadIdx.x] = X.k_nonrad[threadIdx.x]; }
@@ -342,7 +292,6 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         double time, life;
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
-        for (int q = lane; q < n_pad; q += 32) W.s_bits[q] = 0;
         __syncwarp();
         unsigned seen;
         if (P.fill) {
@@ -360,7 +309,6 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         } else {
             time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; }
-            hfxd_bloom_rebuild(W);
         }
         __syncwarp();
         const bool traced = X.trace && dev >= X.trace_first && dev < X.trace_first + X.trace_n;
@@ -370,7 +318,6 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             // stage 0: evaluate the chosen exciton, pick its channel, apply the event
             //       1: refresh a slot whose own site / spin changed (its evaluation names the excitons it meets)
             //       2: refresh the slots marked dirty
-            if ((ev & 127) == 127) hfxd_bloom_rebuild(W);                        // shed the bits of vacated sites
             int stage = 2, tgt = -1, kx = -1, promoted = -1;
             uint32_t job = 0;
             double target = 0.0, base = 0.0, R = 0.0, u_time = 0.0;
@@ -436,7 +383,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                     const int occ_j = hfxd_occ_get(W.occ, oj);
                     __syncwarp();
                     if (occ_j == 0) {
-                        if (lane == 0) { hfxd_occ_set(W.occ, i + X.w_halo, 0); HFXD_OCC_SET(W, oj, spin); }
+                        if (lane == 0) { hfxd_occ_set(W.occ, i + X.w_halo, 0); hfxd_occ_set(W.occ, oj, spin); }
                         ps_after = (uint32_t)fin | ((uint32_t)spin << 30);
                         kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
                         tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;
@@ -451,7 +398,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                                 promoted = hfxd_find(W, fin);
                                 if (lane == 0) {
                                     if (promoted >= 0) W.s_pos[promoted] = (uint32_t)fin | ((uint32_t)HFX_SINGLET << 30);
-                                    HFXD_OCC_SET(W, oj, HFX_SINGLET);
+                                    hfxd_occ_set(W.occ, oj, HFX_SINGLET);
                                     W.s_cnt[HFXD_T_TTA_UP] += 1;
                                 }
                             }
@@ -463,7 +410,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                     tally = singlet ? HFX_T_ISC : HFX_T_RISC;
                     const int flipped = singlet ? HFX_TRIPLET : HFX_SINGLET;
                     ps_after = (uint32_t)site | ((uint32_t)flipped << 30);
-                    if (lane == 0) HFXD_OCC_SET(W, i + X.w_halo, flipped);
+                    if (lane == 0) hfxd_occ_set(W.occ, i + X.w_halo, flipped);
                 } else {
                     kind = HFX_K_DECAY;
                     tally = (chosen == M + 1 ? HFX_T_RAD : (singlet ? HFX_T_NONRAD_S : HFX_T_NONRAD_T)) + a;

@@ -1317,7 +1317,7 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
 // ---- high-density exciton devices (Path XD; model specified by oracle/exciton_dense_oracle.c) ------------
 
 #ifndef HF_XD_WARPS
-#define HF_XD_WARPS 7                  // x HFXD_MIN_BLOCKS = 4 CTAs per SM: 28 devices per SM, 4144 per B200
+#define HF_XD_WARPS 4
 #endif
 constexpr int kXdWarps = HF_XD_WARPS;
 
