@@ -86,6 +86,9 @@ struct HfxdWarp {                      // one warp's view of its device
 // KF — cutoff 4 gives M = 256 = 8 x 32 — and a site away from the x / y seams): no per-slot channel-range tests, no
 // wrap arithmetic, 32-bit offsets.  Everything else takes the generic loop.
 #define HFXD_KF 8
+#ifndef HFXD_FAST_CHUNK
+#define HFXD_FAST_CHUNK 4               // must divide HFXD_KF
+#endif
 __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen, const bool store) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
@@ -110,29 +113,29 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
         const int32_t *lin = W.s_lin + W.lane;
         const double *gl = g + W.lane;
         double *rates = W.s_rates + W.lane;
+        // a ROLLED loop over chunks of HFXD_FAST_CHUNK slots: the hot code stays small enough for the instruction
+        // caches (seven warps per scheduler, each somewhere else in a 5 000-instruction kernel)
+#pragma unroll 1
+        for (int k0 = 0; k0 < HFXD_KF; k0 += HFXD_FAST_CHUNK) {
+            double wj[HFXD_FAST_CHUNK];
+            uint32_t ow[HFXD_FAST_CHUNK];
+            int sh[HFXD_FAST_CHUNK];
 #pragma unroll
-        for (int k0 = 0; k0 < HFXD_KF; k0 += HFXD_CHUNK) {
-            double wj[HFXD_CHUNK];
-            uint32_t ow[HFXD_CHUNK];
-            int sh[HFXD_CHUNK];
+            for (int u = 0; u < HFXD_FAST_CHUNK; ++u) {
+                const int d = lin[32 * (k0 + u)];
+                wj[u] = __ldg(w + d);
+                const int oj = oi32 + d;
+                ow[u] = occ[oj >> 4];
+                sh[u] = 2 * (oj & 15);
+            }
 #pragma unroll
-            for (int u = 0; u < HFXD_CHUNK; ++u)
-                if (k0 + u < HFXD_KF) {
-                    const int d = lin[32 * (k0 + u)];
-                    wj[u] = __ldg(w + d);
-                    const int oj = oi32 + d;
-                    ow[u] = occ[oj >> 4];
-                    sh[u] = 2 * (oj & 15);
-                }
-#pragma unroll
-            for (int u = 0; u < HFXD_CHUNK; ++u)
-                if (k0 + u < HFXD_KF) {
-                    double rate = hfx_rate(pref, gl[32 * (k0 + u)], wj[u], inv_wi);
-                    const int o = (int)((ow[u] >> sh[u]) & 3u);
-                    if (o) { rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]); seen |= 1u << (k0 + u); }
-                    if (store) rates[32 * (k0 + u)] = rate;
-                    S = __dadd_rn(S, rate);
-                }
+            for (int u = 0; u < HFXD_FAST_CHUNK; ++u) {
+                double rate = hfx_rate(pref, gl[32 * (k0 + u)], wj[u], inv_wi);
+                const int o = (int)((ow[u] >> sh[u]) & 3u);
+                if (o) { rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]); seen |= 1u << (k0 + u); }
+                if (store) rates[32 * (k0 + u)] = rate;
+                S = __dadd_rn(S, rate);
+            }
         }
         double rate = 0.0;                                                       // slot KF: ISC / RISC, radiative, non-radiative on lanes 0, 1, 2
         if (W.lane == 0) rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
