@@ -515,6 +515,7 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
     for _ in range(3):
         sim.x_run(X_EVENTS)
     ms, n = sim.run_timing()
+    launch = sim.x_launch_info()
     tab = sim.x_tables()
     m = int(tab["g6"].size)
     from hyperfluorescence_b200 import distributed as hd
@@ -566,6 +567,7 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
            "config": {"workload": label, "lattice": [lattice] * 3, "realisations_per_gpu": n_real,
                       "trajectories_per_gpu": X_TRAJ_PER_GPU, "cutoff": X_CUTOFF,
                       "channels": m + 3, "events_per_trajectory_per_launch": X_EVENTS,
+                      "weights_layout": "4x4x1 bricks" if launch["brick"] else "row-major", "trajectories_per_warp": launch["block"],
                       "model": "own (parity unpinned): DESIGN.md section 9, oracle/exciton_oracle.c"},
            "roofline": {"bound": "hbm", "bytes_per_event": bytes_per_event,
                         "achieved": rate * bytes_per_event / world / 1e9, "peak": peak, "unit": "GB/s",
@@ -574,9 +576,9 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
                         "note": ("the 2 x 17 MB of Boltzmann weights of a 128^3 lattice are L2-resident (ncu: L2 hit 99.9 %, "
                                  "DRAM ~1.5 B/event), so the algorithmic-bytes fraction is not an HBM utilisation; the kernel is "
                                  "bound by the L1 data pipe (75 %) and instruction issue (profiles/r01f_*)") if l2_resident else
-                                ("weights exceed the L2: with 32 trajectories per warp the kernel moves 7.9 KB/event from DRAM at "
-                                 "4.2 TB/s = 65 % of the HBM peak (profiles/r01g_*); the adaptive warp batch trades that for L2 "
-                                 "hits (82 %, 0.5 KB/event from DRAM, profiles/r01h_*)")},
+                                ("weights exceed the L2: row-major with 32 trajectories per warp the kernel moved 7.9 KB/event from DRAM "
+                                 "at 4.2 TB/s (profiles/r01g_*); the adaptive warp batch trades that for L2 hits (profiles/r01h_*) and "
+                                 "the 4 x 4 x 1 brick layout cuts the lines a sphere touches by 36 % (profiles/r02g_brick_product.txt)")},
            "issue": issue_roofline(rate / world, "hfx_run_kernel") if l2_resident else None,
            "photons_per_exciton": (t["rad_tadf"] + t["rad_fluo"] + t["rad_host"]) / decayed}
     if cpu_line:

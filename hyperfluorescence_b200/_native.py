@@ -116,6 +116,7 @@ SIGNATURES = {
     "hf_x_read_realisation_tallies": (C.c_int, [P, P]),
     "hf_x_read_tables": (C.c_int, [P, C.POINTER(I32), P, P, P, P, P]),
     "hf_x_download_weights": (C.c_int, [P, I32, P, P]),
+    "hf_x_launch_info": (C.c_int, [P, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
     "hf_x_read_state": (C.c_int, [P, I64, I64, P, P, P, P, P]),
     "hf_x_read_trace": (C.c_int, [P, I64, P, C.POINTER(I64)]),
     "hf_xd_configure": (C.c_int, [P, I32, P, F64]),
@@ -364,6 +365,12 @@ class Sim:
         ws1, wt1 = np.zeros(self.N), np.zeros(self.N)
         check(load().hf_x_download_weights(self._h, int(realisation), ptr(ws1), ptr(wt1)))
         return ws1, wt1
+
+    def x_launch_info(self):
+        """How hf_x_run is launched: trajectories per warp, brick-layout weights or not, grid (hf_x_launch_info)."""
+        block, brick, grid = I32(0), I32(0), I32(0)
+        check(load().hf_x_launch_info(self._h, C.byref(block), C.byref(brick), C.byref(grid)))
+        return dict(block=block.value, brick=bool(brick.value), grid=grid.value)
 
     def x_state(self, first=0, n=None):
         n = self.n_trajectories - first if n is None else int(n)

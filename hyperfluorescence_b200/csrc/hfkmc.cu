@@ -85,6 +85,9 @@ struct hf_sim {
     unsigned long long *d_x_totals = nullptr;
     int x_warps = 8, x_grid = 1, x_per_sm = 1;
     bool x_tune = false;               // pick the warp batch by measurement at the next hf_x_run
+    bool x_brick = false;              // hfx_run_kernel reads brick-layout copies of the weights (weights larger than the L2)
+    double *d_bs1 = nullptr, *d_bt1 = nullptr;
+    int32_t *d_x_blin = nullptr;
     size_t x_smem = 0;
     // high-density exciton devices (hf_xd_*)
     bool xd_configured = false, xd_spawned = false;
@@ -232,7 +235,16 @@ typedef void (*hfx_kernel_fn)(const HfxParams);
 #define HF_X_WARPS 8
 #endif
 constexpr int kXWarps = HF_X_WARPS;
-static hfx_kernel_fn x_pick_kernel(int M) {
+static hfx_kernel_fn x_pick_brick_kernel(int M) {
+    switch (M) {
+        case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true, 3, true>;
+        case 256: return hfx_run_kernel<kXWarps, 8, 0, 2, true, 8, true>;
+        case 514: return hfx_run_kernel<kXWarps, 16, 2, 2, false, 8, true>;
+        default: return nullptr;                                                          // other cutoffs keep the row-major layout
+    }
+}
+static hfx_kernel_fn x_pick_kernel(int M, bool brick = false) {
+    if (brick) return x_pick_brick_kernel(M);
     switch (M) {                                                                          // the default cutoffs: M at compile time
         case 122: return hfx_run_kernel<kXWarps, 3, 26, 2, true>;                         // cutoff 3
         case 256: return hfx_run_kernel<kXWarps, 8, 0, 2, true>;                          // cutoff 4
@@ -254,6 +266,13 @@ static hfx_kernel_fn x_pick_kernel(int M) {
         case 14: case 15: return hfx_run_kernel<kXWarps, 14, -1, 2, false, 7>;
         default: return hfx_run_kernel<kXWarps, 16, -1, 2, false, 8>;                     // 16 or more slots: the first 16 prefetched
     }
+}
+
+// what hfx_run_kernel is launched with: the brick-layout copies when they exist
+static HfxParams x_launch_params(const hf_sim *s) {
+    HfxParams X = s->X;
+    if (s->x_brick) { X.ws1 = s->d_bs1; X.wt1 = s->d_bt1; X.lin = s->d_x_blin; X.brick = 1; }
+    return X;
 }
 
 void x_set_block(hf_sim *s, int block) {
@@ -288,10 +307,10 @@ int x_autotune(hf_sim *s) {
         cudaMemcpyAsync(save ? totals : s->d_x_totals, save ? s->d_x_totals : totals, 8 * nt, k, s->stream);
     };
     copy(true);
-    HfxParams X = s->X;
+    HfxParams X = x_launch_params(s);
     X.trace = nullptr; X.trace_n = 0; X.trace_len = nullptr;
     X.n_events = 12;
-    const int candidates[] = {32, 16, 8, 4, 3, 2};
+    const int candidates[] = {32, 16, 8, 6, 4, 3, 2};
     cudaEvent_t e0 = get_event(s), e1 = get_event(s);
     int best = 32;
     float best_ms = 0.f;
@@ -301,7 +320,7 @@ int x_autotune(hf_sim *s) {
         float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {                                      // the first repetition warms the caches for this batch size
             cudaEventRecord(e0, s->stream);
-            x_pick_kernel(X.M)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(X);
+            x_pick_kernel(X.M, s->x_brick)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(X);
             cudaEventRecord(e1, s->stream);
             cudaEventSynchronize(e1);
             cudaEventElapsedTime(&ms, e0, e1);
@@ -321,7 +340,40 @@ int x_autotune(hf_sim *s) {
 int x_configure_launch(hf_sim *s) {
     const size_t smem = hfx_smem_bytes(s->X.M, kXWarps);
     if (smem > 200 * 1024) return fail(HF_ERR_UNSUPPORTED, "cutoff too large: %zu B of shared memory", smem);
-    hfx_kernel_fn fn = x_pick_kernel(s->X.M);
+    int l2_bytes = 0;
+    cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, s->device);
+    const double footprint = 8.0 * (double)s->n_real * (double)s->X.w_stride;                // one spin manifold
+    const bool beyond_l2 = l2_bytes > 0 && footprint > 0.5 * (double)l2_bytes;
+    // hfx_run_kernel gathers from a copy of the weights in 4 x 4 x 1 bricks (one 128-byte line each): a cutoff-4 sphere
+    // touches 36 % fewer lines (hf_exciton.cuh).  Measured on one B200, 10^6 trajectories (profiles/r02g_brick_product.txt):
+    // 256^3 x 64 realisations 8.6e8 -> 1.06e9 events/s, 256^3 x 16 9.2e8 -> 1.19e9, and the L2-resident 128^3 1.89e9 ->
+    // 1.97e9.  Needs X and Y to be multiples of 4, one of the compiled cutoffs and offsets that fit the packed table;
+    // HF_X_BRICK=0 keeps the row-major layout.  The dense-device and integrated kernels always read the row-major arrays.
+    cudaFree(s->d_bs1); cudaFree(s->d_bt1); cudaFree(s->d_x_blin);
+    s->d_bs1 = s->d_bt1 = nullptr; s->d_x_blin = nullptr;
+    s->x_brick = false;
+    {
+        bool want = true;
+        if (const char *e = getenv("HF_X_BRICK")) want = atoi(e) != 0;
+        const bool can = s->P.X % 4 == 0 && s->P.Y % 4 == 0 && x_pick_brick_kernel(s->X.M) != nullptr &&
+                         (int64_t)(s->X.R + 1) * s->P.X * s->P.Y < (1ll << 22);
+        if (want && can) {
+            const size_t M = (size_t)s->X.M, RN = (size_t)s->n_real * (size_t)s->X.w_stride;
+            std::vector<int32_t> blin(M);
+            for (size_t m = 0; m < M; ++m) blin[m] = hfx_brick_lin(s->x_offsets[3 * m], s->x_offsets[3 * m + 1], s->x_offsets[3 * m + 2], s->P.X, s->P.Y);
+            int rc;
+            if ((rc = dev_alloc(&s->d_x_blin, M)) || (rc = dev_alloc(&s->d_bs1, RN)) || (rc = dev_alloc(&s->d_bt1, RN))) return rc;
+            HF_CUDA(cudaMemcpyAsync(s->d_x_blin, blin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
+            HF_CUDA(cudaMemsetAsync(s->d_bs1, 0, 8 * RN, s->stream));
+            HF_CUDA(cudaMemsetAsync(s->d_bt1, 0, 8 * RN, s->stream));
+            hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_bs1, s->d_bt1, (int64_t)s->P.N,
+                                                                       (int64_t)s->n_real, s->X.w_stride, s->X.w_halo, s->P.X, s->P.Y);
+            HF_CUDA(cudaStreamSynchronize(s->stream));
+            HF_CUDA(cudaGetLastError());
+            s->x_brick = true;
+        }
+    }
+    hfx_kernel_fn fn = x_pick_kernel(s->X.M, s->x_brick);
     if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     HF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kXWarps * 32, smem));
@@ -334,13 +386,7 @@ int x_configure_launch(hf_sim *s) {
     // is measured: the first hf_x_run after hf_x_spawn times a few events per candidate on a copy of the state
     // (x_autotune).  Results do not depend on the choice.
     s->x_per_sm = per_sm; s->x_warps = kXWarps; s->x_smem = smem;
-    s->x_tune = false;
-    {
-        int l2_bytes = 0;
-        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, s->device);
-        const double footprint = 8.0 * (double)s->n_real * (double)s->X.w_stride;            // one spin manifold
-        s->x_tune = l2_bytes > 0 && footprint > 0.5 * (double)l2_bytes;
-    }
+    s->x_tune = beyond_l2;
     x_set_block(s, 32);
     if (const char *e = getenv("HF_X_BLOCK")) { const int v = atoi(e); if (v >= 1 && v <= 32) { x_set_block(s, v); s->x_tune = false; } }
     return HF_OK;
@@ -503,7 +549,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_sc); cudaFree(s->d_cache_i); cudaFree(s->d_cache_tau); cudaFree(s->d_totals); cudaFree(s->d_sum);
     cudaFree(s->d_replay); cudaFree(s->d_trace); cudaFree(s->d_trace_base);
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
-    cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
+    cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_bs1); cudaFree(s->d_bt1); cudaFree(s->d_x_blin); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
@@ -1239,7 +1285,7 @@ int hf_x_run(hf_sim *s, int64_t n_events) {
     if (s->timing.size() >= 1024) { HF_CUDA(cudaStreamSynchronize(s->stream)); fold_timing(s); }
     cudaEvent_t e0 = get_event(s), e1 = get_event(s);
     HF_CUDA(cudaEventRecord(e0, s->stream));
-    x_pick_kernel(s->X.M)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(s->X);
+    x_pick_kernel(s->X.M, s->x_brick)<<<s->x_grid, kXWarps * 32, s->x_smem, s->stream>>>(x_launch_params(s));
     HF_CUDA(cudaEventRecord(e1, s->stream));
     s->timing.emplace_back(e0, e1);
     HF_CUDA(cudaGetLastError());
@@ -1280,6 +1326,15 @@ int hf_x_read_tables(hf_sim *s, int32_t *n_offsets, int8_t *offsets, double *g6,
     if (kf) memcpy(kf, s->X.kf, sizeof(double) * 9);
     if (kd) memcpy(kd, s->X.kd, sizeof(double) * 9);
     *n_offsets = M;
+    return HF_OK;
+}
+
+int hf_x_launch_info(hf_sim *s, int32_t *block, int32_t *brick, int32_t *grid) {
+    if (!s) return fail(HF_ERR_BAD_ARG, "null handle");
+    if (!s->x_configured) return fail(HF_ERR_STATE, "exciton path not configured");
+    if (block) *block = s->X.block;
+    if (brick) *brick = s->x_brick ? 1 : 0;
+    if (grid) *grid = s->x_grid;
     return HF_OK;
 }
 

@@ -25,7 +25,7 @@ t = sim.x_tallies()
 M = sim.x_tables()["g6"].size
 ev = a.B * a.events * n
 bytes_per_event = M * 9 + (M + 7) // 8 + 2 * 21 + 16
-print(json.dumps(dict(L=a.L, B=a.B, realisations=a.real, cutoff=a.cutoff, M=int(M), events_per_s=ev / (ms * 1e-3), ms_per_launch=ms / n,
+print(json.dumps(dict(launch=sim.x_launch_info(), L=a.L, B=a.B, realisations=a.real, cutoff=a.cutoff, M=int(M), events_per_s=ev / (ms * 1e-3), ms_per_launch=ms / n,
                       bytes_per_event=bytes_per_event, algorithmic_GBs=ev * bytes_per_event / (ms * 1e-3) / 1e9,
                       iqe=(t["rad_tadf"] + t["rad_fluo"]) / max(1, t["generated"] - a.B))))
 sim.close()

@@ -189,8 +189,9 @@ def run_batch_c1(dims, field, seed, first_traj, B, use_c1, species, homo, lumo, 
                 cache_i=cache_i, cache_tau=cache_tau, totals=totals)
 
 
-def x_run(oracle, seed, first_traj, B, n_events, n_calls=1, generic=False):
-    """The exciton kernels under emulation, with the model / lattice held by an ExcitonOracle."""
+def x_run(oracle, seed, first_traj, B, n_events, n_calls=1, generic=False, brick=False):
+    """The exciton kernels under emulation, with the model / lattice held by an ExcitonOracle.
+    brick: the variant that reads the weights from the 4 x 4 x 1 brick layout (X, Y multiples of 4, cutoff 3 / 4 / 5)."""
     o = oracle
     cap = n_events * n_calls
     trace = np.zeros((B, max(cap, 1)), EVENT_DTYPE)
@@ -201,7 +202,7 @@ def x_run(oracle, seed, first_traj, B, n_events, n_calls=1, generic=False):
     rc = lib().emu_x_run(d, _p(o.species), _p(o.ws1), _p(o.wt1), C.c_int32(len(o.g6)), _p(o.off), _p(o.g6), _p(o.gd),
                          _p(o.kf), _p(o.kd), _p(o.k_isc), _p(o.k_risc), _p(o.k_rad), _p(o.k_nonrad),
                          C.c_double(o.params["singlet_fraction"]), C.c_uint64(seed), C.c_uint32(first_traj), C.c_int32(B),
-                         C.c_int64(n_events), C.c_int32(n_calls), C.c_int32(int(generic)), _p(trace), C.c_int64(max(cap, 1)), _p(site), _p(spin),
+                         C.c_int64(n_events), C.c_int32(n_calls), C.c_int32(2 if brick else int(generic)), _p(trace), C.c_int64(max(cap, 1)), _p(site), _p(spin),
                          _p(time), _p(life), _p(draws), _p(totals))
     if rc:
         raise RuntimeError(f"emu_x_run failed ({rc})")

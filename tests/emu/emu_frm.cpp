@@ -258,6 +258,9 @@ static void x_run_body_r16(void *a) { hfx_run_kernel<1, 16, -1, 1, false, 8>(*(c
 static void x_run_body_k3(void *a) { hfx_run_kernel<1, 3, 26, 1, true>(*(const HfxParams *)a); }
 static void x_run_body_k8(void *a) { hfx_run_kernel<1, 8, 0, 1, true>(*(const HfxParams *)a); }
 static void x_run_body_k16(void *a) { hfx_run_kernel<1, 16, 2, 1, false, 8>(*(const HfxParams *)a); }
+static void x_run_body_b3(void *a) { hfx_run_kernel<1, 3, 26, 1, true, 3, true>(*(const HfxParams *)a); }  // brick-layout weights
+static void x_run_body_b8(void *a) { hfx_run_kernel<1, 8, 0, 1, true, 8, true>(*(const HfxParams *)a); }
+static void x_run_body_b16(void *a) { hfx_run_kernel<1, 16, 2, 1, false, 8, true>(*(const HfxParams *)a); }
 
 // Exciton path: B <= 32 trajectories on one lattice, hfx_spawn + n_calls x hfx_run(n_events).
 int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, const double *wt1, int32_t M,
@@ -290,8 +293,19 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     // the device layout: R zero planes below and above the lattice
     P.w_halo = (int64_t)maxr * P.X * P.Y; P.w_stride = P.N + 2 * P.w_halo;
     std::vector<double> hs1((size_t)P.w_stride, 0.0), ht1((size_t)P.w_stride, 0.0);
-    memcpy(hs1.data() + P.w_halo, ws1, sizeof(double) * (size_t)P.N);
-    memcpy(ht1.data() + P.w_halo, wt1, sizeof(double) * (size_t)P.N);
+    const bool brick = generic == 2;                       // the 4 x 4 x 1 brick layout of the weights (compiled cutoffs only)
+    if (brick) {
+        if (P.X % 4 || P.Y % 4 || (M != 122 && M != 256 && M != 514)) return 4;
+        for (int64_t i = 0; i < P.N; ++i) {
+            const int64_t plane = (int64_t)P.X * P.Y, in = i % plane, o = P.w_halo + i - in + hfx_brick2((int)(in % P.X), (int)(in / P.X), P.X);
+            hs1[(size_t)o] = ws1[i]; ht1[(size_t)o] = wt1[i];
+        }
+        for (int m = 0; m < M; ++m) lin[(size_t)m] = hfx_brick_lin(offsets[3 * m], offsets[3 * m + 1], offsets[3 * m + 2], P.X, P.Y);
+        P.brick = 1;
+    } else {
+        memcpy(hs1.data() + P.w_halo, ws1, sizeof(double) * (size_t)P.N);
+        memcpy(ht1.data() + P.w_halo, wt1, sizeof(double) * (size_t)P.N);
+    }
     P.ws1 = hs1.data(); P.wt1 = ht1.data();
     std::vector<int32_t> site((size_t)B), spin((size_t)B);
     std::vector<double> time((size_t)B), life((size_t)B);
@@ -304,7 +318,8 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     if (hfx_smem_bytes(M, 1) > sizeof(hf_smem)) return 2;
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     emu_run_warp(x_spawn_body, &P);
-    void (*body)(void *) = generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : M == 514 ? x_run_body_k16 :
+    void (*body)(void *) = brick ? (M == 122 ? x_run_body_b3 : M == 256 ? x_run_body_b8 : x_run_body_b16) :
+                           generic ? x_run_body_generic : M == 122 ? x_run_body_k3 : M == 256 ? x_run_body_k8 : M == 514 ? x_run_body_k16 :
                            (M >> 5) == 2 ? x_run_body_r2 : (M >> 5) == 5 ? x_run_body_r5 : (M >> 5) == 12 ? x_run_body_r12 :
                            (M >> 5) >= 16 ? x_run_body_r16 : x_run_body_generic;
     for (int c = 0; c < n_calls; ++c) { P.n_events = n_events; emu_run_warp(body, &P); }

@@ -62,14 +62,18 @@ def test_oracle_closed_forms():
     ((12, 13, 6), 2.5, 10, 32, False),     # M = 80 at run time: 2 register slots + a tail of 16 transfer and 3 on-site channels
     ((14, 15, 6), 3.5, 11, 30, False),     # M = 178: 5 register slots
     ((12, 12, 5), 4.5, 12, 9, False),      # M = 388: 12 slots in two halves of 6
-    ((14, 13, 5), 6.0, 13, 6, False)])     # M = 924: the first 16 of 28 slots prefetched, 12 through shared memory
+    ((14, 13, 5), 6.0, 13, 6, False),      # M = 924: the first 16 of 28 slots prefetched, 12 through shared memory
+    ((12, 12, 6), 4.0, 5, 32, "brick"),    # weights in 4 x 4 x 1 bricks: every site needs the periodic wrap ...
+    ((24, 20, 7), 4.0, 8, 27, "brick"),    # ... wrap-free sites too (the packed per-lane offsets)
+    ((16, 12, 6), 3.0, 6, 32, "brick"),    # cutoff 3 with the tail slot
+    ((28, 24, 7), 5.0, 9, 19, "brick")])   # cutoff 5: two halves
 def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, generic):
     """hfx_spawn_kernel + hfx_run_kernel run lane by lane on the host (tests/emu): identical event
     sequences, channels, spins, waiting times, final states and tallies for 32 trajectories."""
     p = dict(xo.default_params(), cutoff=cutoff)
     o, _ = _oracle(dims, seed, p, props=(0.6, 0.3, 0.1))
     n = 250
-    dev = emu.x_run(o, seed * 1000 + 1, 40, B, n // 2, n_calls=2, generic=generic)
+    dev = emu.x_run(o, seed * 1000 + 1, 40, B, n // 2, n_calls=2, generic=generic is True, brick=generic == "brick")
     tot = np.zeros(16, np.int64)
     for b in range(B):
         ref = o.run(seed * 1000 + 1, 40 + b, n)
@@ -86,6 +90,48 @@ def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, gen
     assert tot[2] > 0 and tot[3] > 0 and tot[6:15].sum() > 0                           # Forster, Dexter and decays occurred
     if cutoff <= 4.0 and B >= 27:
         assert tot[4] + tot[5] > 0                                                     # ... and spin flips (rare next to >= 388 transfer channels)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,cutoff", [((24, 24, 12), 4.0), ((20, 28, 9), 3.0), ((32, 24, 11), 5.0)])
+def test_gpu_brick_layout_changes_nothing(dims, cutoff, monkeypatch):
+    """The 4 x 4 x 1 brick layout of the weights (used when they exceed the L2; forced here with HF_X_BRICK=1) is a
+    layout only: traces, final states, tallies and the downloaded (row-major) weights equal the row-major run's."""
+    from hyperfluorescence_b200 import _native as nat
+    out = {}
+    for brick in (0, 1):
+        monkeypatch.setenv("HF_X_BRICK", str(brick))
+        sim = nat.Sim(dims, (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=3000, n_realisations=3, seed=91, first_trajectory=7)
+        try:
+            sim.generate_lattice()
+            p = nat.x_default_params()
+            p.cutoff = cutoff
+            sim.x_configure(p)
+            assert sim.x_launch_info()["brick"] is bool(brick)
+            sim.set_trace(0, 8, 200)
+            sim.x_spawn()
+            sim.x_run(120); sim.x_run(80)
+            sim.sync()
+            st = sim.x_state()
+            out[brick] = (st, sim.x_realisation_tallies(), [sim.x_trace(b, 200) for b in range(8)], sim.x_weights(2))
+        finally:
+            sim.close()
+    a, b = out[0], out[1]
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k]), k
+    for k in a[1]:
+        assert np.array_equal(a[1][k], b[1][k]), k
+    for ta, tb in zip(a[2], b[2]):
+        assert np.array_equal(ta, tb)
+    assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
+    # lattices the bricks do not tile keep the row-major layout
+    monkeypatch.setenv("HF_X_BRICK", "1")
+    sim = nat.Sim((22, 24, 8), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=64, seed=1)
+    try:
+        sim.generate_lattice(); sim.x_configure()
+        assert sim.x_launch_info()["brick"] is False
+    finally:
+        sim.close()
 
 
 @pytest.mark.gpu
