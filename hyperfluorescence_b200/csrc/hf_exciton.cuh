@@ -180,11 +180,30 @@ __host__ __device__ inline size_t hfx_smem_bytes(int M, int warps) {
 // bases (S2R + LEA chains) inside the event loop, which costs more issue slots than the register.
 #if defined(__CUDA_ARCH__)
 #define HFX_PIN32(x) asm volatile("" : "+r"(x))
+#define HFX_PIN64(x) asm volatile("" : "+l"(x))
 #else
 #define HFX_PIN32(x) (void)0
+#define HFX_PIN64(x) (void)0
 #endif
 
-__device__ __forceinline__ double hfx_min1(double v) { return v < 1.0 ? v : 1.0; }
+// min(v, 1) as `v < 1.0 ? v : 1.0`, decided on the high word: for every double (negative, NaN and infinity included)
+// v < 1.0 <=> (int)hi(v) < 0x3ff00000, and the integer compare is 3 instructions where DSETP.MIN + fix-ups are 6.
+// Read-only shared-memory tables through 32-bit shared addresses held in registers (the hot loop of the dense
+// kernel): a generic pointer pinned in a register makes nvcc emit generic loads, an unpinned one makes it rebuild the
+// shared-window base at every use.  Only for data that is not written after the kernel's first barrier.
+#if defined(__CUDA_ARCH__)
+typedef unsigned hfx_sptr;
+__device__ __forceinline__ hfx_sptr hfx_saddr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double hfx_lds_f64(hfx_sptr a) { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int hfx_lds_s32(hfx_sptr a) { int v; asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#else
+typedef uintptr_t hfx_sptr;
+inline hfx_sptr hfx_saddr(const void *p) { return (uintptr_t)p; }
+inline double hfx_lds_f64(hfx_sptr a) { return *(const double *)a; }
+inline int hfx_lds_s32(hfx_sptr a) { return *(const int *)a; }
+#endif
+
+__device__ __forceinline__ double hfx_min1(double v) { return __double2hiint(v) < 0x3ff00000 ? v : 1.0; }
 
 // Offset (in sites) from an exciton on (px, py, .) to the neighbour of packed offset o: periodic in
 // x and y, straight through in z (the halo absorbs z outside [0, Z)).

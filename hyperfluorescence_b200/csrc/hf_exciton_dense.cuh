@@ -11,13 +11,18 @@
 //   T[n_pad]     f64  cached total rate of every exciton (0 for the padding slots)
 //   birth[n_pad] f64  device clock when the exciton was created
 //   occ[]        u32  16 sites per word, 2 bits per site, with the same R-plane halo as the weights
-// Per event the warp (1) scans the cached totals to pick an exciton, (2) evaluates that exciton's
-// M + 3 channels (lane = channel % 32; each lane also fetches the acceptor's occupancy code) and scans
-// them to pick the channel, (3) applies it — lane 0 edits the occupancy words — and (4) re-evaluates the
-// totals of the excitons that can see a changed site.  Those are found without scanning the device: every
-// evaluation of an exciton ON a changed site (the chosen exciton before the event, the same slot after it,
-// a promoted acceptor) already fetches the occupancy codes of all sites in its cutoff sphere, so the lanes
-// that met an occupied site name the neighbours; only those are looked up in the position list.
+//   rec[n_pad]   32 x (f64 L, u32 seen) per exciton, global: the scanned lane sums of its channel rates at its last
+//                evaluation and, per lane, which of the lane's channels pointed at occupied sites (bit 31: lane sum > 0)
+// Per event the warp (1) scans the cached totals to pick an exciton, (2) picks that exciton's channel from its
+// RECORD — the 32 scanned lane sums name the lane, and only that lane's K channels are evaluated again, by K lanes
+// in parallel, bit for bit as at the last evaluation (nothing the exciton can see has changed since: that is what
+// keeps its cached total valid) — (3) applies it — lane 0 edits the occupancy words — and (4) re-evaluates the
+// totals (M + 3 channels, lane = channel % 32; each lane also fetches the acceptor's occupancy code) and records of
+// the excitons that can see a changed site.  Those are found without scanning the device: every evaluation of an
+// exciton ON a changed site (the chosen exciton before the event — its record —, the same slot after it, a promoted
+// acceptor) knows the occupancy codes of all sites in its cutoff sphere, so the lanes that met an occupied site
+// name the neighbours; only those are looked up in the position list.  One full evaluation per event instead of two
+// (round 2: 2 316 -> see profiles/ warp instructions per event).
 #pragma once
 #include "hf_exciton.cuh"
 
@@ -41,6 +46,8 @@ struct HfxdParams {
     double p_tta;                      // triplet-triplet promotion probability
     uint32_t *pos;                     // [B][n_pad]
     double *T, *birth;                 // [B][n_pad]
+    double *rec_L;                     // [B][n_pad][32] scanned lane sums of every exciton's last evaluation
+    uint32_t *rec_seen;                // [B][n_pad][32] occupied-acceptor bits per lane | (lane sum > 0) << 31
     uint32_t *occ;                     // [B][occ_words]
     int64_t occ_words;
     double *time, *life;               // [B] device clock, summed lifetimes of the lost excitons
@@ -76,7 +83,7 @@ struct HfxdWarp {                      // one warp's view of its device
     bool aligned;                      // M == 32 * HFXD_KF and every mask index fits 31 bits: the static fast path
 };
 
-// Lane sums of the channel rates of an exciton (packed site + spin); store: also leave the rates in s_rates.
+// Lane sums of the channel rates of an exciton (packed site + spin).
 // `seen` gets bit k set when this lane's channel of slot k points at an occupied site.  HFXD_CHUNK slots are
 // gathered (weight + occupancy word) before any of them is consumed.  ONE inlined instance per kernel (the event
 // loop is a small state machine around a single call): with five copies the kernel was 7 100 instructions and a
@@ -89,7 +96,7 @@ struct HfxdWarp {                      // one warp's view of its device
 #ifndef HFXD_FAST_CHUNK
 #define HFXD_FAST_CHUNK 2               // must divide HFXD_KF; measured: 2 -> 2.67e8, 4 -> 2.56e8, 8 (fully unrolled) -> 2.19e8 events/s on 4096 x 256
 #endif
-__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen, const bool store) {
+__device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, unsigned &seen) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
     const bool singlet = spin == HFX_SINGLET;
@@ -108,40 +115,49 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     double S = 0.0;
     seen = 0;
     if (W.aligned && nowrap) {
+        // what the loop reads through, pinned in registers: nvcc otherwise rebuilds the pointers (a 64-bit multiply for
+        // the mask, the shared-window base for the tables) at every use
         const uint32_t *occ = W.occ;
-        const int oi32 = (int)oi;                                                // the host checked that the mask index fits
-        const int32_t *lin = W.s_lin + W.lane;
-        const double *gl = g + W.lane;
-        double *rates = W.s_rates + W.lane;
+        const double *wq = w;
+        unsigned oi32 = (unsigned)oi;                                            // the host checked that the mask index fits
+        hfx_sptr lin = hfx_saddr(W.s_lin + W.lane), gl = hfx_saddr(g + W.lane), pr = hfx_saddr(pref), an = hfx_saddr(ann);
+        HFX_PIN64(occ); HFX_PIN64(wq); HFX_PIN32(oi32); HFX_PIN32(lin); HFX_PIN32(gl); HFX_PIN32(pr); HFX_PIN32(an);
         // a ROLLED loop over chunks of HFXD_FAST_CHUNK slots: the hot code stays small enough for the instruction
         // caches (seven warps per scheduler, each somewhere else in a 5 000-instruction kernel)
 #pragma unroll 1
-        for (int k0 = 0; k0 < HFXD_KF; k0 += HFXD_FAST_CHUNK) {
+        for (int k0 = 0; k0 < HFXD_KF; k0 += HFXD_FAST_CHUNK, lin += 4 * 32 * HFXD_FAST_CHUNK, gl += 8 * 32 * HFXD_FAST_CHUNK) {
             double wj[HFXD_FAST_CHUNK];
             uint32_t ow[HFXD_FAST_CHUNK];
             int sh[HFXD_FAST_CHUNK];
 #pragma unroll
             for (int u = 0; u < HFXD_FAST_CHUNK; ++u) {
-                const int d = lin[32 * (k0 + u)];
-                wj[u] = __ldg(w + d);
-                const int oj = oi32 + d;
+                const int d = hfx_lds_s32(lin + 4 * 32 * u);
+                wj[u] = __ldg(wq + d);
+                const unsigned oj = oi32 + (unsigned)d;
                 ow[u] = occ[oj >> 4];
-                sh[u] = 2 * (oj & 15);
+                sh[u] = 2 * (int)(oj & 15u);
             }
+            double rate[HFXD_FAST_CHUNK];
+            unsigned any = 0;
 #pragma unroll
             for (int u = 0; u < HFXD_FAST_CHUNK; ++u) {
-                double rate = hfx_rate(pref, gl[32 * (k0 + u)], wj[u], inv_wi);
-                const int o = (int)((ow[u] >> sh[u]) & 3u);
-                if (o) { rate = __dmul_rn(rate, ann[o == HFX_SINGLET ? 0 : 1]); seen |= 1u << (k0 + u); }
-                if (store) rates[32 * (k0 + u)] = rate;
-                S = __dadd_rn(S, rate);
+                rate[u] = __dmul_rn(__dmul_rn(hfx_lds_f64(pr + 8 * hfx_tag_of(wj[u])), hfx_lds_f64(gl + 8 * 32 * u)),
+                                    hfx_min1(__dmul_rn(wj[u], inv_wi)));         // hfx_rate()
+                ow[u] = (ow[u] >> sh[u]) & 3u;
+                any |= ow[u];
             }
+            if (any) {                                                           // an occupied acceptor: rare, one branch per chunk
+#pragma unroll
+                for (int u = 0; u < HFXD_FAST_CHUNK; ++u)
+                    if (ow[u]) { rate[u] = __dmul_rn(rate[u], hfx_lds_f64(an + (ow[u] == HFX_SINGLET ? 0 : 8))); seen |= 1u << (k0 + u); }
+            }
+#pragma unroll
+            for (int u = 0; u < HFXD_FAST_CHUNK; ++u) S = __dadd_rn(S, rate[u]);
         }
         double rate = 0.0;                                                       // slot KF: ISC / RISC, radiative, non-radiative on lanes 0, 1, 2
         if (W.lane == 0) rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
         else if (W.lane == 1) rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
         else if (W.lane == 2) rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
-        if (store) rates[32 * HFXD_KF] = rate;
         return __dadd_rn(S, rate);
     }
 #pragma unroll 1
@@ -177,7 +193,6 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
                 } else if (c == W.M + 2) {
                     rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
                 }
-                if (store) W.s_rates[c] = rate;
                 S = __dadd_rn(S, rate);
             }
         }
@@ -217,14 +232,19 @@ __device__ __forceinline__ void hfxd_mark_seen(const HfxdWarp &W, int site, unsi
     __syncwarp();
 }
 
-// The canonical pick (oracle: pick()): v[n_slots][32] in shared memory, S = this lane's sum, L = its scan.
-// Returns the chosen index (slot * 32 + lane) and the running sum before it; warp-uniform.
-__device__ __forceinline__ int hfxd_pick(const double *v, int n_slots, double S, double L, double target, int lane, double &base) {
+// The canonical pick (oracle: pick()) in two steps.  Lane: L = this lane's scanned sum, positive = its own sum > 0;
+// returns the chosen lane and the running sum below it.  Slot: walks v[slot][lstar] in shared memory from there; returns
+// the chosen index (slot * 32 + lane) and the running sum before it.  Both warp-uniform.
+__device__ __forceinline__ int hfxd_pick_lane(double L, bool positive, double target, double &acc0) {
     const unsigned over = __ballot_sync(HF_FULL, L > target);
-    const unsigned nonzero = __ballot_sync(HF_FULL, S > 0.0);
+    const unsigned nonzero = __ballot_sync(HF_FULL, positive);
     const int lstar = over ? __ffs(over) - 1 : (nonzero ? 31 - __clz(nonzero) : 0);
     const double below = __shfl_sync(HF_FULL, L, (lstar + 31) & 31);
-    double acc = lstar > 0 ? below : 0.0, b_slot = acc, b_last = acc;
+    acc0 = lstar > 0 ? below : 0.0;
+    return lstar;
+}
+__device__ __forceinline__ int hfxd_pick_slot(const double *v, int n_slots, int lstar, double acc, double target, double &base) {
+    double b_slot = acc, b_last = acc;
     int slot = -1, last = -1;
     for (int q = 0; q < n_slots; ++q) {
         const double r = v[(q << 5) + lstar], before = acc;
@@ -235,6 +255,41 @@ __device__ __forceinline__ int hfxd_pick(const double *v, int n_slots, double S,
     if (slot < 0) { slot = last < 0 ? n_slots - 1 : last; b_slot = b_last; }
     base = b_slot;
     return (slot << 5) + lstar;
+}
+
+// The K channels of lane `lstar` of an exciton (packed site + spin), evaluated by lanes 0 .. K - 1 with the arithmetic
+// of hfxd_lane_sum and left in s_rates[(k << 5) + lstar] (K <= 31, checked by the host).
+__device__ __forceinline__ void hfxd_column(const HfxdWarp &W, uint32_t ps, int lstar) {
+    const HfxParams &X = W.P->X;
+    const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
+    const bool singlet = spin == HFX_SINGLET;
+    const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
+    const int plane = X.X * X.Y;
+    const int64_t i = (int64_t)pz * plane + py * X.X + px;
+    const double *w = (singlet ? W.ws1 : W.wt1) + i;
+    const double wi = __ldg(w);
+    const int a = hfx_tag_of(wi);
+    const int c = (W.lane << 5) + lstar;
+    if (W.lane < W.K) {
+        const double inv_wi = __ddiv_rn(1.0, wi);
+        double rate = 0.0;
+        if (c < W.M) {
+            const bool nowrap = px >= X.R && px < X.X - X.R && py >= X.R && py < X.Y - X.R;
+            const int delta = nowrap ? W.s_lin[c] : hfx_delta(W.s_off[c], px, py, X.X, X.Y, plane);
+            const double wj = __ldg(w + delta);
+            const int o = hfxd_occ_get(W.occ, i + X.w_halo + delta);
+            rate = hfx_rate(W.s_k + (singlet ? 0 : 9) + 3 * a, (singlet ? W.s_g6 : W.s_gd)[c], wj, inv_wi);
+            if (o) rate = __dmul_rn(rate, W.s_ann[(singlet ? 0 : 2) + (o == HFX_SINGLET ? 0 : 1)]);
+        } else if (c == W.M) {
+            rate = singlet ? W.s_k[18 + a] : __dmul_rn(W.s_k[21 + a], hfx_min1(__dmul_rn(__ldg(W.ws1 + i), inv_wi)));
+        } else if (c == W.M + 1) {
+            rate = W.s_k[24 + 2 * a + (singlet ? 0 : 1)];
+        } else if (c == W.M + 2) {
+            rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
+        }
+        W.s_rates[c] = rate;
+    }
+    __syncwarp();
 }
 
 // A new exciton for slot k: the first empty interior site along the device's stream (oracle: replace()).
@@ -292,6 +347,8 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         W.occ = P.occ + dev * P.occ_words;
         uint32_t *g_pos = P.pos + dev * n_pad;
         double *g_T = P.T + dev * n_pad, *g_birth = P.birth + dev * n_pad;
+        double *g_L = P.rec_L + dev * n_pad * 32;
+        uint32_t *g_seen = P.rec_seen + dev * n_pad * 32;
         double time, life;
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
@@ -318,52 +375,34 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         uint64_t trace_at = traced ? X.trace_len[dev - X.trace_first] : 0;
 
         for (int64_t ev = P.fill ? -1 : 0; ev < X.n_events; ++ev) {
-            // stage 0: evaluate the chosen exciton, pick its channel, apply the event
-            //       1: refresh a slot whose own site / spin changed (its evaluation names the excitons it meets)
-            //       2: refresh the slots marked dirty
-            int stage = 2, tgt = -1, kx = -1, promoted = -1;
+            // refresh stage 1: a slot whose own site / spin changed (its evaluation names the excitons it meets)
+            //               2: the slots marked dirty
+            int stage = 2, tgt = -1, promoted = -1;
             uint32_t job = 0;
-            double target = 0.0, base = 0.0, R = 0.0, u_time = 0.0;
             if (ev >= 0) {
                 // (1) the exciton: canonical scan over the cached totals
                 double A = 0.0;
                 for (int q = 0; q < n_slots; ++q) A = __dadd_rn(A, W.s_T[(q << 5) + lane]);
                 const double G = hfx_scan(A, lane);
-                R = __shfl_sync(HF_FULL, G, 31);
+                const double R = __shfl_sync(HF_FULL, G, 31);
                 const HfPhiloxBlock rnd = hf_philox_block(X.k0, X.k1, HF_STREAM_XDENSE, ident, draws >> 1);
                 draws += 2;
-                const double u_sel = hf_block_uniform(rnd, 0);
-                u_time = hf_block_uniform(rnd, 1);
-                target = __dmul_rn(u_sel, R);
-                kx = hfxd_pick(W.s_T, n_slots, A, G, target, lane, base);
-                stage = 0; tgt = kx; job = W.s_pos[kx];
-            }
-            for (;;) {
-                if (stage == 2) {                                                // next slot marked dirty, ascending
-                    int q = -1;
-                    for (int wq = 0; wq < n_slots && q < 0; ++wq) {
-                        const unsigned todo = W.s_dirty[wq];
-                        if (todo) q = (wq << 5) + __ffs(todo) - 1;
-                    }
-                    if (q < 0) break;
-                    tgt = q; job = W.s_pos[q];
-                }
-                const double S = hfxd_lane_sum(W, job, seen, stage == 0);
-                const double L = hfx_scan(S, lane);
-                __syncwarp();
-                if (stage < 2) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen);   // the neighbours of a site that changes / changed
-                if (stage != 0) {
-                    const double tot = __shfl_sync(HF_FULL, L, 31);
-                    if (lane == 0) { W.s_T[tgt] = tot; W.s_dirty[tgt >> 5] &= ~(1u << (tgt & 31)); }
-                    __syncwarp();
-                    if (stage == 1 && promoted >= 0 && tgt != promoted) { tgt = promoted; job = W.s_pos[promoted]; continue; }
-                    stage = 2;
-                    continue;
-                }
-                // (2) the channel of the chosen exciton
-                const uint32_t ps = job;
+                const double u_sel = hf_block_uniform(rnd, 0), u_time = hf_block_uniform(rnd, 1);
+                const double target = __dmul_rn(u_sel, R);
+                double acc0, base;
+                const int xl = hfxd_pick_lane(G, A > 0.0, target, acc0);
+                const int kx = hfxd_pick_slot(W.s_T, n_slots, xl, acc0, target, base);
+                const uint32_t ps = W.s_pos[kx];
+                // (2) its channel, from the record of its last evaluation: the lane by the scanned sums, then that lane's
+                //     K channels again (same inputs, same arithmetic)
+                const double Lk = g_L[kx * 32 + lane];
+                const uint32_t sk = g_seen[kx * 32 + lane];
+                const double target2 = __dsub_rn(target, base);
+                const int lstar = hfxd_pick_lane(Lk, (sk >> 31) != 0u, target2, acc0);
+                hfxd_column(W, ps, lstar);
                 double base2;
-                const int chosen = hfxd_pick(W.s_rates, K, S, L, __dsub_rn(target, base), lane, base2);
+                const int chosen = hfxd_pick_slot(W.s_rates, K, lstar, acc0, target2, base2);
+                hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), sk & 0x7fffffffu);     // the neighbours of the site that changes
                 const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
                 time = __dadd_rn(time, dt);
                 // (3) apply
@@ -441,9 +480,31 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 }
                 trace_at += 1;
                 __syncwarp();
-                // (4) refresh the cached totals: the slot itself in its new state, a promoted acceptor (whose neighbours
-                //     see a different spin), then everybody marked
+                // (4) refresh the cached totals and records: the slot itself in its new state, a promoted acceptor (whose
+                //     neighbours see a different spin), then everybody marked
                 stage = 1; tgt = kx; job = ps_after;
+            }
+            for (;;) {
+                if (stage == 2) {                                                // next slot marked dirty, ascending
+                    int q = -1;
+                    for (int wq = 0; wq < n_slots && q < 0; ++wq) {
+                        const unsigned todo = W.s_dirty[wq];
+                        if (todo) q = (wq << 5) + __ffs(todo) - 1;
+                    }
+                    if (q < 0) break;
+                    tgt = q; job = W.s_pos[q];
+                }
+                const double S = hfxd_lane_sum(W, job, seen);
+                const double L = hfx_scan(S, lane);
+                __syncwarp();
+                if (stage == 1) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen);   // the neighbours of the site that changed
+                g_L[tgt * 32 + lane] = L;
+                g_seen[tgt * 32 + lane] = seen | (S > 0.0 ? 0x80000000u : 0u);
+                const double tot = __shfl_sync(HF_FULL, L, 31);
+                if (lane == 0) { W.s_T[tgt] = tot; W.s_dirty[tgt >> 5] &= ~(1u << (tgt & 31)); }
+                __syncwarp();
+                if (stage == 1 && promoted >= 0 && tgt != promoted) { tgt = promoted; job = W.s_pos[promoted]; continue; }
+                stage = 2;
             }
             __syncwarp();
         }

@@ -92,8 +92,9 @@ struct hf_sim {
     // high-density exciton devices (hf_xd_*)
     bool xd_configured = false, xd_spawned = false;
     HfxdParams XD;
+    uint32_t *d_xd_rec_seen = nullptr;
     uint32_t *d_xd_pos = nullptr, *d_xd_occ = nullptr;
-    double *d_xd_T = nullptr, *d_xd_birth = nullptr, *d_xd_time = nullptr, *d_xd_life = nullptr;
+    double *d_xd_T = nullptr, *d_xd_birth = nullptr, *d_xd_rec_L = nullptr, *d_xd_time = nullptr, *d_xd_life = nullptr;
     uint64_t *d_xd_draws = nullptr;
     unsigned long long *d_xd_totals = nullptr;
     int xd_grid = 1;
@@ -551,7 +552,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_site); cudaFree(s->d_x_spin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
     cudaFree(s->d_ws1); cudaFree(s->d_wt1); cudaFree(s->d_bs1); cudaFree(s->d_bt1); cudaFree(s->d_x_blin); cudaFree(s->d_x_time); cudaFree(s->d_x_life); cudaFree(s->d_x_draws);
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
-    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_rec_L); cudaFree(s->d_xd_rec_seen); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
     cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
     cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab); cudaFree(s->d_inv_dist);
@@ -1377,9 +1378,9 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
 constexpr int kXdWarps = HF_XD_WARPS;
 
 static void xd_free(hf_sim *s) {
-    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_time);
+    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_rec_L); cudaFree(s->d_xd_rec_seen); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
-    s->d_xd_pos = nullptr; s->d_xd_occ = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_time = nullptr;
+    s->d_xd_pos = nullptr; s->d_xd_occ = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_rec_L = nullptr; s->d_xd_rec_seen = nullptr; s->d_xd_time = nullptr;
     s->d_xd_life = nullptr; s->d_xd_draws = nullptr; s->d_xd_totals = nullptr;
 }
 
@@ -1391,6 +1392,7 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     const int64_t n_interior = (int64_t)s->P.X * s->P.Y * (s->P.Z - 2);
     if ((int64_t)n_excitons * 2 > n_interior) return fail(HF_ERR_BAD_ARG, "more excitons than half the interior sites");
     if (!(p_tta >= 0.0 && p_tta <= 1.0)) return fail(HF_ERR_BAD_ARG, "p_tta must be a probability");
+    if (hfx_padded_channels(s->X.M) / 32 > 31) return fail(HF_ERR_UNSUPPORTED, "cutoff too large for the dense devices: %d channels (at most 989)", s->X.M + 3);
     for (int k = 0; k < 4; ++k)
         if (!(annihilation[k] >= 0.0)) return fail(HF_ERR_BAD_ARG, "annihilation factors must be >= 0");
     int rc = use_device(s);
@@ -1408,12 +1410,15 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     if ((rc = dev_alloc(&s->d_xd_pos, B * np))) return rc;
     if ((rc = dev_alloc(&s->d_xd_T, B * np))) return rc;
     if ((rc = dev_alloc(&s->d_xd_birth, B * np))) return rc;
+    if ((rc = dev_alloc(&s->d_xd_rec_L, B * np * 32))) return rc;             // 384 B per exciton: the record of its last evaluation
+    if ((rc = dev_alloc(&s->d_xd_rec_seen, B * np * 32))) return rc;
     if ((rc = dev_alloc(&s->d_xd_occ, B * (size_t)D.occ_words))) return rc;
     if ((rc = dev_alloc(&s->d_xd_time, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_life, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_draws, B))) return rc;
     if ((rc = dev_alloc(&s->d_xd_totals, (size_t)s->n_real * HFXD_T_N))) return rc;
     D.pos = s->d_xd_pos; D.T = s->d_xd_T; D.birth = s->d_xd_birth; D.occ = s->d_xd_occ;
+    D.rec_L = s->d_xd_rec_L; D.rec_seen = s->d_xd_rec_seen;
     D.time = s->d_xd_time; D.life = s->d_xd_life; D.draws = s->d_xd_draws; D.totals = s->d_xd_totals;
     const size_t smem = hfxd_smem_bytes(s->X.M, D.n_pad, kXdWarps);
     if (smem > 227 * 1024) return fail(HF_ERR_UNSUPPORTED, "%d excitons per device need %zu B of shared memory", n_excitons, smem);

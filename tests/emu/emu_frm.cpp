@@ -375,6 +375,9 @@ int emu_xd_run(const int32_t dims[3], const double *ws1, const double *wt1, int3
     uint64_t draws = 0, tlen = 0;
     std::vector<unsigned long long> totals(HFXD_T_N, 0);
     std::vector<HfTraceRec> trace((size_t)(trace_cap + 1));
+    std::vector<double> rec_L((size_t)D.n_pad * 32, 0.0);
+    std::vector<uint32_t> rec_seen((size_t)D.n_pad * 32, 0);
+    D.rec_L = rec_L.data(); D.rec_seen = rec_seen.data();
     D.pos = pos.data(); D.T = T.data(); D.birth = birth.data(); D.occ = occ.data();
     D.time = &time; D.life = &life; D.draws = &draws; D.totals = totals.data();
     P.trace = trace.data(); P.trace_first = 0; P.trace_n = 1; P.trace_cap = trace_cap; P.trace_len = &tlen;

@@ -163,6 +163,7 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline int __double2hiint(double a) { long long b; memcpy(&b, &a, 8); return (int)(b >> 32); }
 static inline long long __double_as_longlong(double a) { long long b; memcpy(&b, &a, 8); return b; }
 static inline double __longlong_as_double(long long a) { double b; memcpy(&b, &a, 8); return b; }
 // fast-math intrinsics used by the screening pass (glibc's math.h reserves the __logf/__expf names)
