@@ -210,8 +210,9 @@ __device__ __forceinline__ int hfxd_find(const HfxdWarp &W, int nb) {
     return -1;
 }
 
-// Mark as dirty the excitons on the occupied sites an evaluation at packed site `site` has met.
-__device__ __forceinline__ void hfxd_mark_seen(const HfxdWarp &W, int site, unsigned seen) {
+// Mark as dirty the excitons on the occupied sites an evaluation at packed site `site` has met; dmask (warp-uniform)
+// gets the bit of every word of s_dirty that was touched.
+__device__ __forceinline__ void hfxd_mark_seen(const HfxdWarp &W, int site, unsigned seen, unsigned &dmask) {
     const HfxParams &X = W.P->X;
     unsigned any = __ballot_sync(HF_FULL, seen != 0);
     while (any) {
@@ -226,7 +227,10 @@ __device__ __forceinline__ void hfxd_mark_seen(const HfxdWarp &W, int site, unsi
             if (xx < 0) xx += X.X; else if (xx >= X.X) xx -= X.X;
             if (yy < 0) yy += X.Y; else if (yy >= X.Y) yy -= X.Y;
             const int q = hfxd_find(W, hf_pack(xx, yy, hf_pz(site) + ((o >> 16) & 255) - 128));
-            if (q >= 0 && W.lane == 0) W.s_dirty[q >> 5] |= 1u << (q & 31);
+            if (q >= 0) {
+                if (W.lane == 0) W.s_dirty[q >> 5] |= 1u << (q & 31);
+                dmask |= 1u << (q >> 5);
+            }
         }
     }
     __syncwarp();
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
         __syncwarp();
-        unsigned seen;
+        unsigned seen, dmask = 0;                                                // dmask: words of s_dirty that may be non-zero
         if (P.fill) {
             // hf_xd_spawn: an empty mask (memset by the host), slots filled in order; their totals are computed by the
             // refresh pass below (ev = -1: every slot marked dirty)
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             }
             __syncwarp();
             if (lane < n_slots) W.s_dirty[lane] = (lane << 5) + 32 <= P.n ? 0xffffffffu : ((lane << 5) < P.n ? (1u << (P.n & 31)) - 1u : 0u);
+            dmask = n_slots >= 32 ? 0xffffffffu : (1u << n_slots) - 1u;
         } else {
             time = P.time[dev]; life = P.life[dev]; draws = P.draws[dev];
             for (int q = lane; q < n_pad; q += 32) { W.s_pos[q] = g_pos[q]; W.s_T[q] = g_T[q]; }
@@ -402,7 +407,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 hfxd_column(W, ps, lstar);
                 double base2;
                 const int chosen = hfxd_pick_slot(W.s_rates, K, lstar, acc0, target2, base2);
-                hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), sk & 0x7fffffffu);     // the neighbours of the site that changes
+                hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), sk & 0x7fffffffu, dmask);     // the neighbours of the site that changes
                 const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
                 time = __dadd_rn(time, dt);
                 // (3) apply
@@ -486,18 +491,17 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
             }
             for (;;) {
                 if (stage == 2) {                                                // next slot marked dirty, ascending
-                    int q = -1;
-                    for (int wq = 0; wq < n_slots && q < 0; ++wq) {
-                        const unsigned todo = W.s_dirty[wq];
-                        if (todo) q = (wq << 5) + __ffs(todo) - 1;
-                    }
-                    if (q < 0) break;
-                    tgt = q; job = W.s_pos[q];
+                    if (!dmask) break;
+                    const int wq = __ffs(dmask) - 1;
+                    const unsigned todo = W.s_dirty[wq];
+                    if (!(todo & (todo - 1u))) dmask &= dmask - 1u;              // the word's last bit (or none): done with it after this
+                    if (!todo) continue;
+                    tgt = (wq << 5) + __ffs(todo) - 1; job = W.s_pos[tgt];
                 }
                 const double S = hfxd_lane_sum(W, job, seen);
                 const double L = hfx_scan(S, lane);
                 __syncwarp();
-                if (stage == 1) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen);   // the neighbours of the site that changed
+                if (stage == 1) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen, dmask);   // the neighbours of the site that changed
                 g_L[tgt * 32 + lane] = L;
                 g_seen[tgt * 32 + lane] = seen | (S > 0.0 ? 0x80000000u : 0u);
                 const double tot = __shfl_sync(HF_FULL, L, 31);
