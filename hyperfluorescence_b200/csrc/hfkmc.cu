@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hfkmc.h"
@@ -85,6 +86,7 @@ struct hf_sim {
     unsigned long long *d_x_totals = nullptr;
     int x_warps = 8, x_grid = 1, x_per_sm = 1;
     bool x_tune = false;               // pick the warp batch by measurement at the next hf_x_run
+    std::unordered_map<void *, size_t> alloc_bytes;   // buffers managed by dev_reuse
     bool x_brick = false;              // hfx_run_kernel reads brick-layout copies of the weights (weights larger than the L2)
     double *d_bs1 = nullptr, *d_bt1 = nullptr;
     int32_t *d_x_blin = nullptr;
@@ -162,6 +164,24 @@ int dev_alloc(T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
     HF_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return HF_OK;
+}
+
+// (Re)configuration paths: keep a buffer that is already large enough.  cudaFree + cudaMalloc of the multi-GB occupancy
+// masks and records of the dense devices cost 15-100 ms per call and dominated the end-to-end step.
+template <typename T>
+int dev_reuse(hf_sim *s, T **p, size_t n) {
+    if (n == 0) n = 1;
+    const size_t bytes = n * sizeof(T);
+    if (*p) {
+        auto it = s->alloc_bytes.find((void *)*p);
+        if (it != s->alloc_bytes.end() && it->second >= bytes) return HF_OK;
+        if (it != s->alloc_bytes.end()) s->alloc_bytes.erase(it);
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    HF_CUDA(cudaMalloc((void **)p, bytes));
+    s->alloc_bytes[(void *)*p] = bytes;
     return HF_OK;
 }
 
@@ -350,8 +370,6 @@ int x_configure_launch(hf_sim *s) {
     // 256^3 x 64 realisations 8.6e8 -> 1.06e9 events/s, 256^3 x 16 9.2e8 -> 1.19e9, and the L2-resident 128^3 1.89e9 ->
     // 1.97e9.  Needs X and Y to be multiples of 4, one of the compiled cutoffs and offsets that fit the packed table;
     // HF_X_BRICK=0 keeps the row-major layout.  The dense-device and integrated kernels always read the row-major arrays.
-    cudaFree(s->d_bs1); cudaFree(s->d_bt1); cudaFree(s->d_x_blin);
-    s->d_bs1 = s->d_bt1 = nullptr; s->d_x_blin = nullptr;
     s->x_brick = false;
     {
         bool want = true;
@@ -363,7 +381,7 @@ int x_configure_launch(hf_sim *s) {
             std::vector<int32_t> blin(M);
             for (size_t m = 0; m < M; ++m) blin[m] = hfx_brick_lin(s->x_offsets[3 * m], s->x_offsets[3 * m + 1], s->x_offsets[3 * m + 2], s->P.X, s->P.Y);
             int rc;
-            if ((rc = dev_alloc(&s->d_x_blin, M)) || (rc = dev_alloc(&s->d_bs1, RN)) || (rc = dev_alloc(&s->d_bt1, RN))) return rc;
+            if ((rc = dev_reuse(s, &s->d_x_blin, M)) || (rc = dev_reuse(s, &s->d_bs1, RN)) || (rc = dev_reuse(s, &s->d_bt1, RN))) return rc;
             HF_CUDA(cudaMemcpyAsync(s->d_x_blin, blin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
             HF_CUDA(cudaMemsetAsync(s->d_bs1, 0, 8 * RN, s->stream));
             HF_CUDA(cudaMemsetAsync(s->d_bt1, 0, 8 * RN, s->stream));
@@ -1215,24 +1233,20 @@ int hf_x_configure(hf_sim *s, const hf_x_params *p) {
         for (int sp = 0; sp < 2; ++sp) { X.k_rad[2 * a + sp] = p->k_rad[a][sp]; X.k_nonrad[2 * a + sp] = p->k_nonrad[a][sp]; }
     }
     X.singlet_fraction = p->singlet_fraction;
-    cudaFree(s->d_x_off); cudaFree(s->d_x_lin); cudaFree(s->d_x_g6); cudaFree(s->d_x_gd);
-    s->d_x_off = nullptr; s->d_x_lin = nullptr; s->d_x_g6 = nullptr; s->d_x_gd = nullptr;
     // weights: R zero planes below and above every realisation (an open-face transfer reads weight 0)
     X.w_halo = (int64_t)X.R * s->P.X * s->P.Y;
     X.w_stride = s->P.N + 2 * X.w_halo;
     const size_t M = packed.size(), RN = (size_t)s->n_real * (size_t)X.w_stride, B = (size_t)s->P.B;
-    if ((rc = dev_alloc(&s->d_x_off, M))) return rc;
-    if ((rc = dev_alloc(&s->d_x_lin, M))) return rc;
-    if ((rc = dev_alloc(&s->d_x_g6, M))) return rc;
-    if ((rc = dev_alloc(&s->d_x_gd, M))) return rc;
+    if ((rc = dev_reuse(s, &s->d_x_off, M))) return rc;
+    if ((rc = dev_reuse(s, &s->d_x_lin, M))) return rc;
+    if ((rc = dev_reuse(s, &s->d_x_g6, M))) return rc;
+    if ((rc = dev_reuse(s, &s->d_x_gd, M))) return rc;
     HF_CUDA(cudaMemcpyAsync(s->d_x_off, packed.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_lin, lin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_g6, s->x_g6.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
     HF_CUDA(cudaMemcpyAsync(s->d_x_gd, s->x_gd.data(), 8 * M, cudaMemcpyHostToDevice, s->stream));
-    cudaFree(s->d_ws1); cudaFree(s->d_wt1);
-    s->d_ws1 = nullptr; s->d_wt1 = nullptr;
-    if ((rc = dev_alloc(&s->d_ws1, RN))) return rc;
-    if ((rc = dev_alloc(&s->d_wt1, RN))) return rc;
+    if ((rc = dev_reuse(s, &s->d_ws1, RN))) return rc;
+    if ((rc = dev_reuse(s, &s->d_wt1, RN))) return rc;
     HF_CUDA(cudaMemsetAsync(s->d_ws1, 0, 8 * RN, s->stream));
     HF_CUDA(cudaMemsetAsync(s->d_wt1, 0, 8 * RN, s->stream));
     if (!s->d_x_site) {
@@ -1377,13 +1391,6 @@ int hf_x_read_state(hf_sim *s, int64_t first, int64_t n, int32_t *site, int32_t 
 #endif
 constexpr int kXdWarps = HF_XD_WARPS;
 
-static void xd_free(hf_sim *s) {
-    cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_rec_L); cudaFree(s->d_xd_rec_seen); cudaFree(s->d_xd_time);
-    cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
-    s->d_xd_pos = nullptr; s->d_xd_occ = nullptr; s->d_xd_T = nullptr; s->d_xd_birth = nullptr; s->d_xd_rec_L = nullptr; s->d_xd_rec_seen = nullptr; s->d_xd_time = nullptr;
-    s->d_xd_life = nullptr; s->d_xd_draws = nullptr; s->d_xd_totals = nullptr;
-}
-
 int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, double p_tta) {
     if (!s || !annihilation) return fail(HF_ERR_BAD_ARG, "null argument");
     if (!s->x_configured) return fail(HF_ERR_STATE, "hf_xd_configure before hf_x_configure");
@@ -1398,7 +1405,6 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     int rc = use_device(s);
     if (rc) return rc;
     HF_CUDA(cudaStreamSynchronize(s->stream));
-    xd_free(s);
     HfxdParams &D = s->XD;
     memset(&D, 0, sizeof(D));
     D.X = s->X;
@@ -1407,16 +1413,16 @@ int hf_xd_configure(hf_sim *s, int32_t n_excitons, const double *annihilation, d
     D.p_tta = p_tta;
     D.occ_words = (s->X.w_stride + 15) / 16;
     const size_t B = (size_t)s->P.B, np = (size_t)D.n_pad;
-    if ((rc = dev_alloc(&s->d_xd_pos, B * np))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_T, B * np))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_birth, B * np))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_rec_L, B * np * 32))) return rc;             // 384 B per exciton: the record of its last evaluation
-    if ((rc = dev_alloc(&s->d_xd_rec_seen, B * np * 32))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_occ, B * (size_t)D.occ_words))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_time, B))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_life, B))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_draws, B))) return rc;
-    if ((rc = dev_alloc(&s->d_xd_totals, (size_t)s->n_real * HFXD_T_N))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_pos, B * np))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_T, B * np))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_birth, B * np))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_rec_L, B * np * 32))) return rc;             // 384 B per exciton: the record of its last evaluation
+    if ((rc = dev_reuse(s, &s->d_xd_rec_seen, B * np * 32))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_occ, B * (size_t)D.occ_words))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_time, B))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_life, B))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_draws, B))) return rc;
+    if ((rc = dev_reuse(s, &s->d_xd_totals, (size_t)s->n_real * HFXD_T_N))) return rc;
     D.pos = s->d_xd_pos; D.T = s->d_xd_T; D.birth = s->d_xd_birth; D.occ = s->d_xd_occ;
     D.rec_L = s->d_xd_rec_L; D.rec_seen = s->d_xd_rec_seen;
     D.time = s->d_xd_time; D.life = s->d_xd_life; D.draws = s->d_xd_draws; D.totals = s->d_xd_totals;
