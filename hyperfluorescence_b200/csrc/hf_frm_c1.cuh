@@ -43,8 +43,11 @@ struct HfC1Counters {
     unsigned move_e, move_h, bound, decay, capture_e, capture_h, recomb_host, recomb_tadf, recomb_fluo, emit_tadf, emit_fluo;
 };
 
+// kReplay = false: the kernel was launched for a handle without a replay table (P.replay == nullptr) and the tests on
+// it disappear from the candidate loop (they were ~4 % of its instructions).
+template <bool kReplay = true>
 __device__ __forceinline__ double hf_c1_uniform(const HfParams &P, int64_t local, uint32_t ident, uint64_t d, bool *exhausted) {
-    if (P.replay) {
+    if (kReplay && P.replay) {
         if (d >= (uint64_t)P.n_replay) { *exhausted = true; return 0.5; }
         return P.replay[local * P.n_replay + (int64_t)d];
     }
@@ -52,6 +55,7 @@ __device__ __forceinline__ double hf_c1_uniform(const HfParams &P, int64_t local
 }
 
 // _electron_reinjection / _hole_reinjection with an empty own list (reseau.py:448-470)
+template <bool kReplay = true>
 __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t, int64_t local, uint32_t ident) {
     if (s.pos(t) >= 0) return HF_ST_CAPACITY;                                    // C = 1 invariant
     const int64_t n = (int64_t)P.X * P.Y;
@@ -59,8 +63,8 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
     const int64_t rem = maxsize % n;
     const double limit = (double)(maxsize - rem) * 0x1p-53;
     bool exhausted = false;
-    double r = hf_c1_uniform(P, local, ident, s.draws++, &exhausted);            // random.py:264-269
-    while (r >= limit && !exhausted) r = hf_c1_uniform(P, local, ident, s.draws++, &exhausted);
+    double r = hf_c1_uniform<kReplay>(P, local, ident, s.draws++, &exhausted);   // random.py:264-269
+    while (r >= limit && !exhausted) r = hf_c1_uniform<kReplay>(P, local, ident, s.draws++, &exhausted);
     if (exhausted) return HF_ST_REPLAY_EXHAUSTED;
     const int64_t k = (int64_t)floor(r * 0x1p53) % n;
     s.set_pos(t, hf_pack((int)(k / P.Y), (int)(k % P.Y), t == 0 ? P.Z - 1 : 0));
@@ -75,8 +79,34 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
 #define HF_C1_MIN_BLOCKS 2
 #endif
 #define HF_C1_MAXCAND 27
+#ifndef HF_C1_PIN_BOUNDS
+#define HF_C1_PIN_BOUNDS 1
+#endif
 // relative half-width of the "could be the minimum" window of the screening pass, see hf_c1_gen
 #define HF_C1_WINDOW 0x1p-9f
+
+// This thread's column of the shared-memory scratch, addressed through a 32-bit shared-window address pinned in a
+// register: with a generic pointer nvcc rebuilt the address (S2R tid, S2UR cta id, ULEA, LEA, IMAD) at every access
+// of the candidate loop.  volatile: the column is only ever accessed through these, in program order.
+#ifndef HF_C1_COL_ASM
+#define HF_C1_COL_ASM 1
+#endif
+#if defined(__CUDA_ARCH__) && HF_C1_COL_ASM
+typedef unsigned hf_c1_col;
+__device__ __forceinline__ hf_c1_col hf_c1_col_of(float *p) { unsigned a = (unsigned)__cvta_generic_to_shared(p); asm volatile("" : "+r"(a)); return a; }
+__device__ __forceinline__ float hf_c1_ld(hf_c1_col c, int off) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(c + 4u * (unsigned)off)); return v; }
+__device__ __forceinline__ void hf_c1_st(hf_c1_col c, int off, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(c + 4u * (unsigned)off), "f"(v)); }
+#else
+typedef float *hf_c1_col;
+__host__ __device__ inline hf_c1_col hf_c1_col_of(float *p) { return p; }
+__host__ __device__ inline float hf_c1_ld(hf_c1_col c, int off) { return c[off]; }
+__host__ __device__ inline void hf_c1_st(hf_c1_col c, int off, float v) { c[off] = v; }
+#endif
+#if defined(__CUDA_ARCH__)
+#define HF_C1_PIN(x) asm volatile("" : "+r"(x))
+#else
+#define HF_C1_PIN(x) (void)0
+#endif
 
 // Exact waiting time of one candidate hop (reseau.py:283-292 / 315-324 with the Coulomb term of
 // 297-313 / 329-345 reduced to the single opposite charge): the same operation sequence as
@@ -132,9 +162,11 @@ __device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, 
 // tests/test_gpu_parity.py::test_adjacent_charges_screening_is_exact keeps the two carriers on neighbouring sites
 // for > 10^6 regenerated events and compares every one with the all-exact C restatement.
 // Result: bit-identical events and taus at ~1.06 exact evaluations per event instead of 26.
-template <int kStride = HF_C1_THREADS>
+template <int kStride = HF_C1_THREADS, bool kReplay = true>
 __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, const double *homo, int t, HfC1 &s,
-                                         int64_t local, uint32_t ident, float *approx /* [l * kStride]: this thread's column */) {
+                                         int64_t local, uint32_t ident, float *approx_ptr /* [l * kStride]: this thread's column */) {
+    const hf_c1_col approx = hf_c1_col_of(approx_ptr);
+    const bool replay = kReplay && P.replay;
     const int pos = s.pos(t), other = s.pos(1 - t);
     const double *__restrict__ E = t ? homo : lumo;
     const int px = hf_px(pos), py = hf_py(pos), pz = hf_pz(pos);
@@ -164,7 +196,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
                         const int cand = hf_pack(cx, cy, cz);
                         if (cand == pos) self_l = l;
                         const double dE = (__ldg(row + cz * plane) - e_init) + fz * (double)(cz - pz);
-                        approx[l * kStride] = cand == other ? -INFINITY : (float)dE;   // onto the opposite charge: k = 1e13
+                        hf_c1_st(approx, l * kStride, cand == other ? -INFINITY : (float)dE);   // onto the opposite charge: k = 1e13
                         ++l;
                     }
                 }
@@ -174,8 +206,14 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     // ---- pass 1: fp32 estimates a_l of 1e13 * tau_l.  Uniform d0 + r belongs to Philox block
     //      (d0 >> 1) + ((p + r) >> 1), half (p + r) & 1 with p = d0 & 1: looping over q = p + r in
     //      pairs makes every lane compute its blocks at the same iterations ----
-    const int n = total - 1;                                                     // never blocked when C = 1
-    const int p = (int)(d0 & 1);
+    int n = total - 1;                                                           // never blocked when C = 1
+    int p = (int)(d0 & 1);
+#if HF_C1_PIN_BOUNDS & 1
+    HF_C1_PIN(n); HF_C1_PIN(p);                                                  // in registers: the loop tests were rebuilding them from the position
+#endif
+#if HF_C1_PIN_BOUNDS & 2
+    HF_C1_PIN(self_l);
+#endif
     const float inv_kt = (float)(1.0 / HF_KT);
     float amin = INFINITY, amin2 = INFINITY;                                     // two smallest estimates
     int lmin = 0;
@@ -183,7 +221,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     bool exhausted = false;
     for (int j = 0; 2 * j < n + p; ++j) {
         HfPhiloxBlock blk = {0, 0, 0, 0};
-        if (!P.replay) blk = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
+        if (!replay) blk = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = 2 * j + h - p;
@@ -191,7 +229,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
             const int l = r + (r >= self_l ? 1 : 0);
             float t0;
             const uint32_t hi = h ? blk.w3 : blk.w1;                             // u = hi * 2^-32 + (lower bits) * 2^-53
-            if (!P.replay && hi - 0x00100000u < 0xffe00000u) {
+            if (!replay && hi - 0x00100000u < 0xffe00000u) {
                 // 2^-12 <= u < 1 - 2^-12 (all but 5e-4 of the draws): the estimate straight from the high word, no fp64.
                 // u_f = hi 2^-32 and v = (~hi) 2^-32 ~ 1 - u are off by < 2^-32 absolute and 2^-24 relative:
                 // relative error of the series <= 1e-6, of -log(v) <= (2^-32 / v + 2^-24) / |log v| <= 3.8e-6.
@@ -202,7 +240,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
                     t0 = -__logf((float)(~hi) * 0x1p-32f);
                 }
             } else {
-                const double u = P.replay ? hf_c1_uniform(P, local, ident, d0 + (uint64_t)r, &exhausted)
+                const double u = replay ? hf_c1_uniform<kReplay>(P, local, ident, d0 + (uint64_t)r, &exhausted)
                                           : hf_block_uniform(blk, (uint64_t)h);
                 if (u < 0x1p-6) {
                     const float uf = (float)u;
@@ -212,11 +250,11 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
                 }
             }
             float a = t0;
-            const float x = approx[l * kStride] * inv_kt;
+            const float x = hf_c1_ld(approx, l * kStride) * inv_kt;
             if (x > 0.0f) a = t0 * __expf(x);
             if (x > 700.0f) forced |= 1u << l;
             if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
-            approx[l * kStride] = a;
+            hf_c1_st(approx, l * kStride, a);
             if (a < amin) { amin2 = amin; amin = a; lmin = l; }
             else if (!(a >= amin2)) amin2 = a;                                   // also catches NaN
         }
@@ -227,7 +265,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     unsigned mask = forced | (1u << lmin);
     if (!(amin2 > thr)) {                                                        // a runner-up inside the window: scan
         for (int i = 0; i < total; ++i)
-            if (i != self_l && !(approx[i * kStride] > thr)) mask |= 1u << i;
+            if (i != self_l && !(hf_c1_ld(approx, i * kStride) > thr)) mask |= 1u << i;
     }
     // ---- pass 2: exact evaluation in candidate order, first minimum ----
     const bool other_has = other >= 0;
@@ -242,7 +280,7 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
         const int cx = hf_bvk_xy(px, P.X, ix), cy = hf_bvk_xy(py, P.Y, iy), cz = hf_bvk_z(pz, P.Z, iz);
         const int cand = hf_pack(cx, cy, cz);
         const uint64_t di = d0 + (uint64_t)(i - (i > self_l ? 1 : 0));
-        const double u = hf_c1_uniform(P, local, ident, di, &exhausted);
+        const double u = hf_c1_uniform<kReplay>(P, local, ident, di, &exhausted);
         bool rate_is_zero;
         const double tau = hf_c1_exact_tau(E, ((int64_t)cz * P.Y + cy) * P.X + cx, e_init, fz, cz - pz, other_has, other,
                                            cand, inv_old, u, &rate_is_zero);
@@ -379,7 +417,7 @@ __device__ __forceinline__ void hf_c1_store(const HfParams &P, const HfC1 &s, co
 // each) would otherwise pay a whole extra wave for its last 10 %.
 #define HF_C1_THREADS_B 288
 #define HF_C1_MIN_BLOCKS_B 3
-template <int kThreads = HF_C1_THREADS, int kMinBlocks = HF_C1_MIN_BLOCKS>
+template <int kThreads = HF_C1_THREADS, int kMinBlocks = HF_C1_MIN_BLOCKS, bool kReplay = true>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) hf_run_c1_kernel(const HfParams P) {
     __shared__ float approx_all[HF_C1_MAXCAND * kThreads];
     float *approx = approx_all + threadIdx.x;
@@ -388,7 +426,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) hf_run_c1_kernel(const H
     HfC1 s;
     HfC1Counters c = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     hf_c1_load(P, s, local);
-    const uint32_t ident = P.first_traj + (uint32_t)local;
+    uint32_t ident = P.first_traj + (uint32_t)local;
+    HF_C1_PIN(ident);                                                            // else rebuilt from tid / ctaid at every Philox block
     const int64_t r = local / P.traj_per_real;
     const uint8_t *species = P.species + r * P.N;
     const double *lumo = P.lumo + r * P.N, *homo = P.homo + r * P.N;
@@ -405,8 +444,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) hf_run_c1_kernel(const H
             // common tail: the queued regenerations (one for a move or a capture, two for a decay)
             for (; st == HF_ST_OK && gen; gen >>= 4) {
                 const int t = gen & 1;
-                if (gen & 4) st = hf_c1_reinject(P, s, t, local, ident);
-                if (st == HF_ST_OK) st = hf_c1_gen<kThreads>(P, lumo, homo, t, s, local, ident, approx);
+                if (gen & 4) st = hf_c1_reinject<kReplay>(P, s, t, local, ident);
+                if (st == HF_ST_OK) st = hf_c1_gen<kThreads, kReplay>(P, lumo, homo, t, s, local, ident, approx);
             }
             if (st != HF_ST_OK) { s.status = st; break; }                        // 587-591
             if (kind == HF_K_MOVE) { if (part == 1) c.move_e += 1; else c.move_h += 1; }

@@ -815,10 +815,10 @@ int hf_run(hf_sim *s, int64_t stop) {
         const double est_a = cost_a - (frac_a > 0 ? 0.5 * (1.0 - frac_a) : 0.0), est_b = cost_b - (frac_b > 0 ? 1.09 * 0.5 * (1.0 - frac_b) : 0.0);
         if (est_b < est_a && !getenv("HF_C1_SHAPE_A")) {
             const int64_t blocks = (s->P.B + HF_C1_THREADS_B - 1) / HF_C1_THREADS_B;
-            hf_run_c1_kernel<HF_C1_THREADS_B, HF_C1_MIN_BLOCKS_B><<<(unsigned)blocks, HF_C1_THREADS_B, 0, s->stream>>>(s->P);
+            (s->P.replay ? hf_run_c1_kernel<HF_C1_THREADS_B, HF_C1_MIN_BLOCKS_B, true> : hf_run_c1_kernel<HF_C1_THREADS_B, HF_C1_MIN_BLOCKS_B, false>)<<<(unsigned)blocks, HF_C1_THREADS_B, 0, s->stream>>>(s->P);
         } else {
             const int64_t blocks = (s->P.B + HF_C1_THREADS - 1) / HF_C1_THREADS;
-            hf_run_c1_kernel<HF_C1_THREADS, HF_C1_MIN_BLOCKS><<<(unsigned)blocks, HF_C1_THREADS, 0, s->stream>>>(s->P);
+            (s->P.replay ? hf_run_c1_kernel<HF_C1_THREADS, HF_C1_MIN_BLOCKS, true> : hf_run_c1_kernel<HF_C1_THREADS, HF_C1_MIN_BLOCKS, false>)<<<(unsigned)blocks, HF_C1_THREADS, 0, s->stream>>>(s->P);
         }
     } else if (s->P.C <= HF_SMALL_MAX_CHARGES && thread_kernels) {
         // one thread per trajectory, lists in per-thread shared memory (hf_frm_small.cuh)
