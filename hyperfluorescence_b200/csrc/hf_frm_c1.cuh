@@ -104,8 +104,14 @@ __host__ __device__ inline void hf_c1_st(hf_c1_col c, int off, float v) { c[off]
 #endif
 #if defined(__CUDA_ARCH__)
 #define HF_C1_PIN(x) asm volatile("" : "+r"(x))
+// MUFU.LG2 / MUFU.EX2 without the denormal pre- and post-scaling __logf / __expf wrap around them (3 + 4 instructions
+// per candidate): used where the argument is known to be a normal number / the result at least 1
+__device__ __forceinline__ float hf_c1_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float hf_c1_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #else
 #define HF_C1_PIN(x) (void)0
+inline float hf_c1_lg2(float x) { return log2f(x); }
+inline float hf_c1_ex2(float x) { return exp2f(x); }
 #endif
 
 // Exact waiting time of one candidate hop (reseau.py:283-292 / 315-324 with the Coulomb term of
@@ -143,16 +149,17 @@ __device__ __forceinline__ double hf_c1_exact_tau(const double *__restrict__ E, 
 // Screen-then-verify.  Evaluating exp(), log(), a square root and three divisions in fp64 for all
 // 26 candidates costs ~420 instructions per candidate (ncu, profiles/r01b_*), yet only the
 // minimum is kept.  Pass 1 computes a cheap fp32 estimate a_i of 1e13 * tau_i for every candidate
-// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by eps = 7e-5:
-//   -log(rng): rng >= 2^-6 away from 1: __logf abs error 2^-21.41 on |log| >= 0.0157  -> 2.7e-5
+// (one MUFU log, one MUFU exp, no Coulomb term) whose relative error is bounded by eps = 1e-4:
+//   -log(rng): rng >= 2^-6 away from 1: lg2.approx * ln 2 (= __logf) abs error 2^-21.41 on |log| >= 0.0157 -> 2.7e-5
 //              plus its fp32 argument (rounded, or built from the high word of the draw)  -> 3.8e-6
 //              otherwise the series u + u^2/2 + u^3/3 (truncation u^3/4 <= 9.5e-7)      -> 2e-6
-//   exp(dE/kT): float rounding of x (6e-8 x) + __expf (2 + 1.173 x ulp), x <= 88        -> 1.2e-5
+//   exp(dE/kT) = 2^x2, x2 = (float)dE * (float)(log2 e / kT): three fp32 roundings, 1.8e-7 relative in x, i.e.
+//              1.6e-5 at x = 88; ex2.approx 2 ulp                                       -> 1.6e-5
 //              neglected Coulomb term of the one opposite charge: C_e |1/r' - 1/r| with r, r' >= 1 is below
 //              C_e = 4.8e-7 eV whatever the geometry (adjacent charges: C_e (1 - 1/2) = 2.4e-7 eV), i.e.
 //              below C_e / kT = 1.86e-5 in x                                            -> 1.9e-5
-//   sum 6.2e-5 < eps.
-// Every candidate whose estimate lies within a factor 1 + W, W = 2^-9 (14x the 2 eps / (1 - eps) = 1.4e-4 the
+//   sum 6.6e-5 < eps.
+// Every candidate whose estimate lies within a factor 1 + W, W = 2^-9 (9.7x the 2 eps / (1 - eps) = 2.0e-4 the
 // argument needs) of the smallest estimate is then evaluated EXACTLY, in candidate order, by hf_c1_exact_tau;
 // the first minimum among those is the reference's min().  A candidate outside the window has
 // tau_i >= a_i (1 - eps) > a_min (1 + W)(1 - eps) > a_min (1 + eps) >= tau of the best
@@ -214,10 +221,11 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
 #if HF_C1_PIN_BOUNDS & 2
     HF_C1_PIN(self_l);
 #endif
-    const float inv_kt = (float)(1.0 / HF_KT);
+    const float inv_kt_log2e = (float)(1.4426950408889634 / HF_KT);              // x / kT in units of ln 2: a = t0 * 2^x2
+    const float x2_forced = (float)(700.0 * 1.4426950408889634);                 // x > 700: the rate may underflow to 0
     float amin = INFINITY, amin2 = INFINITY;                                     // two smallest estimates
+    float x2max = 0.0f;
     int lmin = 0;
-    unsigned forced = 0;
     bool exhausted = false;
     for (int j = 0; 2 * j < n + p; ++j) {
         HfPhiloxBlock blk = {0, 0, 0, 0};
@@ -227,37 +235,47 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
             const int r = 2 * j + h - p;
             if (r < 0 || r >= n) continue;
             const int l = r + (r >= self_l ? 1 : 0);
-            float t0;
+            const float x2 = hf_c1_ld(approx, l * kStride) * inv_kt_log2e;
+            x2max = fmaxf(x2max, x2);
+            float a;
             const uint32_t hi = h ? blk.w3 : blk.w1;                             // u = hi * 2^-32 + (lower bits) * 2^-53
             if (!replay && hi - 0x00100000u < 0xffe00000u) {
                 // 2^-12 <= u < 1 - 2^-12 (all but 5e-4 of the draws): the estimate straight from the high word, no fp64.
                 // u_f = hi 2^-32 and v = (~hi) 2^-32 ~ 1 - u are off by < 2^-32 absolute and 2^-24 relative:
                 // relative error of the series <= 1e-6, of -log(v) <= (2^-32 / v + 2^-24) / |log v| <= 3.8e-6.
+                // t0 > 0 here (u >= 2^-12), so 0 * inf cannot occur.
+                float t0;
                 if (hi < 0x04000000u) {                                          // u < 2^-6
                     const float uf = (float)hi * 0x1p-32f;
                     t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
                 } else {
-                    t0 = -__logf((float)(~hi) * 0x1p-32f);
+                    t0 = hf_c1_lg2((float)(~hi) * 0x1p-32f) * -0.69314718055994531f;   // v in [2^-12, 0.985): a normal number
                 }
+                a = x2 > 0.0f ? t0 * hf_c1_ex2(x2) : t0;
             } else {
                 const double u = replay ? hf_c1_uniform<kReplay>(P, local, ident, d0 + (uint64_t)r, &exhausted)
-                                          : hf_block_uniform(blk, (uint64_t)h);
+                                        : hf_block_uniform(blk, (uint64_t)h);
+                float t0;
                 if (u < 0x1p-6) {
                     const float uf = (float)u;
                     t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
                 } else {
                     t0 = -__logf((float)(1.0 - u));
                 }
+                a = x2 > 0.0f ? t0 * hf_c1_ex2(x2) : t0;
+                if (t0 == 0.0f) a = 0.0f;                                        // 0 * inf
             }
-            float a = t0;
-            const float x = hf_c1_ld(approx, l * kStride) * inv_kt;
-            if (x > 0.0f) a = t0 * __expf(x);
-            if (x > 700.0f) forced |= 1u << l;
-            if (t0 == 0.0f) a = 0.0f;                                            // 0 * inf
             hf_c1_st(approx, l * kStride, a);
             if (a < amin) { amin2 = amin; amin = a; lmin = l; }
             else if (!(a >= amin2)) amin2 = a;                                   // also catches NaN
         }
+    }
+    // candidates with x > 700 are always verified.  Their estimate overflowed to +inf (2^x2, x2 > 1009) or is 0 (t0 = 0;
+    // zeros are verified as minima below); rare enough to find them by a second look, only when one was met
+    unsigned forced = 0;
+    if (x2max > x2_forced) {
+        for (int i = 0; i < total; ++i)
+            if (i != self_l && hf_c1_ld(approx, i * kStride) == INFINITY) forced |= 1u << i;
     }
     if (exhausted) { s.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
     // ---- candidates that could be the minimum: usually only the best estimate ----
