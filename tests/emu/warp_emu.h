@@ -163,6 +163,8 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return sqrt(a); }
+static inline uint32_t __float_as_uint(float a) { uint32_t b; memcpy(&b, &a, 4); return b; }
+static inline float __uint_as_float(uint32_t a) { float b; memcpy(&b, &a, 4); return b; }
 static inline int __double2hiint(double a) { long long b; memcpy(&b, &a, 8); return (int)(b >> 32); }
 static inline long long __double_as_longlong(double a) { long long b; memcpy(&b, &a, 8); return b; }
 static inline double __longlong_as_double(long long a) { double b; memcpy(&b, &a, 8); return b; }
