@@ -10,11 +10,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libemu_frm.so")
 ROOT = os.path.dirname(os.path.dirname(HERE))
-DEPS = [os.path.join(HERE, "emu_frm.cpp"), os.path.join(HERE, "warp_emu.h"),
-        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm.cuh"),
-        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_frm_c1.cuh"),
-        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_exciton.cuh"),
-        os.path.join(ROOT, "hyperfluorescence_b200", "csrc", "hf_philox.cuh")]
+CSRC = os.path.join(ROOT, "hyperfluorescence_b200", "csrc")
+DEPS = [os.path.join(HERE, "emu_frm.cpp"), os.path.join(HERE, "warp_emu.h")] + \
+       [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")]
 
 EVENT_DTYPE = np.dtype([("initial", "<i4"), ("final", "<i4"), ("tau", "<f8"), ("kind", "u1"), ("particule", "u1"),
                         ("pad", "u1", (2,)), ("spins", "<u4"), ("draws", "<u8")])
@@ -22,6 +20,9 @@ assert EVENT_DTYPE.itemsize == 32
 
 
 def build():
+    # HF_EMU_LIB: a prebuilt variant, e.g. one compiled with -fsanitize=address (run python under LD_PRELOAD=libasan.so)
+    if os.environ.get("HF_EMU_LIB"):
+        return os.environ["HF_EMU_LIB"]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in DEPS):
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
                         "-shared", "-fPIC", "-o", LIB, os.path.join(HERE, "emu_frm.cpp")], check=True)
