@@ -70,7 +70,8 @@ struct HfxParams {
     int32_t block;                    // trajectories a warp owns at a time (1..32)
     const int32_t *offsets;           // [M] packed (dx+128) | (dy+128) << 8 | (dz+128) << 16
     const int32_t *lin;               // [M] dz*X*Y + dy*X + dx; brick layout: hfx_brick_lin()
-    int32_t brick;                    // weights in 4 x 4 x 1 bricks (hfx_brick2), X % 4 == Y % 4 == 0
+    int32_t brick;                    // the weights are the brick-layout copy: planes padded by R periodic columns / rows on
+    int32_t bX, bY;                   // every side (then up to multiples of 4): bX x bY, in 4 x 4 x 1 bricks (hfx_brick2)
     const double *g6, *gd;            // [M]
     double kf[9], kd[9];              // [donor][acceptor]
     double k_isc[3], k_risc[3], k_rad[6], k_nonrad[6];
@@ -102,7 +103,9 @@ __device__ __forceinline__ int hfx_tag_of(double w) { return (int)(__double_as_l
 __host__ __device__ __forceinline__ int hfx_brick2(int x, int y, int dim_x) {
     return (((y >> 2) * (dim_x >> 2) + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3);
 }
-// Offset of the neighbour (dx, dy, dz) of a site away from the seams, brick layout.  With x = 4 bx + rx:
+// The brick copy pads every plane with R periodic columns and rows on each side (site (x, y) sits at (x + R, y + R)),
+// so that NO site needs the periodic wrap: the kernel has one gather path and the offsets below hold everywhere.
+// Offset of the neighbour (dx, dy, dz) of a site, brick layout.  With x + R = 4 bx + rx:
 //   delta = dz * plane + 4 dy + dx + 12 * ((rx + dx) >> 2) + (4 X - 16) * ((ry + dy) >> 2)
 // and (rx + dx) >> 2 = (dx >> 2) + ((rx + (dx & 3)) >> 2), the last term being 0 or 1.  Packed per channel:
 // bits 8.. the part that does not depend on (rx, ry); bit rx: add 12; bit 4 + ry: add 4 X - 16.
@@ -116,17 +119,26 @@ __host__ __device__ inline int32_t hfx_brick_lin(int dx, int dy, int dz, int dim
 
 // ws1 / wt1 must be zero-filled beforehand (the halo planes stay +0.0, species tag 0)
 __global__ void hfx_weights_kernel(const uint8_t *species, const double *s1, const double *t1, double *ws1, double *wt1,
-                                   int64_t n_sites, int64_t n_real, int64_t w_stride, int64_t w_halo, int dim_x = 0, int dim_y = 0) {
+                                   int64_t n_sites, int64_t n_real, int64_t w_stride, int64_t w_halo) {
     const int64_t n = n_sites * n_real;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t site = i % n_sites;
-        if (dim_x > 0) {                                                            // brick layout
-            const int64_t plane = (int64_t)dim_x * dim_y, in = site % plane;
-            site = site - in + hfx_brick2((int)(in % dim_x), (int)(in / dim_x), dim_x);
-        }
-        const int64_t o = (i / n_sites) * w_stride + w_halo + site;
+        const int64_t o = (i / n_sites) * w_stride + w_halo + i % n_sites;
         ws1[o] = hfx_tag(exp(-(s1[i] / HF_KT)), species[i]);
         wt1[o] = hfx_tag(exp(-(t1[i] / HF_KT)), species[i]);
+    }
+}
+// The brick-layout copy: bX x bY padded planes (periodic images of the X x Y plane shifted by R), same z halo.
+__global__ void hfx_brick_weights_kernel(const uint8_t *species, const double *s1, const double *t1, double *ws1, double *wt1,
+                                         int X, int Y, int Z, int R, int bX, int bY, int64_t n_real, int64_t w_stride, int64_t w_halo) {
+    const int64_t bplane = (int64_t)bX * bY, per_real = bplane * Z, n = per_real * n_real, n_sites = (int64_t)X * Y * Z;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / per_real, in = i % per_real;
+        const int z = (int)(in / bplane), yp = (int)((in % bplane) / bX), xp = (int)(in % bX);
+        const int x = ((xp - R) % X + X) % X, y = ((yp - R) % Y + Y) % Y;
+        const int64_t src = r * n_sites + ((int64_t)z * Y + y) * X + x;
+        const int64_t o = r * w_stride + w_halo + z * bplane + hfx_brick2(xp, yp, bX);
+        ws1[o] = hfx_tag(exp(-(s1[src] / HF_KT)), species[src]);
+        wt1[o] = hfx_tag(exp(-(t1[src] / HF_KT)), species[src]);
     }
 }
 
@@ -211,9 +223,9 @@ template <bool kBrick = false>
 __device__ __forceinline__ int hfx_delta(int o, int px, int py, int dim_x, int dim_y, int plane) {
     const int dx = (o & 255) - 128, dy = ((o >> 8) & 255) - 128, dz = ((o >> 16) & 255) - 128;
     int xx = px + dx, yy = py + dy;
+    if (kBrick) return dz * plane + hfx_brick2(xx, yy, dim_x) - hfx_brick2(px, py, dim_x);   // padded planes (px, py include the pad): no wrap
     if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
     if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
-    if (kBrick) return dz * plane + hfx_brick2(xx, yy, dim_x) - hfx_brick2(px, py, dim_x);
     return dz * plane + (yy - py) * dim_x + (xx - px);
 }
 
@@ -244,10 +256,10 @@ struct HfxLaneTables {                // this lane's channels of the KF full slo
 template <int KF, int CH = KF, int kBase = 0, bool kBrick = false>
 __device__ __forceinline__ void hfx_gather(const double *wp, int site, int meta, const HfxLaneTables<KF> &T,
                                            const int32_t *s_off_lane, int dim_x, int dim_y, int plane,
-                                           double (&buf)[CH > 0 ? CH : 1]) {
-    if (meta & 8) {
+                                           double (&buf)[CH > 0 ? CH : 1], int pad = 0) {
+    if (kBrick || (meta & 8)) {
         if (kBrick) {
-            const int mx = 1 << (hf_px(site) & 3), my = 16 << (hf_py(site) & 3), c16 = 4 * dim_x - 16;
+            const int mx = 1 << ((hf_px(site) + pad) & 3), my = 16 << ((hf_py(site) + pad) & 3), c16 = 4 * dim_x - 16;
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const int t = T.lin[kBase + k];
@@ -301,7 +313,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
     if (threadIdx.x < 3) { s_k[18 + threadIdx.x] = P.k_isc[threadIdx.x]; s_k[21 + threadIdx.x] = P.k_risc[threadIdx.x]; }
     if (threadIdx.x < 6) { s_k[24 + threadIdx.x] = P.k_rad[threadIdx.x]; s_k[30 + threadIdx.x] = P.k_nonrad[threadIdx.x]; }
     __syncthreads();
-    const int plane = P.X * P.Y, dim_x = P.X, dim_y = P.Y;
+    const int pad = kBrick ? P.R : 0;                                           // brick copy: site (x, y) sits at (x + R, y + R) of a bX x bY plane
+    const int dim_x = kBrick ? P.bX : P.X, dim_y = kBrick ? P.bY : P.Y, plane = dim_x * dim_y;
     HfxLaneTables<KF> T;
 #pragma unroll
     for (int k = 0; k < KF; ++k) { T.lin[k] = s_lin[32 * k + lane]; T.gd[k] = kRegG ? s_gd[32 * k + lane] : 0.0; }
@@ -330,12 +343,12 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
             if (active) {
                 const bool singlet = spin == HFX_SINGLET;
                 const int px = hf_px(site), py = hf_py(site), pz = hf_pz(site);
-                const int64_t i = (int64_t)pz * plane + (kBrick ? hfx_brick2(px, py, dim_x) : py * dim_x + px);
+                const int64_t i = (int64_t)pz * plane + (kBrick ? hfx_brick2(px + pad, py + pad, dim_x) : py * dim_x + px);
                 const double *wp = (singlet ? ws1 : wt1) + i;
                 const double wi = __ldg(wp);
                 const int a = hfx_tag_of(wi);
                 const double inv_wi = __ddiv_rn(1.0, wi);
-                const bool nowrap = px >= P.R && px < dim_x - P.R && py >= P.R && py < dim_y - P.R;
+                const bool nowrap = px >= P.R && px < P.X - P.R && py >= P.R && py < P.Y - P.R;
                 s_wp[lane] = wp;
                 s_inv[lane] = inv_wi;
                 s_sm[lane] = make_int2(site, (singlet ? 1 : 0) | (a << 1) | (nowrap ? 8 : 0));
@@ -349,7 +362,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
             //      together with the rates of exciton e (independent chains), the gathers of e + 1 before both ----
             double buf0[KB], buf1[KB];
             double S_prev = 0.0;
-            if (KF > 0) { const int2 sm0 = s_sm[0]; hfx_gather<KF, kChunk, 0, kBrick>(s_wp[0], sm0.x, sm0.y, T, s_off_lane, dim_x, dim_y, plane, buf0); }
+            if (KF > 0) { const int2 sm0 = s_sm[0]; hfx_gather<KF, kChunk, 0, kBrick>(s_wp[0], sm0.x, sm0.y, T, s_off_lane, dim_x, dim_y, plane, buf0, pad); }
             // one exciton: `cur` holds its gathered weights, the next exciton's go into `nxt`
 #define HFX_PHASE_A(e, cur, nxt)                                                                                              \
             {                                                                                                                 \
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);                                    \
                 if (KF > 0 && (e) + 1 < count) {                                                                              \
                     const int2 smn = s_sm[(e) + 1];                                                                           \
-                    hfx_gather<KF, KF, 0, kBrick>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt);                     \
+                    hfx_gather<KF, KF, 0, kBrick>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt, pad);                     \
                 }                                                                                                             \
                 double S = 0.0, L_prev;                                                                                       \
                 if (meta & 1) {                                                                                               \
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 if (K > KF) {   /* slots not covered above: the remaining transfer channels and the three on-site ones */    \
                     const double *g = (meta & 1) ? s_g6 : s_gd;                                                               \
                     const double *e_wp = s_wp[e];                                                                             \
-                    const int ex = hf_px(sm.x), ey = hf_py(sm.x);                                                             \
+                    const int ex = hf_px(sm.x) + pad, ey = hf_py(sm.x) + pad;                                                             \
                     for (int k = KF; k < K; ++k) {                                                                            \
                         const int c = (k << 5) + lane;                                                                        \
                         double rate = 0.0;                                                                                    \
@@ -397,10 +410,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 const double e_inv = s_inv[e];                                                                                \
                 const double *e_pref = s_k + ((meta & 1) ? 0 : 9) + 3 * ((meta >> 1) & 3);                                    \
                 if (kBase == 0) {                                                                                             \
-                    hfx_gather<KF, kChunk, kChunk, kBrick>(s_wp[e], sm.x, sm.y, T, s_off_lane, dim_x, dim_y, plane, nxt);             \
+                    hfx_gather<KF, kChunk, kChunk, kBrick>(s_wp[e], sm.x, sm.y, T, s_off_lane, dim_x, dim_y, plane, nxt, pad);             \
                 } else if ((e) + 1 < count) {                                                                                 \
                     const int2 smn = s_sm[(e) + 1];                                                                           \
-                    hfx_gather<KF, kChunk, 0, kBrick>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt);          \
+                    hfx_gather<KF, kChunk, 0, kBrick>(s_wp[(e) + 1], smn.x, smn.y, T, s_off_lane, dim_x, dim_y, plane, nxt, pad);          \
                 }                                                                                                             \
                 double S = kBase == 0 ? 0.0 : S_half;                                                                         \
                 if (meta & 1) {                                                                                               \
@@ -419,7 +432,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 } else {                                                                                                      \
                     const double *g = (meta & 1) ? s_g6 : s_gd;                                                               \
                     const double *e_wp = s_wp[e];                                                                             \
-                    const int ex = hf_px(sm.x), ey = hf_py(sm.x);                                                             \
+                    const int ex = hf_px(sm.x) + pad, ey = hf_py(sm.x) + pad;                                                             \
                     for (int k = KF; k < K; ++k) {                                                                            \
                         const int c = (k << 5) + lane;                                                                        \
                         double rate = 0.0;                                                                                    \
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 for (int k = 0; k < K; ++k) {                                     // the chosen lane's rates again, same inputs, same arithmetic
                     const int c = (k << 5) + lstar;
                     double rate = 0.0;
-                    if (c < M) rate = hfx_rate(pref, g[c], __ldg(wp + hfx_delta<kBrick>(s_off[c], px, py, dim_x, dim_y, plane)), inv_wi);
+                    if (c < M) rate = hfx_rate(pref, g[c], __ldg(wp + hfx_delta<kBrick>(s_off[c], px + pad, py + pad, dim_x, dim_y, plane)), inv_wi);
                     else if (c < M + 3) rate = s_on[(c - M) * 32 + lane];
                     acc = __dadd_rn(acc, rate);
                     if (rate > 0.0) last_live = k;
@@ -490,8 +503,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) hfx_run_kernel(const 
                 if (chosen < M) {
                     const int o = s_off[chosen];
                     int xx = px + (o & 255) - 128, yy = py + ((o >> 8) & 255) - 128;
-                    if (xx < 0) xx += dim_x; else if (xx >= dim_x) xx -= dim_x;
-                    if (yy < 0) yy += dim_y; else if (yy >= dim_y) yy -= dim_y;
+                    if (xx < 0) xx += P.X; else if (xx >= P.X) xx -= P.X;
+                    if (yy < 0) yy += P.Y; else if (yy >= P.Y) yy -= P.Y;
                     fin = hf_pack(xx, yy, pz + ((o >> 16) & 255) - 128);
                     kind = singlet ? HFX_K_FORSTER : HFX_K_MOVE;
                     tally = singlet ? HFX_T_FORSTER : HFX_T_DEXTER;

@@ -87,7 +87,8 @@ struct hf_sim {
     int x_warps = 8, x_grid = 1, x_per_sm = 1;
     bool x_tune = false;               // pick the warp batch by measurement at the next hf_x_run
     std::unordered_map<void *, size_t> alloc_bytes;   // buffers managed by dev_reuse
-    bool x_brick = false;              // hfx_run_kernel reads brick-layout copies of the weights (weights larger than the L2)
+    bool x_brick = false;              // hfx_run_kernel reads brick-layout copies of the weights
+    int32_t x_bX = 0, x_bY = 0;        // their padded plane
     double *d_bs1 = nullptr, *d_bt1 = nullptr;
     int32_t *d_x_blin = nullptr;
     size_t x_smem = 0;
@@ -292,7 +293,11 @@ static hfx_kernel_fn x_pick_kernel(int M, bool brick = false) {
 // what hfx_run_kernel is launched with: the brick-layout copies when they exist
 static HfxParams x_launch_params(const hf_sim *s) {
     HfxParams X = s->X;
-    if (s->x_brick) { X.ws1 = s->d_bs1; X.wt1 = s->d_bt1; X.lin = s->d_x_blin; X.brick = 1; }
+    if (s->x_brick) {
+        X.ws1 = s->d_bs1; X.wt1 = s->d_bt1; X.lin = s->d_x_blin; X.brick = 1; X.bX = s->x_bX; X.bY = s->x_bY;
+        X.w_halo = (int64_t)X.R * X.bX * X.bY;
+        X.w_stride = (int64_t)X.Z * X.bX * X.bY + 2 * X.w_halo;
+    }
     return X;
 }
 
@@ -366,30 +371,32 @@ int x_configure_launch(hf_sim *s) {
     const double footprint = 8.0 * (double)s->n_real * (double)s->X.w_stride;                // one spin manifold
     const bool beyond_l2 = l2_bytes > 0 && footprint > 0.5 * (double)l2_bytes;
     // hfx_run_kernel gathers from a copy of the weights in 4 x 4 x 1 bricks (one 128-byte line each): a cutoff-4 sphere
-    // touches 36 % fewer lines (hf_exciton.cuh).  Measured on one B200, 10^6 trajectories (profiles/r02g_brick_product.txt):
-    // 256^3 x 64 realisations 8.6e8 -> 1.06e9 events/s, 256^3 x 16 9.2e8 -> 1.19e9, and the L2-resident 128^3 1.89e9 ->
-    // 1.97e9.  Needs X and Y to be multiples of 4, one of the compiled cutoffs and offsets that fit the packed table;
+    // touches 36 % fewer lines (hf_exciton.cuh).  The copy pads every plane with R periodic columns / rows on each side
+    // (then up to multiples of 4), so no site needs the periodic wrap.  Measured on one B200, 10^6 trajectories
+    // (profiles/r02g_brick_product.txt): 256^3 x 64 realisations 8.6e8 -> 1.06e9 events/s, 256^3 x 16 9.2e8 -> 1.19e9, the
+    // L2-resident 128^3 1.89e9 -> 1.97e9.  Needs one of the compiled cutoffs and offsets that fit the packed table;
     // HF_X_BRICK=0 keeps the row-major layout.  The dense-device and integrated kernels always read the row-major arrays.
     s->x_brick = false;
     {
         bool want = true;
         if (const char *e = getenv("HF_X_BRICK")) want = atoi(e) != 0;
-        const bool can = s->P.X % 4 == 0 && s->P.Y % 4 == 0 && x_pick_brick_kernel(s->X.M) != nullptr &&
-                         (int64_t)(s->X.R + 1) * s->P.X * s->P.Y < (1ll << 22);
+        const int R = s->X.R, bX = (s->P.X + 2 * R + 3) & ~3, bY = (s->P.Y + 2 * R + 3) & ~3;
+        const bool can = x_pick_brick_kernel(s->X.M) != nullptr && (int64_t)(R + 1) * bX * bY < (1ll << 22);
         if (want && can) {
-            const size_t M = (size_t)s->X.M, RN = (size_t)s->n_real * (size_t)s->X.w_stride;
+            const int64_t b_halo = (int64_t)R * bX * bY, b_stride = (int64_t)s->P.Z * bX * bY + 2 * b_halo;
+            const size_t M = (size_t)s->X.M, RN = (size_t)s->n_real * (size_t)b_stride;
             std::vector<int32_t> blin(M);
-            for (size_t m = 0; m < M; ++m) blin[m] = hfx_brick_lin(s->x_offsets[3 * m], s->x_offsets[3 * m + 1], s->x_offsets[3 * m + 2], s->P.X, s->P.Y);
+            for (size_t m = 0; m < M; ++m) blin[m] = hfx_brick_lin(s->x_offsets[3 * m], s->x_offsets[3 * m + 1], s->x_offsets[3 * m + 2], bX, bY);
             int rc;
             if ((rc = dev_reuse(s, &s->d_x_blin, M)) || (rc = dev_reuse(s, &s->d_bs1, RN)) || (rc = dev_reuse(s, &s->d_bt1, RN))) return rc;
             HF_CUDA(cudaMemcpyAsync(s->d_x_blin, blin.data(), 4 * M, cudaMemcpyHostToDevice, s->stream));
             HF_CUDA(cudaMemsetAsync(s->d_bs1, 0, 8 * RN, s->stream));
             HF_CUDA(cudaMemsetAsync(s->d_bt1, 0, 8 * RN, s->stream));
-            hfx_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_bs1, s->d_bt1, (int64_t)s->P.N,
-                                                                       (int64_t)s->n_real, s->X.w_stride, s->X.w_halo, s->P.X, s->P.Y);
+            hfx_brick_weights_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_species, s->d_s1, s->d_t1, s->d_bs1, s->d_bt1, s->P.X, s->P.Y,
+                                                                             s->P.Z, R, bX, bY, (int64_t)s->n_real, b_stride, b_halo);
             HF_CUDA(cudaStreamSynchronize(s->stream));
             HF_CUDA(cudaGetLastError());
-            s->x_brick = true;
+            s->x_brick = true; s->x_bX = bX; s->x_bY = bY;
         }
     }
     hfx_kernel_fn fn = x_pick_kernel(s->X.M, s->x_brick);

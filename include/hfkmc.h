@@ -282,7 +282,7 @@ int hf_x_read_tables(hf_sim *sim, int32_t *n_offsets, int8_t *offsets, double *g
 /* Per-site Boltzmann weights of one realisation. */
 int hf_x_download_weights(hf_sim *sim, int32_t realisation, double *ws1, double *wt1);
 /* How hf_x_run is launched (decided by hf_x_configure and, for weights larger than half the L2, measured by the
- * first hf_x_run): trajectories a warp owns at a time, whether the kernel reads the 4 x 4 x 1 brick-layout copy
+ * first hf_x_run): trajectories a warp owns at a time, whether the kernel reads the padded 4 x 4 x 1 brick-layout copy
  * of the weights, and the grid.  Results never depend on these.  Any pointer may be NULL. */
 int hf_x_launch_info(hf_sim *sim, int32_t *block, int32_t *brick, int32_t *grid);
 /* Exciton state of trajectories [first, first + n): site, spin (HF_X_*), time since creation,

@@ -293,15 +293,21 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     // the device layout: R zero planes below and above the lattice
     P.w_halo = (int64_t)maxr * P.X * P.Y; P.w_stride = P.N + 2 * P.w_halo;
     std::vector<double> hs1((size_t)P.w_stride, 0.0), ht1((size_t)P.w_stride, 0.0);
-    const bool brick = generic == 2;                       // the 4 x 4 x 1 brick layout of the weights (compiled cutoffs only)
+    const bool brick = generic == 2;                       // the padded 4 x 4 x 1 brick layout of the weights (compiled cutoffs only)
     if (brick) {
-        if (P.X % 4 || P.Y % 4 || (M != 122 && M != 256 && M != 514)) return 4;
-        for (int64_t i = 0; i < P.N; ++i) {
-            const int64_t plane = (int64_t)P.X * P.Y, in = i % plane, o = P.w_halo + i - in + hfx_brick2((int)(in % P.X), (int)(in / P.X), P.X);
-            hs1[(size_t)o] = ws1[i]; ht1[(size_t)o] = wt1[i];
-        }
-        for (int m = 0; m < M; ++m) lin[(size_t)m] = hfx_brick_lin(offsets[3 * m], offsets[3 * m + 1], offsets[3 * m + 2], P.X, P.Y);
-        P.brick = 1;
+        if (M != 122 && M != 256 && M != 514) return 4;
+        const int R = maxr, bX = (P.X + 2 * R + 3) & ~3, bY = (P.Y + 2 * R + 3) & ~3;
+        P.brick = 1; P.bX = bX; P.bY = bY;
+        P.w_halo = (int64_t)R * bX * bY; P.w_stride = (int64_t)P.Z * bX * bY + 2 * P.w_halo;
+        hs1.assign((size_t)P.w_stride, 0.0); ht1.assign((size_t)P.w_stride, 0.0);
+        for (int z = 0; z < P.Z; ++z)
+            for (int yp = 0; yp < bY; ++yp)
+                for (int xp = 0; xp < bX; ++xp) {
+                    const int x = ((xp - R) % P.X + P.X) % P.X, y = ((yp - R) % P.Y + P.Y) % P.Y;
+                    const int64_t src = ((int64_t)z * P.Y + y) * P.X + x, o = P.w_halo + (int64_t)z * bX * bY + hfx_brick2(xp, yp, bX);
+                    hs1[(size_t)o] = ws1[src]; ht1[(size_t)o] = wt1[src];
+                }
+        for (int m = 0; m < M; ++m) lin[(size_t)m] = hfx_brick_lin(offsets[3 * m], offsets[3 * m + 1], offsets[3 * m + 2], bX, bY);
     } else {
         memcpy(hs1.data() + P.w_halo, ws1, sizeof(double) * (size_t)P.N);
         memcpy(ht1.data() + P.w_halo, wt1, sizeof(double) * (size_t)P.N);

@@ -63,9 +63,9 @@ def test_oracle_closed_forms():
     ((14, 15, 6), 3.5, 11, 30, False),     # M = 178: 5 register slots
     ((12, 12, 5), 4.5, 12, 9, False),      # M = 388: 12 slots in two halves of 6
     ((14, 13, 5), 6.0, 13, 6, False),      # M = 924: the first 16 of 28 slots prefetched, 12 through shared memory
-    ((12, 12, 6), 4.0, 5, 32, "brick"),    # weights in 4 x 4 x 1 bricks: every site needs the periodic wrap ...
-    ((24, 20, 7), 4.0, 8, 27, "brick"),    # ... wrap-free sites too (the packed per-lane offsets)
-    ((16, 12, 6), 3.0, 6, 32, "brick"),    # cutoff 3 with the tail slot
+    ((12, 12, 6), 4.0, 5, 32, "brick"),    # weights in padded 4 x 4 x 1 bricks: every site sees a periodic image ...
+    ((25, 22, 7), 4.0, 8, 27, "brick"),    # ... dimensions that are not multiples of 4 (extra padding)
+    ((9, 10, 5), 3.0, 6, 32, "brick"),     # cutoff 3 with the tail slot, odd dimensions
     ((28, 24, 7), 5.0, 9, 19, "brick")])   # cutoff 5: two halves
 def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, generic):
     """hfx_spawn_kernel + hfx_run_kernel run lane by lane on the host (tests/emu): identical event
@@ -93,7 +93,7 @@ def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, gen
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dims,cutoff", [((24, 24, 12), 4.0), ((20, 28, 9), 3.0), ((32, 24, 11), 5.0)])
+@pytest.mark.parametrize("dims,cutoff", [((24, 24, 12), 4.0), ((21, 27, 9), 3.0), ((32, 26, 11), 5.0)])
 def test_gpu_brick_layout_changes_nothing(dims, cutoff, monkeypatch):
     """The 4 x 4 x 1 brick layout of the weights (used when they exceed the L2; forced here with HF_X_BRICK=1) is a
     layout only: traces, final states, tallies and the downloaded (row-major) weights equal the row-major run's."""
@@ -124,11 +124,14 @@ def test_gpu_brick_layout_changes_nothing(dims, cutoff, monkeypatch):
     for ta, tb in zip(a[2], b[2]):
         assert np.array_equal(ta, tb)
     assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1], b[3][1])
-    # lattices the bricks do not tile keep the row-major layout
+    # cutoffs without a compiled brick variant keep the row-major layout
     monkeypatch.setenv("HF_X_BRICK", "1")
     sim = nat.Sim((22, 24, 8), (0.84, 0.15, 0.01), 0.1, 1, 1, n_trajectories=64, seed=1)
     try:
-        sim.generate_lattice(); sim.x_configure()
+        sim.generate_lattice()
+        p = nat.x_default_params()
+        p.cutoff = 2.5
+        sim.x_configure(p)
         assert sim.x_launch_info()["brick"] is False
     finally:
         sim.close()
