@@ -61,7 +61,8 @@ __host__ __device__ inline size_t hf_small_thread_bytes(int cap_c, int cap_f, in
 // Screen-then-verify as in hf_c1_gen, with these differences: candidates can be blocked (they draw
 // nothing), and the Coulomb sum has up to 2C - 1 terms.  The fp32 estimate still ignores it: every
 // term is |1/r' - 1/r| <= 1 times HF_ELECTROSTATIC = 4.8e-7 eV, so n terms shift dE / kT by <= 1.86e-5 n
-// and the estimate of 1e13 * tau by the same relative amount on top of hf_c1_gen's 4e-5 =: eps; candidates
+// and the estimate of 1e13 * tau by the same relative amount on top of hf_c1_gen's 5e-5 (its 6.6e-5 less the one
+// Coulomb term it counts itself) =: eps; candidates
 // outside a window of 1 + max(2^-9, 4 eps) around the best estimate cannot win or tie
 // ((1 + 4 eps)(1 - eps) > 1 + eps).  (Measured: faster than the warp kernel up to 12 charges of each type.)  Whenever the reference could raise ZeroDivisionError for
 // geometric reasons (a same-type charge on a candidate: the flag/list desynchronisation of DESIGN.md §0;
@@ -126,42 +127,69 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
     int32_t bfin = -1;
     unsigned verify = amask;
     if (!slow) {
-        // ---- pass 1: fp32 estimates of 1e13 * tau; uniform d0 + r is half (p + r) & 1 of Philox block (d0 >> 1) + ((p + r) >> 1)
-        const int p = (int)(d0 & 1);
-        const float inv_kt = (float)(1.0 / HF_KT);
-        float amin = INFINITY, amin2 = INFINITY;
-        int lmin = 0;
-        unsigned forced = 0, rem = amask;
-        for (int j = 0; 2 * j < n + p; ++j) {
+        // ---- pass 1: fp32 estimates of 1e13 * tau; uniform d0 + r is half (p + r) & 1 of Philox block (d0 >> 1) + ((p + r) >> 1).
+        //      The arithmetic of hf_c1_gen (hf_frm_c1.cuh has the error budget): the estimate straight from the high word
+        //      of the draw, MUFU.LG2 / MUFU.EX2 issued directly, candidates whose rate could underflow found by a max and
+        //      a rare second look, the two smallest estimates as integer keys (candidate index in the 5 low mantissa bits)
+        int p = (int)(d0 & 1), nn = n;
+        int replay = P.replay != nullptr;
+        HF_C1_PIN(p); HF_C1_PIN(nn); HF_C1_PIN(replay);                          // else rebuilt / reloaded at every use in the loop
+        const float inv_kt_log2e = (float)(1.4426950408889634 / HF_KT), x2_forced = (float)(700.0 * 1.4426950408889634);
+        uint32_t key1 = 0x7f800000u, key2 = 0x7f800000u;
+        float x2max = 0.0f;
+        unsigned rem = amask;
+        for (int j = 0; 2 * j < nn + p; ++j) {
             HfPhiloxBlock rnd = {0, 0, 0, 0};
-            if (!P.replay) rnd = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
+            if (!replay) rnd = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int r = 2 * j + h - p;
-                if (r < 0 || r >= n) continue;
+                if (r < 0 || r >= nn) continue;
                 const int l = __ffs(rem) - 1;
                 rem &= rem - 1;
-                const double u = P.replay ? hf_traj_uniform(P, w, d0 + (uint64_t)r, &exhausted) : hf_block_uniform(rnd, (uint64_t)h);
-                float t0;
-                if (u < 0x1p-6) {
-                    const float uf = (float)u;
-                    t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                const float x2 = approx[l] * inv_kt_log2e;
+                x2max = fmaxf(x2max, x2);
+                float a;
+                const uint32_t hi = h ? rnd.w3 : rnd.w1;
+                if (!replay && hi - 0x00100000u < 0xffe00000u) {                 // 2^-12 <= u < 1 - 2^-12: no fp64, t0 > 0
+                    float t0;
+                    if (hi < 0x04000000u) {
+                        const float uf = (float)hi * 0x1p-32f;
+                        t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                    } else {
+                        t0 = hf_c1_lg2((float)(~hi) * 0x1p-32f) * -0.69314718055994531f;
+                    }
+                    a = x2 > 0.0f ? t0 * hf_c1_ex2(x2) : t0;
                 } else {
-                    t0 = -__logf((float)(1.0 - u));
+                    const double u = replay ? hf_traj_uniform(P, w, d0 + (uint64_t)r, &exhausted) : hf_block_uniform(rnd, (uint64_t)h);
+                    float t0;
+                    if (u < 0x1p-6) {
+                        const float uf = (float)u;
+                        t0 = uf * (1.0f + uf * (0.5f + uf * (1.0f / 3.0f)));
+                    } else {
+                        t0 = -__logf((float)(1.0 - u));
+                    }
+                    a = x2 > 0.0f ? t0 * hf_c1_ex2(x2) : t0;
+                    if (t0 == 0.0f) a = 0.0f;                                    // 0 * inf
                 }
-                float a = t0;
-                const float x = approx[l] * inv_kt;
-                if (x > 0.0f) a = t0 * __expf(x);
-                if (x > 700.0f) forced |= 1u << l;
-                if (t0 == 0.0f) a = 0.0f;                                        // 0 * inf
                 approx[l] = a;
-                if (a < amin) { amin2 = amin; amin = a; lmin = l; }
-                else if (!(a >= amin2)) amin2 = a;                               // also catches NaN
+                const uint32_t key = (__float_as_uint(a) & ~31u) | (uint32_t)l;
+                key2 = hf_c1_umin(key2, hf_c1_umax(key1, key));
+                key1 = hf_c1_umin(key1, key);
             }
         }
         if (exhausted) { w.draws = d0 + (uint64_t)n; return HF_ST_REPLAY_EXHAUSTED; }
-        // window: 4 x the estimate's error bound, 4e-5 + C_e (ns + no) / kT (2^-9 up to 8 charges of each type)
-        const float thr = amin * (1.0f + fmaxf(HF_C1_WINDOW, 4.0f * (4e-5f + (float)(HF_ELECTROSTATIC / HF_KT) * (float)(ns + no))));
+        const float amin = __uint_as_float(key1 & ~31u), amin2 = __uint_as_float(key2 & ~31u);
+        const int lmin = (int)(key1 & 31u);
+        unsigned forced = 0;                                                     // x > 700: estimate +inf (or 0, verified as a minimum)
+        if (x2max > x2_forced) {
+            for (unsigned m = amask; m; m &= m - 1) {
+                const int i = __ffs(m) - 1;
+                if (approx[i] == INFINITY) forced |= 1u << i;
+            }
+        }
+        // window: 4 x the estimate's error bound, 5e-5 + C_e (ns + no) / kT (2^-9 up to 8 charges of each type)
+        const float thr = amin * (1.0f + fmaxf(HF_C1_WINDOW, 4.0f * (5e-5f + (float)(HF_ELECTROSTATIC / HF_KT) * (float)(ns + no))));
         verify = forced | (1u << lmin);
         if (!(amin2 > thr)) {
             for (unsigned m = amask; m; m &= m - 1) {
