@@ -79,6 +79,9 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
 #define HF_C1_MIN_BLOCKS 2
 #endif
 #define HF_C1_MAXCAND 27
+#ifndef HF_C1_UNROLL
+#define HF_C1_UNROLL 1
+#endif
 #ifndef HF_C1_PIN_BOUNDS
 #define HF_C1_PIN_BOUNDS 1
 #endif
@@ -231,6 +234,13 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     uint32_t key1 = 0x7f800000u, key2 = 0x7f800000u;
     float x2max = 0.0f;
     bool exhausted = false;
+#if HF_C1_UNROLL == 2
+#pragma unroll 2
+#elif HF_C1_UNROLL == 3
+#pragma unroll 3
+#elif HF_C1_UNROLL == 1
+#pragma unroll 1
+#endif
     for (int j = 0; 2 * j < n + p; ++j) {
         HfPhiloxBlock blk = {0, 0, 0, 0};
         if (!replay) blk = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
