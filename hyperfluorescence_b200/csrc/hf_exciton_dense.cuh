@@ -35,6 +35,9 @@
 #ifndef HFXD_MIN_BLOCKS
 #define HFXD_MIN_BLOCKS 7              // 7 CTAs x 4 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
 #endif
+#ifndef HFXD_PIN_RECORDS
+#define HFXD_PIN_RECORDS 0                 // measured: pinning the two record pointers costs more (registers) than the multiplies it saves: 3.79e8 -> 3.66e8
+#endif
 #ifndef HFXD_CHUNK
 #define HFXD_CHUNK 3                   // slots whose gathers (weight + occupancy word) are in flight together
 #endif
@@ -351,8 +354,11 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
         W.occ = P.occ + dev * P.occ_words;
         uint32_t *g_pos = P.pos + dev * n_pad;
         double *g_T = P.T + dev * n_pad, *g_birth = P.birth + dev * n_pad;
-        double *g_L = P.rec_L + dev * n_pad * 32;
-        uint32_t *g_seen = P.rec_seen + dev * n_pad * 32;
+        double *g_L = P.rec_L + dev * n_pad * 32 + lane;                         // this lane's column of the device's records
+        uint32_t *g_seen = P.rec_seen + dev * n_pad * 32 + lane;
+#if HFXD_PIN_RECORDS
+        HFX_PIN64(g_L); HFX_PIN64(g_seen);                                       // else rebuilt (two 64-bit multiplies) at every use
+#endif
         double time, life;
         uint64_t draws;
         W.s_cnt[lane] = 0; W.s_dirty[lane] = 0;
@@ -400,8 +406,8 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 const uint32_t ps = W.s_pos[kx];
                 // (2) its channel, from the record of its last evaluation: the lane by the scanned sums, then that lane's
                 //     K channels again (same inputs, same arithmetic)
-                const double Lk = g_L[kx * 32 + lane];
-                const uint32_t sk = g_seen[kx * 32 + lane];
+                const double Lk = g_L[kx * 32];
+                const uint32_t sk = g_seen[kx * 32];
                 const double target2 = __dsub_rn(target, base);
                 const int lstar = hfxd_pick_lane(Lk, (sk >> 31) != 0u, target2, acc0);
                 hfxd_column(W, ps, lstar);
@@ -502,8 +508,8 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 const double L = hfx_scan(S, lane);
                 __syncwarp();
                 if (stage == 1) hfxd_mark_seen(W, (int)(job & 0x3fffffffu), seen, dmask);   // the neighbours of the site that changed
-                g_L[tgt * 32 + lane] = L;
-                g_seen[tgt * 32 + lane] = seen | (S > 0.0 ? 0x80000000u : 0u);
+                g_L[tgt * 32] = L;
+                g_seen[tgt * 32] = seen | (S > 0.0 ? 0x80000000u : 0u);
                 const double tot = __shfl_sync(HF_FULL, L, 31);
                 if (lane == 0) { W.s_T[tgt] = tot; W.s_dirty[tgt >> 5] &= ~(1u << (tgt & 31)); }
                 __syncwarp();
