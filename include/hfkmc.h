@@ -267,7 +267,10 @@ enum {
 
 int hf_x_default_params(hf_x_params *out);
 /* Build the neighbour / rate tables, the per-site Boltzmann weights exp(-S1/kT), exp(-T1/kT) of
- * every realisation (needs a lattice) and the exciton state of every trajectory. */
+ * every realisation (needs a lattice) and the exciton state of every trajectory.  Device memory: two f64 arrays of
+ * (Z + 2R) X Y sites per realisation, plus — for cutoffs 3, 4, 5 — a copy of both in the padded brick layout the step
+ * kernel gathers from ((Z + 2R) (X + 2R) (Y + 2R) sites rounded up to multiples of 4 in x and y; hf_x_launch_info).
+ * Calling it again (new parameters, or new energies after hf_upload_lattice) reuses the buffers. */
 int hf_x_configure(hf_sim *sim, const hf_x_params *params);
 /* Create the first exciton of every trajectory (fills the slot of _form_exciton, reseau.py:434-438). */
 int hf_x_spawn(hf_sim *sim);
