@@ -265,3 +265,44 @@ __global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_run_
     }
     hf_store_state<1, kX>(P, w, 0);
 }
+
+// Lattice._charges_injection + _events_creation (reseau.py:207-276) for 2 <= charges <= HF_SMALL_MAX_CHARGES, one thread
+// per trajectory: the statements of hf_inject_kernel with L = 1, for the SET variant of random.sample (X * Y > setsize,
+// random.py:421-448; the pool variant needs X * Y integers of scratch per trajectory and keeps the warp kernel).
+// Same draws in the same order, hence the same sites, flags and initial events (golden init_* arrays under emulation,
+// test_thread_inject_equals_warp_inject on the device).  2.56e6 trajectories of the GA leg: 57 ms -> see DESIGN.md section 3.
+__global__ void __launch_bounds__(HF_SMALL_THREADS, HF_SMALL_MIN_BLOCKS) hf_inject_small_kernel(const HfParams P) {
+    extern __shared__ __align__(16) unsigned char hf_smem[];
+    const int64_t local = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= P.B) return;
+    const size_t stride = hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P));
+    HfWarp w;
+    hf_small_carve(w, hf_smem + threadIdx.x * stride, P.cap_c, P.cap_f, hf_xcap(P));
+    hf_load_state<1, false>(P, w, local, 0);   // zero-initialised by the host
+    const int64_t molecules = (int64_t)P.X * P.Y;
+    int st = HF_ST_OK;
+    bool exhausted = false;
+    for (int t = 0; t < 2; ++t) {                                                // 219, 225
+        const int z = t == 0 ? P.Z - 1 : 0;
+        for (int i = 0; i < P.C; ++i) {
+            int64_t j = hf_randbelow(P, w, molecules, &exhausted);
+            int cand = hf_pack((int)(j / P.Y), (int)(j % P.Y), z);
+            while (hf_contains<1>(w.pos(t), i, cand, 0) && !exhausted) {
+                j = hf_randbelow(P, w, molecules, &exhausted);
+                cand = hf_pack((int)(j / P.Y), (int)(j % P.Y), z);
+            }
+            w.pos(t)[i] = cand;
+        }
+        w.set_n_pos(t, P.C);
+    }
+    if (exhausted) st = HF_ST_REPLAY_EXHAUSTED;
+    for (int i = 0; i < P.C && st == HF_ST_OK; ++i)                              // 226-228
+        for (int t = 0; t < 2; ++t)
+            if (!hf_toggle_flag<1>(P, w, t, w.pos(t)[i], 0)) st = HF_ST_CAPACITY;
+    for (int t = 0; t < 2 && st == HF_ST_OK; ++t)                                // 240-276
+        for (int i = 0; i < P.C && st == HF_ST_OK; ++i)
+            st = hf_gen_move_event_serial(P, w, t, w.pos(t)[i], false);
+    w.injection = 2ull * (uint64_t)P.C;                                          // 118
+    w.status = st;
+    hf_store_state<1, false>(P, w, 0);
+}

@@ -783,8 +783,18 @@ int hf_inject(hf_sim *s) {
         s->injected = true;
         return HF_OK;
     }
-    int32_t *pool = nullptr;
     const int64_t molecules = (int64_t)P.X * P.Y;
+    if (P.C <= HF_SMALL_MAX_CHARGES && P.dist == 1 && !(s->cfg.flags & HF_FLAG_WARP_KERNEL) && molecules > P.setsize && !getenv("HF_INJECT_WARP")) {
+        // one thread per trajectory (hf_frm_small.cuh), set variant of random.sample
+        const size_t smem = hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P)) * HF_SMALL_THREADS;
+        if (smem > 48 * 1024) HF_CUDA(cudaFuncSetAttribute(hf_inject_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int64_t blocks = (P.B + HF_SMALL_THREADS - 1) / HF_SMALL_THREADS;
+        hf_inject_small_kernel<<<(unsigned)blocks, HF_SMALL_THREADS, smem, s->stream>>>(P);
+        HF_CUDA(cudaGetLastError());
+        s->injected = true;
+        return HF_OK;
+    }
+    int32_t *pool = nullptr;
     if (molecules <= P.setsize)
         if ((rc = dev_alloc(&pool, (size_t)((int64_t)s->grid * s->warps * molecules)))) return rc;
     switch (s->warps) {

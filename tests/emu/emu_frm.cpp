@@ -82,6 +82,7 @@ void inject_body(void *a) { auto *x = (InjectArgs *)a; hf_inject_kernel<1>(*x->P
 void run_body(void *a) { const HfParams &P = *(const HfParams *)a; if (P.xi.mode) hf_run_kernel<1, true>(P); else hf_run_kernel<1, false>(P); }
 void run_c1_body(void *a) { hf_run_c1_kernel<HF_C1_THREADS, HF_C1_MIN_BLOCKS>(*(const HfParams *)a); }
 void inject_c1_body(void *a) { hf_inject_c1_kernel(*(const HfParams *)a); }
+void inject_small_body(void *a) { hf_inject_small_kernel(*(const HfParams *)a); }
 void run_small_body(void *a) { const HfParams &P = *(const HfParams *)a; if (P.xi.mode) hf_run_small_kernel<true>(P); else hf_run_small_kernel<false>(P); }
 
 struct ShuffleArgs { const HfParams *P; int32_t *pool; int64_t total, n_host, n_tadf; uint8_t *layer; };
@@ -157,7 +158,11 @@ int emu_run(const int32_t dims[3], double field, int32_t charges, uint64_t seed,
     blockDim.x = 32; gridDim.x = 1; blockIdx.x = 0;
     b.pool.assign((size_t)((int64_t)P.X * P.Y), 0);
     InjectArgs ia{&P, b.pool.data()};
-    emu_run_warp(inject_body, &ia);
+    // the product's choice: thread-per-trajectory injection with the thread kernels when random.sample takes its set variant
+    const bool small_inject = small_kernel && charges >= 1 && charges <= HF_SMALL_MAX_CHARGES && distance == 1 &&
+                              (int64_t)P.X * P.Y > P.setsize && hf_small_thread_bytes(P.cap_c, P.cap_f, hf_xcap(P)) * 32 <= sizeof(hf_smem);
+    if (small_inject) emu_run_warp(inject_small_body, &P);
+    else emu_run_warp(inject_body, &ia);
     const int cap = P.cap_c;
     init_counts_out[0] = b.sc[0].n_pos[0]; init_counts_out[1] = b.sc[0].n_pos[1];
     init_counts_out[2] = b.sc[0].n_ev[0]; init_counts_out[3] = b.sc[0].n_ev[1];

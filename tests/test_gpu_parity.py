@@ -301,6 +301,26 @@ def test_thread_kernel_equals_warp_kernel(nat, name, steps, charges):
         assert thread["tallies"]["recombination"] > 1000
 
 
+@pytest.mark.parametrize("charges,dims", [(2, (10, 10, 5)), (4, (10, 10, 5)), (12, (12, 9, 6)), (5, (6, 5, 4))])
+def test_thread_inject_equals_warp_inject(nat, charges, dims, monkeypatch):
+    """hf_inject for 2..12 charges runs one thread per trajectory (hf_inject_small_kernel) when random.sample takes its
+    set variant; HF_INJECT_WARP=1 keeps the warp kernel: positions, flags, initial events (taus bit for bit), draw
+    counts and status of 2048 trajectories must be identical (reseau.py:207-276)."""
+    out = []
+    for warp in ("1", None):
+        if warp: monkeypatch.setenv("HF_INJECT_WARP", warp)
+        else: monkeypatch.delenv("HF_INJECT_WARP", raising=False)
+        sim = nat.Sim(dims, (0.84, 0.15, 0.01), 0.1, charges, 1, n_trajectories=2048, seed=4242, first_trajectory=3)
+        sim.generate_lattice(); sim.inject(); sim.sync()
+        out.append([(sim.positions(t, 0).tolist(), sim.positions(t, 1).tolist(), sorted(sim.flags(t, 0).tolist()),
+                     sorted(sim.flags(t, 1).tolist()), [a.tolist() for a in sim.move_events(t, 0)],
+                     [a.tolist() for a in sim.move_events(t, 1)],
+                     (lambda i: (i.draws, i.injection, i.status))(sim.info(t))) for t in range(0, 2048, 13)])
+        sim.close()
+    assert out[0] == out[1]
+    assert any(len(o[4][0]) == charges for o in out[0])
+
+
 def test_sharding_is_invisible(nat):
     """Two handles holding trajectories [0,96) and [96,192) give the same box totals as one handle
     holding [0,192): Philox ids are global, so results do not depend on how ranks split the work."""
