@@ -579,8 +579,8 @@ def exciton_rate(rank, local_rank, world, lattice=X_L, realisations_total=1, lab
                         "frac": rate * bytes_per_event / world / 1e9 / peak, "kernel": "hfx_run_kernel",
                         "traffic": exciton_traffic(X_TRAJ_PER_GPU * X_EVENTS) if l2_resident else None,
                         "note": ("the 2 x 17 MB of Boltzmann weights of a 128^3 lattice are L2-resident (ncu: L2 hit 99.9 %, "
-                                 "DRAM ~1.5 B/event), so the algorithmic-bytes fraction is not an HBM utilisation; the kernel is "
-                                 "bound by the L1 data pipe (75 %) and instruction issue (profiles/r01f_*)") if l2_resident else
+                                 "DRAM ~1.6 B/event), so the algorithmic-bytes fraction is not an HBM utilisation; the kernel is "
+                                 "bound by instruction issue and the L1 data pipe (`issue`; profiles/r02h_*, r01f_*)") if l2_resident else
                                 ("weights exceed the L2: row-major with 32 trajectories per warp the kernel moved 7.9 KB/event from DRAM "
                                  "at 4.2 TB/s (profiles/r01g_*); the adaptive warp batch trades that for L2 hits (profiles/r01h_*) and "
                                  "the 4 x 4 x 1 brick layout cuts the lines a sphere touches by 36 % (profiles/r02g_brick_product.txt)")},
