@@ -35,6 +35,7 @@
 #ifndef HFXD_MIN_BLOCKS
 #define HFXD_MIN_BLOCKS 7              // 7 CTAs x 4 warps = 28 devices per SM: the 4096 devices of BASELINE configs[3] are ONE wave on 148 SMs
 #endif
+#define HFXD_SCRATCH 32                // doubles of per-warp scratch: the rates of one lane's channels
 #ifndef HFXD_PIN_RECORDS
 #define HFXD_PIN_RECORDS 0                 // measured: pinning the two record pointers costs more (registers) than the multiplies it saves: 3.79e8 -> 3.66e8
 #endif
@@ -60,10 +61,11 @@ struct HfxdParams {
 };
 
 __host__ __device__ inline size_t hfxd_smem_bytes(int M, int n_pad, int warps) {
-    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)   per warp: T (f64) | rates (f64) | pos (u32) | counters (u32)
+    // CTA: g6, gd (f64) | k[36], ann[4] (f64) | lin, off (i32)
+    // per warp: T (f64) | the chosen lane's K <= 31 rates (32 f64) | pos (u32) | counters (u32)
     // (birth[] stays in global memory: it is touched once per LOST exciton, by one lane)
     return 8 * (2 * (size_t)M + HFX_N_K + 4) + 4 * 2 * (size_t)((M + 1) & ~1) +
-           (size_t)warps * (8 * ((size_t)n_pad + hfx_padded_channels(M)) + 4 * ((size_t)n_pad + 64));
+           (size_t)warps * (8 * ((size_t)n_pad + HFXD_SCRATCH) + 4 * ((size_t)n_pad + 64));
 }
 
 __device__ __forceinline__ int hfxd_occ_get(const uint32_t *occ, int64_t idx) {
@@ -250,11 +252,12 @@ __device__ __forceinline__ int hfxd_pick_lane(double L, bool positive, double ta
     acc0 = lstar > 0 ? below : 0.0;
     return lstar;
 }
+template <bool kCompact = false>      // kCompact: v[slot] holds the chosen lane's values only
 __device__ __forceinline__ int hfxd_pick_slot(const double *v, int n_slots, int lstar, double acc, double target, double &base) {
     double b_slot = acc, b_last = acc;
     int slot = -1, last = -1;
     for (int q = 0; q < n_slots; ++q) {
-        const double r = v[(q << 5) + lstar], before = acc;
+        const double r = v[kCompact ? q : (q << 5) + lstar], before = acc;
         acc = __dadd_rn(acc, r);
         if (r > 0.0) { last = q; b_last = before; }
         if (slot < 0 && acc > target) { slot = q; b_slot = before; }
@@ -265,7 +268,7 @@ __device__ __forceinline__ int hfxd_pick_slot(const double *v, int n_slots, int 
 }
 
 // The K channels of lane `lstar` of an exciton (packed site + spin), evaluated by lanes 0 .. K - 1 with the arithmetic
-// of hfxd_lane_sum and left in s_rates[(k << 5) + lstar] (K <= 31, checked by the host).
+// of hfxd_lane_sum and left in s_rates[k] (K <= 31, checked by the host).
 __device__ __forceinline__ void hfxd_column(const HfxdWarp &W, uint32_t ps, int lstar) {
     const HfxParams &X = W.P->X;
     const int site = (int)(ps & 0x3fffffffu), spin = (int)(ps >> 30);
@@ -294,7 +297,7 @@ __device__ __forceinline__ void hfxd_column(const HfxdWarp &W, uint32_t ps, int 
         } else if (c == W.M + 2) {
             rate = W.s_k[30 + 2 * a + (singlet ? 0 : 1)];
         }
-        W.s_rates[c] = rate;
+        W.s_rates[W.lane] = rate;
     }
     __syncwarp();
 }
@@ -333,11 +336,11 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
     int32_t *s_lin = reinterpret_cast<int32_t *>(s_ann + 4);
     int32_t *s_off = s_lin + ((M + 1) & ~1);
     unsigned char *wsm = reinterpret_cast<unsigned char *>(s_off + ((M + 1) & ~1)) +
-                         (size_t)warp * (8 * ((size_t)n_pad + padded) + 4 * ((size_t)n_pad + 64));
+                         (size_t)warp * (8 * ((size_t)n_pad + HFXD_SCRATCH) + 4 * ((size_t)n_pad + 64));
     HfxdWarp W;
     W.P = &P; W.s_g6 = s_g6; W.s_gd = s_gd; W.s_k = s_k; W.s_ann = s_ann; W.s_lin = s_lin; W.s_off = s_off;
     W.s_T = reinterpret_cast<double *>(wsm); W.s_rates = W.s_T + n_pad;
-    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + padded); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
+    W.s_pos = reinterpret_cast<uint32_t *>(W.s_rates + HFXD_SCRATCH); W.s_cnt = W.s_pos + n_pad; W.s_dirty = W.s_cnt + 32;
     W.lane = lane; W.K = K; W.M = M;
     W.aligned = M == 32 * HFXD_KF && X.w_stride < 0x7fffffff;
     for (int m = threadIdx.x; m < M; m += kWarps * 32) { s_g6[m] = X.g6[m]; s_gd[m] = X.gd[m]; s_lin[m] = X.lin[m]; s_off[m] = X.offsets[m]; }
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(kWarps * 32, HFXD_MIN_BLOCKS) hfxd_run_kernel(
                 const int lstar = hfxd_pick_lane(Lk, (sk >> 31) != 0u, target2, acc0);
                 hfxd_column(W, ps, lstar);
                 double base2;
-                const int chosen = hfxd_pick_slot(W.s_rates, K, lstar, acc0, target2, base2);
+                const int chosen = hfxd_pick_slot<true>(W.s_rates, K, lstar, acc0, target2, base2);
                 hfxd_mark_seen(W, (int)(ps & 0x3fffffffu), sk & 0x7fffffffu, dmask);     // the neighbours of the site that changes
                 const double dt = __ddiv_rn(-log(__dsub_rn(1.0, u_time)), R);
                 time = __dadd_rn(time, dt);
