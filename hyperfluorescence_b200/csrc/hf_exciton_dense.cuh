@@ -95,8 +95,8 @@ struct HfxdWarp {                      // one warp's view of its device
 // third of its issue stalls were instruction fetches.
 //
 // Fast path (KF = M / 32 full slots of transfer channels followed by the three on-site channels on lanes 0-2 of slot
-// KF — cutoff 4 gives M = 256 = 8 x 32 — and a site away from the x / y seams): no per-slot channel-range tests, no
-// wrap arithmetic, 32-bit offsets.  Everything else takes the generic loop.
+// KF — cutoff 4 gives M = 256 = 8 x 32): no per-slot channel-range tests, 32-bit offsets, and the periodic-wrap arithmetic
+// only for sites next to the x / y seams (a warp-uniform branch).  Every other cutoff takes the generic loop.
 #define HFXD_KF 8
 #ifndef HFXD_FAST_CHUNK
 #define HFXD_FAST_CHUNK 2               // must divide HFXD_KF; measured: 2 -> 2.67e8, 4 -> 2.56e8, 8 (fully unrolled) -> 2.19e8 events/s on 4096 x 256
@@ -119,13 +119,14 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
     const int64_t oi = i + X.w_halo;
     double S = 0.0;
     seen = 0;
-    if (W.aligned && nowrap) {
+    if (W.aligned) {
         // what the loop reads through, pinned in registers: nvcc otherwise rebuilds the pointers (a 64-bit multiply for
         // the mask, the shared-window base for the tables) at every use
         const uint32_t *occ = W.occ;
         const double *wq = w;
         unsigned oi32 = (unsigned)oi;                                            // the host checked that the mask index fits
         hfx_sptr lin = hfx_saddr(W.s_lin + W.lane), gl = hfx_saddr(g + W.lane), pr = hfx_saddr(pref), an = hfx_saddr(ann);
+        const hfx_sptr lin_to_off = hfx_saddr(W.s_off) - hfx_saddr(W.s_lin);      // a site next to a seam takes its offsets from the packed table
         HFX_PIN64(occ); HFX_PIN64(wq); HFX_PIN32(oi32); HFX_PIN32(lin); HFX_PIN32(gl); HFX_PIN32(pr); HFX_PIN32(an);
         // a ROLLED loop over chunks of HFXD_FAST_CHUNK slots: the hot code stays small enough for the instruction
         // caches (seven warps per scheduler, each somewhere else in a 5 000-instruction kernel)
@@ -136,7 +137,8 @@ __device__ __forceinline__ double hfxd_lane_sum(const HfxdWarp &W, uint32_t ps, 
             int sh[HFXD_FAST_CHUNK];
 #pragma unroll
             for (int u = 0; u < HFXD_FAST_CHUNK; ++u) {
-                const int d = hfx_lds_s32(lin + 4 * 32 * u);
+                int d = hfx_lds_s32(lin + 4 * 32 * u);
+                if (!nowrap) d = hfx_delta(hfx_lds_s32(lin + lin_to_off + 4 * 32 * u), px, py, X.X, X.Y, plane);   // warp-uniform branch
                 wj[u] = __ldg(wq + d);
                 const unsigned oj = oi32 + (unsigned)d;
                 ow[u] = occ[oj >> 4];
