@@ -21,6 +21,7 @@
 // of continuing with a wrong state.  State is exchanged through the same global arrays as the
 // warp kernel (cap_c = 1, cap_f = 2), so the two kernels can be cross-checked on the same handle.
 #pragma once
+#include <type_traits>
 #include "hf_frm.cuh"
 
 struct HfC1 {
@@ -79,8 +80,8 @@ __device__ __forceinline__ int hf_c1_reinject(const HfParams &P, HfC1 &s, int t,
 #define HF_C1_MIN_BLOCKS 2
 #endif
 #define HF_C1_MAXCAND 27
-#ifndef HF_C1_UNROLL
-#define HF_C1_UNROLL 1
+#ifndef HF_C1_PEEL
+#define HF_C1_PEEL 1
 #endif
 #ifndef HF_C1_PIN_BOUNDS
 #define HF_C1_PIN_BOUNDS 1
@@ -234,20 +235,18 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
     uint32_t key1 = 0x7f800000u, key2 = 0x7f800000u;
     float x2max = 0.0f;
     bool exhausted = false;
-#if HF_C1_UNROLL == 2
-#pragma unroll 2
-#elif HF_C1_UNROLL == 3
-#pragma unroll 3
-#elif HF_C1_UNROLL == 1
-#pragma unroll 1
-#endif
-    for (int j = 0; 2 * j < n + p; ++j) {
+    // One Philox block = two candidates.  Only the first and the last block of an event can hold a uniform that belongs to
+    // no candidate (r < 0 when the draw counter is odd, r >= n at the end): they run the checked copy of the body, the
+    // 11-12 blocks in between the unchecked one (5 instructions per candidate less).
+    const int jn = (n + p + 1) >> 1;
+    auto block = [&](const int j, auto checked) {
+        constexpr bool kChecked = decltype(checked)::value;
         HfPhiloxBlock blk = {0, 0, 0, 0};
         if (!replay) blk = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, ident, (d0 >> 1) + (uint64_t)j);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = 2 * j + h - p;
-            if (r < 0 || r >= n) continue;
+            if (kChecked && (r < 0 || r >= n)) continue;
             const int l = r + (r >= self_l ? 1 : 0);
             const float x2 = hf_c1_ld(approx, l * kStride) * inv_kt_log2e;
             x2max = fmaxf(x2max, x2);
@@ -284,7 +283,16 @@ __device__ __forceinline__ int hf_c1_gen(const HfParams &P, const double *lumo, 
             key2 = hf_c1_umin(key2, hf_c1_umax(key1, key));
             key1 = hf_c1_umin(key1, key);
         }
-    }
+    };
+#if HF_C1_PEEL
+    if (jn > 0) block(0, std::true_type{});
+#pragma unroll 1
+    for (int j = 1; j < jn - 1; ++j) block(j, std::false_type{});
+    if (jn > 1) block(jn - 1, std::true_type{});
+#else
+#pragma unroll 1
+    for (int j = 0; j < jn; ++j) block(j, std::true_type{});
+#endif
     const float amin = __uint_as_float(key1 & ~31u), amin2 = __uint_as_float(key2 & ~31u);
     const int lmin = (int)(key1 & 31u);
     // candidates with x > 700 are always verified.  Their estimate overflowed to +inf (2^x2, x2 > 1009) or is 0 (t0 = 0;
