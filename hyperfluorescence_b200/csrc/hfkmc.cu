@@ -87,6 +87,10 @@ struct hf_sim {
     int x_warps = 8, x_grid = 1, x_per_sm = 1;
     bool x_tune = false;               // pick the warp batch by measurement at the next hf_x_run
     std::unordered_map<void *, size_t> alloc_bytes;   // buffers managed by dev_reuse
+    uint8_t *d_gen_layer = nullptr;    // scratch of lattice generation and of the per-realisation reduction, kept between
+    int32_t *d_gen_pool = nullptr;     // calls: cudaMalloc + cudaFree per GA sweep cost 0.1-0.9 s every few calls
+    int64_t *d_gen_counts = nullptr;
+    unsigned long long *d_real_out = nullptr;
     bool x_brick = false;              // hfx_run_kernel reads brick-layout copies of the weights
     int32_t x_bX = 0, x_bY = 0;        // their padded plane
     double *d_bs1 = nullptr, *d_bt1 = nullptr;
@@ -579,6 +583,7 @@ int hf_destroy(hf_sim *s) {
     cudaFree(s->d_x_trace_len); cudaFree(s->d_x_totals);
     cudaFree(s->d_xd_pos); cudaFree(s->d_xd_occ); cudaFree(s->d_xd_T); cudaFree(s->d_xd_birth); cudaFree(s->d_xd_rec_L); cudaFree(s->d_xd_rec_seen); cudaFree(s->d_xd_time);
     cudaFree(s->d_xd_life); cudaFree(s->d_xd_draws); cudaFree(s->d_xd_totals);
+    cudaFree(s->d_gen_layer); cudaFree(s->d_gen_pool); cudaFree(s->d_gen_counts); cudaFree(s->d_real_out);
     cudaFree(s->d_pi_site); cudaFree(s->d_pi_meta); cudaFree(s->d_pi_final); cudaFree(s->d_pi_n);
     cudaFree(s->d_pi_tau); cudaFree(s->d_pi_clock); cudaFree(s->d_pi_draws); cudaFree(s->d_pi_tab); cudaFree(s->d_inv_dist);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -624,16 +629,16 @@ static int generate_lattice_impl(hf_sim *s, const double *props /* [n_real][3] *
         counts[(size_t)r] = n_host;
         counts[(size_t)(s->n_real + r)] = n_tadf;
     }
-    uint8_t *d_layer = nullptr;
-    int32_t *d_pool = nullptr;
-    int64_t *d_counts = nullptr;
-    if ((rc = dev_alloc(&d_layer, (size_t)(xy * s->n_real)))) return rc;
-    if ((rc = dev_alloc(&d_counts, counts.size()))) { cudaFree(d_layer); return rc; }
+    if ((rc = dev_reuse(s, &s->d_gen_layer, (size_t)(xy * s->n_real)))) return rc;
+    if ((rc = dev_reuse(s, &s->d_gen_counts, counts.size()))) return rc;
     // realisations are shuffled in batches so that the pool scratch stays below ~1 GiB
     int batch = (int)((int64_t)(1 << 28) / total);
     if (batch < 1) batch = 1;
     if (batch > s->n_real) batch = s->n_real;
-    if ((rc = dev_alloc(&d_pool, (size_t)(total * batch)))) { cudaFree(d_layer); cudaFree(d_counts); return rc; }
+    if ((rc = dev_reuse(s, &s->d_gen_pool, (size_t)(total * batch)))) return rc;
+    uint8_t *d_layer = s->d_gen_layer;
+    int32_t *d_pool = s->d_gen_pool;
+    int64_t *d_counts = s->d_gen_counts;
     cudaMemcpyAsync(d_counts, counts.data(), counts.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream);
     for (int r0 = 0; r0 < s->n_real; r0 += batch) {
         const int nb = s->n_real - r0 < batch ? s->n_real - r0 : batch;
@@ -642,9 +647,6 @@ static int generate_lattice_impl(hf_sim *s, const double *props /* [n_real][3] *
     }
     hf_fill_sites<<<s->sm_count * 8, 256, 0, s->stream>>>(P, d_layer, s->n_real, s->d_species, s->d_homo, s->d_lumo, s->d_s1, s->d_t1);
     cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_layer);
-    cudaFree(d_pool);
-    cudaFree(d_counts);
     if (e != cudaSuccess) return fail(HF_ERR_CUDA, "lattice generation failed: %s", cudaGetErrorString(e));
     HF_CUDA(cudaGetLastError());
     s->have_lattice = true;
@@ -669,12 +671,11 @@ int hf_read_realisation_tallies(hf_sim *s, uint64_t *out) {
     if (!s || !out) return fail(HF_ERR_BAD_ARG, "null argument");
     int rc = use_device(s);
     if (rc) return rc;
-    unsigned long long *d_out = nullptr;
-    if ((rc = dev_alloc(&d_out, (size_t)(5 * s->n_real)))) return rc;
+    if ((rc = dev_reuse(s, &s->d_real_out, (size_t)(5 * s->n_real)))) return rc;
+    unsigned long long *d_out = s->d_real_out;
     hf_reduce_realisations_kernel<<<s->n_real, 256, 0, s->stream>>>(s->d_sc, s->P.traj_per_real, d_out);
     cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * 5 * (size_t)s->n_real, cudaMemcpyDeviceToHost, s->stream);
     cudaError_t e = cudaStreamSynchronize(s->stream);
-    cudaFree(d_out);
     if (e != cudaSuccess) return fail(HF_ERR_CUDA, "hf_read_realisation_tallies failed: %s", cudaGetErrorString(e));
     return HF_OK;
 }
