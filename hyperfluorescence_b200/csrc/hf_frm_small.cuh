@@ -138,6 +138,8 @@ __device__ __forceinline__ int hf_gen_move_event_serial(const HfParams &P, HfWar
         uint32_t key1 = 0x7f800000u, key2 = 0x7f800000u;
         float x2max = 0.0f;
         unsigned rem = amask;
+        // (peeling the first / last block as hf_c1_gen does was measured 11 % SLOWER here: this kernel is bound by
+        //  instruction fetch and the extra copy of the body costs more than the tests it removes)
         for (int j = 0; 2 * j < nn + p; ++j) {
             HfPhiloxBlock rnd = {0, 0, 0, 0};
             if (!replay) rnd = hf_philox_block_rk(P.rk, HF_STREAM_TRAJ, w.ident, (d0 >> 1) + (uint64_t)j);
