@@ -210,6 +210,11 @@ def x_run(oracle, seed, first_traj, B, n_events, n_calls=1, generic=False, brick
     return dict(trace=trace, site=site, spin=spin, time=time, lifetime_sum=life, draws=draws, totals=totals)
 
 
+def brick_selftest(bX, bY, r_max):
+    """Mismatches between the packed brick offsets of hfx_brick_lin and the brick addresses (0 = none)."""
+    return int(lib().emu_brick_selftest(C.c_int32(bX), C.c_int32(bY), C.c_int32(r_max)))
+
+
 def xd_run(oracle, seed, device, n_excitons, n_events, n_calls=1):
     """The high-density kernel (one device = one warp) under emulation, model held by a DenseExcitonOracle."""
     o = oracle

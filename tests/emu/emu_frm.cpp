@@ -344,6 +344,27 @@ int emu_x_run(const int32_t dims[3], const uint8_t *species, const double *ws1, 
     return 0;
 }
 
+// Exhaustive check of the packed brick offsets (hfx_brick_lin) against the brick addresses themselves: every offset
+// with |d| <= r_max, every site of a bX x bY plane whose neighbour stays inside it.  Returns the number of mismatches.
+int emu_brick_selftest(int32_t bX, int32_t bY, int32_t r_max) {
+    int bad = 0;
+    const int plane = bX * bY;
+    for (int dz = -r_max; dz <= r_max; ++dz)
+        for (int dy = -r_max; dy <= r_max; ++dy)
+            for (int dx = -r_max; dx <= r_max; ++dx) {
+                const int32_t t = hfx_brick_lin(dx, dy, dz, bX, bY);
+                for (int y = r_max; y < bY - r_max; ++y)
+                    for (int x = r_max; x < bX - r_max; ++x) {
+                        int d = t >> 8;                                  // what hfx_gather<.., kBrick> computes
+                        if (t & (1 << (x & 3))) d += 12;
+                        if (t & (16 << (y & 3))) d += 4 * bX - 16;
+                        const int want = dz * plane + hfx_brick2(x + dx, y + dy, bX) - hfx_brick2(x, y, bX);
+                        bad += d != want;
+                    }
+            }
+    return bad;
+}
+
 static void xd_run_body(void *a) { hfxd_run_kernel<1>(*(const HfxdParams *)a); }
 
 // High-density devices: ONE device (one warp), fill + n_calls x hfxd_run(n_events).

@@ -92,6 +92,14 @@ def test_emulated_exciton_kernel_equals_specification(dims, cutoff, seed, B, gen
         assert tot[4] + tot[5] > 0                                                     # ... and spin flips (rare next to >= 388 transfer channels)
 
 
+@pytest.mark.parametrize("bX,bY,r", [(16, 12, 3), (24, 20, 4), (136, 136, 4), (40, 36, 5)])
+def test_brick_offsets_are_exact(bX, bY, r):
+    """hfx_brick_lin packs, per neighbour offset, the part of the brick-address difference that does not depend on the
+    site and two carry flags per residue; the gather adds 12 / 4 X' - 16 when they are set.  Exhaustively equal to the
+    difference of the brick addresses for every offset within the cutoff and every site of the padded plane."""
+    assert emu.brick_selftest(bX, bY, r) == 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims,cutoff", [((24, 24, 12), 4.0), ((21, 27, 9), 3.0), ((32, 26, 11), 5.0)])
 def test_gpu_brick_layout_changes_nothing(dims, cutoff, monkeypatch):
